@@ -1,0 +1,81 @@
+"""Seeded synthetic inputs for the BASELINE.json configurations.
+
+Pure numpy; used by bench.py, the tests and smoke() so the CUDA path, the oracle and the CPU
+baseline all see identical inputs.  Nothing here computes MPC results.
+"""
+import numpy as np
+
+# PMPC/main_parallel.py:107-118 -- per-shape cost weights (Qp, Qv, R)
+PMPC_SHAPE_WEIGHTS = {"cube": (600.0, 5.0, 0.1), "cylinder": (400.0, 2.5, 0.2), "sphere": (200.0, 2.0, 0.2)}
+PMPC_MASSES = (1.0, 2.0)            # NLP-inert (mass never enters mpc_3d.py)
+PMPC_FRICTIONS = (0.05, 0.10, 0.20)
+
+
+def pmpc_objects():
+    """The 18 shape x mass x friction objects: list of dict(shape, mass, mu, Qp, Qv, R)."""
+    objs = []
+    for shape, (Qp, Qv, R) in PMPC_SHAPE_WEIGHTS.items():
+        for mass in PMPC_MASSES:
+            for mu in PMPC_FRICTIONS:
+                objs.append(dict(shape=shape, mass=mass, mu=mu, Qp=Qp, Qv=Qv, R=R))
+    return objs
+
+
+def pmpc_config1():
+    """BASELINE config 1: cube, 1 kg, mu=0.10, PMPC/main.py:59-69 weights, README example target."""
+    return dict(state=np.array([[0.0, 0.0, 0.0, 0.0, 0.43, 0.0]]),
+                target=np.array([[0.1, 0.0, 0.05, 0.0, 0.4, 0.0]]),
+                Qp=np.array([400.0]), Qv=np.array([2.0]), R=np.array([0.2]), mu=np.array([0.10]))
+
+
+def pmpc_config2(states_per_object=64, seed=1):
+    """BASELINE config 2: 18 objects x ``states_per_object`` random (x0, target) pairs. B = 18*S."""
+    rng = np.random.default_rng(seed)
+    objs = pmpc_objects()
+    S = states_per_object
+    B = len(objs) * S
+    state = np.zeros((B, 6))
+    target = np.zeros((B, 6))
+    state[:, 0] = rng.uniform(-0.15, 0.15, B)
+    state[:, 2] = rng.uniform(-0.10, 0.10, B)
+    state[:, 1] = rng.uniform(-0.2, 0.2, B)
+    state[:, 3] = rng.uniform(-0.2, 0.2, B)
+    state[:, 4] = 0.43
+    target[:, 0] = rng.uniform(-0.125, 0.125, B)
+    target[:, 2] = rng.uniform(-0.125, 0.125, B)
+    target[:, 4] = 0.4
+    rep = lambda key: np.repeat(np.array([o[key] for o in objs], dtype=np.float64), S)
+    return dict(state=state, target=target, Qp=rep("Qp"), Qv=rep("Qv"), R=rep("R"), mu=rep("mu"),
+                mass=rep("mass"), shape=np.repeat(np.arange(len(objs)) // 6, S))
+
+
+def rmpc_config3(B=4096, seed=2):
+    """BASELINE config 3 initial conditions: x0, target offsets, surrogate-plant friction/damping."""
+    rng = np.random.default_rng(seed)
+    x0 = np.zeros((B, 4))
+    x0[:, 0] = rng.uniform(-0.1, 0.1, B)
+    x0[:, 2] = rng.uniform(-0.1, 0.1, B)
+    x0[:, 1] = rng.uniform(-0.15, 0.15, B)
+    x0[:, 3] = rng.uniform(-0.15, 0.15, B)
+    target = np.zeros((B, 4))
+    target[:, 0] = rng.uniform(-0.1, 0.1, B)
+    target[:, 2] = rng.uniform(-0.1, 0.1, B)
+    mu_plant = rng.choice(np.array([0.05, 0.1, 0.2]), B)
+    c_plant = rng.uniform(0.0, 0.5, B)
+    return dict(x0=x0, target=target, mu_plant=mu_plant, c_plant=c_plant)
+
+
+def lmpc_config4(B=16384, seed=3):
+    """BASELINE config 4 initial conditions: state, target, initial 34-parameter vectors."""
+    rng = np.random.default_rng(seed)
+    state = np.zeros((B, 8))
+    state[:, 0] = rng.uniform(-0.1, 0.1, B)
+    state[:, 2] = rng.uniform(-0.1, 0.1, B)
+    state[:, 1] = rng.uniform(-0.1, 0.1, B)
+    state[:, 3] = rng.uniform(-0.1, 0.1, B)
+    target = np.zeros((B, 8))
+    target[:, 0] = rng.uniform(-0.1, 0.1, B)
+    target[:, 2] = rng.uniform(-0.1, 0.1, B)
+    pvec = np.clip(1.0 + 0.1 * rng.standard_normal((B, 34)), 0.01, 1.9)
+    u_prev = np.zeros((B, 2))
+    return dict(state=state, target=target, pvec=pvec, u_prev=u_prev)
