@@ -1,0 +1,64 @@
+"""ctypes binding of the C ABI in include/dart_b200.h (lib/libdart_b200.so, built by __graft_entry__.build()).
+
+There is no CPU implementation behind this module: if the shared library is missing, or no CUDA
+device is present, every entry point raises.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libdart_b200.so")
+
+DART_PMPC, DART_RMPC, DART_LMPC = 0, 1, 2
+STATUS_CONVERGED, STATUS_MAXITER, STATUS_INFEASIBLE, STATUS_NUMERIC = 0, 1, 2, 3
+ERRORS = {0: "ok", -1: "bad argument", -2: "no CUDA device", -3: "CUDA error", -4: "allocation failed", -5: "unsupported configuration"}
+
+
+class DartCfg(C.Structure):
+    """Mirror of ``dart_cfg`` (include/dart_b200.h)."""
+    _fields_ = [
+        ("method", C.c_int32), ("N", C.c_int32), ("Ts", C.c_double), ("g", C.c_double),
+        ("u_lo", C.c_double), ("u_hi", C.c_double), ("du_lo", C.c_double), ("du_hi", C.c_double),
+        ("vmax", C.c_double), ("v_eps", C.c_double),
+        ("Qp", C.c_double), ("Qv", C.c_double), ("R", C.c_double), ("Rdu", C.c_double), ("mu", C.c_double),
+        ("Q", C.c_double * 8), ("Qt", C.c_double * 8), ("Rl", C.c_double * 4),
+        ("tol", C.c_double), ("max_iter", C.c_int32), ("mu_init", C.c_double),
+        ("lanes", C.c_int32), ("block_threads", C.c_int32),
+    ]
+
+
+class DartError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load libdart_b200.so once; raise loudly when it is absent (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DartError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(nvcc, sm_100a). dart_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    dp, ip, vp = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.c_void_p
+    L.dart_default_cfg.argtypes = [C.c_int32, C.POINTER(DartCfg)]
+    L.dart_create.argtypes = [C.POINTER(vp), C.POINTER(DartCfg), C.c_int]
+    L.dart_destroy.argtypes = [vp]
+    for f in ("dart_nx", "dart_nref", "dart_naux", "dart_nw"):
+        getattr(L, f).argtypes = [vp]
+    L.dart_solve.argtypes = [vp, C.c_int32] + [vp] * 9 + [vp]
+    L.dart_solve_host.argtypes = [vp, C.c_int32] + [vp] * 9
+    L.dart_launch_count.argtypes = [vp]
+    L.dart_launch_count.restype = C.c_int64
+    L.dart_last_launch_config.argtypes = [vp, ip, ip, ip, ip]
+    L.dart_tilt_to_quat.argtypes = [C.c_int32, vp, vp, vp]
+    _lib = L
+    return L
+
+
+def check(rc, what):
+    if rc != 0:
+        raise DartError(f"{what} failed: {ERRORS.get(rc, rc)} ({rc})")

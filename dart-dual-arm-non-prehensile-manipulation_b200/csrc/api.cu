@@ -1,0 +1,194 @@
+// C ABI (include/dart_b200.h) over the sm_100a kernels.  No CPU fallback: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+#include <string.h>
+#include <new>
+
+#include "launch.h"
+#include "opts.h"
+
+using namespace dart;
+
+struct dart_solver {
+    dart_cfg cfg;
+    int device;
+    SolverOpts opts;
+    int64_t launches;
+    LaunchInfo last;
+    // staging for the *_host entry point
+    cudaStream_t stream;
+    void* pin;   size_t pin_bytes;
+    void* dev;   size_t dev_bytes;
+};
+
+extern "C" int dart_default_cfg(int32_t method, dart_cfg* c) {
+    if (!c) return DART_ERR_ARG;
+    memset(c, 0, sizeof(*c));
+    c->method = method;
+    c->Ts = 0.002;
+    c->tol = 1e-8;
+    c->mu_init = 0.1;
+    c->max_iter = 200;
+    switch (method) {
+        case DART_PMPC:   // PMPC/main.py:59-69
+            c->N = 15; c->g = -9.81; c->u_lo = -0.6; c->u_hi = 0.6; c->Qp = 400.0; c->Qv = 2.0; c->R = 0.2; c->mu = 0.1;
+            return DART_OK;
+        case DART_RMPC:   // RMPC/dev_dual/rob_ctrl.py:281-284
+            c->N = 20; c->g = -9.81; c->u_lo = -0.6; c->u_hi = 0.6; c->du_lo = -0.06; c->du_hi = 0.06;
+            c->vmax = 0.2; c->v_eps = 0.1; c->Qp = 80.0; c->Qv = 2.0; c->R = 0.02; c->Rdu = 1.0;
+            return DART_OK;
+        case DART_LMPC: { // LMPC/src/run.py:118-126
+            c->N = 20; c->g = 9.81; c->u_lo = -0.4; c->u_hi = 0.4;
+            const double Q[8] = {200.0, 2.0, 200.0, 2.0, 0.0, 0.0, 0.0, 0.0};
+            for (int i = 0; i < 8; ++i) { c->Q[i] = Q[i]; c->Qt[i] = Q[i]; }
+            c->Rl[0] = 0.1; c->Rl[1] = 0.1; c->Rl[2] = 1.0; c->Rl[3] = 1.0;
+            return DART_OK;
+        }
+        default: return DART_ERR_ARG;
+    }
+}
+
+static int sizes(const dart_cfg& c, int& nx, int& nref, int& naux, int& nw) {
+    switch (c.method) {
+        case DART_PMPC: nx = 6; nref = 6; naux = 4; nw = PmpcAxis::nw(c.N); return DART_OK;
+        case DART_RMPC: nx = 4; nref = (c.N + 1) * 4; naux = 16; nw = Rmpc::nw(c.N); return DART_OK;
+        case DART_LMPC: nx = 8; nref = 8; naux = 36; nw = LmpcAxis::nw(c.N); return DART_OK;
+        default: return DART_ERR_ARG;
+    }
+}
+
+extern "C" int dart_create(dart_handle* out, const dart_cfg* cfg, int device) {
+    if (!out || !cfg) return DART_ERR_ARG;
+    int nx, nref, naux, nw;
+    if (sizes(*cfg, nx, nref, naux, nw) != DART_OK) return DART_ERR_ARG;
+    if (cfg->N < 1 || cfg->N > 64 || !(cfg->Ts > 0.0) || !(cfg->u_hi > cfg->u_lo)) return DART_ERR_ARG;
+    if (cfg->method == DART_RMPC && (!(cfg->du_hi > cfg->du_lo) || !(cfg->vmax > 0.0) || !(cfg->v_eps > 0.0))) return DART_ERR_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return DART_ERR_NO_DEVICE; }
+    if (device < 0 || device >= ndev) return DART_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return DART_ERR_CUDA;
+    dart_solver* h = new (std::nothrow) dart_solver();
+    if (!h) return DART_ERR_ALLOC;
+    h->cfg = *cfg;
+    h->device = device;
+    fill_opts(*cfg, h->opts);
+    h->launches = 0;
+    memset(&h->last, 0, sizeof(h->last));
+    h->pin = nullptr; h->pin_bytes = 0; h->dev = nullptr; h->dev_bytes = 0;
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return DART_ERR_CUDA; }
+    *out = h;
+    return DART_OK;
+}
+
+extern "C" int dart_destroy(dart_handle h) {
+    if (!h) return DART_ERR_ARG;
+    cudaSetDevice(h->device);
+    if (h->pin) cudaFreeHost(h->pin);
+    if (h->dev) cudaFree(h->dev);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return DART_OK;
+}
+
+extern "C" int dart_nx(dart_handle h) { int a, b, c, d; if (!h || sizes(h->cfg, a, b, c, d)) return DART_ERR_ARG; return a; }
+extern "C" int dart_nref(dart_handle h) { int a, b, c, d; if (!h || sizes(h->cfg, a, b, c, d)) return DART_ERR_ARG; return b; }
+extern "C" int dart_naux(dart_handle h) { int a, b, c, d; if (!h || sizes(h->cfg, a, b, c, d)) return DART_ERR_ARG; return c; }
+extern "C" int dart_nw(dart_handle h) { int a, b, c, d; if (!h || sizes(h->cfg, a, b, c, d)) return DART_ERR_ARG; return d; }
+
+extern "C" int dart_solve(dart_handle h, int32_t B, const double* x0, const double* ref, const double* aux,
+                          const double* warm_w, double* w_out, double* u0_out, double* J_out, int32_t* status,
+                          int32_t* iters, void* stream) {
+    if (!h || B < 0 || !x0 || !ref || !u0_out || !J_out) return DART_ERR_ARG;
+    if (h->cfg.method != DART_PMPC && !aux) return DART_ERR_ARG;
+    if (B == 0) return DART_OK;
+    KArgs a;
+    a.B = B; a.N = h->cfg.N; a.o = h->opts; a.cfg = h->cfg;
+    a.x0 = x0; a.ref = ref; a.aux = aux; a.warm = warm_w;
+    a.w_out = w_out; a.u0 = u0_out; a.J = J_out; a.status = status; a.iters = iters;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = launch_solve(a, h->cfg.lanes, h->cfg.block_threads, st, &h->last);
+    if (rc != DART_OK) return rc;
+    h->launches += 1;
+    if (h->cfg.method == DART_PMPC && w_out) {
+        rc = launch_pmpc_z(a, st);
+        if (rc != DART_OK) return rc;
+        h->launches += 1;
+    }
+    return DART_OK;
+}
+
+static int ensure(dart_solver* h, size_t bytes) {
+    if (bytes <= h->pin_bytes) return DART_OK;
+    if (h->pin) cudaFreeHost(h->pin);
+    if (h->dev) cudaFree(h->dev);
+    h->pin = nullptr; h->dev = nullptr; h->pin_bytes = h->dev_bytes = 0;
+    size_t cap = bytes + bytes / 4 + 4096;
+    if (cudaMallocHost(&h->pin, cap) != cudaSuccess) return DART_ERR_ALLOC;
+    if (cudaMalloc(&h->dev, cap) != cudaSuccess) { cudaFreeHost(h->pin); h->pin = nullptr; return DART_ERR_ALLOC; }
+    h->pin_bytes = h->dev_bytes = cap;
+    return DART_OK;
+}
+
+extern "C" int dart_solve_host(dart_handle h, int32_t B, const double* x0, const double* ref, const double* aux,
+                               const double* warm_w, double* w_out, double* u0_out, double* J_out,
+                               int32_t* status, int32_t* iters) {
+    if (!h || B < 0 || !x0 || !ref || !u0_out || !J_out) return DART_ERR_ARG;
+    if (h->cfg.method != DART_PMPC && !aux) return DART_ERR_ARG;
+    if (B == 0) return DART_OK;
+    if (cudaSetDevice(h->device) != cudaSuccess) return DART_ERR_CUDA;
+    int nx, nref, naux, nw;
+    sizes(h->cfg, nx, nref, naux, nw);
+    // one packed input block [x0 | ref | aux | warm] and one packed output block [u0 | J | w | status | iters]
+    const size_t n_x0 = (size_t)B * nx, n_ref = (size_t)B * nref, n_aux = aux ? (size_t)B * naux : 0,
+                 n_warm = warm_w ? (size_t)B * nw : 0;
+    const size_t in_d = n_x0 + n_ref + n_aux + n_warm;
+    const size_t n_w = w_out ? (size_t)B * nw : 0;
+    const size_t out_d = (size_t)B * 2 + B + n_w;
+    const size_t out_i = (size_t)B * 2;
+    const size_t bytes = (in_d + out_d) * sizeof(double) + out_i * sizeof(int32_t);
+    int rc = ensure(h, bytes);
+    if (rc != DART_OK) return rc;
+    double* pin = (double*)h->pin;
+    double* dev = (double*)h->dev;
+    size_t o = 0;
+    memcpy(pin + o, x0, n_x0 * 8); const size_t o_x0 = o; o += n_x0;
+    memcpy(pin + o, ref, n_ref * 8); const size_t o_ref = o; o += n_ref;
+    size_t o_aux = 0, o_warm = 0;
+    if (aux) { memcpy(pin + o, aux, n_aux * 8); o_aux = o; o += n_aux; }
+    if (warm_w) { memcpy(pin + o, warm_w, n_warm * 8); o_warm = o; o += n_warm; }
+    if (cudaMemcpyAsync(dev, pin, in_d * 8, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) return DART_ERR_CUDA;
+    double* d_out = dev + in_d;
+    double* d_u0 = d_out;
+    double* d_J = d_out + (size_t)B * 2;
+    double* d_w = w_out ? d_out + (size_t)B * 3 : nullptr;
+    int32_t* d_st = (int32_t*)(d_out + out_d);
+    int32_t* d_it = d_st + B;
+    rc = dart_solve(h, B, dev + o_x0, dev + o_ref, aux ? dev + o_aux : nullptr, warm_w ? dev + o_warm : nullptr,
+                    d_w, d_u0, d_J, d_st, d_it, (void*)h->stream);
+    if (rc != DART_OK) return rc;
+    double* p_out = pin + in_d;
+    if (cudaMemcpyAsync(p_out, d_out, out_d * 8 + out_i * 4, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) return DART_ERR_CUDA;
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return DART_ERR_CUDA;
+    memcpy(u0_out, p_out, (size_t)B * 2 * 8);
+    memcpy(J_out, p_out + (size_t)B * 2, (size_t)B * 8);
+    if (w_out) memcpy(w_out, p_out + (size_t)B * 3, n_w * 8);
+    const int32_t* p_i = (const int32_t*)(p_out + out_d);
+    if (status) memcpy(status, p_i, (size_t)B * 4);
+    if (iters) memcpy(iters, p_i + B, (size_t)B * 4);
+    return DART_OK;
+}
+
+extern "C" int64_t dart_launch_count(dart_handle h) { return h ? h->launches : -1; }
+
+extern "C" int dart_last_launch_config(dart_handle h, int32_t* lanes, int32_t* block_threads, int32_t* grid, int32_t* smem_bytes) {
+    if (!h) return DART_ERR_ARG;
+    if (lanes) *lanes = h->last.lanes;
+    if (block_threads) *block_threads = h->last.block_threads;
+    if (grid) *grid = h->last.grid;
+    if (smem_bytes) *smem_bytes = h->last.smem_bytes;
+    return DART_OK;
+}
+
+extern "C" int dart_tilt_to_quat(int32_t B, const double* u, double* quat, void* stream) {
+    if (B < 0 || !u || !quat) return DART_ERR_ARG;
+    return launch_tilt_to_quat(B, u, quat, (cudaStream_t)stream);
+}

@@ -1,0 +1,178 @@
+// sm_100a kernels: batched NMPC solve (one tile of G lanes per sub-problem) and the tilt->quaternion epilogue.
+#include <cuda_runtime.h>
+
+#include "models.cuh"
+#include "launch.h"
+
+namespace dart {
+
+template <int G>
+struct DevTile {
+    unsigned mask;
+    int ln;
+    __device__ __forceinline__ DevTile() {
+        const int l = threadIdx.x & 31;
+        ln = l & (G - 1);
+        mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (l - ln));
+    }
+    __device__ __forceinline__ int lane() const { return ln; }
+    __device__ __forceinline__ int size() const { return G; }
+    __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+    __device__ __forceinline__ double sum(double v) const {
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o, G);
+        return v;
+    }
+    __device__ __forceinline__ double max(double v) const {
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(mask, v, o, G));
+        return v;
+    }
+    __device__ __forceinline__ double min(double v) const {
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(mask, v, o, G));
+        return v;
+    }
+};
+
+// Per-tile result slot at the head of each workspace stride (4 doubles).
+constexpr int kSlot = 4;
+
+template <class M, int G>
+__global__ void __launch_bounds__(256) nmpc_solve_kernel(const KArgs a, const int ws_stride) {
+    extern __shared__ double smem[];
+    constexpr int NAX = M::NAXIS;
+    static_assert(G * NAX <= 32, "all axes of one instance must share a warp");
+    const DevTile<G> tile;
+    const int tpb = blockDim.x / G;
+    const int tib = threadIdx.x / G;
+    const long prob = (long)blockIdx.x * tpb + tib;
+    const int inst = (int)(prob / NAX), axis = (int)(prob % NAX);
+    double* slot = smem + (size_t)tib * ws_stride;
+    const bool active = inst < a.B;
+    double J = 0.0, kkt = 0.0;
+    int32_t status = ST_CONVERGED, iters = 0;
+    if (active) solve_one<M, DevTile<G>>(tile, a, inst, axis, slot + kSlot, J, status, iters, kkt);
+    if (NAX == 1) {
+        if (active && tile.lane() == 0) {
+            a.J[inst] = J;
+            if (a.status) a.status[inst] = status;
+            if (a.iters) a.iters[inst] = iters;
+        }
+        return;
+    }
+    // combine the axes of one instance (adjacent tiles of the same warp), in a fixed order
+    if (tile.lane() == 0) {
+        slot[0] = J;
+        slot[1] = (double)status;
+        slot[2] = (double)iters;
+        slot[3] = kkt;
+    }
+    const int l = threadIdx.x & 31;
+    const int gl = l & (G * NAX - 1);
+    const unsigned gmask = (G * NAX == 32) ? 0xffffffffu : (((1u << (G * NAX)) - 1u) << (l - gl));
+    __syncwarp(gmask);
+    if (active && gl == 0) {
+        double Js = 0.0;
+        int32_t st = 0, itx = 0;
+        for (int ax = 0; ax < NAX; ++ax) {
+            const double* s2 = slot + (size_t)ax * ws_stride;
+            Js += s2[0];
+            st = max(st, (int32_t)s2[1]);
+            itx = max(itx, (int32_t)s2[2]);
+        }
+        a.J[inst] = Js;
+        if (a.status) a.status[inst] = st;
+        if (a.iters) a.iters[inst] = itx;
+    }
+}
+
+template <class M, int G>
+static int launch_t(const KArgs& a, int block_threads, cudaStream_t st, LaunchInfo* info) {
+    const int ws = Workspace<M>::doubles(a.N) + kSlot;
+    const int ws_stride = (ws + 1) & ~1;
+    int bt = block_threads > 0 ? block_threads : 0;
+    const int unit = G * M::NAXIS;                       // lanes per instance
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int max_smem = 0;
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (bt == 0) {
+        // one warp per block unless the batch is large: keeps every SM busy at small B, and lets
+        // shared memory (the occupancy limiter) pack at large B.
+        bt = 32;
+        const long probs = (long)a.B * M::NAXIS;
+        if (probs * G > 148L * 32 * 8) bt = 64;
+    }
+    if (bt % 32 != 0 || bt < unit) return DART_ERR_ARG;
+    int tpb = bt / G;
+    size_t smem = (size_t)tpb * ws_stride * sizeof(double);
+    while (smem > (size_t)max_smem && bt > 32) { bt -= 32; tpb = bt / G; smem = (size_t)tpb * ws_stride * sizeof(double); }
+    if (smem > (size_t)max_smem) return DART_ERR_UNSUPPORTED;
+    auto kern = nmpc_solve_kernel<M, G>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return DART_ERR_CUDA;
+    const long probs = (long)a.B * M::NAXIS;
+    const int grid = (int)((probs + tpb - 1) / tpb);
+    kern<<<grid, bt, smem, st>>>(a, ws_stride);
+    if (info) { info->lanes = G; info->block_threads = bt; info->grid = grid; info->smem_bytes = (int)smem; }
+    return cudaGetLastError() == cudaSuccess ? DART_OK : DART_ERR_CUDA;
+}
+
+template <class M>
+static int launch_g(const KArgs& a, int lanes, int block_threads, cudaStream_t st, LaunchInfo* info) {
+    switch (lanes) {
+        case 1: return launch_t<M, 1>(a, block_threads, st, info);
+        case 2: return launch_t<M, 2>(a, block_threads, st, info);
+        case 4: return launch_t<M, 4>(a, block_threads, st, info);
+        case 8: return launch_t<M, 8>(a, block_threads, st, info);
+        case 16: return launch_t<M, 16>(a, block_threads, st, info);
+        case 32:
+            if constexpr (M::NAXIS == 1) return launch_t<M, 32>(a, block_threads, st, info);
+            return DART_ERR_ARG;
+        default: return DART_ERR_ARG;
+    }
+}
+
+int launch_solve(const KArgs& a, int lanes, int block_threads, cudaStream_t st, LaunchInfo* info) {
+    switch (a.cfg.method) {
+        case DART_PMPC: return launch_g<PmpcAxis>(a, lanes > 0 ? lanes : 4, block_threads, st, info);
+        case DART_RMPC: return launch_g<Rmpc>(a, lanes > 0 ? lanes : 16, block_threads, st, info);
+        case DART_LMPC: return launch_g<LmpcAxis>(a, lanes > 0 ? lanes : 8, block_threads, st, info);
+        default: return DART_ERR_ARG;
+    }
+}
+
+// PMPC: z rows of the decision vector (one thread per instance; tiny, only when w_out is requested)
+__global__ void pmpc_z_kernel(const KArgs a) {
+    const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst < a.B) pmpc_z_rollout(a, inst);
+}
+
+int launch_pmpc_z(const KArgs& a, cudaStream_t st) {
+    if (!a.w_out) return DART_OK;
+    pmpc_z_kernel<<<(a.B + 127) / 128, 128, 0, st>>>(a);
+    return cudaGetLastError() == cudaSuccess ? DART_OK : DART_ERR_CUDA;
+}
+
+// Euler xyz [u1, -u0, 0] -> wxyz (PMPC/main.py:107-116)
+__global__ void tilt_to_quat_kernel(int B, const double* __restrict__ u, double* __restrict__ q) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const double ax = u[2 * i + 1], ay = -u[2 * i];
+    double sx, cx, sy, cy;
+    sincos(0.5 * ax, &sx, &cx);
+    sincos(0.5 * ay, &sy, &cy);
+    const double cz = 1.0, sz = 0.0;
+    q[4 * i + 0] = cx * cy * cz + sx * sy * sz;
+    q[4 * i + 1] = sx * cy * cz - cx * sy * sz;
+    q[4 * i + 2] = cx * sy * cz + sx * cy * sz;
+    q[4 * i + 3] = cx * cy * sz - sx * sy * cz;
+}
+
+int launch_tilt_to_quat(int B, const double* u, double* q, cudaStream_t st) {
+    if (B <= 0) return DART_OK;
+    tilt_to_quat_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, u, q);
+    return cudaGetLastError() == cudaSuccess ? DART_OK : DART_ERR_CUDA;
+}
+
+}  // namespace dart

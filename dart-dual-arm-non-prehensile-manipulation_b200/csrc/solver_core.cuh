@@ -1,0 +1,570 @@
+// Batched tray-tilt NMPC: primal-dual interior-point method with a Riccati KKT factorisation.
+//
+// One *problem* (a whole NLP, or one decoupled axis of it) is solved by a tile of G lanes of a warp.
+// Horizon data lives in a per-problem shared-memory workspace; lanes split the horizon for everything
+// that is parallel over stages (RK4 + analytic Jacobians, costs, barrier terms, KKT residuals) and split
+// the columns of the stage matrices [A B d] for the serial Riccati sweep.  Tile-wide reductions are
+// warp shuffles.  The same code compiles for the host with a 1-lane tile (tests/hostemu), which is how the
+// solver logic is unit-tested on machines without a GPU; the product never runs it on the CPU.
+//
+// Replaces ca.nlpsol('ipopt') + MUMPS at the reference call sites
+//   PMPC/src/controller/mpc_3d.py:82,124-132
+//   RMPC/dev_dual/controller/np_mpc_adaptive_with_linear_regressor.py:157-162,214-215
+//   LMPC/src/controller/rlmpc2.py:480-491,508-515
+// Algorithm (IPOPT-flavoured, Waechter & Biegler 2006): slack form for every inequality row,
+// monotone barrier schedule, fraction-to-boundary rule, filter-type step acceptance.  Multiple shooting
+// as in the reference (states are decision variables; x_0 is eliminated).  Hessian = constant cost Hessian
+// + barrier terms + the Lagrangian curvature of the tilt input, -tan(u_i) (B^T lambda)_i, which is exact
+// for models that are affine in g*sin(u_i) (PMPC) and O(Ts^2)-accurate for RMPC/LMPC.  First derivatives
+// are exact (forward sensitivities through RK4), so the fixed point is the NLP's KKT point.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#ifdef DART_TRACE
+#include <stdio.h>
+#endif
+
+#if defined(__CUDACC__)
+#define DART_HD __host__ __device__ __forceinline__
+#define DART_UNROLL _Pragma("unroll")
+#else
+#define DART_HD inline
+#define DART_UNROLL
+#endif
+
+namespace dart {
+
+enum Status : int32_t { ST_CONVERGED = 0, ST_MAXITER = 1, ST_INFEASIBLE = 2, ST_NUMERIC = 3 };
+
+struct SolverOpts {
+    double tol, mu0, kappa_mu, theta_mu, kappa_eps, tau_min, bound_push, eta, smax;
+    double s_phi, s_theta, delta_sw, gamma_theta, gamma_phi, theta_small;
+    int max_iter, max_backtrack;
+};
+
+DART_HD double dmax(double a, double b) { return a > b ? a : b; }
+DART_HD double dmin(double a, double b) { return a < b ? a : b; }
+
+// Host stand-in for a tile of one lane.
+struct HostTile {
+    DART_HD int lane() const { return 0; }
+    DART_HD int size() const { return 1; }
+    DART_HD void sync() const {}
+    DART_HD double sum(double v) const { return v; }
+    DART_HD double max(double v) const { return v; }
+    DART_HD double min(double v) const { return v; }
+};
+
+template <class M>
+struct Workspace {
+    static constexpr int n = M::NX, m = M::NU, nr = M::NR, ny = n + m, nc = n + m + 1;
+    double *X, *U, *A, *Bm, *D, *LAM, *LN, *PP, *PV, *K, *KFF, *DX, *DU, *BL;
+    double *S, *ZL, *ZU, *ISL, *ISU, *RC, *DS, *DZL, *DZU, *MM, *REF;
+
+    DART_HD static int doubles(int N) {
+        return (N + 1) * n + N * m + N * n * n + N * n * m + N * n + N * n + N * n + (N + 1) * n * n + (N + 1) * n +
+               N * m * n + N * m + (N + 1) * n + N * m + N * m + 9 * N * nr + ny * nc + M::ref_doubles(N);
+    }
+    DART_HD void bind(double* p, int N) {
+        X = p;   p += (N + 1) * n;
+        U = p;   p += N * m;
+        A = p;   p += N * n * n;
+        Bm = p;  p += N * n * m;
+        D = p;   p += N * n;
+        LAM = p; p += N * n;
+        LN = p;  p += N * n;
+        PP = p;  p += (N + 1) * n * n;
+        PV = p;  p += (N + 1) * n;
+        K = p;   p += N * m * n;
+        KFF = p; p += N * m;
+        DX = p;  p += (N + 1) * n;
+        DU = p;  p += N * m;
+        BL = p;  p += N * m;
+        S = p;   p += N * nr;
+        ZL = p;  p += N * nr;
+        ZU = p;  p += N * nr;
+        ISL = p; p += N * nr;
+        ISU = p; p += N * nr;
+        RC = p;  p += N * nr;
+        DS = p;  p += N * nr;
+        DZL = p; p += N * nr;
+        DZU = p; p += N * nr;
+        MM = p;  p += ny * nc;
+        REF = p;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------
+template <class M, class T>
+struct Solver {
+    static constexpr int n = M::NX, m = M::NU, nr = M::NR, ny = n + m, nc = n + m + 1, np = M::NP;
+    using Prm = typename M::Prm;
+    using W = Workspace<M>;
+
+    const T& tile;
+    const Prm& prm;
+    const SolverOpts& o;
+    const int N;
+    W& w;
+
+    DART_HD Solver(const T& t, const Prm& p, const SolverOpts& oo, int NN, W& ww) : tile(t), prm(p), o(oo), N(NN), w(ww) {}
+
+    DART_HD double yval(int k, int i) const { return i < n ? w.X[k * n + i] : w.U[k * m + (i - n)]; }
+    DART_HD double rowval(int k, int r) const {
+        double t = M::row_sa(r) * yval(k, M::row_ia(r));
+        if (M::row_ib(r) >= 0) t += M::row_sb(r) * yval(k, M::row_ib(r));
+        return t;
+    }
+    DART_HD static bool masked(int k, int r) { return k == 0 && M::row_skip0(r); }
+
+    // cost gradient wrt y_i at stage k (stage cost incl. tilt-rate term)
+    DART_HD double cost_grad(int k, int i) const {
+        double g = 2.0 * M::wy(prm, i) * (yval(k, i) - M::ry(prm, w.REF, k, i));
+        if (M::NAUG > 0) {
+            if (i >= n) {
+                int j = i - n;
+                g += 2.0 * M::wd(prm, j) * (w.U[k * m + j] - w.X[k * n + np + j]);
+            } else if (i >= np) {
+                int j = i - np;
+                g -= 2.0 * M::wd(prm, j) * (w.U[k * m + j] - w.X[k * n + np + j]);
+            }
+        }
+        return g;
+    }
+
+    // ---- E1: dynamics, Jacobians, defects, objective, barrier logs, constraint violation (stage-parallel)
+    DART_HD void eval1(double& f, double& L, double& th, double& pinf) {
+        double f_ = 0.0, L_ = 0.0, th_ = 0.0, pi_ = 0.0;
+        for (int k = tile.lane(); k < N; k += tile.size()) {
+            double x[n], u[m], F[n], Aloc[np * np], Bloc[np * m];
+            DART_UNROLL for (int i = 0; i < n; ++i) x[i] = w.X[k * n + i];
+            DART_UNROLL for (int j = 0; j < m; ++j) u[j] = w.U[k * m + j];
+            M::dyn(prm, x, u, F, Aloc, Bloc);
+            double* Ak = w.A + k * n * n;
+            double* Bk = w.Bm + k * n * m;
+            DART_UNROLL for (int a = 0; a < n; ++a) {
+                DART_UNROLL for (int b = 0; b < n; ++b) Ak[a * n + b] = (a < np && b < np) ? Aloc[a * np + b] : 0.0;
+                DART_UNROLL for (int j = 0; j < m; ++j)
+                    Bk[a * m + j] = (a < np) ? Bloc[a * m + j] : ((a - np) == j ? 1.0 : 0.0);
+            }
+            DART_UNROLL for (int a = np; a < n; ++a) F[a] = u[a - np];
+            DART_UNROLL for (int a = 0; a < n; ++a) {
+                double d = F[a] - w.X[(k + 1) * n + a];
+                w.D[k * n + a] = d;
+                th_ += fabs(d);
+                pi_ = dmax(pi_, fabs(d));
+            }
+            DART_UNROLL for (int i = 0; i < ny; ++i) {
+                double e = (i < n ? x[i] : u[i - n]) - M::ry(prm, w.REF, k, i);
+                f_ += M::wy(prm, i) * e * e;
+            }
+            if (M::NAUG > 0) {
+                DART_UNROLL for (int j = 0; j < m; ++j) {
+                    double e = u[j] - x[np + j];
+                    f_ += M::wd(prm, j) * e * e;
+                }
+            }
+            DART_UNROLL for (int r = 0; r < nr; ++r) {
+                if (masked(k, r)) continue;
+                double lo, hi;
+                M::bounds(prm, r, lo, hi);
+                double s = w.S[k * nr + r];
+                double rc = rowval(k, r) - s;
+                double sl = s - lo, su = hi - s;
+                w.RC[k * nr + r] = rc;
+                w.ISL[k * nr + r] = 1.0 / sl;
+                w.ISU[k * nr + r] = 1.0 / su;
+                L_ += log(sl) + log(su);
+                th_ += fabs(rc);
+                pi_ = dmax(pi_, fabs(rc));
+            }
+        }
+        if (tile.lane() == 0) {
+            DART_UNROLL for (int i = 0; i < n; ++i) {
+                double e = w.X[N * n + i] - M::rT(prm, w.REF, N, i);
+                f_ += M::wT(prm, i) * e * e;
+            }
+        }
+        f = tile.sum(f_);
+        L = tile.sum(L_);
+        th = tile.sum(th_);
+        pinf = tile.max(pi_);
+        tile.sync();
+    }
+
+    // ---- E2: KKT residuals with the current multipliers (stage-parallel)
+    DART_HD void eval2(double& dinf, double& zs_min, double& zs_max, double& lam_sum, double& z_sum, int& nact) {
+        double di = 0.0, zmn = 1e300, zmx = 0.0, ls = 0.0, zs = 0.0;
+        int na = 0;
+        for (int k = tile.lane(); k < N; k += tile.size()) {
+            const double* Ak = w.A + k * n * n;
+            const double* Bk = w.Bm + k * n * m;
+            double lam[n];
+            DART_UNROLL for (int a = 0; a < n; ++a) { lam[a] = w.LAM[k * n + a]; ls += fabs(lam[a]); }
+            double g[ny];
+            DART_UNROLL for (int i = 0; i < ny; ++i) g[i] = cost_grad(k, i);
+            DART_UNROLL for (int i = 0; i < n; ++i) {
+                double acc = 0.0;
+                DART_UNROLL for (int a = 0; a < n; ++a) acc += Ak[a * n + i] * lam[a];
+                g[i] += acc - (k >= 1 ? w.LAM[(k - 1) * n + i] : 0.0);
+            }
+            DART_UNROLL for (int j = 0; j < m; ++j) {
+                double acc = 0.0;
+                DART_UNROLL for (int a = 0; a < n; ++a) acc += Bk[a * m + j] * lam[a];
+                w.BL[k * m + j] = acc;
+                g[n + j] += acc;
+            }
+            DART_UNROLL for (int r = 0; r < nr; ++r) {
+                if (masked(k, r)) continue;
+                double zl = w.ZL[k * nr + r], zu = w.ZU[k * nr + r];
+                double nu = zu - zl;
+                g[M::row_ia(r)] += M::row_sa(r) * nu;
+                if (M::row_ib(r) >= 0) g[M::row_ib(r)] += M::row_sb(r) * nu;
+                double lo, hi;
+                M::bounds(prm, r, lo, hi);
+                double s = w.S[k * nr + r];
+                double a = zl * (s - lo), b = zu * (hi - s);
+                zmn = dmin(zmn, dmin(a, b));
+                zmx = dmax(zmx, dmax(a, b));
+                zs += fabs(zl) + fabs(zu);
+                na += 1;
+            }
+            DART_UNROLL for (int i = 0; i < ny; ++i)
+                if (i >= n || k >= 1) di = dmax(di, fabs(g[i]));
+        }
+        if (tile.lane() == 0) {
+            DART_UNROLL for (int i = 0; i < n; ++i) {
+                double gT = 2.0 * M::wT(prm, i) * (w.X[N * n + i] - M::rT(prm, w.REF, N, i)) - w.LAM[(N - 1) * n + i];
+                di = dmax(di, fabs(gT));
+            }
+        }
+        dinf = tile.max(di);
+        zs_min = tile.min(zmn);
+        zs_max = tile.max(zmx);
+        lam_sum = tile.sum(ls);
+        z_sum = tile.sum(zs);
+        nact = (int)(tile.sum((double)na) + 0.5);
+        tile.sync();
+    }
+
+    // m x m SPD solve helpers (m <= 2 in all models; generic Cholesky kept for clarity)
+    DART_HD static bool chol(double* H) {   // in place, lower; returns false if not PD
+        DART_UNROLL for (int j = 0; j < m; ++j) {
+            double d = H[j * m + j];
+            DART_UNROLL for (int q = 0; q < j; ++q) d -= H[j * m + q] * H[j * m + q];
+            if (!(d > 0.0)) return false;
+            d = sqrt(d);
+            H[j * m + j] = d;
+            DART_UNROLL for (int i = j + 1; i < m; ++i) {
+                double v = H[i * m + j];
+                DART_UNROLL for (int q = 0; q < j; ++q) v -= H[i * m + q] * H[j * m + q];
+                H[i * m + j] = v / d;
+            }
+        }
+        return true;
+    }
+    DART_HD static void chol_solve(const double* Lc, double* b) {
+        DART_UNROLL for (int i = 0; i < m; ++i) {
+            double v = b[i];
+            DART_UNROLL for (int q = 0; q < i; ++q) v -= Lc[i * m + q] * b[q];
+            b[i] = v / Lc[i * m + i];
+        }
+        DART_UNROLL for (int i = m - 1; i >= 0; --i) {
+            double v = b[i];
+            DART_UNROLL for (int q = i + 1; q < m; ++q) v -= Lc[q * m + i] * b[q];
+            b[i] = v / Lc[i * m + i];
+        }
+    }
+
+    // ---- Riccati backward sweep; lanes own columns of [A B d]
+    DART_HD void backward(double mu) {
+        const int lane = tile.lane(), G = tile.size();
+        for (int c = lane; c <= n; c += G) {
+            if (c < n) {
+                DART_UNROLL for (int i = 0; i < n; ++i) w.PP[N * n * n + i * n + c] = (i == c) ? 2.0 * M::wT(prm, c) : 0.0;
+            } else {
+                DART_UNROLL for (int i = 0; i < n; ++i)
+                    w.PV[N * n + i] = 2.0 * M::wT(prm, i) * (w.X[N * n + i] - M::rT(prm, w.REF, N, i));
+            }
+        }
+        tile.sync();
+        for (int k = N - 1; k >= 0; --k) {
+            const double* Ak = w.A + k * n * n;
+            const double* Bk = w.Bm + k * n * m;
+            const double* Pn = w.PP + (k + 1) * n * n;
+            const double* pn = w.PV + (k + 1) * n;
+            for (int c = lane; c < nc; c += G) {
+                double t[n], ww[n], col[ny];
+                DART_UNROLL for (int a = 0; a < n; ++a)
+                    t[a] = (c < n) ? Ak[a * n + c] : (c < ny ? Bk[a * m + (c - n)] : w.D[k * n + a]);
+                DART_UNROLL for (int a = 0; a < n; ++a) {
+                    double acc = (c == nc - 1) ? pn[a] : 0.0;
+                    DART_UNROLL for (int b = 0; b < n; ++b) acc += Pn[a * n + b] * t[b];
+                    ww[a] = acc;
+                }
+                DART_UNROLL for (int i = 0; i < n; ++i) {
+                    double acc = 0.0;
+                    DART_UNROLL for (int a = 0; a < n; ++a) acc += Ak[a * n + i] * ww[a];
+                    col[i] = acc;
+                }
+                DART_UNROLL for (int j = 0; j < m; ++j) {
+                    double acc = 0.0;
+                    DART_UNROLL for (int a = 0; a < n; ++a) acc += Bk[a * m + j] * ww[a];
+                    col[n + j] = acc;
+                }
+                if (c < ny) {
+                    // Hessian column c: cost + tilt-rate coupling + barrier rows + input curvature
+                    col[c] += 2.0 * M::wy(prm, c);
+                    if (M::NAUG > 0) {
+                        if (c >= n) {
+                            int j = c - n;
+                            col[c] += 2.0 * M::wd(prm, j);
+                            col[np + j] -= 2.0 * M::wd(prm, j);
+                        } else if (c >= np) {
+                            int j = c - np;
+                            col[c] += 2.0 * M::wd(prm, j);
+                            col[n + j] -= 2.0 * M::wd(prm, j);
+                        }
+                    }
+                    DART_UNROLL for (int r = 0; r < nr; ++r) {
+                        if (masked(k, r)) continue;
+                        const int ia = M::row_ia(r), ib = M::row_ib(r);
+                        if (ia != c && ib != c) continue;
+                        double sig = w.ZL[k * nr + r] * w.ISL[k * nr + r] + w.ZU[k * nr + r] * w.ISU[k * nr + r];
+                        double sc = (ia == c) ? M::row_sa(r) : M::row_sb(r);
+                        col[ia] += sig * sc * M::row_sa(r);
+                        if (ib >= 0) col[ib] += sig * sc * M::row_sb(r);
+                    }
+                    if (c >= n) col[c] += -tan(w.U[k * m + (c - n)]) * w.BL[k * m + (c - n)];
+                } else {
+                    // condensed gradient column
+                    DART_UNROLL for (int i = 0; i < ny; ++i) col[i] += cost_grad(k, i);
+                    DART_UNROLL for (int r = 0; r < nr; ++r) {
+                        if (masked(k, r)) continue;
+                        double isl = w.ISL[k * nr + r], isu = w.ISU[k * nr + r];
+                        double sig = w.ZL[k * nr + r] * isl + w.ZU[k * nr + r] * isu;
+                        double nuhat = mu * (isu - isl) + sig * w.RC[k * nr + r];
+                        col[M::row_ia(r)] += M::row_sa(r) * nuhat;
+                        if (M::row_ib(r) >= 0) col[M::row_ib(r)] += M::row_sb(r) * nuhat;
+                    }
+                }
+                DART_UNROLL for (int i = 0; i < ny; ++i) w.MM[c * ny + i] = col[i];
+            }
+            tile.sync();
+            // every lane factors the same m x m block H = M[n.., n..] (+ escalating shift if not PD)
+            double Lc[m * m];
+            double shift = 0.0;
+            for (int tries = 0; tries < 40; ++tries) {
+                DART_UNROLL for (int i = 0; i < m; ++i)
+                    DART_UNROLL for (int j = 0; j < m; ++j)
+                        Lc[i * m + j] = w.MM[(n + j) * ny + n + i] + (i == j ? shift : 0.0);
+                if (chol(Lc)) break;
+                shift = (shift == 0.0) ? 1e-4 : shift * 8.0;
+            }
+            for (int c = lane; c < nc; c += G) {
+                if (c >= n && c < ny) continue;
+                double kt[m];
+                DART_UNROLL for (int j = 0; j < m; ++j) kt[j] = -w.MM[c * ny + n + j];
+                chol_solve(Lc, kt);
+                DART_UNROLL for (int j = 0; j < m; ++j) {
+                    if (c < n) w.K[k * m * n + j * n + c] = kt[j];
+                    else w.KFF[k * m + j] = kt[j];
+                }
+                DART_UNROLL for (int i = 0; i < n; ++i) {
+                    double v = w.MM[c * ny + i];
+                    DART_UNROLL for (int j = 0; j < m; ++j) v += w.MM[i * ny + n + j] * kt[j];
+                    if (c < n) w.PP[k * n * n + i * n + c] = v;
+                    else w.PV[k * n + i] = v;
+                }
+            }
+            tile.sync();
+        }
+    }
+
+    // ---- forward sweep (every lane runs the short affine recurrence in registers; lane 0 stores)
+    DART_HD void forward() {
+        double dx[n];
+        DART_UNROLL for (int i = 0; i < n; ++i) dx[i] = 0.0;
+        if (tile.lane() == 0) {
+            DART_UNROLL for (int i = 0; i < n; ++i) w.DX[i] = 0.0;
+        }
+        for (int k = 0; k < N; ++k) {
+            const double* Ak = w.A + k * n * n;
+            const double* Bk = w.Bm + k * n * m;
+            double du[m], nx[n];
+            DART_UNROLL for (int j = 0; j < m; ++j) {
+                double acc = w.KFF[k * m + j];
+                DART_UNROLL for (int i = 0; i < n; ++i) acc += w.K[k * m * n + j * n + i] * dx[i];
+                du[j] = acc;
+            }
+            DART_UNROLL for (int a = 0; a < n; ++a) {
+                double acc = w.D[k * n + a];
+                DART_UNROLL for (int i = 0; i < n; ++i) acc += Ak[a * n + i] * dx[i];
+                DART_UNROLL for (int j = 0; j < m; ++j) acc += Bk[a * m + j] * du[j];
+                nx[a] = acc;
+            }
+            if (tile.lane() == 0) {
+                DART_UNROLL for (int j = 0; j < m; ++j) w.DU[k * m + j] = du[j];
+                DART_UNROLL for (int a = 0; a < n; ++a) w.DX[(k + 1) * n + a] = nx[a];
+            }
+            DART_UNROLL for (int a = 0; a < n; ++a) dx[a] = nx[a];
+        }
+        tile.sync();
+    }
+
+    // ---- new multipliers, slack/dual steps, step-length limits, directional derivative (stage-parallel)
+    DART_HD void post(double mu, double& ap, double& ad, double& dphi) {
+        const double tau = dmax(o.tau_min, 1.0 - mu);
+        double ap_ = 1.0, ad_ = 1.0, dp = 0.0;
+        for (int k = tile.lane(); k < N; k += tile.size()) {
+            DART_UNROLL for (int a = 0; a < n; ++a) {
+                double acc = w.PV[(k + 1) * n + a];
+                DART_UNROLL for (int b = 0; b < n; ++b) acc += w.PP[(k + 1) * n * n + a * n + b] * w.DX[(k + 1) * n + b];
+                w.LN[k * n + a] = acc;
+            }
+            DART_UNROLL for (int i = 0; i < ny; ++i) {
+                double d = (i < n) ? w.DX[k * n + i] : w.DU[k * m + (i - n)];
+                dp += cost_grad(k, i) * d;
+            }
+            DART_UNROLL for (int r = 0; r < nr; ++r) {
+                if (masked(k, r)) { w.DS[k * nr + r] = 0.0; w.DZL[k * nr + r] = 0.0; w.DZU[k * nr + r] = 0.0; continue; }
+                const int ia = M::row_ia(r), ib = M::row_ib(r);
+                double dy = M::row_sa(r) * ((ia < n) ? w.DX[k * n + ia] : w.DU[k * m + (ia - n)]);
+                if (ib >= 0) dy += M::row_sb(r) * ((ib < n) ? w.DX[k * n + ib] : w.DU[k * m + (ib - n)]);
+                double ds = dy + w.RC[k * nr + r];
+                double isl = w.ISL[k * nr + r], isu = w.ISU[k * nr + r];
+                double zl = w.ZL[k * nr + r], zu = w.ZU[k * nr + r];
+                double dzl = mu * isl - zl - zl * isl * ds;
+                double dzu = mu * isu - zu + zu * isu * ds;
+                w.DS[k * nr + r] = ds;
+                w.DZL[k * nr + r] = dzl;
+                w.DZU[k * nr + r] = dzu;
+                dp -= mu * ds * (isl - isu);
+                if (ds < 0.0) ap_ = dmin(ap_, -tau / (isl * ds));
+                if (ds > 0.0) ap_ = dmin(ap_, tau / (isu * ds));
+                if (dzl < 0.0) ad_ = dmin(ad_, -tau * zl / dzl);
+                if (dzu < 0.0) ad_ = dmin(ad_, -tau * zu / dzu);
+            }
+        }
+        if (tile.lane() == 0) {
+            DART_UNROLL for (int i = 0; i < n; ++i)
+                dp += 2.0 * M::wT(prm, i) * (w.X[N * n + i] - M::rT(prm, w.REF, N, i)) * w.DX[N * n + i];
+        }
+        ap = tile.min(ap_);
+        ad = tile.min(ad_);
+        dphi = tile.sum(dp);
+        tile.sync();
+    }
+
+    DART_HD void move_primal(double da) {
+        for (int k = tile.lane(); k < N; k += tile.size()) {
+            DART_UNROLL for (int i = 0; i < n; ++i) w.X[(k + 1) * n + i] += da * w.DX[(k + 1) * n + i];
+            DART_UNROLL for (int j = 0; j < m; ++j) w.U[k * m + j] += da * w.DU[k * m + j];
+            DART_UNROLL for (int r = 0; r < nr; ++r) w.S[k * nr + r] += da * w.DS[k * nr + r];
+        }
+        tile.sync();
+    }
+
+    DART_HD void move_dual(double alpha, double ad, double mu) {
+        const double ks = 1e10;
+        for (int k = tile.lane(); k < N; k += tile.size()) {
+            DART_UNROLL for (int a = 0; a < n; ++a) w.LAM[k * n + a] += alpha * (w.LN[k * n + a] - w.LAM[k * n + a]);
+            DART_UNROLL for (int r = 0; r < nr; ++r) {
+                if (masked(k, r)) continue;
+                double lo, hi;
+                M::bounds(prm, r, lo, hi);
+                double s = w.S[k * nr + r];
+                double sl = s - lo, su = hi - s;
+                double zl = w.ZL[k * nr + r] + ad * w.DZL[k * nr + r];
+                double zu = w.ZU[k * nr + r] + ad * w.DZU[k * nr + r];
+                w.ZL[k * nr + r] = dmin(dmax(zl, mu / (ks * sl)), ks * mu / sl);
+                w.ZU[k * nr + r] = dmin(dmax(zu, mu / (ks * su)), ks * mu / su);
+            }
+        }
+        tile.sync();
+    }
+
+    // ---- slack/dual initialisation (IPOPT bound_push / bound_frac; z = mu0 / slack)
+    DART_HD void init_rows(double mu) {
+        for (int k = tile.lane(); k < N; k += tile.size()) {
+            DART_UNROLL for (int r = 0; r < nr; ++r) {
+                double lo, hi;
+                M::bounds(prm, r, lo, hi);
+                double push = dmin(o.bound_push * dmax(1.0, dmax(fabs(lo), fabs(hi))), o.bound_push * (hi - lo));
+                double s = dmin(dmax(rowval(k, r), lo + push), hi - push);
+                if (M::row_ib(r) < 0 && M::row_ia(r) >= n) w.U[k * m + (M::row_ia(r) - n)] = s / M::row_sa(r);
+                w.S[k * nr + r] = s;
+                bool mk = masked(k, r);
+                w.ZL[k * nr + r] = mk ? 0.0 : mu / (s - lo);
+                w.ZU[k * nr + r] = mk ? 0.0 : mu / (hi - s);
+            }
+            DART_UNROLL for (int a = 0; a < n; ++a) w.LAM[k * n + a] = 0.0;
+        }
+        tile.sync();
+        if (M::NAUG > 0) {
+            for (int k = tile.lane(); k < N; k += tile.size())
+                DART_UNROLL for (int j = 0; j < m; ++j) w.X[(k + 1) * n + np + j] = w.U[k * m + j];
+            tile.sync();
+        }
+    }
+
+    // ---- the interior-point loop.  X (all N+1 states, X[0] = x0), U and REF must be set by the caller.
+    DART_HD void run(double& J, int32_t& status, int32_t& iters, double& kkt) {
+        double mu = o.mu0;
+        init_rows(mu);
+        double f, L, th, pinf, dinf, zs_min, zs_max, lam_sum, z_sum;
+        int nact;
+        eval1(f, L, th, pinf);
+        eval2(dinf, zs_min, zs_max, lam_sum, z_sum, nact);
+        const double mu_min = o.tol / 10.0;
+        int it = 0;
+        int32_t st = ST_MAXITER;
+        double E0 = 0.0;
+        for (;; ++it) {
+            const double s_d = dmax(o.smax, (lam_sum + z_sum) / (double)(N * n + 2 * nact)) / o.smax;
+            const double s_c = dmax(o.smax, z_sum / (double)(2 * (nact > 0 ? nact : 1))) / o.smax;
+            const double base = dmax(dinf / s_d, pinf);
+            E0 = dmax(base, (nact > 0 ? zs_max : 0.0) / s_c);
+            if (E0 <= o.tol) { st = ST_CONVERGED; break; }
+            if (!(E0 == E0) || E0 > 1e300) { st = ST_NUMERIC; break; }
+            if (it >= o.max_iter) break;
+            for (int q = 0; q < 8; ++q) {
+                double cm = (nact > 0) ? dmax(fabs(zs_max - mu), fabs(zs_min - mu)) : 0.0;
+                double Emu = dmax(base, cm / s_c);
+                if (Emu <= o.kappa_eps * mu && mu > mu_min) mu = dmax(mu_min, dmin(o.kappa_mu * mu, pow(mu, o.theta_mu)));
+                else break;
+            }
+            backward(mu);
+            forward();
+            double ap, ad, dphi;
+            post(mu, ap, ad, dphi);
+            const double phi0 = f - mu * L, th0 = th;
+            const double th_max = 1e4 * dmax(1.0, th0);
+            double alpha = ap, applied = 0.0;
+            for (int bt = 0;; ++bt) {
+                move_primal(alpha - applied);
+                applied = alpha;
+                eval1(f, L, th, pinf);
+                const double phit = f - mu * L;
+                bool switching = (dphi < 0.0) && (alpha * pow(fabs(dphi), o.s_phi) > o.delta_sw * pow(th0, o.s_theta));
+                bool armijo = phit <= phi0 + o.eta * alpha * dphi + 10.0 * 2.220446049250313e-16 * fabs(phi0);
+                bool suff = (th <= (1.0 - o.gamma_theta) * th0) || (phit <= phi0 - o.gamma_phi * th0);
+                bool ok = ((switching && th0 <= o.theta_small) ? armijo : suff) && (th <= th_max) && (phit == phit) &&
+                          (fabs(phit) < 1e300);
+                if (ok || bt + 1 >= o.max_backtrack) break;
+                alpha *= 0.5;
+            }
+#ifdef DART_TRACE
+            printf("it %d mu %.3e E0 %.3e dinf %.3e pinf %.3e zsmax %.3e ap %.4f ad %.4f alpha %.5f dphi %.3e th0 %.3e f %.10g\n", it, mu, E0, dinf / s_d, pinf, zs_max / s_c, ap, ad, alpha, dphi, th0, f);
+#endif
+            move_dual(alpha, ad, mu);
+            eval2(dinf, zs_min, zs_max, lam_sum, z_sum, nact);
+        }
+        J = f;
+        status = st;
+        iters = it;
+        kkt = E0;
+    }
+};
+
+}  // namespace dart

@@ -1,0 +1,125 @@
+/* dart_b200 -- C ABI of the B200-native batched tray-tilt NMPC engine.
+ *
+ * Drop-in boundary for the high-level MPC solve of DART (dart-icra/DART-Dual-Arm-Non-Prehensile-
+ * Manipulation).  The reference has no FFI: its boundary is three Python classes and one queue
+ * protocol (citations relative to the reference tree):
+ *
+ *   PMPC.solve(target)                       PMPC/src/controller/mpc_3d.py:115-138
+ *   mpc_worker(...) queue service loop       PMPC/main_parallel.py:10-43
+ *   AdaptiveNPMPCSmooth.solve(x0,u_prev,th,R)  RMPC/dev_dual/controller/np_mpc_adaptive_with_linear_regressor.py:212-222
+ *   RLS.update(phi, y)                       same file :17-27 (called from RMPC/dev_dual/rob_ctrl.py:340-343)
+ *   reference governor + build_ref_traj      rob_ctrl.py:346-351, np_mpc_adaptive...py:201-210
+ *   RLMPC._solver_worker NLP solve           LMPC/src/controller/rlmpc2.py:494-519
+ *   Policy.mean_net forward + param update   rlmpc2.py:71-80, 742-759, 606-616
+ *
+ * Each entry point below is the batched form of one of those calls (batch axis B first, B = 1
+ * reproduces the reference call).  Plain pointers and sizes only; no torch types.  All arrays are
+ * row-major and float64 unless stated.  "dev" pointers are CUDA device pointers, "host" pointers are
+ * ordinary host memory.  Every function returns 0 on success or a negative dart_error; none throws,
+ * none synchronises the device except the *_host variants.  A handle is bound to one device and must
+ * not be used from two threads at once.  There is no CPU implementation behind this ABI: without a
+ * CUDA device dart_create fails with DART_ERR_NO_DEVICE.
+ */
+#ifndef DART_B200_H
+#define DART_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DART_PMPC 0
+#define DART_RMPC 1
+#define DART_LMPC 2
+
+#define DART_STATUS_CONVERGED 0   /* KKT error <= tol                                             */
+#define DART_STATUS_MAXITER 1     /* iteration cap hit; last iterate returned (reference: silent)  */
+#define DART_STATUS_INFEASIBLE 2  /* stage-0 velocity cap violated by the given x0 (RMPC)          */
+#define DART_STATUS_NUMERIC 3     /* NaN/Inf encountered                                           */
+
+typedef enum {
+    DART_OK = 0,
+    DART_ERR_ARG = -1,
+    DART_ERR_NO_DEVICE = -2,
+    DART_ERR_CUDA = -3,
+    DART_ERR_ALLOC = -4,
+    DART_ERR_UNSUPPORTED = -5
+} dart_error;
+
+/* Problem description = the reference's constructor arguments / parameter dicts.
+ * PMPC: mpc_3d.py:12 and PMPC/main.py:59-69.  RMPC: np_mpc_adaptive...py:35-38 and rob_ctrl.py:281-288.
+ * LMPC: LMPC/src/run.py:118-126.  Fields of the other methods are ignored. */
+typedef struct {
+    int32_t method;      /* DART_PMPC | DART_RMPC | DART_LMPC */
+    int32_t N;           /* horizon: 15 (PMPC), 20 (RMPC, LMPC) */
+    double Ts;           /* model.opt.timestep = 0.002 */
+    double g;            /* PMPC: model.opt.gravity[2] = -9.81; RMPC: gz = -9.81; LMPC: unused (literal 9.81) */
+    /* bounds */
+    double u_lo, u_hi;   /* tilt bounds */
+    double du_lo, du_hi; /* RMPC tilt-rate bounds */
+    double vmax;         /* RMPC velocity cap */
+    double v_eps;        /* RMPC tanh smoothing */
+    /* weights */
+    double Qp, Qv, R;    /* PMPC (R = tilt weight); RMPC uses Qp, Qv, Ru = R */
+    double Rdu;          /* RMPC tilt-rate weight */
+    double mu;           /* PMPC viscous friction coefficient */
+    double Q[8], Qt[8];  /* LMPC stage / terminal state weights */
+    double Rl[4];        /* LMPC [R_a, R_b, R_da, R_db] */
+    /* solver options (0 selects the default in brackets) */
+    double tol;          /* [1e-8]  KKT tolerance (IPOPT 'tol')            */
+    int32_t max_iter;    /* [PMPC 3000->capped 200, RMPC 200, LMPC 200]     */
+    double mu_init;      /* [0.1]   initial barrier parameter               */
+    int32_t lanes;       /* [auto]  lanes of a warp cooperating on one sub-problem: 1,2,4,8,16 (32 where allowed) */
+    int32_t block_threads; /* [auto] threads per block (multiple of 32)     */
+} dart_cfg;
+
+typedef struct dart_solver* dart_handle;
+
+/* Fill cfg with the reference's defaults for a method (values cited above). */
+int dart_default_cfg(int32_t method, dart_cfg* cfg);
+
+int dart_create(dart_handle* out, const dart_cfg* cfg, int device);
+int dart_destroy(dart_handle h);
+
+/* Sizes of the per-instance arrays for this handle. */
+int dart_nx(dart_handle h);    /* state size: 6 / 4 / 8                         */
+int dart_nref(dart_handle h);  /* target/reference size: 6 / (N+1)*4 / 8          */
+int dart_naux(dart_handle h);  /* PMPC 4 [Qp,Qv,R,mu]; RMPC 16 [u_prev,theta_hat]; LMPC 36 [u_prev,pvec] */
+int dart_nw(dart_handle h);    /* decision vector size (N+1)*nx + N*2, reference layout w = [vec(X); vec(U)] */
+
+/* One batched NLP solve (replaces the solver call inside PMPC.solve / AdaptiveNPMPCSmooth.solve /
+ * _solver_worker).  All pointers are device pointers on the handle's device.
+ *   x0      [B, nx]    current state (PMPC: what get_state() returns)
+ *   ref     [B, nref]  PMPC target(6) | RMPC Rref_flat((N+1)*4) | LMPC target(8)
+ *   aux     [B, naux]  PMPC: NULL -> weights/mu from cfg for every instance; RMPC, LMPC: required
+ *   warm_w  [B, nw]    primal warm start in the reference layout, or NULL for the reference's cold start
+ *                      (tile(x0) and zeros, mpc_3d.py:123)
+ *   w_out   [B, nw]    optimal decision vector (reference's sol['x']); may be NULL
+ *   u0_out  [B, 2]     first tilt command U_opt[0]
+ *   J_out   [B]        optimal objective (reference's sol['f'])
+ *   status  [B] int32  DART_STATUS_*            iters [B] int32 Newton iterations; either may be NULL
+ * Asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default stream). */
+int dart_solve(dart_handle h, int32_t B, const double* x0, const double* ref, const double* aux,
+               const double* warm_w, double* w_out, double* u0_out, double* J_out, int32_t* status,
+               int32_t* iters, void* stream);
+
+/* Same call with HOST pointers: stages through pinned buffers, copies inputs to the device, solves,
+ * copies results back and synchronises.  This is the call the Python drop-in classes make. */
+int dart_solve_host(dart_handle h, int32_t B, const double* x0, const double* ref, const double* aux,
+                    const double* warm_w, double* w_out, double* u0_out, double* J_out,
+                    int32_t* status, int32_t* iters);
+
+/* Number of kernels launched by this handle since creation (for bench.py's gpu_launches). */
+int64_t dart_launch_count(dart_handle h);
+
+/* Iteration statistics of the last dart_solve*: sum over instances of Newton iterations (device read; syncs). */
+int dart_last_launch_config(dart_handle h, int32_t* lanes, int32_t* block_threads, int32_t* grid, int32_t* smem_bytes);
+
+/* tilt -> tray quaternion wxyz, Euler xyz [u1, -u0, 0] (PMPC/main.py:107-116). u [B,2] -> quat [B,4], device. */
+int dart_tilt_to_quat(int32_t B, const double* u, double* quat, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DART_B200_H */

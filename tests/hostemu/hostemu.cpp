@@ -1,0 +1,45 @@
+// TEST HARNESS ONLY -- compiles the device solver source (solver_core.cuh, models.cuh) for the host with a
+// one-lane tile so that the interior-point/Riccati logic can be unit-tested on machines without a GPU.
+// It is built into tests/hostemu/_build/ by tests/hostemu/build.py, is never loaded by the product package,
+// and is not a CPU fallback: the C ABI in csrc/api.cu has no path to it.
+#include <vector>
+#include "../../dart-dual-arm-non-prehensile-manipulation_b200/csrc/models.cuh"
+#include "../../dart-dual-arm-non-prehensile-manipulation_b200/csrc/opts.h"
+
+using namespace dart;
+
+template <class M>
+static void run_all(const KArgs& a) {
+    HostTile tile;
+    std::vector<double> ws(Workspace<M>::doubles(a.N) + 8);
+    for (int inst = 0; inst < a.B; ++inst) {
+        double Js = 0.0;
+        int32_t st = 0, itx = 0;
+        for (int ax = 0; ax < M::NAXIS; ++ax) {
+            double J = 0, kkt = 0;
+            int32_t s = 0, it = 0;
+            solve_one<M, HostTile>(tile, a, inst, ax, ws.data(), J, s, it, kkt);
+            Js += J;
+            st = s > st ? s : st;
+            itx = it > itx ? it : itx;
+        }
+        a.J[inst] = Js;
+        if (a.status) a.status[inst] = st;
+        if (a.iters) a.iters[inst] = itx;
+        if (a.cfg.method == DART_PMPC) pmpc_z_rollout(a, inst);
+    }
+}
+
+extern "C" int hostemu_solve(const dart_cfg* cfg, int B, const double* x0, const double* ref, const double* aux,
+                             const double* warm, double* w_out, double* u0, double* J, int32_t* status, int32_t* iters) {
+    KArgs a;
+    a.B = B; a.N = cfg->N; a.cfg = *cfg;
+    fill_opts(*cfg, a.o);
+    a.x0 = x0; a.ref = ref; a.aux = aux; a.warm = warm; a.w_out = w_out; a.u0 = u0; a.J = J; a.status = status; a.iters = iters;
+    switch (cfg->method) {
+        case DART_PMPC: run_all<PmpcAxis>(a); return 0;
+        case DART_RMPC: run_all<Rmpc>(a); return 0;
+        case DART_LMPC: run_all<LmpcAxis>(a); return 0;
+    }
+    return -1;
+}
