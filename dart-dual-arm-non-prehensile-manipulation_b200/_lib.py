@@ -55,6 +55,7 @@ def lib():
     L.dart_launch_count.restype = C.c_int64
     L.dart_last_launch_config.argtypes = [vp, ip, ip, ip, ip]
     L.dart_tilt_to_quat.argtypes = [C.c_int32, vp, vp, vp]
+    L.dart_measure_fp64_tflops.argtypes = [C.c_int, dp]
     _lib = L
     return L
 

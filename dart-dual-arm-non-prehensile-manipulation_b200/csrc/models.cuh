@@ -341,7 +341,7 @@ DART_HD void solve_one(const T& tile, const KArgs& a, int inst, int axis, double
     tile.sync();
     Solver<M, T> s(tile, prm, a.o, N, w);
     s.run(J, status, iters, kkt);
-    if (M::infeasible0(prm, x0) && status == ST_CONVERGED) status = ST_INFEASIBLE;
+    if (M::infeasible0(prm, x0) && status != ST_NUMERIC) status = ST_INFEASIBLE;
     if (a.w_out) {
         double* wo = a.w_out + (long)inst * nwf;
         for (int k = tile.lane(); k <= N; k += tile.size()) {

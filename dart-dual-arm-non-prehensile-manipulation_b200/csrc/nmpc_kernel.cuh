@@ -1,4 +1,5 @@
-// sm_100a kernels: batched NMPC solve (one tile of G lanes per sub-problem) and the tilt->quaternion epilogue.
+// sm_100a kernel template: batched NMPC solve, one tile of G lanes of a warp per sub-problem.
+#pragma once
 #include <cuda_runtime.h>
 
 #include "models.cuh"
@@ -121,9 +122,8 @@ static int launch_t(const KArgs& a, int block_threads, cudaStream_t st, LaunchIn
 template <class M>
 static int launch_g(const KArgs& a, int lanes, int block_threads, cudaStream_t st, LaunchInfo* info) {
     switch (lanes) {
-        case 1: return launch_t<M, 1>(a, block_threads, st, info);
-        case 2: return launch_t<M, 2>(a, block_threads, st, info);
-        case 4: return launch_t<M, 4>(a, block_threads, st, info);
+        case 2: if constexpr (M::NX <= 2) return launch_t<M, 2>(a, block_threads, st, info); return DART_ERR_ARG;
+        case 4: if constexpr (M::NX <= 5) return launch_t<M, 4>(a, block_threads, st, info); return DART_ERR_ARG;
         case 8: return launch_t<M, 8>(a, block_threads, st, info);
         case 16: return launch_t<M, 16>(a, block_threads, st, info);
         case 32:
@@ -133,46 +133,5 @@ static int launch_g(const KArgs& a, int lanes, int block_threads, cudaStream_t s
     }
 }
 
-int launch_solve(const KArgs& a, int lanes, int block_threads, cudaStream_t st, LaunchInfo* info) {
-    switch (a.cfg.method) {
-        case DART_PMPC: return launch_g<PmpcAxis>(a, lanes > 0 ? lanes : 4, block_threads, st, info);
-        case DART_RMPC: return launch_g<Rmpc>(a, lanes > 0 ? lanes : 16, block_threads, st, info);
-        case DART_LMPC: return launch_g<LmpcAxis>(a, lanes > 0 ? lanes : 8, block_threads, st, info);
-        default: return DART_ERR_ARG;
-    }
-}
-
-// PMPC: z rows of the decision vector (one thread per instance; tiny, only when w_out is requested)
-__global__ void pmpc_z_kernel(const KArgs a) {
-    const int inst = blockIdx.x * blockDim.x + threadIdx.x;
-    if (inst < a.B) pmpc_z_rollout(a, inst);
-}
-
-int launch_pmpc_z(const KArgs& a, cudaStream_t st) {
-    if (!a.w_out) return DART_OK;
-    pmpc_z_kernel<<<(a.B + 127) / 128, 128, 0, st>>>(a);
-    return cudaGetLastError() == cudaSuccess ? DART_OK : DART_ERR_CUDA;
-}
-
-// Euler xyz [u1, -u0, 0] -> wxyz (PMPC/main.py:107-116)
-__global__ void tilt_to_quat_kernel(int B, const double* __restrict__ u, double* __restrict__ q) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B) return;
-    const double ax = u[2 * i + 1], ay = -u[2 * i];
-    double sx, cx, sy, cy;
-    sincos(0.5 * ax, &sx, &cx);
-    sincos(0.5 * ay, &sy, &cy);
-    const double cz = 1.0, sz = 0.0;
-    q[4 * i + 0] = cx * cy * cz + sx * sy * sz;
-    q[4 * i + 1] = sx * cy * cz - cx * sy * sz;
-    q[4 * i + 2] = cx * sy * cz + sx * cy * sz;
-    q[4 * i + 3] = cx * cy * sz - sx * sy * cz;
-}
-
-int launch_tilt_to_quat(int B, const double* u, double* q, cudaStream_t st) {
-    if (B <= 0) return DART_OK;
-    tilt_to_quat_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, u, q);
-    return cudaGetLastError() == cudaSuccess ? DART_OK : DART_ERR_CUDA;
-}
 
 }  // namespace dart

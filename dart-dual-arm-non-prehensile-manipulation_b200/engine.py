@@ -1,0 +1,126 @@
+"""Handle wrapper over the C ABI: one batched NMPC engine per (method, device)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import DartCfg, check
+
+
+def _p(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def _f64(a, shape, name):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if a.shape != shape:
+        raise ValueError(f"{name}: expected shape {shape}, got {a.shape}")
+    return a
+
+
+class NMPCEngine:
+    """Batched solve of B independent tray-tilt NLPs on one GPU.
+
+    Host entry (``solve``) mirrors the data the reference passes to ``self.solver(x0=, p=, ...)``;
+    device entry (``solve_device``) takes torch CUDA tensors and is asynchronous on the current stream.
+    """
+
+    def __init__(self, cfg: DartCfg, device: int = 0):
+        self._lib = _lib.lib()
+        self.cfg = cfg
+        self.device = int(device)
+        self._h = C.c_void_p()
+        check(self._lib.dart_create(C.byref(self._h), C.byref(cfg), self.device), "dart_create")
+        self.nx = self._lib.dart_nx(self._h)
+        self.nref = self._lib.dart_nref(self._h)
+        self.naux = self._lib.dart_naux(self._h)
+        self.nw = self._lib.dart_nw(self._h)
+        self.N = cfg.N
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.dart_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ host arrays
+    def solve(self, x0, ref, aux=None, warm_w=None, want_w=True):
+        x0 = np.ascontiguousarray(np.atleast_2d(x0), dtype=np.float64)
+        B = x0.shape[0]
+        x0 = _f64(x0, (B, self.nx), "x0")
+        ref = _f64(np.atleast_2d(ref), (B, self.nref), "ref")
+        aux = _f64(None if aux is None else np.atleast_2d(aux), (B, self.naux), "aux")
+        warm_w = _f64(None if warm_w is None else np.atleast_2d(warm_w), (B, self.nw), "warm_w")
+        w = np.empty((B, self.nw)) if want_w else None
+        u0 = np.empty((B, 2))
+        J = np.empty(B)
+        status = np.empty(B, dtype=np.int32)
+        iters = np.empty(B, dtype=np.int32)
+        check(self._lib.dart_solve_host(self._h, B, _p(x0), _p(ref), _p(aux), _p(warm_w), _p(w), _p(u0), _p(J),
+                                        _p(status), _p(iters)), "dart_solve_host")
+        return dict(u0=u0, J=J, w=w, status=status, iters=iters)
+
+    # ------------------------------------------------------------------ torch CUDA tensors
+    def solve_device(self, x0, ref, aux=None, warm_w=None, w_out=None, u0_out=None, J_out=None, status=None, iters=None):
+        import torch
+        B = x0.shape[0]
+
+        def ptr(t, shape, dtype, name):
+            if t is None:
+                return None
+            if (not t.is_cuda) or t.device.index != self.device or t.dtype != dtype or not t.is_contiguous() \
+                    or tuple(t.shape) != shape:
+                raise ValueError(f"{name}: need contiguous {dtype} CUDA:{self.device} tensor of shape {shape}")
+            return C.c_void_p(t.data_ptr())
+
+        f64, i32 = torch.float64, torch.int32
+        dev = torch.device("cuda", self.device)
+        if u0_out is None:
+            u0_out = torch.empty((B, 2), dtype=f64, device=dev)
+        if J_out is None:
+            J_out = torch.empty((B,), dtype=f64, device=dev)
+        if status is None:
+            status = torch.empty((B,), dtype=i32, device=dev)
+        if iters is None:
+            iters = torch.empty((B,), dtype=i32, device=dev)
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        check(self._lib.dart_solve(self._h, B, ptr(x0, (B, self.nx), f64, "x0"), ptr(ref, (B, self.nref), f64, "ref"),
+                                   ptr(aux, (B, self.naux), f64, "aux"), ptr(warm_w, (B, self.nw), f64, "warm_w"),
+                                   ptr(w_out, (B, self.nw), f64, "w_out"), ptr(u0_out, (B, 2), f64, "u0_out"),
+                                   ptr(J_out, (B,), f64, "J_out"), ptr(status, (B,), i32, "status"),
+                                   ptr(iters, (B,), i32, "iters"), stream), "dart_solve")
+        return dict(u0=u0_out, J=J_out, w=w_out, status=status, iters=iters)
+
+    @property
+    def launch_count(self):
+        return int(self._lib.dart_launch_count(self._h))
+
+    def last_launch_config(self):
+        v = [C.c_int32() for _ in range(4)]
+        check(self._lib.dart_last_launch_config(self._h, *[C.byref(x) for x in v]), "dart_last_launch_config")
+        return dict(lanes=v[0].value, block_threads=v[1].value, grid=v[2].value, smem_bytes=v[3].value)
+
+
+def tilt_to_quat_device(u, quat=None):
+    """Device epilogue: tilt command [B,2] -> tray quaternion wxyz [B,4] (PMPC/main.py:107-116)."""
+    import torch
+    B = u.shape[0]
+    if quat is None:
+        quat = torch.empty((B, 4), dtype=torch.float64, device=u.device)
+    stream = C.c_void_p(torch.cuda.current_stream(u.device).cuda_stream)
+    check(_lib.lib().dart_tilt_to_quat(B, C.c_void_p(u.data_ptr()), C.c_void_p(quat.data_ptr()), stream), "dart_tilt_to_quat")
+    return quat
+
+
+def measure_fp64_tflops(device=0):
+    """FP64 FMA-pipe peak of the device (TFLOP/s) from the library's DFMA microbenchmark."""
+    v = C.c_double()
+    check(_lib.lib().dart_measure_fp64_tflops(int(device), C.byref(v)), "dart_measure_fp64_tflops")
+    return v.value

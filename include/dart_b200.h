@@ -119,6 +119,10 @@ int dart_last_launch_config(dart_handle h, int32_t* lanes, int32_t* block_thread
 /* tilt -> tray quaternion wxyz, Euler xyz [u1, -u0, 0] (PMPC/main.py:107-116). u [B,2] -> quat [B,4], device. */
 int dart_tilt_to_quat(int32_t B, const double* u, double* quat, void* stream);
 
+/* Measured FP64 FMA-pipe peak of the device in TFLOP/s (DFMA microbenchmark, CUDA-event timed): the roofline
+ * denominator bench.py reports the solver kernels against. */
+int dart_measure_fp64_tflops(int device, double* tflops);
+
 #ifdef __cplusplus
 }
 #endif

@@ -309,6 +309,6 @@ def solve(prob: StageProblem, X0=None, U0=None, opts: Options = None, trace=None
         zl = np.where(msk > 0, np.clip(zl, mu3 / (ks * sl), ks * mu3 / sl), 0.0)
         zu = np.where(msk > 0, np.clip(zu, mu3 / (ks * su), ks * mu3 / su), 0.0)
 
-    status = np.where(infeasible0 & (status == STATUS_CONVERGED), STATUS_INFEASIBLE, status)
+    status = np.where(infeasible0 & (status != STATUS_NUMERIC), STATUS_INFEASIBLE, status)
     return dict(X=X, U=U, J=prob.objective(X, U), status=status, iters=iters, lam=lam, zl=zl, zu=zu, s=s,
                 kkt=kkt_final, mu=mu)

@@ -1,0 +1,129 @@
+"""GPU parity tests proper: the CUDA path through the C ABI against the oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): |u0 - u0_oracle| <= 1e-4 rad, |J - J_oracle| / |J_oracle| <= 1e-6.
+"""
+import numpy as np
+import pytest
+
+import dart_b200
+from oracle import ipm, models, problems
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pmpc_engine(built):
+    return dart_b200.NMPCEngine(dart_b200.pmpc_cfg(), device=0)
+
+
+def test_pmpc_config2_full_batch_parity(pmpc_engine):
+    """BASELINE config 2 at full size: 18 objects x 64 states = 1152 instances."""
+    c, aux, p = helpers.pmpc_case(64)
+    out = pmpc_engine.solve(c["state"], c["target"], aux=aux)
+    ref = ipm.solve(p)
+    du0, dJ = helpers.assert_parity(out, ref, "pmpc config 2")
+    print(f"pmpc config2: B={p.B} max|du0|={du0:.2e} max rel dJ={dJ:.2e} iters mean={out['iters'].mean():.2f} max={out['iters'].max()}")
+
+
+def test_pmpc_config1_single_instance(pmpc_engine):
+    c1 = dart_b200.workloads.pmpc_config1()
+    out = pmpc_engine.solve(c1["state"], c1["target"])
+    ref = ipm.solve(problems.pmpc_problem(c1["state"], c1["target"], Qp=400, Qv=2, R=0.2, mu=0.1))
+    helpers.assert_parity(out, ref, "pmpc config 1")
+
+
+def test_pmpc_decision_vector_layout_and_z_rows(pmpc_engine):
+    """w = [vec(X); vec(U)] (mpc_3d.py:69,137): x/y columns are dynamically feasible, z columns follow pmpc_step."""
+    c, aux, p = helpers.pmpc_case(2)
+    out = pmpc_engine.solve(c["state"], c["target"], aux=aux)
+    N = 15
+    X = out["w"][:, :(N + 1) * 6].reshape(-1, N + 1, 6)
+    U = out["w"][:, (N + 1) * 6:].reshape(-1, N, 2)
+    assert np.array_equal(U[:, 0], out["u0"])
+    assert np.abs(X[:, 0] - c["state"]).max() == 0
+    for k in range(N):
+        nxt = models.pmpc_step(X[:, k], U[:, k], -9.81, c["mu"], 0.002)
+        assert np.abs(nxt - X[:, k + 1]).max() < 1e-8
+    assert (np.abs(U) <= 0.6).all()
+
+
+@pytest.mark.parametrize("lanes", [2, 4, 8, 16])
+def test_pmpc_lane_widths_agree(built, lanes):
+    c, aux, p = helpers.pmpc_case(8)
+    base = dart_b200.NMPCEngine(dart_b200.pmpc_cfg(), device=0).solve(c["state"], c["target"], aux=aux)
+    eng = dart_b200.NMPCEngine(dart_b200.pmpc_cfg(lanes=lanes), device=0)
+    out = eng.solve(c["state"], c["target"], aux=aux)
+    assert eng.last_launch_config()["lanes"] == lanes
+    assert (out["status"] == 0).all()
+    assert np.abs(out["u0"] - base["u0"]).max() < 1e-6
+    assert (np.abs(out["J"] - base["J"]) / np.abs(base["J"])).max() < 1e-8
+
+
+def test_rmpc_parity(built):
+    d, p = helpers.rmpc_case(256)
+    eng = dart_b200.NMPCEngine(dart_b200.rmpc_cfg(), device=0)
+    out = eng.solve(d["x0"], d["ref"], aux=d["aux"])
+    ref = ipm.solve(p)
+    du0, dJ = helpers.assert_parity(out, ref, "rmpc")
+    assert np.abs(out["iters"] - ref["iters"]).max() <= 1
+    print(f"rmpc: max|du0|={du0:.2e} max rel dJ={dJ:.2e} iters mean={out['iters'].mean():.2f}")
+
+
+@pytest.mark.parametrize("lanes", [8, 32])
+def test_rmpc_lane_widths_agree(built, lanes):
+    d, p = helpers.rmpc_case(64)
+    base = dart_b200.NMPCEngine(dart_b200.rmpc_cfg(), device=0).solve(d["x0"], d["ref"], aux=d["aux"])
+    out = dart_b200.NMPCEngine(dart_b200.rmpc_cfg(lanes=lanes), device=0).solve(d["x0"], d["ref"], aux=d["aux"])
+    assert (out["status"] == 0).all()
+    assert np.abs(out["u0"] - base["u0"]).max() < 1e-6
+
+
+def test_rmpc_warm_start_and_infeasible_flag(built):
+    d, p = helpers.rmpc_case(16)
+    eng = dart_b200.NMPCEngine(dart_b200.rmpc_cfg(), device=0)
+    a = eng.solve(d["x0"], d["ref"], aux=d["aux"])
+    b = eng.solve(d["x0"], d["ref"], aux=d["aux"], warm_w=a["w"])
+    assert (b["status"] == 0).all() and np.abs(a["u0"] - b["u0"]).max() < 1e-5
+    x0 = d["x0"].copy(); x0[3, 3] = -0.35
+    c = eng.solve(x0, d["ref"], aux=d["aux"])
+    assert c["status"][3] == dart_b200.STATUS_INFEASIBLE
+
+
+def test_lmpc_parity(built):
+    d, p = helpers.lmpc_case(256)
+    eng = dart_b200.NMPCEngine(dart_b200.lmpc_cfg(), device=0)
+    out = eng.solve(d["x0"], d["ref"], aux=d["aux"])
+    ref = ipm.solve(p)
+    du0, dJ = helpers.assert_parity(out, ref, "lmpc")
+    print(f"lmpc: max|du0|={du0:.2e} max rel dJ={dJ:.2e} iters mean={out['iters'].mean():.2f}")
+
+
+def test_device_pointer_entry_and_quaternion(pmpc_engine):
+    import torch
+    c, aux, p = helpers.pmpc_case(4)
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    out = pmpc_engine.solve_device(t(c["state"]), t(c["target"]), aux=t(aux))
+    torch.cuda.synchronize()
+    host = pmpc_engine.solve(c["state"], c["target"], aux=aux, want_w=False)
+    assert np.array_equal(out["u0"].cpu().numpy(), host["u0"]) and np.array_equal(out["J"].cpu().numpy(), host["J"])
+    q = dart_b200.tilt_to_quat_device(out["u0"]).cpu().numpy()
+    assert np.abs(q - models.tilt_to_quat(host["u0"])).max() < 1e-15
+
+
+def test_batch_permutation_invariance(pmpc_engine):
+    c, aux, p = helpers.pmpc_case(8)
+    perm = np.random.default_rng(0).permutation(p.B)
+    a = pmpc_engine.solve(c["state"], c["target"], aux=aux, want_w=False)
+    b = pmpc_engine.solve(c["state"][perm], c["target"][perm], aux=aux[perm], want_w=False)
+    assert np.array_equal(a["u0"][perm], b["u0"]) and np.array_equal(a["J"][perm], b["J"])
+
+
+def test_empty_and_ragged_batches(pmpc_engine):
+    c, aux, p = helpers.pmpc_case(1)
+    for B in (1, 3, 17):
+        out = pmpc_engine.solve(c["state"][:B], c["target"][:B], aux=aux[:B], want_w=False)
+        assert out["u0"].shape == (B, 2) and (out["status"] == 0).all()
+    out = pmpc_engine.solve(np.zeros((0, 6)), np.zeros((0, 6)), aux=np.zeros((0, 4)), want_w=False)
+    assert out["u0"].shape == (0, 2)

@@ -1,0 +1,63 @@
+"""Solver logic of the CUDA source, compiled for the host with a 1-lane tile, against the oracle.
+
+This is how the interior-point/Riccati code is unit-tested without a GPU; the GPU parity tests proper
+(test_gpu_*.py) go through the C ABI.
+"""
+import numpy as np
+import pytest
+
+import dart_b200
+from oracle import ipm
+from tests import helpers
+
+
+def test_pmpc_matches_oracle(hostemu):
+    c, aux, p = helpers.pmpc_case(4)
+    out = hostemu.solve(dart_b200.pmpc_cfg(), c["state"], c["target"], aux)
+    helpers.assert_parity(out, ipm.solve(p), "pmpc")
+
+
+def test_pmpc_cfg_defaults_when_no_aux(hostemu):
+    c1 = dart_b200.workloads.pmpc_config1()
+    out = hostemu.solve(dart_b200.pmpc_cfg(), c1["state"], c1["target"], None)
+    from oracle import problems
+    ref = ipm.solve(problems.pmpc_problem(c1["state"], c1["target"], Qp=400, Qv=2, R=0.2, mu=0.1))
+    helpers.assert_parity(out, ref, "pmpc config 1")
+
+
+def test_rmpc_matches_oracle_iterate_for_iterate(hostemu):
+    d, p = helpers.rmpc_case(32)
+    out = hostemu.solve(dart_b200.rmpc_cfg(), d["x0"], d["ref"], d["aux"])
+    ref = ipm.solve(p)
+    helpers.assert_parity(out, ref, "rmpc")
+    # same formulation, same algorithm: iteration counts coincide
+    assert np.abs(out["iters"] - ref["iters"]).max() <= 1
+
+
+def test_lmpc_matches_oracle(hostemu):
+    d, p = helpers.lmpc_case(32)
+    out = hostemu.solve(dart_b200.lmpc_cfg(), d["x0"], d["ref"], d["aux"])
+    helpers.assert_parity(out, ipm.solve(p), "lmpc")
+
+
+def test_warm_start_layout_roundtrip(hostemu):
+    d, p = helpers.rmpc_case(8)
+    cfg = dart_b200.rmpc_cfg()
+    a = hostemu.solve(cfg, d["x0"], d["ref"], d["aux"])
+    b = hostemu.solve(cfg, d["x0"], d["ref"], d["aux"], warm=a["w"])
+    assert (b["status"] == 0).all()
+    assert np.abs(a["u0"] - b["u0"]).max() < 1e-5
+    assert np.abs(a["J"] - b["J"]).max() <= 1e-7 * np.abs(a["J"]).max()
+
+
+def test_rmpc_infeasible_x0_flagged(hostemu):
+    d, _ = helpers.rmpc_case(4)
+    x0 = d["x0"].copy(); x0[0, 1] = 0.3      # |v0| > vmax acts on the fixed x_0 (np_mpc...:124-127)
+    out = hostemu.solve(dart_b200.rmpc_cfg(), x0, d["ref"], d["aux"])
+    assert out["status"][0] == dart_b200.STATUS_INFEASIBLE and (out["status"][1:] == 0).all()
+
+
+def test_max_iter_status(hostemu):
+    c, aux, _ = helpers.pmpc_case(1)
+    out = hostemu.solve(dart_b200.pmpc_cfg(max_iter=2), c["state"], c["target"], aux)
+    assert (out["status"] == dart_b200.STATUS_MAXITER).all() and (out["iters"] == 2).all()
