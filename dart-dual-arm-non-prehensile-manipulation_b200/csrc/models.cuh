@@ -32,11 +32,14 @@ struct KArgs {
 // Jacobians for the NP physical states.
 template <class Md>
 DART_HD void rk4_sens(const typename Md::Prm& p, const double* x, const double* u, double h, double* F,
-                      double* A, double* Bm) {
+                      double* A, double* Bm, double* tanu) {
     constexpr int np = Md::NP, m = Md::NU;
     double k[np], fx[np * np], fu[np * m], Sx[np * np], Su[np * m], xs[np], acc[np];
+    // the input is held over the step and enters only through sin/cos: evaluate them once
+    double su[m], cu[m];
+    DART_UNROLL for (int j = 0; j < m; ++j) { sincos(u[j], &su[j], &cu[j]); tanu[j] = su[j] / cu[j]; }
     // stage 1
-    Md::deriv(p, x, u, k, fx, fu);
+    Md::deriv(p, x, su, cu, k, fx, fu);
     DART_UNROLL for (int i = 0; i < np * np; ++i) { Sx[i] = fx[i]; A[i] = fx[i]; }
     DART_UNROLL for (int i = 0; i < np * m; ++i) { Su[i] = fu[i]; Bm[i] = fu[i]; }
     DART_UNROLL for (int i = 0; i < np; ++i) { acc[i] = k[i]; xs[i] = x[i] + 0.5 * h * k[i]; }
@@ -44,7 +47,7 @@ DART_HD void rk4_sens(const typename Md::Prm& p, const double* x, const double* 
     DART_UNROLL for (int st = 2; st <= 4; ++st) {
         const double c = (st == 4) ? h : 0.5 * h;      // step used to reach this stage's evaluation point
         const double wgt = (st == 4) ? 1.0 : 2.0;
-        Md::deriv(p, xs, u, k, fx, fu);
+        Md::deriv(p, xs, su, cu, k, fx, fu);
         double Nx[np * np], Nu[np * m];
         DART_UNROLL for (int a = 0; a < np; ++a) {
             DART_UNROLL for (int b = 0; b < np; ++b) {
@@ -72,6 +75,7 @@ DART_HD void rk4_sens(const typename Md::Prm& p, const double* x, const double* 
 // =============================================================================================== PMPC
 struct PmpcAxis {
     static constexpr int NX = 2, NU = 1, NR = 1, NP = 2, NAUG = 0, NAXIS = 2;
+    static constexpr bool SERIAL_RICCATI = true;
     static constexpr int NXF = 6;   // states per stage in the reference's decision vector
     struct Prm { double Qp, Qv, R, mu, g, Ts, ulo, uhi, rp, rv; };
 
@@ -81,16 +85,15 @@ struct PmpcAxis {
     DART_HD static int nref_in(int) { return 6; }
     DART_HD static int naux_in() { return 4; }
 
-    DART_HD static void deriv(const Prm& p, const double* x, const double* u, double* f, double* fx, double* fu) {
-        double s, c;
-        sincos(u[0], &s, &c);
+    DART_HD static void deriv(const Prm& p, const double* x, const double* su, const double* cu, double* f, double* fx,
+                              double* fu) {
         f[0] = x[1];
-        f[1] = p.g * s - p.mu * x[1];
+        f[1] = p.g * su[0] - p.mu * x[1];
         fx[0] = 0.0; fx[1] = 1.0; fx[2] = 0.0; fx[3] = -p.mu;
-        fu[0] = 0.0; fu[1] = p.g * c;
+        fu[0] = 0.0; fu[1] = p.g * cu[0];
     }
-    DART_HD static void dyn(const Prm& p, const double* x, const double* u, double* F, double* A, double* Bm) {
-        rk4_sens<PmpcAxis>(p, x, u, p.Ts, F, A, Bm);
+    DART_HD static void dyn(const Prm& p, const double* x, const double* u, double* F, double* A, double* Bm, double* tanu) {
+        rk4_sens<PmpcAxis>(p, x, u, p.Ts, F, A, Bm, tanu);
     }
     DART_HD static double wy(const Prm& p, int i) { return i == 0 ? p.Qp : (i == 1 ? p.Qv : p.R); }
     DART_HD static double ry(const Prm& p, const double*, int, int i) { return i == 0 ? p.rp : (i == 1 ? p.rv : 0.0); }
@@ -130,6 +133,7 @@ struct PmpcAxis {
 // =============================================================================================== RMPC
 struct Rmpc {
     static constexpr int NX = 6, NU = 2, NR = 6, NP = 4, NAUG = 2, NAXIS = 1;
+    static constexpr bool SERIAL_RICCATI = false;
     static constexpr int NXF = 4;
     struct Prm { double Qp, Qv, Ru, Rdu, gz, Ts, ulo, uhi, dlo, dhi, vmax, inv_eps; double th[14]; };
 
@@ -139,10 +143,9 @@ struct Rmpc {
     DART_HD static int nref_in(int N) { return (N + 1) * 4; }
     DART_HD static int naux_in() { return 16; }
 
-    DART_HD static void deriv(const Prm& p, const double* x, const double* u, double* f, double* fx, double* fu) {
-        double sa, ca, sb, cb;
-        sincos(u[0], &sa, &ca);
-        sincos(u[1], &sb, &cb);
+    DART_HD static void deriv(const Prm& p, const double* x, const double* su, const double* cu, double* f, double* fx,
+                              double* fu) {
+        const double sa = su[0], ca = cu[0], sb = su[1], cb = cu[1];
         const double tx = tanh(x[1] * p.inv_eps), ty = tanh(x[3] * p.inv_eps);
         const double dtx = (1.0 - tx * tx) * p.inv_eps, dty = (1.0 - ty * ty) * p.inv_eps;
         const double* a = p.th;
@@ -160,8 +163,8 @@ struct Rmpc {
         fu[1 * 2 + 0] = p.gz * ca;
         fu[3 * 2 + 1] = p.gz * cb;
     }
-    DART_HD static void dyn(const Prm& p, const double* x, const double* u, double* F, double* A, double* Bm) {
-        rk4_sens<Rmpc>(p, x, u, p.Ts, F, A, Bm);
+    DART_HD static void dyn(const Prm& p, const double* x, const double* u, double* F, double* A, double* Bm, double* tanu) {
+        rk4_sens<Rmpc>(p, x, u, p.Ts, F, A, Bm, tanu);
     }
     DART_HD static double wy(const Prm& p, int i) {
         return (i == 0 || i == 2) ? p.Qp : ((i == 1 || i == 3) ? p.Qv : (i >= 6 ? p.Ru : 0.0));
@@ -205,6 +208,7 @@ struct Rmpc {
 // =============================================================================================== LMPC
 struct LmpcAxis {
     static constexpr int NX = 5, NU = 1, NR = 1, NP = 4, NAUG = 1, NAXIS = 2;
+    static constexpr bool SERIAL_RICCATI = false;
     static constexpr int NXF = 8;
     struct Prm {
         double Ts, ulo, uhi;
@@ -230,10 +234,11 @@ struct LmpcAxis {
         S = t * lvl + B * v;
         dS = (1.0 - t * t) * ieps * lvl + t * (Fs - Fc) * E * (-sg * ivs) + B;
     }
-    DART_HD static void deriv(const Prm& p, const double* x, const double* u, double* f, double* fx, double* fu) {
+    DART_HD static void deriv(const Prm& p, const double* x, const double* su, const double* cu, double* f, double* fx,
+                              double* fu) {
         const double pos = x[0], v = x[1], th = x[2], om = x[3];
-        double sa, ca, st, ct;
-        sincos(u[0], &sa, &ca);
+        const double sa = su[0], ca = cu[0];
+        double st, ct;
         sincos(th, &st, &ct);
         double Ff, dFf, Fr, dFr, Tr, dTr;
         stribeck(v, p.Fs, p.Fc, p.Bv, p.ivs, p.ieps, Ff, dFf);
@@ -256,8 +261,8 @@ struct LmpcAxis {
         fx[3 * 4 + 3] = (p.r * p.rs * dFr - dTr - p.crot) * p.iI;
         fu[0] = 0.0; fu[1] = 9.81 * ca; fu[2] = 0.0; fu[3] = 0.0;
     }
-    DART_HD static void dyn(const Prm& p, const double* x, const double* u, double* F, double* A, double* Bm) {
-        rk4_sens<LmpcAxis>(p, x, u, p.Ts, F, A, Bm);
+    DART_HD static void dyn(const Prm& p, const double* x, const double* u, double* F, double* A, double* Bm, double* tanu) {
+        rk4_sens<LmpcAxis>(p, x, u, p.Ts, F, A, Bm, tanu);
     }
     DART_HD static double wy(const Prm& p, int i) { return i < 4 ? p.Q[i] : (i == 4 ? 0.0 : p.Ru); }
     DART_HD static double ry(const Prm& p, const double*, int, int i) { return i < 4 ? p.ref[i] : 0.0; }

@@ -99,11 +99,11 @@ static int launch_t(const KArgs& a, int block_threads, cudaStream_t st, LaunchIn
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (bt == 0) {
-        // one warp per block unless the batch is large: keeps every SM busy at small B, and lets
-        // shared memory (the occupancy limiter) pack at large B.
-        bt = 32;
+        // measured on B200 (tools/sweep.py): few problems -> 4 warps per block; a filled GPU -> one warp per
+        // block, so shared memory (the occupancy limiter) packs at warp granularity.
         const long probs = (long)a.B * M::NAXIS;
-        if (probs * G > 148L * 32 * 8) bt = 64;
+        bt = (probs * G > 148L * 32 * 16) ? 32 : 128;
+        if (bt < unit) bt = unit;
     }
     if (bt % 32 != 0 || bt < unit) return DART_ERR_ARG;
     int tpb = bt / G;

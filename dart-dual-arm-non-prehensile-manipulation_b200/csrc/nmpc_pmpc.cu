@@ -3,6 +3,6 @@
 
 namespace dart {
 int launch_solve_pmpc(const KArgs& a, int lanes, int block_threads, cudaStream_t st, LaunchInfo* info) {
-    return launch_g<PmpcAxis>(a, lanes > 0 ? lanes : 4, block_threads, st, info);
+    return launch_g<PmpcAxis>(a, lanes > 0 ? lanes : ((long)a.B * 2 > 8192 ? 8 : 16), block_threads, st, info);
 }
 }  // namespace dart

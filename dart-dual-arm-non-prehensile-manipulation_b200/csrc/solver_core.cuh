@@ -55,15 +55,23 @@ struct HostTile {
     DART_HD double min(double v) const { return v; }
 };
 
+// Every lane runs the whole loop redundantly (same values, same addresses): no exchange, no syncs.
+struct SerialTile {
+    DART_HD int lane() const { return 0; }
+    DART_HD int size() const { return 1; }
+    DART_HD void sync() const {}
+};
+
 template <class M>
 struct Workspace {
     static constexpr int n = M::NX, m = M::NU, nr = M::NR, ny = n + m, nc = n + m + 1;
     double *X, *U, *A, *Bm, *D, *LAM, *LN, *PP, *PV, *K, *KFF, *DX, *DU, *BL;
-    double *S, *ZL, *ZU, *ISL, *ISU, *RC, *DS, *DZL, *DZU, *MM, *REF;
+    double *S, *ZL, *ZU, *ISL, *ISU, *RC, *DS, *DZL, *DZU, *MM, *TANU, *HS, *GR, *REF;
 
     DART_HD static int doubles(int N) {
         return (N + 1) * n + N * m + N * n * n + N * n * m + N * n + N * n + N * n + (N + 1) * n * n + (N + 1) * n +
-               N * m * n + N * m + (N + 1) * n + N * m + N * m + 9 * N * nr + ny * nc + M::ref_doubles(N);
+               N * m * n + N * m + (N + 1) * n + N * m + N * m + 9 * N * nr + ny * nc + N * m + N * ny * ny + N * ny +
+               M::ref_doubles(N);
     }
     DART_HD void bind(double* p, int N) {
         X = p;   p += (N + 1) * n;
@@ -90,6 +98,9 @@ struct Workspace {
         DZL = p; p += N * nr;
         DZU = p; p += N * nr;
         MM = p;  p += ny * nc;
+        TANU = p; p += N * m;
+        HS = p;  p += N * ny * ny;
+        GR = p;  p += N * ny;
         REF = p;
     }
 };
@@ -139,7 +150,9 @@ struct Solver {
             double x[n], u[m], F[n], Aloc[np * np], Bloc[np * m];
             DART_UNROLL for (int i = 0; i < n; ++i) x[i] = w.X[k * n + i];
             DART_UNROLL for (int j = 0; j < m; ++j) u[j] = w.U[k * m + j];
-            M::dyn(prm, x, u, F, Aloc, Bloc);
+            double tanu[m];
+            M::dyn(prm, x, u, F, Aloc, Bloc, tanu);
+            DART_UNROLL for (int j = 0; j < m; ++j) w.TANU[k * m + j] = tanu[j];
             double* Ak = w.A + k * n * n;
             double* Bk = w.Bm + k * n * m;
             DART_UNROLL for (int a = 0; a < n; ++a) {
@@ -171,10 +184,12 @@ struct Solver {
                 double s = w.S[k * nr + r];
                 double rc = rowval(k, r) - s;
                 double sl = s - lo, su = hi - s;
+                const double prod = sl * su;
+                const double ip = 1.0 / prod;
                 w.RC[k * nr + r] = rc;
-                w.ISL[k * nr + r] = 1.0 / sl;
-                w.ISU[k * nr + r] = 1.0 / su;
-                L_ += log(sl) + log(su);
+                w.ISL[k * nr + r] = su * ip;
+                w.ISU[k * nr + r] = sl * ip;
+                L_ += log(prod);
                 th_ += fabs(rc);
                 pi_ = dmax(pi_, fabs(rc));
             }
@@ -248,7 +263,12 @@ struct Solver {
     }
 
     // m x m SPD solve helpers (m <= 2 in all models; generic Cholesky kept for clarity)
-    DART_HD static bool chol(double* H) {   // in place, lower; returns false if not PD
+    DART_HD static bool chol(double* H) {   // in place, lower; returns false if not PD (m == 1: H[0] <- 1/H[0])
+        if (m == 1) {
+            if (!(H[0] > 0.0)) return false;
+            H[0] = 1.0 / H[0];
+            return true;
+        }
         DART_UNROLL for (int j = 0; j < m; ++j) {
             double d = H[j * m + j];
             DART_UNROLL for (int q = 0; q < j; ++q) d -= H[j * m + q] * H[j * m + q];
@@ -264,6 +284,7 @@ struct Solver {
         return true;
     }
     DART_HD static void chol_solve(const double* Lc, double* b) {
+        if (m == 1) { b[0] *= Lc[0]; return; }
         DART_UNROLL for (int i = 0; i < m; ++i) {
             double v = b[i];
             DART_UNROLL for (int q = 0; q < i; ++q) v -= Lc[i * m + q] * b[q];
@@ -276,9 +297,50 @@ struct Solver {
         }
     }
 
-    // ---- Riccati backward sweep; lanes own columns of [A B d]
-    DART_HD void backward(double mu) {
-        const int lane = tile.lane(), G = tile.size();
+    // ---- stage Hessian blocks and condensed gradients for the current mu and multipliers (stage-parallel)
+    DART_HD void prep(double mu) {
+        for (int k = tile.lane(); k < N; k += tile.size()) {
+            double H[ny * ny], g[ny];
+            DART_UNROLL for (int i = 0; i < ny * ny; ++i) H[i] = 0.0;
+            DART_UNROLL for (int i = 0; i < ny; ++i) { H[i * ny + i] = 2.0 * M::wy(prm, i); g[i] = cost_grad(k, i); }
+            if (M::NAUG > 0) {
+                DART_UNROLL for (int j = 0; j < m; ++j) {
+                    const double wd2 = 2.0 * M::wd(prm, j);
+                    H[(n + j) * ny + n + j] += wd2;
+                    H[(np + j) * ny + np + j] += wd2;
+                    H[(n + j) * ny + np + j] -= wd2;
+                    H[(np + j) * ny + n + j] -= wd2;
+                }
+            }
+            DART_UNROLL for (int r = 0; r < nr; ++r) {
+                if (masked(k, r)) continue;
+                const int ia = M::row_ia(r), ib = M::row_ib(r);
+                const double sa = M::row_sa(r), sb = M::row_sb(r);
+                const double isl = w.ISL[k * nr + r], isu = w.ISU[k * nr + r];
+                const double sig = w.ZL[k * nr + r] * isl + w.ZU[k * nr + r] * isu;
+                const double nuhat = mu * (isu - isl) + sig * w.RC[k * nr + r];
+                H[ia * ny + ia] += sig * sa * sa;
+                g[ia] += sa * nuhat;
+                if (ib >= 0) {
+                    H[ib * ny + ib] += sig * sb * sb;
+                    H[ia * ny + ib] += sig * sa * sb;
+                    H[ib * ny + ia] += sig * sa * sb;
+                    g[ib] += sb * nuhat;
+                }
+            }
+            // Lagrangian curvature of the tilt input: -tan(u_j) (B^T lambda)_j
+            DART_UNROLL for (int j = 0; j < m; ++j) H[(n + j) * ny + n + j] += -w.TANU[k * m + j] * w.BL[k * m + j];
+            DART_UNROLL for (int i = 0; i < ny * ny; ++i) w.HS[k * ny * ny + i] = H[i];
+            DART_UNROLL for (int i = 0; i < ny; ++i) w.GR[k * ny + i] = g[i];
+        }
+        tile.sync();
+    }
+
+    // ---- Riccati backward sweep; lanes of `tl` own columns of [A B d].  With a SerialTile every lane runs
+    // all columns itself (no exchange, no syncs) -- the faster choice for the 2-state problems.
+    template <class TL>
+    DART_HD void backward(const TL& tl) {
+        const int lane = tl.lane(), G = tl.size();
         for (int c = lane; c <= n; c += G) {
             if (c < n) {
                 DART_UNROLL for (int i = 0; i < n; ++i) w.PP[N * n * n + i * n + c] = (i == c) ? 2.0 * M::wT(prm, c) : 0.0;
@@ -287,14 +349,15 @@ struct Solver {
                     w.PV[N * n + i] = 2.0 * M::wT(prm, i) * (w.X[N * n + i] - M::rT(prm, w.REF, N, i));
             }
         }
-        tile.sync();
+        tl.sync();
         for (int k = N - 1; k >= 0; --k) {
             const double* Ak = w.A + k * n * n;
             const double* Bk = w.Bm + k * n * m;
             const double* Pn = w.PP + (k + 1) * n * n;
             const double* pn = w.PV + (k + 1) * n;
+            const double* Hk = w.HS + k * ny * ny;
             for (int c = lane; c < nc; c += G) {
-                double t[n], ww[n], col[ny];
+                double t[n], ww[n];
                 DART_UNROLL for (int a = 0; a < n; ++a)
                     t[a] = (c < n) ? Ak[a * n + c] : (c < ny ? Bk[a * m + (c - n)] : w.D[k * n + a]);
                 DART_UNROLL for (int a = 0; a < n; ++a) {
@@ -302,55 +365,17 @@ struct Solver {
                     DART_UNROLL for (int b = 0; b < n; ++b) acc += Pn[a * n + b] * t[b];
                     ww[a] = acc;
                 }
-                DART_UNROLL for (int i = 0; i < n; ++i) {
-                    double acc = 0.0;
-                    DART_UNROLL for (int a = 0; a < n; ++a) acc += Ak[a * n + i] * ww[a];
-                    col[i] = acc;
-                }
-                DART_UNROLL for (int j = 0; j < m; ++j) {
-                    double acc = 0.0;
-                    DART_UNROLL for (int a = 0; a < n; ++a) acc += Bk[a * m + j] * ww[a];
-                    col[n + j] = acc;
-                }
-                if (c < ny) {
-                    // Hessian column c: cost + tilt-rate coupling + barrier rows + input curvature
-                    col[c] += 2.0 * M::wy(prm, c);
-                    if (M::NAUG > 0) {
-                        if (c >= n) {
-                            int j = c - n;
-                            col[c] += 2.0 * M::wd(prm, j);
-                            col[np + j] -= 2.0 * M::wd(prm, j);
-                        } else if (c >= np) {
-                            int j = c - np;
-                            col[c] += 2.0 * M::wd(prm, j);
-                            col[n + j] -= 2.0 * M::wd(prm, j);
-                        }
+                DART_UNROLL for (int i = 0; i < ny; ++i) {
+                    double acc = (c < ny) ? Hk[i * ny + c] : w.GR[k * ny + i];
+                    if (i < n) {
+                        DART_UNROLL for (int a = 0; a < n; ++a) acc += Ak[a * n + i] * ww[a];
+                    } else {
+                        DART_UNROLL for (int a = 0; a < n; ++a) acc += Bk[a * m + (i - n)] * ww[a];
                     }
-                    DART_UNROLL for (int r = 0; r < nr; ++r) {
-                        if (masked(k, r)) continue;
-                        const int ia = M::row_ia(r), ib = M::row_ib(r);
-                        if (ia != c && ib != c) continue;
-                        double sig = w.ZL[k * nr + r] * w.ISL[k * nr + r] + w.ZU[k * nr + r] * w.ISU[k * nr + r];
-                        double sc = (ia == c) ? M::row_sa(r) : M::row_sb(r);
-                        col[ia] += sig * sc * M::row_sa(r);
-                        if (ib >= 0) col[ib] += sig * sc * M::row_sb(r);
-                    }
-                    if (c >= n) col[c] += -tan(w.U[k * m + (c - n)]) * w.BL[k * m + (c - n)];
-                } else {
-                    // condensed gradient column
-                    DART_UNROLL for (int i = 0; i < ny; ++i) col[i] += cost_grad(k, i);
-                    DART_UNROLL for (int r = 0; r < nr; ++r) {
-                        if (masked(k, r)) continue;
-                        double isl = w.ISL[k * nr + r], isu = w.ISU[k * nr + r];
-                        double sig = w.ZL[k * nr + r] * isl + w.ZU[k * nr + r] * isu;
-                        double nuhat = mu * (isu - isl) + sig * w.RC[k * nr + r];
-                        col[M::row_ia(r)] += M::row_sa(r) * nuhat;
-                        if (M::row_ib(r) >= 0) col[M::row_ib(r)] += M::row_sb(r) * nuhat;
-                    }
+                    w.MM[c * ny + i] = acc;
                 }
-                DART_UNROLL for (int i = 0; i < ny; ++i) w.MM[c * ny + i] = col[i];
             }
-            tile.sync();
+            tl.sync();
             // every lane factors the same m x m block H = M[n.., n..] (+ escalating shift if not PD)
             double Lc[m * m];
             double shift = 0.0;
@@ -370,6 +395,7 @@ struct Solver {
                     if (c < n) w.K[k * m * n + j * n + c] = kt[j];
                     else w.KFF[k * m + j] = kt[j];
                 }
+                if (k == 0) continue;            // P_0 / p_0 are never used (x_0 is fixed)
                 DART_UNROLL for (int i = 0; i < n; ++i) {
                     double v = w.MM[c * ny + i];
                     DART_UNROLL for (int j = 0; j < m; ++j) v += w.MM[i * ny + n + j] * kt[j];
@@ -377,7 +403,7 @@ struct Solver {
                     else w.PV[k * n + i] = v;
                 }
             }
-            tile.sync();
+            tl.sync();
         }
     }
 
@@ -415,7 +441,7 @@ struct Solver {
     // ---- new multipliers, slack/dual steps, step-length limits, directional derivative (stage-parallel)
     DART_HD void post(double mu, double& ap, double& ad, double& dphi) {
         const double tau = dmax(o.tau_min, 1.0 - mu);
-        double ap_ = 1.0, ad_ = 1.0, dp = 0.0;
+        double ap_ = 1.0, ad_ = 1.0, dp = 0.0, rp_ = 0.0, rd_ = 0.0;
         for (int k = tile.lane(); k < N; k += tile.size()) {
             DART_UNROLL for (int a = 0; a < n; ++a) {
                 double acc = w.PV[(k + 1) * n + a];
@@ -440,18 +466,21 @@ struct Solver {
                 w.DZL[k * nr + r] = dzl;
                 w.DZU[k * nr + r] = dzu;
                 dp -= mu * ds * (isl - isu);
-                if (ds < 0.0) ap_ = dmin(ap_, -tau / (isl * ds));
-                if (ds > 0.0) ap_ = dmin(ap_, tau / (isu * ds));
-                if (dzl < 0.0) ad_ = dmin(ad_, -tau * zl / dzl);
-                if (dzu < 0.0) ad_ = dmin(ad_, -tau * zu / dzu);
+                rp_ = dmax(rp_, dmax(-ds * isl, ds * isu));
+                const double iz = 1.0 / (zl * zu);
+                rd_ = dmax(rd_, dmax(-dzl * zu * iz, -dzu * zl * iz));
             }
         }
         if (tile.lane() == 0) {
             DART_UNROLL for (int i = 0; i < n; ++i)
                 dp += 2.0 * M::wT(prm, i) * (w.X[N * n + i] - M::rT(prm, w.REF, N, i)) * w.DX[N * n + i];
         }
-        ap = tile.min(ap_);
-        ad = tile.min(ad_);
+        rp_ = tile.max(rp_);
+        rd_ = tile.max(rd_);
+        ap_ = (rp_ > tau) ? tau / rp_ : 1.0;
+        ad_ = (rd_ > tau) ? tau / rd_ : 1.0;
+        ap = ap_;
+        ad = ad_;
         dphi = tile.sum(dp);
         tile.sync();
     }
@@ -471,14 +500,11 @@ struct Solver {
             DART_UNROLL for (int a = 0; a < n; ++a) w.LAM[k * n + a] += alpha * (w.LN[k * n + a] - w.LAM[k * n + a]);
             DART_UNROLL for (int r = 0; r < nr; ++r) {
                 if (masked(k, r)) continue;
-                double lo, hi;
-                M::bounds(prm, r, lo, hi);
-                double s = w.S[k * nr + r];
-                double sl = s - lo, su = hi - s;
+                const double isl = w.ISL[k * nr + r], isu = w.ISU[k * nr + r];   // of the accepted point (eval1)
                 double zl = w.ZL[k * nr + r] + ad * w.DZL[k * nr + r];
                 double zu = w.ZU[k * nr + r] + ad * w.DZU[k * nr + r];
-                w.ZL[k * nr + r] = dmin(dmax(zl, mu / (ks * sl)), ks * mu / sl);
-                w.ZU[k * nr + r] = dmin(dmax(zu, mu / (ks * su)), ks * mu / su);
+                w.ZL[k * nr + r] = dmin(dmax(zl, mu * isl / ks), ks * mu * isl);
+                w.ZU[k * nr + r] = dmin(dmax(zu, mu * isu / ks), ks * mu * isu);
             }
         }
         tile.sync();
@@ -534,7 +560,9 @@ struct Solver {
                 if (Emu <= o.kappa_eps * mu && mu > mu_min) mu = dmax(mu_min, dmin(o.kappa_mu * mu, pow(mu, o.theta_mu)));
                 else break;
             }
-            backward(mu);
+            prep(mu);
+            if (M::SERIAL_RICCATI) backward(SerialTile());
+            else backward(tile);
             forward();
             double ap, ad, dphi;
             post(mu, ap, ad, dphi);
