@@ -9,3 +9,5 @@ from ._lib import (DART_LMPC, DART_PMPC, DART_RMPC, STATUS_CONVERGED, STATUS_INF
 from .config import cfg_from_yaml, lmpc_cfg, load_config, pmpc_cfg, rmpc_cfg   # noqa: F401
 from .engine import NMPCEngine, measure_fp64_tflops, tilt_to_quat_device        # noqa: F401
 from .pmpc import PMPC, GravityModel, StateHolder, mpc_worker   # noqa: F401
+from .rmpc import RLS, AdaptiveNPMPCSmooth, RMPCBatch, rls_update_device   # noqa: F401
+from .lmpc import RLMPC, LMPCBatch, PolicyMLP, init_policy_weights, load_checkpoint_weights   # noqa: F401

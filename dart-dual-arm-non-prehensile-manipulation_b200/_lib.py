@@ -55,6 +55,16 @@ def lib():
     L.dart_launch_count.restype = C.c_int64
     L.dart_last_launch_config.argtypes = [vp, ip, ip, ip, ip]
     L.dart_tilt_to_quat.argtypes = [C.c_int32, vp, vp, vp]
+    L.dart_rls_update.argtypes = [C.c_int32, C.c_int32, vp, vp, vp, vp, C.c_double, vp]
+    L.dart_rmpc_prologue.argtypes = [C.c_int32, C.c_int32] + [C.c_double] * 6 + [vp] * 9 + [vp]
+    fp = C.POINTER(C.c_float)
+    L.dart_policy_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int32, C.c_int32, C.c_int32] + [vp] * 6
+    L.dart_policy_destroy.argtypes = [vp]
+    L.dart_policy_forward.argtypes = [vp, C.c_int32, vp, vp, vp]
+    L.dart_policy_launch_count.argtypes = [vp]
+    L.dart_policy_launch_count.restype = C.c_int64
+    L.dart_policy_obs_push.argtypes = [C.c_int32, C.c_int32, vp, vp, vp, vp, C.c_int32, vp, vp, vp, vp, vp]
+    L.dart_policy_param_update.argtypes = [C.c_int32, vp, vp, C.c_int32] + [C.c_double] * 5 + [vp]
     L.dart_measure_fp64_tflops.argtypes = [C.c_int, dp]
     _lib = L
     return L

@@ -1,0 +1,273 @@
+"""Drop-in for the reference's learning-based controller ``RLMPC`` and its policy, batched and device-resident.
+
+Mirrors LMPC/src/controller/rlmpc2.py: ``Policy.mean_net`` (:33-46, :71-80), the solver worker's NLP
+(:236-519), the RL worker's observation build / parameter update in evaluation mode (:641-668, :742-759,
+:606-616) and the ``RLMPC`` facade (:110-226, :986-1065).  The reference runs the solver and the policy in two
+unsynchronised daemon processes over shared-memory mailboxes; here one ``step`` does, in order and on the
+device: observation push -> policy forward -> (every ``update_every``-th step) parameter update -> NLP solve
+warm-started from the previous solution.  Training (PPO) is out of scope; the action is the policy mean.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+from .config import lmpc_cfg
+from .engine import NMPCEngine
+
+OBS_DIM, HIDDEN, ACT_DIM, BASE_DIM, HISTORY = 520, 64, 34, 52, 10
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise _lib.DartError("dart_b200 LMPC needs a CUDA device (no CPU fallback)")
+    return torch
+
+
+def init_policy_weights(seed=3, obs_dim=OBS_DIM, act_dim=ACT_DIM, hidden=HIDDEN, layers=2):
+    """Random actor weights exactly as ``Policy._init_weights`` draws them (orthogonal, gain sqrt(2), zero bias)."""
+    import torch
+    torch.manual_seed(seed)
+    dims = [obs_dim] + [hidden] * layers + [act_dim]
+    out = []
+    for i in range(len(dims) - 1):
+        lin = torch.nn.Linear(dims[i], dims[i + 1])
+        torch.nn.init.orthogonal_(lin.weight, gain=float(np.sqrt(2)))
+        torch.nn.init.constant_(lin.bias, 0.0)
+        out.append((lin.weight.detach().numpy().copy(), lin.bias.detach().numpy().copy()))
+    return out
+
+
+def load_checkpoint_weights(path, trust_pickle=False):
+    """Actor weights from a reference checkpoint (``torch.save({"model": state_dict, ...})``, rlmpc2.py:917-922).
+    The files contain numpy scalars, so a safe ``weights_only`` load may fail; ``trust_pickle=True`` opts into
+    the reference's own ``weights_only=False`` load (only for files you trust)."""
+    import torch
+    try:
+        ck = torch.load(path, map_location="cpu", weights_only=True)
+    except Exception:
+        if not trust_pickle:
+            raise
+        ck = torch.load(path, map_location="cpu", weights_only=False)
+    sd = ck["model"]
+    return [(sd[f"mean_net.{i}.weight"].float().numpy().copy(), sd[f"mean_net.{i}.bias"].float().numpy().copy())
+            for i in (0, 2, 4)]
+
+
+class PolicyMLP:
+    """``Policy.mean_net`` forward on the tcgen05 kernel: obs [B,520] f32 CUDA tensor -> mean [B,34] f32."""
+
+    def __init__(self, weights=None, seed=3, device=0):
+        self._lib = _lib.lib()
+        self.device = int(device)
+        self.weights = init_policy_weights(seed) if weights is None else weights
+        flat = []
+        for W, b in self.weights:
+            flat += [np.ascontiguousarray(W, dtype=np.float32), np.ascontiguousarray(b, dtype=np.float32)]
+        if [a.shape for a in flat] != [(64, 520), (64,), (64, 64), (64,), (34, 64), (34,)]:
+            raise ValueError("PolicyMLP supports the reference architecture 520 -> 64 -> 64 -> 34")
+        self._h = C.c_void_p()
+        check(self._lib.dart_policy_create(C.byref(self._h), self.device, OBS_DIM, HIDDEN, ACT_DIM,
+                                           *[C.c_void_p(a.ctypes.data) for a in flat]), "dart_policy_create")
+
+    def forward(self, obs, out=None):
+        torch = _torch()
+        B = obs.shape[0]
+        if obs.dtype != torch.float32 or not obs.is_cuda or not obs.is_contiguous() or tuple(obs.shape) != (B, OBS_DIM):
+            raise ValueError("obs: need contiguous float32 CUDA tensor [B,520]")
+        if out is None:
+            out = torch.empty((B, ACT_DIM), dtype=torch.float32, device=obs.device)
+        stream = C.c_void_p(torch.cuda.current_stream(obs.device).cuda_stream)
+        check(self._lib.dart_policy_forward(self._h, B, C.c_void_p(obs.data_ptr()), C.c_void_p(out.data_ptr()), stream),
+              "dart_policy_forward")
+        return out
+
+    @property
+    def launch_count(self):
+        return int(self._lib.dart_policy_launch_count(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.dart_policy_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class LMPCBatch:
+    """B learning-based controllers resident on one GPU (one ``step`` = 3-4 launches)."""
+
+    def __init__(self, B, pvec0, weights=None, seed=3, device=0, max_param_abs=2.0, max_delta_abs=0.02, min_k=1e-2,
+                 k_ceiling_margin=None, shm_smooth_alpha=0.5, update_every=8, warm_start=True, **cfg_kw):
+        torch = _torch()
+        self.torch = torch
+        self.B = int(B)
+        self.dev = torch.device("cuda", device)
+        self.cfg = lmpc_cfg(**cfg_kw)
+        self.engine = NMPCEngine(self.cfg, device=device)
+        self.policy = PolicyMLP(weights, seed, device)
+        self.k_max, self.max_delta, self.min_k = float(max_param_abs), float(max_delta_abs), float(min_k)
+        self.margin = max(1e-3, 0.05 * self.k_max) if k_ceiling_margin is None else float(k_ceiling_margin)
+        self.alpha, self.update_every = float(shm_smooth_alpha), int(update_every)
+        f64, f32 = torch.float64, torch.float32
+        self.aux = torch.zeros((B, 36), dtype=f64, device=self.dev)               # [u_prev(2), pvec(34)]
+        self.aux[:, 2:] = torch.from_numpy(np.ascontiguousarray(pvec0, dtype=np.float64)).to(self.dev)
+        self.u_prev = torch.zeros((B, 2), dtype=f64, device=self.dev)              # views['control'] of the reference
+        self.obs = [torch.zeros((B, OBS_DIM), dtype=f32, device=self.dev) for _ in range(2)]
+        self.mean = torch.zeros((B, BASE_DIM), dtype=f64, device=self.dev)
+        self.M2 = torch.zeros((B, BASE_DIM), dtype=f64, device=self.dev)
+        self.action = torch.empty((B, ACT_DIM), dtype=f32, device=self.dev)
+        self.w = torch.zeros((B, self.engine.nw), dtype=f64, device=self.dev)     # reference: w0 = zeros (rlmpc2.py:492)
+        self.w_next = torch.empty_like(self.w)
+        self.u0 = torch.empty((B, 2), dtype=f64, device=self.dev)
+        self.J = torch.empty((B,), dtype=f64, device=self.dev)
+        self.status = torch.empty((B,), dtype=torch.int32, device=self.dev)
+        self.iters = torch.empty((B,), dtype=torch.int32, device=self.dev)
+        self.timestep = 0
+        self.count = 0
+        self.warm_start = warm_start
+
+    @property
+    def pvec(self):
+        return self.aux[:, 2:]
+
+    @property
+    def control(self):
+        return self.u_prev
+
+    def step(self, state, target):
+        """state, target: CUDA tensors [B,8].  Returns the device tensor of first tilt commands [B,2]."""
+        torch, L = self.torch, _lib.lib()
+        p = lambda t: C.c_void_p(t.data_ptr())
+        stream = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+        self.count += 1
+        obs_in, obs_out = self.obs
+        check(L.dart_policy_obs_push(self.B, self.count, p(state), p(target), p(self.u_prev), C.c_void_p(self.aux.data_ptr() + 16),
+                                     36, p(self.mean), p(self.M2), p(obs_in), p(obs_out), stream), "dart_policy_obs_push")
+        self.obs = [obs_out, obs_in]
+        self.policy.forward(obs_out, self.action)
+        if self.timestep % self.update_every == 0:
+            check(L.dart_policy_param_update(self.B, p(self.action), C.c_void_p(self.aux.data_ptr() + 16), 36, self.k_max,
+                                             self.max_delta, self.min_k, self.margin, self.alpha, stream),
+                  "dart_policy_param_update")
+        self.engine.solve_device(state, target, aux=self.aux, warm_w=self.w if self.warm_start else None,
+                                 w_out=self.w_next, u0_out=self.u0, J_out=self.J, status=self.status, iters=self.iters)
+        self.w, self.w_next = self.w_next, self.w
+        self.u_prev.copy_(self.u0)
+        self.aux[:, :2] = self.u0
+        self.timestep += 1
+        return self.u0
+
+
+class _Event:
+    """multiprocessing.Event look-alike (the reference's callers touch ``events['reset']``)."""
+
+    def __init__(self):
+        self._f = False
+
+    def set(self):
+        self._f = True
+
+    def clear(self):
+        self._f = False
+
+    def is_set(self):
+        return self._f
+
+    def wait(self, timeout=None):
+        return self._f
+
+
+class RLMPC:
+    """Same constructor, attributes and methods as the reference facade (rlmpc2.py:110-226, 986-1065), synchronous:
+    ``solve(target)`` returns this step's first move instead of whatever the solver process last published."""
+
+    def __init__(self, model, data, params, device=0):
+        self._device = device
+        self.setup(model, data, params)
+        nx, nu, N = int(params["nx"]), int(params["nu"]), int(params["N"])
+        self.shapes = {"state": (nx,), "state_next": (nx,), "target": (nx,), "w_opt": (nx * (N + 1) + nu * N,), "loss": (1,),
+                       "control": (nu,), "model_params": (self.params_len,), "state_deriv": (nx,), "in_contact": (1,),
+                       "RLstatus": (1,)}
+        self.views = {k: np.zeros(s, dtype=np.float64) for k, s in self.shapes.items()}
+        rng = np.random.default_rng(params.get("seed", None))
+        # rlmpc2.py:143 initial mailbox content, then the RL worker's own initialisation (:618-623)
+        k_max = params.get("max_param_abs", 0.5)
+        min_k = params.get("min_k", 1e-2)
+        margin = params.get("k_ceiling_margin", max(1e-3, 0.05 * k_max))
+        base = params.get("init_k_frac", 0.5) * k_max
+        jitter = rng.uniform(-params.get("init_k_jitter", 0.05), params.get("init_k_jitter", 0.05), size=self.params_len) * k_max
+        k0 = np.clip(np.full(self.params_len, base) + jitter, min_k, k_max - margin)
+        self.last_control = np.array([0.0, 0.0])
+        self.events = {k: _Event() for k in ("state_ready", "ctrl_ready", "data_ready", "terminate", "reset")}
+        weights = None
+        ck = os.path.join(self.checkpoint_dir, "best_agent.pth")
+        if not params.get("train", True) and os.path.exists(ck):
+            weights = load_checkpoint_weights(ck, trust_pickle=params.get("trust_checkpoint_pickle", False))
+        self._batch = LMPCBatch(1, k0[None, :], weights=weights, seed=params.get("policy_seed", 3), device=device,
+                                max_param_abs=k_max, max_delta_abs=params.get("max_delta_abs", 0.1), min_k=min_k,
+                                k_ceiling_margin=margin, shm_smooth_alpha=params.get("shm_smooth_alpha", 0.5),
+                                Ts=params["Ts"], N=N, Q=params["Q"], Qt=params["Qt"], R=params["R"],
+                                u_bounds=params["u_bounds"])
+        self.views["model_params"][:] = k0
+        self.loss = np.zeros(1)
+
+    def rebind(self, model, data):
+        self.setup(model, data, self.params)
+
+    def setup(self, model, data, params):
+        self.model, self.data, self.params = model, data, params
+        self.mu = params.get("mu", 0.2)
+        self.body_name = params.get("body_name", "cube2")
+        self.params_len = 34
+        here = os.path.dirname(os.path.abspath(__file__))
+        self.checkpoint_dir = params.get("checkpoint_dir") or os.path.join(here, "checkpoints", "unnamed")
+
+    def get_state(self):
+        """rlmpc2.py:1034-1042: [px, vx, py, vy, theta_x, omega_x, theta_y, omega_y]."""
+        from scipy.spatial.transform import Rotation as Rot
+        b = self.data.body(self.params.get("body_name", self.body_name))
+        theta = Rot.from_matrix(np.asarray(b.xmat).reshape(3, 3)).as_euler("xyz", degrees=False)[:2]
+        return np.array([b.xpos[0], b.cvel[3], b.xpos[1], b.cvel[4], theta[0], b.cvel[0], theta[1], b.cvel[1]])
+
+    def measure(self):
+        state = self.get_state()
+        self.views["state"][:] = state
+        return {"state": state, "state_deriv": self.views["state_deriv"].copy(), "contact": float(self.views["in_contact"][0])}
+
+    def solve(self, target):
+        torch = _torch()
+        state = self.get_state()
+        self.views["state"][:] = state
+        self.views["target"][:] = target
+        dev = self._batch.dev
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)[None, :]).to(dev)
+        u0 = self._batch.step(t(state), t(target)).cpu().numpy()[0]
+        self.last_control = u0.astype(np.float64)
+        self.loss = self._batch.J.cpu().numpy().copy()
+        self.views["w_opt"][:] = self._batch.w.cpu().numpy()[0]
+        self.views["loss"][:] = self.loss
+        self.views["control"][:] = self.last_control
+        self.views["model_params"][:] = self._batch.pvec.cpu().numpy()[0]
+        return self.last_control.copy(), self.loss
+
+    def close(self):
+        self.events["terminate"].set()
+        if getattr(self, "_batch", None) is not None:
+            self._batch.engine.close()
+            self._batch.policy.close()
+            self._batch = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False

@@ -113,11 +113,55 @@ int dart_solve_host(dart_handle h, int32_t B, const double* x0, const double* re
 /* Number of kernels launched by this handle since creation (for bench.py's gpu_launches). */
 int64_t dart_launch_count(dart_handle h);
 
-/* Iteration statistics of the last dart_solve*: sum over instances of Newton iterations (device read; syncs). */
+/* Launch configuration chosen for the last dart_solve* call. */
 int dart_last_launch_config(dart_handle h, int32_t* lanes, int32_t* block_threads, int32_t* grid, int32_t* smem_bytes);
 
 /* tilt -> tray quaternion wxyz, Euler xyz [u1, -u0, 0] (PMPC/main.py:107-116). u [B,2] -> quat [B,4], device. */
 int dart_tilt_to_quat(int32_t B, const double* u, double* quat, void* stream);
+
+/* Batched RLS.update (np_mpc_adaptive_with_linear_regressor.py:17-27): E estimators per instance share phi.
+ *   theta [B,E,7] in/out   P [B,E,7,7] in/out   phi [B,7]   y [B,E]   lam = forgetting factor.  Device pointers. */
+int dart_rls_update(int32_t B, int32_t E, double* theta, double* P, const double* phi, const double* y,
+                    double lam, void* stream);
+
+/* One RMPC closed-loop step's pre-solve glue (rob_ctrl.py:335-351) fused into one launch: finite-difference
+ * acceleration, regressor of prev_state, the x and y RLS updates, reference governor, build_ref_traj, and the
+ * solver's aux rows.  Device pointers:
+ *   xk, prev_state, target [B,4]   u_prev [B,2]   r_v [B,4] in/out   theta [B,2,7] in/out   P [B,2,7,7] in/out
+ *   ref [B,(N+1)*4] out (Rref_flat)   aux [B,16] out ([u_prev, theta_hat] as dart_solve expects for RMPC) */
+int dart_rmpc_prologue(int32_t B, int32_t N, double Ts, double v_eps, double lam, double dr_max, double alpha_rg,
+                       double step_fraction, const double* xk, const double* prev_state, const double* target,
+                       const double* u_prev, double* r_v, double* theta, double* P, double* ref, double* aux,
+                       void* stream);
+
+/* ---- LMPC parameter-adaptation policy (rlmpc2.py:33-80, 641-668, 742-759, 606-616) ---- */
+typedef struct dart_policy* dart_policy_handle;
+
+/* Actor weights as torch stores them (Linear.weight is [out, in], float32, host pointers):
+ * W1 [64,520] b1 [64]  W2 [64,64] b2 [64]  W3 [34,64] b3 [34].  Only the reference architecture
+ * (obs_dim 520 = 10 x 52 history, hidden 64 x 2, act_dim 34) is supported. */
+int dart_policy_create(dart_policy_handle* out, int device, int32_t obs_dim, int32_t hidden, int32_t act_dim,
+                       const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
+                       const float* b3);
+int dart_policy_destroy(dart_policy_handle h);
+
+/* Policy.mean_net forward: obs [B,520] f32 (device, 16-byte aligned) -> act_mean [B,34] f32 (device).
+ * TMA-fed tcgen05 (TF32 inputs, FP32 accumulate) with all three layers fused on chip. */
+int dart_policy_forward(dart_policy_handle h, int32_t B, const float* obs, float* act_mean, void* stream);
+int64_t dart_policy_launch_count(dart_policy_handle h);
+
+/* Observation build (rlmpc2.py:641-668): base = [state(8), target(8), control(2), cur_k(34)] rounded to f32,
+ * Welford update of mean/M2 [B,52] (count = pushes so far including this one), normalise, append to the 10-deep
+ * history: obs_out [B,520] = [obs_in[:,52:], normalised base].  obs_in != obs_out.  Device pointers.
+ * cur_k has row stride ld_k (34, or 36 when it points into the LMPC aux rows at column 2). */
+int dart_policy_obs_push(int32_t B, int32_t count, const double* state, const double* target, const double* control,
+                         const double* cur_k, int32_t ld_k, double* mean, double* M2, const float* obs_in,
+                         float* obs_out, void* stream);
+
+/* Parameter update (rlmpc2.py:742-759 then write_params_to_shm :606-616): pvec [B, ld_pvec] f64 in/out
+ * (the 34 model parameters), action [B,34] f32.  Device pointers. */
+int dart_policy_param_update(int32_t B, const float* action, double* pvec, int32_t ld_pvec, double k_max,
+                             double max_delta, double min_k, double k_ceiling_margin, double alpha, void* stream);
 
 /* Measured FP64 FMA-pipe peak of the device in TFLOP/s (DFMA microbenchmark, CUDA-event timed): the roofline
  * denominator bench.py reports the solver kernels against. */

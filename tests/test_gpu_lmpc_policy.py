@@ -1,0 +1,126 @@
+"""LMPC policy kernels (tcgen05 MLP, observation build, parameter update) and the device-resident LMPC step."""
+import numpy as np
+import pytest
+
+import dart_b200
+from oracle import ipm, policy, problems
+
+pytestmark = pytest.mark.gpu
+
+# The MLP multiplies TF32-rounded inputs (10-bit mantissa) and accumulates in FP32; the reference multiplies in FP32.
+# Bound used here: |mean - mean_fp32| <= 4e-3 absolute on outputs of O(1).  Through the parameter update the action is
+# scaled by max_delta_abs = 0.02, so this is <= 8e-5 in logit space and far inside the 1e-4 rad bar on the tilt command.
+TOL_MLP = 4e-3
+
+
+def _torch_ref(weights, obs, dtype):
+    import torch
+    h = torch.from_numpy(obs).to(dtype)
+    for i, (W, b) in enumerate(weights):
+        h = h @ torch.from_numpy(W).to(dtype).T + torch.from_numpy(b).to(dtype)
+        if i < 2:
+            h = torch.tanh(h)
+    return h.numpy()
+
+
+@pytest.mark.parametrize("B", [1, 127, 128, 1000, 16384])
+def test_policy_mlp_vs_torch(built, B):
+    import torch
+    rng = np.random.default_rng(B)
+    weights = dart_b200.init_policy_weights(seed=3)
+    weights = [(W, (0.05 * rng.standard_normal(b.shape)).astype(np.float32)) for W, b in weights]   # exercise the bias path
+    obs = rng.standard_normal((B, 520)).astype(np.float32)
+    pol = dart_b200.PolicyMLP(weights, device=0)
+    out = pol.forward(torch.from_numpy(obs).cuda()).cpu().numpy()
+    ref32 = _torch_ref(weights, obs, torch.float32)
+    ref64 = _torch_ref(weights, obs, torch.float64)
+    assert np.abs(ref32 - policy.mlp_forward(obs, weights)).max() < 1e-4          # oracle restatement == torch
+    err = np.abs(out - ref64).max()
+    print(f"B={B}: max|mean - fp64 ref| = {err:.2e}  (fp32 torch vs fp64: {np.abs(ref32 - ref64).max():.2e})")
+    assert err <= TOL_MLP
+
+
+def test_policy_mlp_with_reference_checkpoint_shapes(built):
+    """Real-architecture weights (random here; the reference's .pth files are untrusted pickles we do not ship)."""
+    import torch
+    weights = policy.orthogonal_policy_weights(seed=3)
+    mine = dart_b200.init_policy_weights(seed=3)
+    for (a, b), (c, d) in zip(weights, mine):
+        assert np.array_equal(a, c) and np.array_equal(b, d)
+
+
+def test_obs_push_and_param_update_vs_oracle(built):
+    import torch
+    import ctypes as C
+    rng = np.random.default_rng(5)
+    B = 33
+    dev = torch.device("cuda", 0)
+    L = dart_b200._lib.lib()
+    norm = policy.ObsNormalizer(B)
+    mean = torch.zeros((B, 52), dtype=torch.float64, device=dev); M2 = torch.zeros_like(mean)
+    obs = [torch.zeros((B, 520), dtype=torch.float32, device=dev) for _ in range(2)]
+    p = lambda t: C.c_void_p(t.data_ptr())
+    for step in range(1, 14):
+        st, tg = rng.standard_normal((B, 8)), rng.standard_normal((B, 8))
+        ct, k = 0.3 * rng.standard_normal((B, 2)), rng.uniform(0.05, 1.8, (B, 34))
+        ref = norm.push(st, tg, ct, k)
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        rc = L.dart_policy_obs_push(B, step, p(t(st)), p(t(tg)), p(t(ct)), p(t(k)), 34, p(mean), p(M2), p(obs[0]), p(obs[1]), None)
+        assert rc == 0
+        torch.cuda.synchronize()
+        obs = [obs[1], obs[0]]
+        got = obs[0].cpu().numpy()
+        assert np.abs(got - ref).max() <= 2e-6 * max(1.0, np.abs(ref).max()), step
+    # parameter update
+    act = (0.5 * rng.standard_normal((B, 34))).astype(np.float32)
+    k = rng.uniform(0.02, 1.85, (B, 34))
+    kd = torch.from_numpy(k.copy()).to(dev)
+    assert L.dart_policy_param_update(B, p(torch.from_numpy(act).to(dev)), p(kd), 34, 2.0, 0.02, 1e-2, 0.1, 0.5, None) == 0
+    ref = policy.write_params(policy.param_update(k, act, 2.0, 0.02, 1e-2), k, 2.0, 1e-2, 0.1, 0.5)
+    assert np.abs(kd.cpu().numpy() - ref).max() <= 1e-6
+
+
+def test_lmpc_batch_step_matches_oracle_pipeline(built):
+    """Three steps of LMPCBatch: pvec after the update and the solve's u0/J against the oracle run on the same inputs."""
+    import torch
+    B = 48
+    c = dart_b200.workloads.lmpc_config4(B, seed=3)
+    dev = torch.device("cuda", 0)
+    weights = dart_b200.init_policy_weights(seed=3)
+    ctl = dart_b200.LMPCBatch(B, c["pvec"], weights=weights, device=0)
+    norm = policy.ObsNormalizer(B)
+    k = c["pvec"].copy(); control = np.zeros((B, 2)); Xw = Uw = None
+    state = c["state"].copy()
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    for step in range(3):
+        u_gpu = ctl.step(t(state), t(c["target"])).cpu().numpy()
+        obs = norm.push(state, c["target"], control, k)
+        a = policy.mlp_forward(obs, weights)
+        if step % 8 == 0:
+            k = policy.write_params(policy.param_update(k, a, 2.0, 0.02, 1e-2), k, 2.0, 1e-2, 0.1, 0.5)
+        assert np.abs(ctl.pvec.cpu().numpy() - k).max() <= 2e-5       # TF32 action -> 0.02 * 4e-3 in logit space
+        prob = problems.lmpc_problem(state, control, ctl.pvec.cpu().numpy(), c["target"])   # same pvec: isolates the solve
+        X0 = np.zeros((B, 21, 10)) if Xw is None else Xw
+        U0 = np.zeros((B, 20, 2)) if Uw is None else Uw
+        sol = ipm.solve(prob, X0=X0, U0=U0)
+        assert (sol["status"] == 0).all() and (ctl.status.cpu().numpy() == 0).all()
+        assert np.abs(u_gpu - sol["U"][:, 0]).max() <= 1e-4
+        assert (np.abs(ctl.J.cpu().numpy() - sol["J"]) / np.abs(sol["J"])).max() <= 1e-6
+        Xw, Uw = sol["X"], sol["U"]
+        control = sol["U"][:, 0].copy()
+        state = state + 0.002 * np.concatenate([state[:, 1:2], 0 * state[:, :1], state[:, 3:4], 0 * state[:, :1], 0 * state[:, :4]], axis=1)
+
+
+def test_rlmpc_facade(built):
+    model = dart_b200.GravityModel(-9.81, 0.002); data = dart_b200.StateHolder()
+    b = data.body("cube2"); b.xmat = np.eye(3).reshape(-1); b.xpos[:] = [0.01, -0.02, 0.43]
+    params = {"Ts": 0.002, "nx": 8, "nu": 2, "N": 20, "Q": [200.0, 2.0, 200.0, 2.0, 0, 0, 0, 0], "Qt": [200.0, 2.0, 200.0, 2.0, 0, 0, 0, 0],
+              "R": [0.1, 0.1, 1.0, 1.0], "u_bounds": (-0.4, 0.4), "body_name": "cube2", "g": 9.81, "max_param_abs": 2.0,
+              "max_delta_abs": 0.02, "train": False, "seed": 0, "checkpoint_dir": "/nonexistent"}
+    with dart_b200.RLMPC(model, data, params) as ctl:
+        tgt = np.array([0.05, 0, 0.05, 0, 0, 0, 0, 0])
+        u, loss = ctl.solve(tgt)
+        assert u.shape == (2,) and np.all(np.abs(u) <= 0.4) and ctl.views["w_opt"].shape == (208,)
+        assert np.array_equal(ctl.views["control"], u)
+        u2, _ = ctl.solve(tgt)
+        assert np.all(np.isfinite(u2))
