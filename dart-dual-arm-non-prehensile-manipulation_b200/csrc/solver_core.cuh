@@ -543,7 +543,7 @@ struct Solver {
         eval1(f, L, th, pinf);
         eval2(dinf, zs_min, zs_max, lam_sum, z_sum, nact);
         const double mu_min = o.tol / 10.0;
-        int it = 0;
+        int it = 0, tiny = 0;
         int32_t st = ST_MAXITER;
         double E0 = 0.0;
         for (;; ++it) {
@@ -585,6 +585,9 @@ struct Solver {
 #ifdef DART_TRACE
             printf("it %d mu %.3e E0 %.3e dinf %.3e pinf %.3e zsmax %.3e ap %.4f ad %.4f alpha %.5f dphi %.3e th0 %.3e f %.10g\n", it, mu, E0, dinf / s_d, pinf, zs_max / s_c, ap, ad, alpha, dphi, th0, f);
 #endif
+            // the step vanished three times in a row: no restoration phase here -- stop and say so
+            tiny = (alpha <= 1e-6) ? tiny + 1 : 0;
+            if (tiny >= 3) { st = (pinf > 1e-4) ? ST_INFEASIBLE : ST_MAXITER; ++it; break; }
             move_dual(alpha, ad, mu);
             eval2(dinf, zs_min, zs_max, lam_sum, z_sum, nact);
         }

@@ -35,7 +35,7 @@ extern "C" {
 
 #define DART_STATUS_CONVERGED 0   /* KKT error <= tol                                             */
 #define DART_STATUS_MAXITER 1     /* iteration cap hit; last iterate returned (reference: silent)  */
-#define DART_STATUS_INFEASIBLE 2  /* stage-0 velocity cap violated by the given x0 (RMPC)          */
+#define DART_STATUS_INFEASIBLE 2  /* x0 violates a stage-0 cap, or the step vanished with violation left   */
 #define DART_STATUS_NUMERIC 3     /* NaN/Inf encountered                                           */
 
 typedef enum {

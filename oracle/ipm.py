@@ -140,6 +140,7 @@ def solve(prob: StageProblem, X0=None, U0=None, opts: Options = None, trace=None
     zu = (mu[:, None, None] / (hi - s)) * msk
     lam = np.zeros((B, N, n))                 # lam[:,k] multiplies F(x_k,u_k) - x_{k+1}
     iters = np.zeros(B, dtype=np.int32)
+    tiny = np.zeros(B, dtype=np.int32)
     done = np.zeros(B, dtype=bool)
     nv = N * (m + n)
     ne = N * n
@@ -294,6 +295,9 @@ def solve(prob: StageProblem, X0=None, U0=None, opts: Options = None, trace=None
             if accepted.all():
                 break
             alpha = np.where(accepted, alpha, alpha * 0.5)
+        # the step vanished three times in a row (no restoration phase): stop, flag infeasible if violation remains
+        tiny = np.where((~done) & (alpha <= 1e-6), tiny + 1, 0)
+        stall = (~done) & (tiny >= 3)
         upd = (~done)
         a3 = np.where(upd, alpha, 0.0)[:, None, None]
         X = X + a3 * dX
@@ -308,6 +312,11 @@ def solve(prob: StageProblem, X0=None, U0=None, opts: Options = None, trace=None
         sl, su = s - lo, hi - s
         zl = np.where(msk > 0, np.clip(zl, mu3 / (ks * sl), ks * mu3 / sl), 0.0)
         zu = np.where(msk > 0, np.clip(zu, mu3 / (ks * su), ks * mu3 / su), 0.0)
+        if stall.any():
+            Fn = prob.step(X[:, :N], U)
+            pin = np.maximum(np.abs(Fn - X[:, 1:]).max(axis=(1, 2)), np.abs((prob.row_values(X, U) - s) * msk).max(axis=(1, 2)))
+            status[stall] = np.where(pin[stall] > 1e-4, STATUS_INFEASIBLE, STATUS_MAXITER)
+            done |= stall
 
     status = np.where(infeasible0 & (status != STATUS_NUMERIC), STATUS_INFEASIBLE, status)
     return dict(X=X, U=U, J=prob.objective(X, U), status=status, iters=iters, lam=lam, zl=zl, zu=zu, s=s,

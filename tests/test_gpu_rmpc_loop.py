@@ -61,11 +61,14 @@ def test_closed_loop_matches_oracle_loop(built):
     c = dart_b200.workloads.rmpc_config3(B, seed=2)
     x = c["x0"].copy(); x[:, [1, 3]] *= 0.5
     dev = torch.device("cuda", 0)
-    ctl = dart_b200.RMPCBatch(B, c["target"], x, device=0)
+    # P0 = 1 keeps the early RLS transients small enough that every NLP of the episode stays feasible (with the
+    # reference's P0 = 1e3 the first few estimates make the velocity-capped NLP infeasible: see the next test)
+    P0 = 1.0
+    ctl = dart_b200.RMPCBatch(B, c["target"], x, device=0, rls_P0=P0)
     rv0 = np.zeros((B, 4)); rv0[:, [0, 2]] = x[:, [0, 2]]
     ctl.set_virtual_reference(rv0)
     # oracle-side state
-    th = np.zeros((B, 2, 7)); P = np.tile(np.eye(7) * 1e3, (B, 2, 1, 1))
+    th = np.zeros((B, 2, 7)); P = np.tile(np.eye(7) * P0, (B, 2, 1, 1))
     r_v = rv0.copy(); prev = x.copy(); u_prev = np.zeros((B, 2)); Xw = None; Uw = None
     x_o = x.copy()
     for t in range(T):
@@ -92,6 +95,31 @@ def test_closed_loop_matches_oracle_loop(built):
         x = _plant_step(x, u_gpu, c["mu_plant"], c["c_plant"])
     assert (ctl.status.cpu().numpy() == 0).all()
     assert np.abs(x - x_o).max() < 1e-6
+
+
+def test_infeasible_nlp_is_flagged_like_the_oracle(built):
+    """Reference RLS start (P0 = 1e3): after two steps theta_hat ~ 20 makes the velocity caps unattainable.  The
+    reference silently returns IPOPT's restoration iterate; here both solvers stop early and flag status 2."""
+    import torch
+    B = 16
+    c = dart_b200.workloads.rmpc_config3(B, seed=2)
+    x = c["x0"].copy(); x[:, [1, 3]] *= 0.5
+    dev = torch.device("cuda", 0)
+    ctl = dart_b200.RMPCBatch(B, c["target"], x, device=0)
+    rv0 = np.zeros((B, 4)); rv0[:, [0, 2]] = x[:, [0, 2]]
+    ctl.set_virtual_reference(rv0)
+    for t in range(3):
+        u = ctl.step(torch.from_numpy(x).to(dev)).cpu().numpy()
+        if t == 2:
+            theta = ctl.theta.cpu().numpy().reshape(B, 14)
+            ref = ctl.ref.cpu().numpy(); aux = ctl.aux.cpu().numpy()
+            sol = ipm.solve(problems.rmpc_problem(x, aux[:, :2], theta, ref), X0=None, U0=None)
+            st = ctl.status.cpu().numpy()
+            assert (st == 2).sum() >= 3 and ((st == 2) == (sol["status"] == 2)).all()
+            assert ctl.iters.cpu().numpy().max() < 80          # early exit, not the 200-iteration cap
+            ok = st == 0
+            assert np.abs(u - sol["U"][:, 0])[ok].max() <= 1e-3   # different warm starts, same optimum where feasible
+        x = _plant_step(x, u, c["mu_plant"], c["c_plant"])
 
 
 def test_adaptive_class_dropin(built):
