@@ -11,3 +11,4 @@ from .engine import NMPCEngine, measure_fp64_tflops, tilt_to_quat_device        
 from .pmpc import PMPC, GravityModel, StateHolder, mpc_worker   # noqa: F401
 from .rmpc import RLS, AdaptiveNPMPCSmooth, RMPCBatch, rls_update_device   # noqa: F401
 from .lmpc import RLMPC, LMPCBatch, PolicyMLP, init_policy_weights, load_checkpoint_weights   # noqa: F401
+from .parallel import ShardedSolver, shard_bounds   # noqa: F401

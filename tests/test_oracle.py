@@ -30,11 +30,11 @@ def test_ipm_agrees_with_slsqp(which):
         _, _, p = helpers.pmpc_case(1)
         idx = [0, 7, 13]
     elif which == "rmpc":
-        _, p = helpers.rmpc_case(4)
-        idx = [0, 1, 2]
+        _, p = helpers.rmpc_case(2)
+        idx = [0, 1]
     else:
-        _, p = helpers.lmpc_case(3)
-        idx = [0, 1, 2]
+        _, p = helpers.lmpc_case(2)
+        idx = [0, 1]
     r = ipm.solve(p)
     assert (r["status"] == 0).all()
     for b in idx:
