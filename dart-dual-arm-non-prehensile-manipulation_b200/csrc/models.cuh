@@ -77,6 +77,7 @@ struct PmpcAxis {
     static constexpr int NX = 2, NU = 1, NR = 1, NP = 2, NAUG = 0, NAXIS = 2;
     static constexpr bool SERIAL_RICCATI = true;
     static constexpr int NXF = 6;   // states per stage in the reference's decision vector
+    static constexpr int NDEF = 15; // the reference's horizon (compile-time instantiation)
     struct Prm { double Qp, Qv, R, mu, g, Ts, ulo, uhi, rp, rv; };
 
     DART_HD static int ref_doubles(int) { return 0; }
@@ -135,6 +136,7 @@ struct Rmpc {
     static constexpr int NX = 6, NU = 2, NR = 6, NP = 4, NAUG = 2, NAXIS = 1;
     static constexpr bool SERIAL_RICCATI = false;
     static constexpr int NXF = 4;
+    static constexpr int NDEF = 20;
     struct Prm { double Qp, Qv, Ru, Rdu, gz, Ts, ulo, uhi, dlo, dhi, vmax, inv_eps; double th[14]; };
 
     DART_HD static int ref_doubles(int N) { return (N + 1) * 4; }
@@ -210,6 +212,7 @@ struct LmpcAxis {
     static constexpr int NX = 5, NU = 1, NR = 1, NP = 4, NAUG = 1, NAXIS = 2;
     static constexpr bool SERIAL_RICCATI = false;
     static constexpr int NXF = 8;
+    static constexpr int NDEF = 20;
     struct Prm {
         double Ts, ulo, uhi;
         double Q[4], Qt[4], Ru, Rdu, ref[4];
@@ -316,11 +319,11 @@ struct LmpcAxis {
 // =============================================================================================== driver
 // Solve sub-problem (inst, axis) with the lanes of `tile`; `base` is this tile's workspace.
 // Returns per-problem J/status/iters/kkt; writes X/U of this sub-problem into w_out (reference layout).
-template <class M, class T>
+template <class M, class T, int NC = 0>
 DART_HD void solve_one(const T& tile, const KArgs& a, int inst, int axis, double* base, double& J, int32_t& status,
                        int32_t& iters, double& kkt) {
     constexpr int n = M::NX, m = M::NU, np = M::NP;
-    const int N = a.N;
+    const int N = (NC > 0) ? NC : a.N;
     Workspace<M> w;
     w.bind(base, N);
     typename M::Prm prm;
@@ -344,7 +347,7 @@ DART_HD void solve_one(const T& tile, const KArgs& a, int inst, int axis, double
         }
     }
     tile.sync();
-    Solver<M, T> s(tile, prm, a.o, N, w);
+    Solver<M, T, NC> s(tile, prm, a.o, N, w);
     s.run(J, status, iters, kkt);
     if (M::infeasible0(prm, x0) && status != ST_NUMERIC) status = ST_INFEASIBLE;
     if (a.w_out) {

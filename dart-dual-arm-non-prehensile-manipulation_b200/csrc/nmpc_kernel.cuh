@@ -39,7 +39,7 @@ struct DevTile {
 // Per-tile result slot at the head of each workspace stride (4 doubles).
 constexpr int kSlot = 4;
 
-template <class M, int G>
+template <class M, int G, int NC>
 __global__ void __launch_bounds__(256) nmpc_solve_kernel(const KArgs a, const int ws_stride) {
     extern __shared__ double smem[];
     constexpr int NAX = M::NAXIS;
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(256) nmpc_solve_kernel(const KArgs a, const in
     const bool active = inst < a.B;
     double J = 0.0, kkt = 0.0;
     int32_t status = ST_CONVERGED, iters = 0;
-    if (active) solve_one<M, DevTile<G>>(tile, a, inst, axis, slot + kSlot, J, status, iters, kkt);
+    if (active) solve_one<M, DevTile<G>, NC>(tile, a, inst, axis, slot + kSlot, J, status, iters, kkt);
     if (NAX == 1) {
         if (active && tile.lane() == 0) {
             a.J[inst] = J;
@@ -88,8 +88,8 @@ __global__ void __launch_bounds__(256) nmpc_solve_kernel(const KArgs a, const in
     }
 }
 
-template <class M, int G>
-static int launch_t(const KArgs& a, int block_threads, cudaStream_t st, LaunchInfo* info) {
+template <class M, int G, int NC>
+static int launch_n(const KArgs& a, int block_threads, cudaStream_t st, LaunchInfo* info) {
     const int ws = Workspace<M>::doubles(a.N) + kSlot;
     const int ws_stride = (ws + 1) & ~1;
     int bt = block_threads > 0 ? block_threads : 0;
@@ -110,13 +110,19 @@ static int launch_t(const KArgs& a, int block_threads, cudaStream_t st, LaunchIn
     size_t smem = (size_t)tpb * ws_stride * sizeof(double);
     while (smem > (size_t)max_smem && bt > 32) { bt -= 32; tpb = bt / G; smem = (size_t)tpb * ws_stride * sizeof(double); }
     if (smem > (size_t)max_smem) return DART_ERR_UNSUPPORTED;
-    auto kern = nmpc_solve_kernel<M, G>;
+    auto kern = nmpc_solve_kernel<M, G, NC>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return DART_ERR_CUDA;
     const long probs = (long)a.B * M::NAXIS;
     const int grid = (int)((probs + tpb - 1) / tpb);
     kern<<<grid, bt, smem, st>>>(a, ws_stride);
     if (info) { info->lanes = G; info->block_threads = bt; info->grid = grid; info->smem_bytes = (int)smem; }
     return cudaGetLastError() == cudaSuccess ? DART_OK : DART_ERR_CUDA;
+}
+
+template <class M, int G>
+static int launch_t(const KArgs& a, int block_threads, cudaStream_t st, LaunchInfo* info) {
+    if (a.N == M::NDEF) return launch_n<M, G, M::NDEF>(a, block_threads, st, info);
+    return launch_n<M, G, 0>(a, block_threads, st, info);
 }
 
 template <class M>

@@ -106,7 +106,8 @@ struct Workspace {
 };
 
 // ------------------------------------------------------------------------------------------------------
-template <class M, class T>
+// NC > 0: horizon known at compile time (constant offsets, unrollable stage loops); NC == 0: runtime horizon.
+template <class M, class T, int NC = 0>
 struct Solver {
     static constexpr int n = M::NX, m = M::NU, nr = M::NR, ny = n + m, nc = n + m + 1, np = M::NP;
     using Prm = typename M::Prm;
@@ -118,7 +119,8 @@ struct Solver {
     const int N;
     W& w;
 
-    DART_HD Solver(const T& t, const Prm& p, const SolverOpts& oo, int NN, W& ww) : tile(t), prm(p), o(oo), N(NN), w(ww) {}
+    DART_HD Solver(const T& t, const Prm& p, const SolverOpts& oo, int NN, W& ww)
+        : tile(t), prm(p), o(oo), N(NC > 0 ? NC : NN), w(ww) {}
 
     DART_HD double yval(int k, int i) const { return i < n ? w.X[k * n + i] : w.U[k * m + (i - n)]; }
     DART_HD double rowval(int k, int r) const {
@@ -407,33 +409,136 @@ struct Solver {
         }
     }
 
-    // ---- forward sweep (every lane runs the short affine recurrence in registers; lane 0 stores)
+    // ---- Riccati backward sweep for small problems: every lane runs the whole recursion with P, p and the stage
+    // matrix in REGISTERS (the loop-carried dependency never touches shared memory); stage data loads do not depend
+    // on P, so they are off the critical path.  Lane 0 stores the gains and P_k / p_k for the later phases.
+    DART_HD void backward_serial() {
+        const bool wr = tile.lane() == 0;
+        double P[n * n], pv[n];
+        DART_UNROLL for (int i = 0; i < n; ++i) {
+            DART_UNROLL for (int j = 0; j < n; ++j) P[i * n + j] = (i == j) ? 2.0 * M::wT(prm, i) : 0.0;
+            pv[i] = 2.0 * M::wT(prm, i) * (w.X[N * n + i] - M::rT(prm, w.REF, N, i));
+        }
+        if (wr) {
+            DART_UNROLL for (int i = 0; i < n * n; ++i) w.PP[N * n * n + i] = P[i];
+            DART_UNROLL for (int i = 0; i < n; ++i) w.PV[N * n + i] = pv[i];
+        }
+        double Tm[n * nc], HG[ny * nc];
+        auto load = [&](int k, double* T_, double* H_) {
+            DART_UNROLL for (int a = 0; a < n; ++a) {
+                DART_UNROLL for (int b = 0; b < n; ++b) T_[a * nc + b] = w.A[k * n * n + a * n + b];
+                DART_UNROLL for (int j = 0; j < m; ++j) T_[a * nc + n + j] = w.Bm[k * n * m + a * m + j];
+                T_[a * nc + ny] = w.D[k * n + a];
+            }
+            DART_UNROLL for (int i = 0; i < ny; ++i) {
+                DART_UNROLL for (int c = 0; c < ny; ++c) H_[i * nc + c] = w.HS[k * ny * ny + i * ny + c];
+                H_[i * nc + ny] = w.GR[k * ny + i];
+            }
+        };
+        load(N - 1, Tm, HG);
+        for (int k = N - 1; k >= 0; --k) {
+            // next stage's data first: these loads do not depend on P, keep them ahead of the dependent chain
+            double Tn[n * nc], Hn[ny * nc];
+            load(k > 0 ? k - 1 : 0, Tn, Hn);
+            double Wm[n * nc], Mm[ny * nc];
+            DART_UNROLL for (int a = 0; a < n; ++a)
+                DART_UNROLL for (int c = 0; c < nc; ++c) {
+                    double acc = (c == nc - 1) ? pv[a] : 0.0;
+                    DART_UNROLL for (int b = 0; b < n; ++b) acc += P[a * n + b] * Tm[b * nc + c];
+                    Wm[a * nc + c] = acc;
+                }
+            DART_UNROLL for (int i = 0; i < ny; ++i)
+                DART_UNROLL for (int c = 0; c < nc; ++c) {
+                    double acc = HG[i * nc + c];
+                    DART_UNROLL for (int a = 0; a < n; ++a) acc += Tm[a * nc + i] * Wm[a * nc + c];
+                    Mm[i * nc + c] = acc;
+                }
+            double Lc[m * m];
+            double shift = 0.0;
+            for (int tries = 0; tries < 40; ++tries) {
+                DART_UNROLL for (int i = 0; i < m; ++i)
+                    DART_UNROLL for (int j = 0; j < m; ++j) Lc[i * m + j] = Mm[(n + i) * nc + n + j] + (i == j ? shift : 0.0);
+                if (chol(Lc)) break;
+                shift = (shift == 0.0) ? 1e-4 : shift * 8.0;
+            }
+            double Kt[m * (n + 1)];      // columns 0..n-1: feedback gains, column n: feed-forward
+            DART_UNROLL for (int c = 0; c <= n; ++c) {
+                double kt[m];
+                const int cc = (c < n) ? c : ny;
+                DART_UNROLL for (int j = 0; j < m; ++j) kt[j] = -Mm[(n + j) * nc + cc];
+                chol_solve(Lc, kt);
+                DART_UNROLL for (int j = 0; j < m; ++j) Kt[j * (n + 1) + c] = kt[j];
+            }
+            if (k > 0) {
+                DART_UNROLL for (int i = 0; i < n; ++i) {
+                    DART_UNROLL for (int c = 0; c <= n; ++c) {
+                        const int cc = (c < n) ? c : ny;
+                        double v = Mm[i * nc + cc];
+                        DART_UNROLL for (int j = 0; j < m; ++j) v += Mm[i * nc + n + j] * Kt[j * (n + 1) + c];
+                        if (c < n) P[i * n + c] = v; else pv[i] = v;
+                    }
+                }
+            }
+            if (wr) {
+                DART_UNROLL for (int j = 0; j < m; ++j) {
+                    DART_UNROLL for (int c = 0; c < n; ++c) w.K[k * m * n + j * n + c] = Kt[j * (n + 1) + c];
+                    w.KFF[k * m + j] = Kt[j * (n + 1) + n];
+                }
+                if (k > 0) {
+                    DART_UNROLL for (int i = 0; i < n * n; ++i) w.PP[k * n * n + i] = P[i];
+                    DART_UNROLL for (int i = 0; i < n; ++i) w.PV[k * n + i] = pv[i];
+                }
+            }
+            DART_UNROLL for (int i = 0; i < n * nc; ++i) Tm[i] = Tn[i];
+            DART_UNROLL for (int i = 0; i < ny * nc; ++i) HG[i] = Hn[i];
+        }
+        tile.sync();
+    }
+
+    // ---- forward sweep: every lane runs the short affine recurrence in registers (lane 0 stores).  The stage data
+    // of step k+1 is loaded before the dependent arithmetic of step k so shared-memory latency stays off the chain.
     DART_HD void forward() {
         double dx[n];
         DART_UNROLL for (int i = 0; i < n; ++i) dx[i] = 0.0;
-        if (tile.lane() == 0) {
+        const bool wr = tile.lane() == 0;
+        if (wr) {
             DART_UNROLL for (int i = 0; i < n; ++i) w.DX[i] = 0.0;
         }
+        double Kc[m * n], kc[m], Ac[n * n], Bc[n * m], dc[n];
+        auto load = [&](int k, double* K_, double* k_, double* A_, double* B_, double* d_) {
+            DART_UNROLL for (int i = 0; i < m * n; ++i) K_[i] = w.K[k * m * n + i];
+            DART_UNROLL for (int i = 0; i < m; ++i) k_[i] = w.KFF[k * m + i];
+            DART_UNROLL for (int i = 0; i < n * n; ++i) A_[i] = w.A[k * n * n + i];
+            DART_UNROLL for (int i = 0; i < n * m; ++i) B_[i] = w.Bm[k * n * m + i];
+            DART_UNROLL for (int i = 0; i < n; ++i) d_[i] = w.D[k * n + i];
+        };
+        load(0, Kc, kc, Ac, Bc, dc);
         for (int k = 0; k < N; ++k) {
-            const double* Ak = w.A + k * n * n;
-            const double* Bk = w.Bm + k * n * m;
+            double Kn[m * n], kn[m], An[n * n], Bn[n * m], dn[n];
+            const int kk = (k + 1 < N) ? k + 1 : k;
+            load(kk, Kn, kn, An, Bn, dn);
             double du[m], nx[n];
             DART_UNROLL for (int j = 0; j < m; ++j) {
-                double acc = w.KFF[k * m + j];
-                DART_UNROLL for (int i = 0; i < n; ++i) acc += w.K[k * m * n + j * n + i] * dx[i];
+                double acc = kc[j];
+                DART_UNROLL for (int i = 0; i < n; ++i) acc += Kc[j * n + i] * dx[i];
                 du[j] = acc;
             }
             DART_UNROLL for (int a = 0; a < n; ++a) {
-                double acc = w.D[k * n + a];
-                DART_UNROLL for (int i = 0; i < n; ++i) acc += Ak[a * n + i] * dx[i];
-                DART_UNROLL for (int j = 0; j < m; ++j) acc += Bk[a * m + j] * du[j];
+                double acc = dc[a];
+                DART_UNROLL for (int i = 0; i < n; ++i) acc += Ac[a * n + i] * dx[i];
+                DART_UNROLL for (int j = 0; j < m; ++j) acc += Bc[a * m + j] * du[j];
                 nx[a] = acc;
             }
-            if (tile.lane() == 0) {
+            if (wr) {
                 DART_UNROLL for (int j = 0; j < m; ++j) w.DU[k * m + j] = du[j];
                 DART_UNROLL for (int a = 0; a < n; ++a) w.DX[(k + 1) * n + a] = nx[a];
             }
             DART_UNROLL for (int a = 0; a < n; ++a) dx[a] = nx[a];
+            DART_UNROLL for (int i = 0; i < m * n; ++i) Kc[i] = Kn[i];
+            DART_UNROLL for (int i = 0; i < m; ++i) kc[i] = kn[i];
+            DART_UNROLL for (int i = 0; i < n * n; ++i) Ac[i] = An[i];
+            DART_UNROLL for (int i = 0; i < n * m; ++i) Bc[i] = Bn[i];
+            DART_UNROLL for (int i = 0; i < n; ++i) dc[i] = dn[i];
         }
         tile.sync();
     }
@@ -542,26 +647,28 @@ struct Solver {
         int nact;
         eval1(f, L, th, pinf);
         eval2(dinf, zs_min, zs_max, lam_sum, z_sum, nact);
+        const double inv_nd = 1.0 / (double)(N * n + 2 * nact), inv_nc = 1.0 / (double)(2 * (nact > 0 ? nact : 1));
         const double mu_min = o.tol / 10.0;
         int it = 0, tiny = 0;
         int32_t st = ST_MAXITER;
         double E0 = 0.0;
         for (;; ++it) {
-            const double s_d = dmax(o.smax, (lam_sum + z_sum) / (double)(N * n + 2 * nact)) / o.smax;
-            const double s_c = dmax(o.smax, z_sum / (double)(2 * (nact > 0 ? nact : 1))) / o.smax;
-            const double base = dmax(dinf / s_d, pinf);
-            E0 = dmax(base, (nact > 0 ? zs_max : 0.0) / s_c);
+            // IPOPT's scaled optimality error; is_d = 1/s_d, is_c = 1/s_c (s_* = max(smax, mean multiplier)/smax)
+            const double is_d = o.smax / dmax(o.smax, (lam_sum + z_sum) * inv_nd);
+            const double is_c = o.smax / dmax(o.smax, z_sum * inv_nc);
+            const double base = dmax(dinf * is_d, pinf);
+            E0 = dmax(base, (nact > 0 ? zs_max : 0.0) * is_c);
             if (E0 <= o.tol) { st = ST_CONVERGED; break; }
             if (!(E0 == E0) || E0 > 1e300) { st = ST_NUMERIC; break; }
             if (it >= o.max_iter) break;
             for (int q = 0; q < 8; ++q) {
                 double cm = (nact > 0) ? dmax(fabs(zs_max - mu), fabs(zs_min - mu)) : 0.0;
-                double Emu = dmax(base, cm / s_c);
-                if (Emu <= o.kappa_eps * mu && mu > mu_min) mu = dmax(mu_min, dmin(o.kappa_mu * mu, pow(mu, o.theta_mu)));
+                double Emu = dmax(base, cm * is_c);
+                if (Emu <= o.kappa_eps * mu && mu > mu_min) mu = dmax(mu_min, dmin(o.kappa_mu * mu, (o.theta_mu == 1.5) ? mu * sqrt(mu) : pow(mu, o.theta_mu)));
                 else break;
             }
             prep(mu);
-            if (M::SERIAL_RICCATI) backward(SerialTile());
+            if (M::SERIAL_RICCATI) backward_serial();
             else backward(tile);
             forward();
             double ap, ad, dphi;
@@ -574,7 +681,12 @@ struct Solver {
                 applied = alpha;
                 eval1(f, L, th, pinf);
                 const double phit = f - mu * L;
-                bool switching = (dphi < 0.0) && (alpha * pow(fabs(dphi), o.s_phi) > o.delta_sw * pow(th0, o.s_theta));
+                // alpha |dphi|^s_phi > delta th0^s_theta, compared in the log domain (only needed when th0 is small)
+                // single precision is ample for this heuristic test (and keeps three FP64 logs off the serial path)
+                bool switching = false;
+                if (dphi < 0.0 && th0 <= o.theta_small)
+                    switching = (th0 <= 0.0) || (log2f((float)alpha) + (float)o.s_phi * log2f((float)(-dphi)) >
+                                                 log2f((float)o.delta_sw) + (float)o.s_theta * log2f((float)th0));
                 bool armijo = phit <= phi0 + o.eta * alpha * dphi + 10.0 * 2.220446049250313e-16 * fabs(phi0);
                 bool suff = (th <= (1.0 - o.gamma_theta) * th0) || (phit <= phi0 - o.gamma_phi * th0);
                 bool ok = ((switching && th0 <= o.theta_small) ? armijo : suff) && (th <= th_max) && (phit == phit) &&
@@ -583,7 +695,7 @@ struct Solver {
                 alpha *= 0.5;
             }
 #ifdef DART_TRACE
-            printf("it %d mu %.3e E0 %.3e dinf %.3e pinf %.3e zsmax %.3e ap %.4f ad %.4f alpha %.5f dphi %.3e th0 %.3e f %.10g\n", it, mu, E0, dinf / s_d, pinf, zs_max / s_c, ap, ad, alpha, dphi, th0, f);
+            printf("it %d mu %.3e E0 %.3e dinf %.3e pinf %.3e zsmax %.3e ap %.4f ad %.4f alpha %.5f dphi %.3e th0 %.3e f %.10g\n", it, mu, E0, dinf * is_d, pinf, zs_max * is_c, ap, ad, alpha, dphi, th0, f);
 #endif
             // the step vanished three times in a row: no restoration phase here -- stop and say so
             tiny = (alpha <= 1e-6) ? tiny + 1 : 0;

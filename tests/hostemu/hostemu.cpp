@@ -18,7 +18,9 @@ static void run_all(const KArgs& a) {
         for (int ax = 0; ax < M::NAXIS; ++ax) {
             double J = 0, kkt = 0;
             int32_t s = 0, it = 0;
-            solve_one<M, HostTile>(tile, a, inst, ax, ws.data(), J, s, it, kkt);
+            // same dispatch as the device launcher: compile-time horizon when it is the reference's
+            if (a.N == M::NDEF) solve_one<M, HostTile, M::NDEF>(tile, a, inst, ax, ws.data(), J, s, it, kkt);
+            else solve_one<M, HostTile, 0>(tile, a, inst, ax, ws.data(), J, s, it, kkt);
             Js += J;
             st = s > st ? s : st;
             itx = it > itx ? it : itx;
