@@ -185,11 +185,12 @@ def run_ours(args):
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
     comm = torch.cuda.Stream(device=dev) if world > 1 else None
     solved_evt = torch.cuda.Event()
+    if world > 1:
+        eng.set_result_rows(rows)        # the solve kernel writes the packed [u0x, u0y, J, status] rows itself
 
     def step():
         eng.solve_device(x0_d, tg_d, aux=aux_d, u0_out=u0, J_out=J, status=st, iters=it)
         if world > 1:
-            rows[:, 0:2] = u0; rows[:, 2] = J; rows[:, 3] = st.to(torch.float64)
             solved_evt.record()
             comm.wait_event(solved_evt)
             with torch.cuda.stream(comm):

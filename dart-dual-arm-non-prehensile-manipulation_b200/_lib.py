@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libdart_b200.so")
+LIB_PATH = os.environ.get("DART_B200_LIB") or os.path.join(HERE, "lib", "libdart_b200.so")   # override: A/B builds
 
 DART_PMPC, DART_RMPC, DART_LMPC = 0, 1, 2
 STATUS_CONVERGED, STATUS_MAXITER, STATUS_INFEASIBLE, STATUS_NUMERIC = 0, 1, 2, 3
@@ -51,6 +51,8 @@ def lib():
         getattr(L, f).argtypes = [vp]
     L.dart_solve.argtypes = [vp, C.c_int32] + [vp] * 9 + [vp]
     L.dart_solve_host.argtypes = [vp, C.c_int32] + [vp] * 9
+    if hasattr(L, "dart_set_result_rows"):          # absent only in older A/B builds loaded through DART_B200_LIB
+        L.dart_set_result_rows.argtypes = [vp, vp]
     L.dart_launch_count.argtypes = [vp]
     L.dart_launch_count.restype = C.c_int64
     L.dart_last_launch_config.argtypes = [vp, ip, ip, ip, ip]

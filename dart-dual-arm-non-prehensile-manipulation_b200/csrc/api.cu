@@ -18,6 +18,7 @@ struct dart_solver {
     cudaStream_t stream;
     void* pin;   size_t pin_bytes;
     void* dev;   size_t dev_bytes;
+    double* rows;      // dart_set_result_rows
 };
 
 extern "C" int dart_default_cfg(int32_t method, dart_cfg* c) {
@@ -73,7 +74,7 @@ extern "C" int dart_create(dart_handle* out, const dart_cfg* cfg, int device) {
     fill_opts(*cfg, h->opts);
     h->launches = 0;
     memset(&h->last, 0, sizeof(h->last));
-    h->pin = nullptr; h->pin_bytes = 0; h->dev = nullptr; h->dev_bytes = 0;
+    h->pin = nullptr; h->pin_bytes = 0; h->dev = nullptr; h->dev_bytes = 0; h->rows = nullptr;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return DART_ERR_CUDA; }
     *out = h;
     return DART_OK;
@@ -103,7 +104,7 @@ extern "C" int dart_solve(dart_handle h, int32_t B, const double* x0, const doub
     KArgs a;
     a.B = B; a.N = h->cfg.N; a.o = h->opts; a.cfg = h->cfg;
     a.x0 = x0; a.ref = ref; a.aux = aux; a.warm = warm_w;
-    a.w_out = w_out; a.u0 = u0_out; a.J = J_out; a.status = status; a.iters = iters;
+    a.w_out = w_out; a.u0 = u0_out; a.J = J_out; a.status = status; a.iters = iters; a.rows = h->rows;
     cudaStream_t st = (cudaStream_t)stream;
     int rc = launch_solve(a, h->cfg.lanes, h->cfg.block_threads, st, &h->last);
     if (rc != DART_OK) return rc;
@@ -174,6 +175,12 @@ extern "C" int dart_solve_host(dart_handle h, int32_t B, const double* x0, const
     const int32_t* p_i = (const int32_t*)(p_out + out_d);
     if (status) memcpy(status, p_i, (size_t)B * 4);
     if (iters) memcpy(iters, p_i + B, (size_t)B * 4);
+    return DART_OK;
+}
+
+extern "C" int dart_set_result_rows(dart_handle h, double* rows) {
+    if (!h) return DART_ERR_ARG;
+    h->rows = rows;
     return DART_OK;
 }
 

@@ -26,6 +26,7 @@ struct KArgs {
     const double *x0, *ref, *aux, *warm;
     double *w_out, *u0, *J;
     int32_t *status, *iters;
+    double* rows;      // optional packed result rows [B,4] = [u0x, u0y, J, status] for the multi-GPU gather
 };
 
 // Generic RK4 step with forward sensitivities.  Md::deriv(prm, x, u, f, fx, fu) gives xdot and its

@@ -59,6 +59,10 @@ __global__ void __launch_bounds__(256) nmpc_solve_kernel(const KArgs a, const in
             a.J[inst] = J;
             if (a.status) a.status[inst] = status;
             if (a.iters) a.iters[inst] = iters;
+            if (a.rows) {
+                double* r = a.rows + (long)inst * 4;
+                r[0] = a.u0[(long)inst * 2]; r[1] = a.u0[(long)inst * 2 + 1]; r[2] = J; r[3] = (double)status;
+            }
         }
         return;
     }
@@ -85,13 +89,23 @@ __global__ void __launch_bounds__(256) nmpc_solve_kernel(const KArgs a, const in
         a.J[inst] = Js;
         if (a.status) a.status[inst] = st;
         if (a.iters) a.iters[inst] = itx;
+        if (a.rows) {       // u0 of every axis was stored before the group sync above
+            double* r = a.rows + (long)inst * 4;
+            r[0] = a.u0[(long)inst * 2]; r[1] = a.u0[(long)inst * 2 + 1]; r[2] = Js; r[3] = (double)st;
+        }
     }
 }
 
 template <class M, int G, int NC>
 static int launch_n(const KArgs& a, int block_threads, cudaStream_t st, LaunchInfo* info) {
     const int ws = Workspace<M>::doubles(a.N) + kSlot;
-    const int ws_stride = (ws + 1) & ~1;
+    // Shared memory has 16 banks of 8 bytes.  In the serial sweeps all lanes of a tile read the same address and the
+    // 32/G tiles of a warp differ by the workspace stride, so the stride is padded to make them land on distinct
+    // banks (stride = 16/T mod 16 for T tiles per warp); a stride that is a multiple of 16 would serialise them.
+    constexpr int T = 32 / G;
+    constexpr int want = (T > 1) ? (16 / T) % 16 : 0;
+    int ws_stride = ws;
+    while (T > 1 && (ws_stride % 16) != want) ++ws_stride;
     int bt = block_threads > 0 ? block_threads : 0;
     const int unit = G * M::NAXIS;                       // lanes per instance
     int dev = 0;

@@ -2,8 +2,9 @@
 //
 //   policy_mlp_kernel   Policy.mean_net forward (LMPC/src/controller/rlmpc2.py:33-46,71-80):
 //                       [B,520] f32 -> Linear(520,64) -> tanh -> Linear(64,64) -> tanh -> Linear(64,34).
-//                       One persistent CTA per SM walks 128-row tiles.  Layer 1 streams the observation tile and
-//                       W1 through a 4-stage TMA/mbarrier pipeline into tcgen05.mma (kind::tf32, M=128, N=64,
+//                       Two persistent CTAs per SM walk 128-row tiles.  Layer 1 streams the observation tile and
+//                       W1 through a 2-stage TMA/mbarrier pipeline (x2 CTAs, so one CTA streams while the other is in
+//                       its epilogue) into tcgen05.mma (kind::tf32, M=128, N=64,
 //                       fp32 accumulate in TMEM).  The epilogue warps read the accumulator with tcgen05.ld, add
 //                       the bias, apply tanh and write the activations straight back to shared memory in the
 //                       K-major 128B-swizzled operand layout, so layers 2 and 3 run as further tcgen05.mma on
@@ -26,7 +27,7 @@ constexpr int OBS = 520, HID = 64, ACT = 34, N3 = 48;
 constexpr int MT = 128;                 // rows (instances) per tile = UMMA M
 constexpr int BK = 32;                  // fp32 elements per 128-byte swizzle row
 constexpr int NKB = (OBS + BK - 1) / BK;   // 17 K blocks, the last one zero-filled by TMA past column 520
-constexpr int STAGES = 4;
+constexpr int STAGES = 2;                 // x 2 resident CTAs per SM: one streams while the other is in its epilogue
 constexpr int A_BYTES = MT * 128, B_BYTES = HID * 128, W3_BYTES = N3 * 128;
 constexpr int OFF_A = 0;
 constexpr int OFF_B = OFF_A + STAGES * A_BYTES;
@@ -119,7 +120,7 @@ __device__ __forceinline__ void acc_to_hidden(uint32_t tmem_acc, int row, const 
     }
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(NTHREADS, 2)
 policy_mlp_kernel(const __grid_constant__ CUtensorMap tm_obs, const __grid_constant__ CUtensorMap tm_w1,
                   const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_w3, const MlpArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -408,7 +409,7 @@ extern "C" int dart_policy_forward(dart_policy_handle h, int32_t B, const float*
     if (rc != DART_OK) return rc;
     MlpArgs a;
     a.B = B; a.ntiles = (B + MT - 1) / MT; a.b1 = h->b1; a.b2 = h->b2; a.b3 = h->b3; a.mean = act_mean;
-    const int grid = a.ntiles < h->sms ? a.ntiles : h->sms;
+    const int grid = a.ntiles < 2 * h->sms ? a.ntiles : 2 * h->sms;     // two persistent CTAs per SM
     policy_mlp_kernel<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tm_obs, h->tm_w1, h->tm_w2, h->tm_w3, a);
     h->launches += 1;
     return cudaGetLastError() == cudaSuccess ? DART_OK : DART_ERR_CUDA;

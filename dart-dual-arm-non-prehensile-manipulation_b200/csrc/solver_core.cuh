@@ -64,24 +64,24 @@ struct SerialTile {
 
 template <class M>
 struct Workspace {
-    static constexpr int n = M::NX, m = M::NU, nr = M::NR, ny = n + m, nc = n + m + 1;
-    double *X, *U, *A, *Bm, *D, *LAM, *LN, *PP, *PV, *K, *KFF, *DX, *DU, *BL;
-    double *S, *ZL, *ZU, *ISL, *ISU, *RC, *DS, *DZL, *DZU, *MM, *TANU, *HS, *GR, *REF;
+    static constexpr int n = M::NX, m = M::NU, nr = M::NR, ny = n + m, nc = n + m + 1, np = M::NP;
+    // A, Bm: physical NP x NP / NP x NU blocks only (carried-input rows are structural); PP, HS: packed symmetric
+    static constexpr int npa = np * np, npb = np * m, nps = n * (n + 1) / 2, nys = ny * (ny + 1) / 2;
+    double *X, *U, *A, *Bm, *D, *LAM, *PP, *PV, *K, *KFF, *DX, *DU, *BL;
+    double *S, *ZL, *ZU, *ISL, *ISU, *RC, *DS, *MM, *TANU, *HS, *GR, *REF;
 
     DART_HD static int doubles(int N) {
-        return (N + 1) * n + N * m + N * n * n + N * n * m + N * n + N * n + N * n + (N + 1) * n * n + (N + 1) * n +
-               N * m * n + N * m + (N + 1) * n + N * m + N * m + 9 * N * nr + ny * nc + N * m + N * ny * ny + N * ny +
-               M::ref_doubles(N);
+        return (N + 1) * n + N * m + N * npa + N * npb + N * n + N * n + (N + 1) * nps + (N + 1) * n + N * m * n + N * m +
+               (N + 1) * n + N * m + N * m + 7 * N * nr + ny * nc + N * m + N * nys + N * ny + M::ref_doubles(N);
     }
     DART_HD void bind(double* p, int N) {
         X = p;   p += (N + 1) * n;
         U = p;   p += N * m;
-        A = p;   p += N * n * n;
-        Bm = p;  p += N * n * m;
+        A = p;   p += N * npa;
+        Bm = p;  p += N * npb;
         D = p;   p += N * n;
         LAM = p; p += N * n;
-        LN = p;  p += N * n;
-        PP = p;  p += (N + 1) * n * n;
+        PP = p;  p += (N + 1) * nps;
         PV = p;  p += (N + 1) * n;
         K = p;   p += N * m * n;
         KFF = p; p += N * m;
@@ -95,11 +95,9 @@ struct Workspace {
         ISU = p; p += N * nr;
         RC = p;  p += N * nr;
         DS = p;  p += N * nr;
-        DZL = p; p += N * nr;
-        DZU = p; p += N * nr;
         MM = p;  p += ny * nc;
         TANU = p; p += N * m;
-        HS = p;  p += N * ny * ny;
+        HS = p;  p += N * nys;
         GR = p;  p += N * ny;
         REF = p;
     }
@@ -121,6 +119,17 @@ struct Solver {
 
     DART_HD Solver(const T& t, const Prm& p, const SolverOpts& oo, int NN, W& ww)
         : tile(t), prm(p), o(oo), N(NC > 0 ? NC : NN), w(ww) {}
+
+    static constexpr int npa = W::npa, npb = W::npb, nps = W::nps, nys = W::nys;
+    // packed upper-triangular index of a symmetric d x d matrix
+    DART_HD static constexpr int sidx(int i, int j, int d) {
+        return i <= j ? i * d - i * (i - 1) / 2 + (j - i) : j * d - j * (j - 1) / 2 + (i - j);
+    }
+    // full stage Jacobians from the stored physical blocks (carried-input rows: A = 0, B = identity)
+    DART_HD double Aat(int k, int a, int b) const { return (a < np && b < np) ? w.A[k * npa + a * np + b] : 0.0; }
+    DART_HD double Bat(int k, int a, int j) const { return (a < np) ? w.Bm[k * npb + a * m + j] : ((a - np) == j ? 1.0 : 0.0); }
+    DART_HD double Pat(int k, int a, int b) const { return w.PP[k * nps + sidx(a, b, n)]; }
+    DART_HD double Hat(int k, int i, int c) const { return w.HS[k * nys + sidx(i, c, ny)]; }
 
     DART_HD double yval(int k, int i) const { return i < n ? w.X[k * n + i] : w.U[k * m + (i - n)]; }
     DART_HD double rowval(int k, int r) const {
@@ -155,13 +164,8 @@ struct Solver {
             double tanu[m];
             M::dyn(prm, x, u, F, Aloc, Bloc, tanu);
             DART_UNROLL for (int j = 0; j < m; ++j) w.TANU[k * m + j] = tanu[j];
-            double* Ak = w.A + k * n * n;
-            double* Bk = w.Bm + k * n * m;
-            DART_UNROLL for (int a = 0; a < n; ++a) {
-                DART_UNROLL for (int b = 0; b < n; ++b) Ak[a * n + b] = (a < np && b < np) ? Aloc[a * np + b] : 0.0;
-                DART_UNROLL for (int j = 0; j < m; ++j)
-                    Bk[a * m + j] = (a < np) ? Bloc[a * m + j] : ((a - np) == j ? 1.0 : 0.0);
-            }
+            DART_UNROLL for (int i = 0; i < npa; ++i) w.A[k * npa + i] = Aloc[i];
+            DART_UNROLL for (int i = 0; i < npb; ++i) w.Bm[k * npb + i] = Bloc[i];
             DART_UNROLL for (int a = np; a < n; ++a) F[a] = u[a - np];
             DART_UNROLL for (int a = 0; a < n; ++a) {
                 double d = F[a] - w.X[(k + 1) * n + a];
@@ -214,20 +218,20 @@ struct Solver {
         double di = 0.0, zmn = 1e300, zmx = 0.0, ls = 0.0, zs = 0.0;
         int na = 0;
         for (int k = tile.lane(); k < N; k += tile.size()) {
-            const double* Ak = w.A + k * n * n;
-            const double* Bk = w.Bm + k * n * m;
             double lam[n];
             DART_UNROLL for (int a = 0; a < n; ++a) { lam[a] = w.LAM[k * n + a]; ls += fabs(lam[a]); }
             double g[ny];
             DART_UNROLL for (int i = 0; i < ny; ++i) g[i] = cost_grad(k, i);
             DART_UNROLL for (int i = 0; i < n; ++i) {
                 double acc = 0.0;
-                DART_UNROLL for (int a = 0; a < n; ++a) acc += Ak[a * n + i] * lam[a];
+                DART_UNROLL for (int a = 0; a < np; ++a)
+                    if (i < np) acc += w.A[k * npa + a * np + i] * lam[a];
                 g[i] += acc - (k >= 1 ? w.LAM[(k - 1) * n + i] : 0.0);
             }
             DART_UNROLL for (int j = 0; j < m; ++j) {
                 double acc = 0.0;
-                DART_UNROLL for (int a = 0; a < n; ++a) acc += Bk[a * m + j] * lam[a];
+                DART_UNROLL for (int a = 0; a < np; ++a) acc += w.Bm[k * npb + a * m + j] * lam[a];
+                if (M::NAUG > 0) acc += lam[np + j];
                 w.BL[k * m + j] = acc;
                 g[n + j] += acc;
             }
@@ -332,7 +336,8 @@ struct Solver {
             }
             // Lagrangian curvature of the tilt input: -tan(u_j) (B^T lambda)_j
             DART_UNROLL for (int j = 0; j < m; ++j) H[(n + j) * ny + n + j] += -w.TANU[k * m + j] * w.BL[k * m + j];
-            DART_UNROLL for (int i = 0; i < ny * ny; ++i) w.HS[k * ny * ny + i] = H[i];
+            DART_UNROLL for (int i = 0; i < ny; ++i)
+                DART_UNROLL for (int c = i; c < ny; ++c) w.HS[k * nys + sidx(i, c, ny)] = H[i * ny + c];
             DART_UNROLL for (int i = 0; i < ny; ++i) w.GR[k * ny + i] = g[i];
         }
         tile.sync();
@@ -345,7 +350,8 @@ struct Solver {
         const int lane = tl.lane(), G = tl.size();
         for (int c = lane; c <= n; c += G) {
             if (c < n) {
-                DART_UNROLL for (int i = 0; i < n; ++i) w.PP[N * n * n + i * n + c] = (i == c) ? 2.0 * M::wT(prm, c) : 0.0;
+                DART_UNROLL for (int i = 0; i < n; ++i)
+                    if (i <= c) w.PP[N * nps + sidx(i, c, n)] = (i == c) ? 2.0 * M::wT(prm, c) : 0.0;
             } else {
                 DART_UNROLL for (int i = 0; i < n; ++i)
                     w.PV[N * n + i] = 2.0 * M::wT(prm, i) * (w.X[N * n + i] - M::rT(prm, w.REF, N, i));
@@ -353,26 +359,24 @@ struct Solver {
         }
         tl.sync();
         for (int k = N - 1; k >= 0; --k) {
-            const double* Ak = w.A + k * n * n;
-            const double* Bk = w.Bm + k * n * m;
-            const double* Pn = w.PP + (k + 1) * n * n;
             const double* pn = w.PV + (k + 1) * n;
-            const double* Hk = w.HS + k * ny * ny;
             for (int c = lane; c < nc; c += G) {
                 double t[n], ww[n];
                 DART_UNROLL for (int a = 0; a < n; ++a)
-                    t[a] = (c < n) ? Ak[a * n + c] : (c < ny ? Bk[a * m + (c - n)] : w.D[k * n + a]);
+                    t[a] = (c < n) ? Aat(k, a, c) : (c < ny ? Bat(k, a, c - n) : w.D[k * n + a]);
                 DART_UNROLL for (int a = 0; a < n; ++a) {
                     double acc = (c == nc - 1) ? pn[a] : 0.0;
-                    DART_UNROLL for (int b = 0; b < n; ++b) acc += Pn[a * n + b] * t[b];
+                    DART_UNROLL for (int b = 0; b < n; ++b) acc += Pat(k + 1, a, b) * t[b];
                     ww[a] = acc;
                 }
                 DART_UNROLL for (int i = 0; i < ny; ++i) {
-                    double acc = (c < ny) ? Hk[i * ny + c] : w.GR[k * ny + i];
+                    double acc = (c < ny) ? Hat(k, i, c) : w.GR[k * ny + i];
                     if (i < n) {
-                        DART_UNROLL for (int a = 0; a < n; ++a) acc += Ak[a * n + i] * ww[a];
+                        DART_UNROLL for (int a = 0; a < np; ++a)
+                            if (i < np) acc += w.A[k * npa + a * np + i] * ww[a];
                     } else {
-                        DART_UNROLL for (int a = 0; a < n; ++a) acc += Bk[a * m + (i - n)] * ww[a];
+                        DART_UNROLL for (int a = 0; a < np; ++a) acc += w.Bm[k * npb + a * m + (i - n)] * ww[a];
+                        if (M::NAUG > 0) acc += ww[np + (i - n)];
                     }
                     w.MM[c * ny + i] = acc;
                 }
@@ -401,7 +405,7 @@ struct Solver {
                 DART_UNROLL for (int i = 0; i < n; ++i) {
                     double v = w.MM[c * ny + i];
                     DART_UNROLL for (int j = 0; j < m; ++j) v += w.MM[i * ny + n + j] * kt[j];
-                    if (c < n) w.PP[k * n * n + i * n + c] = v;
+                    if (c < n) { if (i <= c) w.PP[k * nps + sidx(i, c, n)] = v; }
                     else w.PV[k * n + i] = v;
                 }
             }
@@ -420,18 +424,19 @@ struct Solver {
             pv[i] = 2.0 * M::wT(prm, i) * (w.X[N * n + i] - M::rT(prm, w.REF, N, i));
         }
         if (wr) {
-            DART_UNROLL for (int i = 0; i < n * n; ++i) w.PP[N * n * n + i] = P[i];
+            DART_UNROLL for (int i = 0; i < n; ++i)
+                DART_UNROLL for (int j = i; j < n; ++j) w.PP[N * nps + sidx(i, j, n)] = P[i * n + j];
             DART_UNROLL for (int i = 0; i < n; ++i) w.PV[N * n + i] = pv[i];
         }
         double Tm[n * nc], HG[ny * nc];
         auto load = [&](int k, double* T_, double* H_) {
             DART_UNROLL for (int a = 0; a < n; ++a) {
-                DART_UNROLL for (int b = 0; b < n; ++b) T_[a * nc + b] = w.A[k * n * n + a * n + b];
-                DART_UNROLL for (int j = 0; j < m; ++j) T_[a * nc + n + j] = w.Bm[k * n * m + a * m + j];
+                DART_UNROLL for (int b = 0; b < n; ++b) T_[a * nc + b] = Aat(k, a, b);
+                DART_UNROLL for (int j = 0; j < m; ++j) T_[a * nc + n + j] = Bat(k, a, j);
                 T_[a * nc + ny] = w.D[k * n + a];
             }
             DART_UNROLL for (int i = 0; i < ny; ++i) {
-                DART_UNROLL for (int c = 0; c < ny; ++c) H_[i * nc + c] = w.HS[k * ny * ny + i * ny + c];
+                DART_UNROLL for (int c = 0; c < ny; ++c) H_[i * nc + c] = Hat(k, i, c);
                 H_[i * nc + ny] = w.GR[k * ny + i];
             }
         };
@@ -485,7 +490,8 @@ struct Solver {
                     w.KFF[k * m + j] = Kt[j * (n + 1) + n];
                 }
                 if (k > 0) {
-                    DART_UNROLL for (int i = 0; i < n * n; ++i) w.PP[k * n * n + i] = P[i];
+                    DART_UNROLL for (int i = 0; i < n; ++i)
+                        DART_UNROLL for (int j = i; j < n; ++j) w.PP[k * nps + sidx(i, j, n)] = P[i * n + j];
                     DART_UNROLL for (int i = 0; i < n; ++i) w.PV[k * n + i] = pv[i];
                 }
             }
@@ -508,8 +514,10 @@ struct Solver {
         auto load = [&](int k, double* K_, double* k_, double* A_, double* B_, double* d_) {
             DART_UNROLL for (int i = 0; i < m * n; ++i) K_[i] = w.K[k * m * n + i];
             DART_UNROLL for (int i = 0; i < m; ++i) k_[i] = w.KFF[k * m + i];
-            DART_UNROLL for (int i = 0; i < n * n; ++i) A_[i] = w.A[k * n * n + i];
-            DART_UNROLL for (int i = 0; i < n * m; ++i) B_[i] = w.Bm[k * n * m + i];
+            DART_UNROLL for (int a = 0; a < n; ++a) {
+                DART_UNROLL for (int b = 0; b < n; ++b) A_[a * n + b] = Aat(k, a, b);
+                DART_UNROLL for (int j = 0; j < m; ++j) B_[a * m + j] = Bat(k, a, j);
+            }
             DART_UNROLL for (int i = 0; i < n; ++i) d_[i] = w.D[k * n + i];
         };
         load(0, Kc, kc, Ac, Bc, dc);
@@ -543,33 +551,27 @@ struct Solver {
         tile.sync();
     }
 
-    // ---- new multipliers, slack/dual steps, step-length limits, directional derivative (stage-parallel)
+    // ---- slack steps, step-length limits, directional derivative, then the dual step z += ad dz (stage-parallel).
+    // dz is recomputed in the second pass instead of being stored; the new equality multipliers are formed in move_dual.
     DART_HD void post(double mu, double& ap, double& ad, double& dphi) {
         const double tau = dmax(o.tau_min, 1.0 - mu);
         double ap_ = 1.0, ad_ = 1.0, dp = 0.0, rp_ = 0.0, rd_ = 0.0;
         for (int k = tile.lane(); k < N; k += tile.size()) {
-            DART_UNROLL for (int a = 0; a < n; ++a) {
-                double acc = w.PV[(k + 1) * n + a];
-                DART_UNROLL for (int b = 0; b < n; ++b) acc += w.PP[(k + 1) * n * n + a * n + b] * w.DX[(k + 1) * n + b];
-                w.LN[k * n + a] = acc;
-            }
             DART_UNROLL for (int i = 0; i < ny; ++i) {
                 double d = (i < n) ? w.DX[k * n + i] : w.DU[k * m + (i - n)];
                 dp += cost_grad(k, i) * d;
             }
             DART_UNROLL for (int r = 0; r < nr; ++r) {
-                if (masked(k, r)) { w.DS[k * nr + r] = 0.0; w.DZL[k * nr + r] = 0.0; w.DZU[k * nr + r] = 0.0; continue; }
+                if (masked(k, r)) { w.DS[k * nr + r] = 0.0; continue; }
                 const int ia = M::row_ia(r), ib = M::row_ib(r);
                 double dy = M::row_sa(r) * ((ia < n) ? w.DX[k * n + ia] : w.DU[k * m + (ia - n)]);
                 if (ib >= 0) dy += M::row_sb(r) * ((ib < n) ? w.DX[k * n + ib] : w.DU[k * m + (ib - n)]);
-                double ds = dy + w.RC[k * nr + r];
-                double isl = w.ISL[k * nr + r], isu = w.ISU[k * nr + r];
-                double zl = w.ZL[k * nr + r], zu = w.ZU[k * nr + r];
-                double dzl = mu * isl - zl - zl * isl * ds;
-                double dzu = mu * isu - zu + zu * isu * ds;
+                const double ds = dy + w.RC[k * nr + r];
+                const double isl = w.ISL[k * nr + r], isu = w.ISU[k * nr + r];
+                const double zl = w.ZL[k * nr + r], zu = w.ZU[k * nr + r];
+                const double dzl = mu * isl - zl - zl * isl * ds;
+                const double dzu = mu * isu - zu + zu * isu * ds;
                 w.DS[k * nr + r] = ds;
-                w.DZL[k * nr + r] = dzl;
-                w.DZU[k * nr + r] = dzu;
                 dp -= mu * ds * (isl - isu);
                 rp_ = dmax(rp_, dmax(-ds * isl, ds * isu));
                 const double iz = 1.0 / (zl * zu);
@@ -587,6 +589,16 @@ struct Solver {
         ap = ap_;
         ad = ad_;
         dphi = tile.sum(dp);
+        for (int k = tile.lane(); k < N; k += tile.size()) {
+            DART_UNROLL for (int r = 0; r < nr; ++r) {
+                if (masked(k, r)) continue;
+                const double ds = w.DS[k * nr + r];
+                const double isl = w.ISL[k * nr + r], isu = w.ISU[k * nr + r];
+                const double zl = w.ZL[k * nr + r], zu = w.ZU[k * nr + r];
+                w.ZL[k * nr + r] = zl + ad_ * (mu * isl - zl - zl * isl * ds);
+                w.ZU[k * nr + r] = zu + ad_ * (mu * isu - zu + zu * isu * ds);
+            }
+        }
         tile.sync();
     }
 
@@ -602,12 +614,15 @@ struct Solver {
     DART_HD void move_dual(double alpha, double ad, double mu) {
         const double ks = 1e10;
         for (int k = tile.lane(); k < N; k += tile.size()) {
-            DART_UNROLL for (int a = 0; a < n; ++a) w.LAM[k * n + a] += alpha * (w.LN[k * n + a] - w.LAM[k * n + a]);
+            DART_UNROLL for (int a = 0; a < n; ++a) {      // new multiplier of stage k+1: P_{k+1} dx_{k+1} + p_{k+1}
+                double ln = w.PV[(k + 1) * n + a];
+                DART_UNROLL for (int b = 0; b < n; ++b) ln += Pat(k + 1, a, b) * w.DX[(k + 1) * n + b];
+                w.LAM[k * n + a] += alpha * (ln - w.LAM[k * n + a]);
+            }
             DART_UNROLL for (int r = 0; r < nr; ++r) {
                 if (masked(k, r)) continue;
                 const double isl = w.ISL[k * nr + r], isu = w.ISU[k * nr + r];   // of the accepted point (eval1)
-                double zl = w.ZL[k * nr + r] + ad * w.DZL[k * nr + r];
-                double zu = w.ZU[k * nr + r] + ad * w.DZU[k * nr + r];
+                const double zl = w.ZL[k * nr + r], zu = w.ZU[k * nr + r];        // already stepped in post()
                 w.ZL[k * nr + r] = dmin(dmax(zl, mu * isl / ks), ks * mu * isl);
                 w.ZU[k * nr + r] = dmin(dmax(zu, mu * isu / ks), ks * mu * isu);
             }

@@ -98,6 +98,11 @@ class NMPCEngine:
                                    ptr(iters, (B,), i32, "iters"), stream), "dart_solve")
         return dict(u0=u0_out, J=J_out, w=w_out, status=status, iters=iters)
 
+    def set_result_rows(self, rows):
+        """rows: CUDA float64 tensor [B,4] (or None); later solves also write [u0x, u0y, J, status] rows into it."""
+        self._rows = rows
+        check(self._lib.dart_set_result_rows(self._h, None if rows is None else C.c_void_p(rows.data_ptr())), "dart_set_result_rows")
+
     @property
     def launch_count(self):
         return int(self._lib.dart_launch_count(self._h))

@@ -110,6 +110,11 @@ int dart_solve_host(dart_handle h, int32_t B, const double* x0, const double* re
                     const double* warm_w, double* w_out, double* u0_out, double* J_out,
                     int32_t* status, int32_t* iters);
 
+/* Optional: subsequent dart_solve calls on this handle also write packed result rows [B,4] = [u0x, u0y, J, status]
+ * (device pointer, float64; NULL switches it off) -- the buffer a multi-GPU caller all-gathers, replacing the
+ * (u_cmd, loss, solve_time) tuples of main_parallel.py's control_queue (:43, :201-205). */
+int dart_set_result_rows(dart_handle h, double* rows);
+
 /* Number of kernels launched by this handle since creation (for bench.py's gpu_launches). */
 int64_t dart_launch_count(dart_handle h);
 
