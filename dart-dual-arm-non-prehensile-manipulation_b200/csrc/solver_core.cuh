@@ -27,9 +27,12 @@
 #if defined(__CUDACC__)
 #define DART_HD __host__ __device__ __forceinline__
 #define DART_UNROLL _Pragma("unroll")
+#define DART_PRAGMA_(x) _Pragma(#x)
+#define DART_UNROLL_N(k) DART_PRAGMA_(unroll k)
 #else
 #define DART_HD inline
 #define DART_UNROLL
+#define DART_UNROLL_N(k)
 #endif
 
 namespace dart {
@@ -441,6 +444,7 @@ struct Solver {
             }
         };
         load(N - 1, Tm, HG);
+        DART_UNROLL_N(3)
         for (int k = N - 1; k >= 0; --k) {
             // next stage's data first: these loads do not depend on P, keep them ahead of the dependent chain
             double Tn[n * nc], Hn[ny * nc];
@@ -459,12 +463,23 @@ struct Solver {
                     Mm[i * nc + c] = acc;
                 }
             double Lc[m * m];
-            double shift = 0.0;
-            for (int tries = 0; tries < 40; ++tries) {
-                DART_UNROLL for (int i = 0; i < m; ++i)
-                    DART_UNROLL for (int j = 0; j < m; ++j) Lc[i * m + j] = Mm[(n + i) * nc + n + j] + (i == j ? shift : 0.0);
-                if (chol(Lc)) break;
-                shift = (shift == 0.0) ? 1e-4 : shift * 8.0;
+            if (m == 1) {
+                // scalar pivot: reciprocal on the fast path, escalating shift only if it is not positive
+                double h = Mm[n * nc + n];
+                if (!(h > 0.0)) {
+                    double shift = 1e-4;
+                    while (!(h + shift > 0.0) && shift < 1e30) shift *= 8.0;
+                    h += shift;
+                }
+                Lc[0] = 1.0 / h;
+            } else {
+                double shift = 0.0;
+                for (int tries = 0; tries < 40; ++tries) {
+                    DART_UNROLL for (int i = 0; i < m; ++i)
+                        DART_UNROLL for (int j = 0; j < m; ++j) Lc[i * m + j] = Mm[(n + i) * nc + n + j] + (i == j ? shift : 0.0);
+                    if (chol(Lc)) break;
+                    shift = (shift == 0.0) ? 1e-4 : shift * 8.0;
+                }
             }
             double Kt[m * (n + 1)];      // columns 0..n-1: feedback gains, column n: feed-forward
             DART_UNROLL for (int c = 0; c <= n; ++c) {
@@ -521,6 +536,7 @@ struct Solver {
             DART_UNROLL for (int i = 0; i < n; ++i) d_[i] = w.D[k * n + i];
         };
         load(0, Kc, kc, Ac, Bc, dc);
+        DART_UNROLL_N(3)
         for (int k = 0; k < N; ++k) {
             double Kn[m * n], kn[m], An[n * n], Bn[n * m], dn[n];
             const int kk = (k + 1 < N) ? k + 1 : k;
