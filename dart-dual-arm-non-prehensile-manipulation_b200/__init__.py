@@ -12,3 +12,4 @@ from .pmpc import PMPC, GravityModel, StateHolder, mpc_worker   # noqa: F401
 from .rmpc import RLS, AdaptiveNPMPCSmooth, RMPCBatch, rls_update_device   # noqa: F401
 from .lmpc import RLMPC, LMPCBatch, PolicyMLP, init_policy_weights, load_checkpoint_weights   # noqa: F401
 from .parallel import ShardedSolver, shard_bounds   # noqa: F401
+from .episodes import PMPCEpisodes   # noqa: F401

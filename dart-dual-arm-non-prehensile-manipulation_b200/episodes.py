@@ -1,0 +1,75 @@
+"""Device-resident PMPC closed-loop episodes on the surrogate plant, with the reference logger's metrics.
+
+Replaces, for B instances at once, the while-loop of PMPC/main.py:90-125 (solve every simulated step, apply the first
+tilt command) with MuJoCo swapped for the surrogate plant of SURVEY 8(d)/8(f).1.  Two launches per simulated step,
+no host synchronisation inside the episode.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+from .config import pmpc_cfg
+from .engine import NMPCEngine
+
+
+class PMPCEpisodes:
+    def __init__(self, state, target, params, mu_plant=None, coulomb=None, device=0, tol=0.01, **cfg_kw):
+        import torch
+        if not torch.cuda.is_available():
+            raise _lib.DartError("dart_b200 episodes need a CUDA device (no CPU fallback)")
+        self.torch = torch
+        self.dev = torch.device("cuda", device)
+        self.cfg = pmpc_cfg(**cfg_kw)
+        self.engine = NMPCEngine(self.cfg, device=device)
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(self.dev)
+        self.B = state.shape[0]
+        self.state, self.target, self.params = t(state), t(target), t(params)
+        self.mu_plant = t(params[:, 3] if mu_plant is None else mu_plant)
+        self.coulomb = None if coulomb is None else t(coulomb)
+        f64 = torch.float64
+        self.u0 = torch.zeros((self.B, 2), dtype=f64, device=self.dev)
+        self.J = torch.empty((self.B,), dtype=f64, device=self.dev)
+        self.status = torch.empty((self.B,), dtype=torch.int32, device=self.dev)
+        self.iters = torch.empty((self.B,), dtype=torch.int32, device=self.dev)
+        self.conv_time = torch.full((self.B,), -1.0, dtype=f64, device=self.dev)
+        self.effort = torch.zeros((self.B,), dtype=f64, device=self.dev)
+        self.err = torch.zeros((self.B,), dtype=f64, device=self.dev)
+        self.tol = float(tol)
+        self.step_index = 0
+        self.not_converged_solves = torch.zeros((), dtype=torch.int64, device=self.dev)
+        self.iter_sum = torch.zeros((), dtype=torch.int64, device=self.dev)
+
+    def step(self):
+        torch = self.torch
+        self.engine.solve_device(self.state, self.target, aux=self.params, u0_out=self.u0, J_out=self.J,
+                                 status=self.status, iters=self.iters)
+        self.not_converged_solves += (self.status != 0).sum()
+        self.iter_sum += self.iters.sum()
+        p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+        stream = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+        check(_lib.lib().dart_pmpc_plant_step(self.B, self.cfg.Ts, self.cfg.g, p(self.mu_plant), p(self.coulomb), p(self.u0),
+                                              p(self.target), p(self.state), self.step_index, self.tol, p(self.conv_time),
+                                              p(self.effort), p(self.err), stream), "dart_pmpc_plant_step")
+        self.step_index += 1
+
+    def run(self, steps, trace_every=0):
+        """Run ``steps`` simulated steps; returns the metrics dict (numpy).  ``trace_every`` > 0 records
+        (state, u0, J, iters) of instance 0 every that many steps (config 1's per-step solve trace)."""
+        trace = []
+        for k in range(steps):
+            if trace_every and k % trace_every == 0:
+                s0 = self.state[0].cpu().numpy().copy()
+            self.step()
+            if trace_every and k % trace_every == 0:
+                trace.append(np.concatenate([[k * self.cfg.Ts], s0, self.u0[0].cpu().numpy(), [float(self.J[0].item()), float(self.iters[0].item())]]))
+        self.torch.cuda.synchronize()
+        T = self.step_index * self.cfg.Ts
+        ct = self.conv_time.cpu().numpy()
+        final_err = np.linalg.norm((self.state[:, [0, 2]] - self.target[:, [0, 2]]).cpu().numpy(), axis=1)
+        return dict(steady_state_error=final_err, convergence_time=np.where(ct < 0, T, ct), converged=ct >= 0,
+                    control_effort=self.effort.cpu().numpy(), sim_time=T, solves=self.step_index * self.B,
+                    not_converged_solves=int(self.not_converged_solves.item()),
+                    mean_iters=float(self.iter_sum.item()) / max(1, self.step_index * self.B),
+                    trace=np.array(trace) if trace else None)

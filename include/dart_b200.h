@@ -168,6 +168,14 @@ int dart_policy_obs_push(int32_t B, int32_t count, const double* state, const do
 int dart_policy_param_update(int32_t B, const float* action, double* pvec, int32_t ld_pvec, double k_max,
                              double max_delta, double min_k, double k_ceiling_margin, double alpha, void* stream);
 
+/* Surrogate closed loop (no MuJoCo): one plant step of the PMPC model (mpc_3d.py:87-104, tilt held over Ts) with
+ * per-instance viscous mu [B] and optional unmodelled Coulomb coefficient [B] (NULL = none), plus the episode
+ * metrics of PMPC/src/logger.py:155-176 accumulated in place: err [B] = position error of the logged state,
+ * conv_time [B] (initialise to -1) = first logged time with err < tol, effort [B] += |u| Ts.  Device pointers. */
+int dart_pmpc_plant_step(int32_t B, double Ts, double g, const double* mu, const double* coulomb, const double* u,
+                         const double* target, double* state, int32_t step_index, double tol, double* conv_time,
+                         double* effort, double* err, void* stream);
+
 /* Measured FP64 FMA-pipe peak of the device in TFLOP/s (DFMA microbenchmark, CUDA-event timed): the roofline
  * denominator bench.py reports the solver kernels against. */
 int dart_measure_fp64_tflops(int device, double* tflops);

@@ -28,4 +28,4 @@ Golden vectors under ``tests/golden`` are produced by ``tests/golden/make_golden
 from this oracle.
 """
 
-from . import models, problems, ipm, rls, policy, crosscheck  # noqa: F401
+from . import models, problems, ipm, rls, policy, crosscheck, closed_loop  # noqa: F401

@@ -1,0 +1,41 @@
+"""Device-resident PMPC closed loop on the surrogate plant vs the oracle's loop, plus long-episode properties."""
+import numpy as np
+import pytest
+
+import dart_b200
+from oracle import closed_loop
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+def test_short_episode_matches_oracle_loop(built):
+    c, aux, _ = helpers.pmpc_case(1)
+    B, T = 18, 15
+    rng = np.random.default_rng(0)
+    coul = rng.uniform(0.0, 0.05, B)
+    ep = dart_b200.PMPCEpisodes(c["state"], c["target"], aux, coulomb=coul, device=0)
+    m = ep.run(T)
+    o = closed_loop.pmpc_episode(c["state"], c["target"], aux, T, coulomb=coul)
+    # commands agree to <= 1e-4 rad per step: x/y velocities then differ by <= Ts*g*1e-4 = 2e-6 per step, the z rows
+    # (vz_new = -g |theta|^2) by <= 2*g*0.6*1e-4 = 1.2e-3
+    d = np.abs(ep.state.cpu().numpy() - o["state"])
+    assert d[:, :4].max() < 5e-5 and d[:, 4:].max() < 5e-3, (d[:, :4].max(), d[:, 4:].max())
+    assert np.abs(ep.u0.cpu().numpy() - o["u"][-1]).max() <= helpers.TOL_U0
+    assert np.abs(m["control_effort"] - o["effort"]).max() < 1e-6
+    assert m["not_converged_solves"] == 0
+
+
+def test_config1_episode_settles(built):
+    """BASELINE config 1 (cube, mu = 0.10, main.py weights) on the model-as-plant: 10 cm move settles within 1 cm."""
+    c1 = dart_b200.workloads.pmpc_config1()
+    aux = np.stack([c1["Qp"], c1["Qv"], c1["R"], c1["mu"]], axis=1)
+    ep = dart_b200.PMPCEpisodes(c1["state"], c1["target"], aux, device=0)
+    m = ep.run(2500, trace_every=50)
+    assert m["not_converged_solves"] == 0
+    assert m["converged"][0] and m["convergence_time"][0] < 5.0
+    assert m["steady_state_error"][0] < 0.01
+    tr = m["trace"]
+    assert tr.shape[1] == 11 and np.all(np.abs(tr[:, 7:9]) <= 0.6 + 1e-12)
+    err = np.hypot(tr[:, 1] - 0.1, tr[:, 3] - 0.05)
+    assert err[-1] < err[0] * 0.1
