@@ -234,17 +234,29 @@ policy_mlp_kernel(const __grid_constant__ CUtensorMap tm_obs, const __grid_const
             mbar_arrive(HRDY);
             mbar_wait(ACCF(2), tph);
             fence_after();
-            const long grow = (long)tile * MT + row;
+            // layer-3 result: stage the [128,34] tile in shared memory (the activation buffer is free once ACC3 is
+            // complete) and write it out with coalesced 16-byte stores -- the tile is contiguous in global memory.
+            float* stage = reinterpret_cast<float*>(hbuf);
 #pragma unroll
             for (int c0 = 0; c0 < N3; c0 += 16) {
                 uint32_t r[16];
                 tmem_ld16(tl + ACC3 + c0, r);
-                if (grow < a.B) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (c0 + j < ACT) a.mean[grow * ACT + c0 + j] = __uint_as_float(r[j]) + __ldg(a.b3 + c0 + j);
-                }
+                for (int j = 0; j < 16; ++j)
+                    if (c0 + j < ACT) stage[row * ACT + c0 + j] = __uint_as_float(r[j]) + __ldg(a.b3 + c0 + j);
             }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            {
+                const long row0 = (long)tile * MT;
+                const int valid = (a.B - row0 < MT) ? (int)(a.B - row0) : MT;
+                const int nflt = valid * ACT;
+                float* g = a.mean + row0 * ACT;                   // 16-byte aligned: MT * ACT * 4 is a multiple of 16
+                const int et = (warp - 2) * 32 + lane;
+                const int nv = nflt >> 2;
+                for (int i = et; i < nv; i += 128) reinterpret_cast<float4*>(g)[i] = reinterpret_cast<const float4*>(stage)[i];
+                for (int i = (nv << 2) + et; i < nflt; i += 128) g[i] = stage[i];
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");        // the next tile's epilogue reuses the buffer
             fence_before();
         }
     }
@@ -403,7 +415,8 @@ extern "C" int dart_policy_destroy(dart_policy_handle h) {
 extern "C" int dart_policy_forward(dart_policy_handle h, int32_t B, const float* obs, float* act_mean, void* stream) {
     if (!h || B < 0 || !obs || !act_mean) return DART_ERR_ARG;
     if (B == 0) return DART_OK;
-    if ((reinterpret_cast<uintptr_t>(obs) & 15) != 0) return DART_ERR_ARG;        // TMA needs 16-byte aligned rows
+    if ((reinterpret_cast<uintptr_t>(obs) & 15) != 0 || (reinterpret_cast<uintptr_t>(act_mean) & 15) != 0)
+        return DART_ERR_ARG;        // TMA rows and the coalesced output stores need 16-byte alignment
     CUtensorMap tm_obs;
     int rc = make_map(&tm_obs, obs, (uint64_t)B, OBS, MT);
     if (rc != DART_OK) return rc;
