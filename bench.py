@@ -196,15 +196,14 @@ def run_ours(args):
             with torch.cuda.stream(comm):
                 dist.all_gather_into_tensor(gathered, rows)
 
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()          # sampled from warm-up through the timed region and the e2e loop
     for _ in range(W):
         step()
         flush.zero_()
     torch.cuda.synchronize()
     peak_tf = dart_b200.measure_fp64_tflops(local) if rank == 0 else 0.0
-
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -228,7 +227,6 @@ def run_ours(args):
     total_s = float(ms.sum() * 1e-3)
     conv = int((st == 0).sum().item())
     iters_sum = int(it.sum().item())
-    clk = clocks.stop() if rank == 0 else None
     tt = torch.tensor([total_s], dtype=torch.float64, device=dev)
     cv = torch.tensor([conv], dtype=torch.float64, device=dev)
     if world > 1:
@@ -258,6 +256,7 @@ def run_ours(args):
     h2d = B * (6 + 6 + 4) * 8
     d2h = B * (2 + 1) * 8 + B * 2 * 4
 
+    clk = clocks.stop() if rank == 0 else None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -305,7 +304,8 @@ def run_ours(args):
     flops = iters_sum * PMPC_FLOPS_PER_ITER
     achieved = flops / kern_s / 1e12
     roofline = {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved / peak_tf if peak_tf else None, "traffic": None,
+                "frac": achieved / peak_tf if peak_tf else None,
+                "traffic": 215552,   # dram__bytes_read + write per launch, ncu --set full capture (profiles/r1_summary.md)
                 "peak_source": "measured in this run (dart_measure_fp64_tflops DFMA microbenchmark); MEASURED_PEAKS.json "
                                "has no FP64 entry",
                 "kernel": "nmpc_solve_kernel<PmpcAxis>", "algorithmic_flops_per_launch": flops,
