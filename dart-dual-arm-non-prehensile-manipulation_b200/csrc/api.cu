@@ -19,6 +19,7 @@ struct dart_solver {
     void* pin;   size_t pin_bytes;
     void* dev;   size_t dev_bytes;
     double* rows;      // dart_set_result_rows
+    int32_t rows_cap;
 };
 
 extern "C" int dart_default_cfg(int32_t method, dart_cfg* c) {
@@ -74,7 +75,7 @@ extern "C" int dart_create(dart_handle* out, const dart_cfg* cfg, int device) {
     fill_opts(*cfg, h->opts);
     h->launches = 0;
     memset(&h->last, 0, sizeof(h->last));
-    h->pin = nullptr; h->pin_bytes = 0; h->dev = nullptr; h->dev_bytes = 0; h->rows = nullptr;
+    h->pin = nullptr; h->pin_bytes = 0; h->dev = nullptr; h->dev_bytes = 0; h->rows = nullptr; h->rows_cap = 0;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return DART_ERR_CUDA; }
     *out = h;
     return DART_OK;
@@ -101,6 +102,7 @@ extern "C" int dart_solve(dart_handle h, int32_t B, const double* x0, const doub
     if (!h || B < 0 || !x0 || !ref || !u0_out || !J_out) return DART_ERR_ARG;
     if (h->cfg.method != DART_PMPC && !aux) return DART_ERR_ARG;
     if (B == 0) return DART_OK;
+    if (h->rows && B > h->rows_cap) return DART_ERR_ARG;       // the registered result-row buffer is too small
     KArgs a;
     a.B = B; a.N = h->cfg.N; a.o = h->opts; a.cfg = h->cfg;
     a.x0 = x0; a.ref = ref; a.aux = aux; a.warm = warm_w;
@@ -178,9 +180,10 @@ extern "C" int dart_solve_host(dart_handle h, int32_t B, const double* x0, const
     return DART_OK;
 }
 
-extern "C" int dart_set_result_rows(dart_handle h, double* rows) {
-    if (!h) return DART_ERR_ARG;
+extern "C" int dart_set_result_rows(dart_handle h, double* rows, int32_t capacity_rows) {
+    if (!h || (rows && capacity_rows <= 0)) return DART_ERR_ARG;
     h->rows = rows;
+    h->rows_cap = rows ? capacity_rows : 0;
     return DART_OK;
 }
 

@@ -100,8 +100,11 @@ class NMPCEngine:
 
     def set_result_rows(self, rows):
         """rows: CUDA float64 tensor [B,4] (or None); later solves also write [u0x, u0y, J, status] rows into it."""
+        if rows is not None and (rows.dim() != 2 or rows.shape[1] != 4 or not rows.is_contiguous() or str(rows.dtype) != "torch.float64"):
+            raise ValueError("result rows: need a contiguous float64 CUDA tensor [capacity, 4]")
         self._rows = rows
-        check(self._lib.dart_set_result_rows(self._h, None if rows is None else C.c_void_p(rows.data_ptr())), "dart_set_result_rows")
+        check(self._lib.dart_set_result_rows(self._h, None if rows is None else C.c_void_p(rows.data_ptr()),
+                                             0 if rows is None else int(rows.shape[0])), "dart_set_result_rows")
 
     @property
     def launch_count(self):

@@ -111,9 +111,10 @@ int dart_solve_host(dart_handle h, int32_t B, const double* x0, const double* re
                     int32_t* status, int32_t* iters);
 
 /* Optional: subsequent dart_solve calls on this handle also write packed result rows [B,4] = [u0x, u0y, J, status]
- * (device pointer, float64; NULL switches it off) -- the buffer a multi-GPU caller all-gathers, replacing the
+ * (device pointer, float64, room for capacity_rows rows; NULL switches it off; a solve with B > capacity_rows is
+ * refused with DART_ERR_ARG) -- the buffer a multi-GPU caller all-gathers, replacing the
  * (u_cmd, loss, solve_time) tuples of main_parallel.py's control_queue (:43, :201-205). */
-int dart_set_result_rows(dart_handle h, double* rows);
+int dart_set_result_rows(dart_handle h, double* rows, int32_t capacity_rows);
 
 /* Number of kernels launched by this handle since creation (for bench.py's gpu_launches). */
 int64_t dart_launch_count(dart_handle h);

@@ -127,3 +127,24 @@ def test_empty_and_ragged_batches(pmpc_engine):
         assert out["u0"].shape == (B, 2) and (out["status"] == 0).all()
     out = pmpc_engine.solve(np.zeros((0, 6)), np.zeros((0, 6)), aux=np.zeros((0, 4)), want_w=False)
     assert out["u0"].shape == (0, 2)
+
+
+def test_result_rows_and_capacity_check(pmpc_engine):
+    import torch
+    c, aux, p = helpers.pmpc_case(2)
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    rows = torch.zeros((p.B, 4), dtype=torch.float64, device=dev)
+    pmpc_engine.set_result_rows(rows)
+    try:
+        out = pmpc_engine.solve_device(t(c["state"]), t(c["target"]), aux=t(aux))
+        torch.cuda.synchronize()
+        r = rows.cpu().numpy()
+        assert np.array_equal(r[:, :2], out["u0"].cpu().numpy()) and np.array_equal(r[:, 2], out["J"].cpu().numpy())
+        assert np.array_equal(r[:, 3], out["status"].cpu().numpy().astype(np.float64))
+        small = torch.zeros((4, 4), dtype=torch.float64, device=dev)
+        pmpc_engine.set_result_rows(small)
+        with pytest.raises(dart_b200.DartError):
+            pmpc_engine.solve_device(t(c["state"]), t(c["target"]), aux=t(aux))
+    finally:
+        pmpc_engine.set_result_rows(None)
