@@ -271,11 +271,20 @@ struct Solver {
         tile.sync();
     }
 
-    // m x m SPD solve helpers (m <= 2 in all models; generic Cholesky kept for clarity)
-    DART_HD static bool chol(double* H) {   // in place, lower; returns false if not PD (m == 1: H[0] <- 1/H[0])
+    // m x m SPD "factorisation" + solve.  m = 1: reciprocal; m = 2: explicit inverse from the determinant (one
+    // division, no square root); larger m: Cholesky.  Returns false when the block is not positive definite.
+    DART_HD static bool chol(double* H) {
         if (m == 1) {
             if (!(H[0] > 0.0)) return false;
             H[0] = 1.0 / H[0];
+            return true;
+        }
+        if (m == 2) {
+            const double a = H[0], b = 0.5 * (H[1] + H[2]), d = H[3];
+            const double det = a * d - b * b;
+            if (!(a > 0.0) || !(det > 0.0)) return false;
+            const double id = 1.0 / det;
+            H[0] = d * id; H[1] = -b * id; H[2] = -b * id; H[3] = a * id;
             return true;
         }
         DART_UNROLL for (int j = 0; j < m; ++j) {
@@ -294,6 +303,12 @@ struct Solver {
     }
     DART_HD static void chol_solve(const double* Lc, double* b) {
         if (m == 1) { b[0] *= Lc[0]; return; }
+        if (m == 2) {
+            const double b0 = b[0], b1 = b[1];
+            b[0] = Lc[0] * b0 + Lc[1] * b1;
+            b[1] = Lc[2] * b0 + Lc[3] * b1;
+            return;
+        }
         DART_UNROLL for (int i = 0; i < m; ++i) {
             double v = b[i];
             DART_UNROLL for (int q = 0; q < i; ++q) v -= Lc[i * m + q] * b[q];

@@ -1,0 +1,17 @@
+"""Small driver for ncu: a few solves of one method at its BASELINE batch size (dev tool). usage: profile_method.py rmpc|lmpc"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch, dart_b200
+from tests import helpers
+m = sys.argv[1]
+if m == "rmpc":
+    d, _ = helpers.rmpc_case(4096); cfg = dart_b200.rmpc_cfg()
+else:
+    d, _ = helpers.lmpc_case(16384); cfg = dart_b200.lmpc_cfg()
+eng = dart_b200.NMPCEngine(cfg, 0)
+t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+x, r, a = t(d["x0"]), t(d["ref"]), t(d["aux"])
+for _ in range(4):
+    out = eng.solve_device(x, r, aux=a)
+torch.cuda.synchronize()
+print("ok", int((out["status"] == 0).sum()), eng.last_launch_config())
