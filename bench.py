@@ -128,7 +128,7 @@ def run_reference(args):
         os.environ[k] = "1"                      # one solver process per core, as main_parallel.py fans out
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    sp = max(1, args.cpu_sample)
+    sp = max(1, args.cpu_sample, min(cores, 64) // 2)     # at least ~9 instances per worker process
     rates, times = [], []
     with mp.get_context("spawn").Pool(cores) as pool:
         budget = time.perf_counter() + 200.0
@@ -153,8 +153,16 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------------- GPU arm
+def ensure_built():
+    lib = os.path.join(ROOT, "dart-dual-arm-non-prehensile-manipulation_b200", "lib", "libdart_b200.so")
+    if not os.path.exists(lib) and int(os.environ.get("LOCAL_RANK", "0")) == 0:
+        import __graft_entry__ as g
+        g.build_cuda()
+
+
 def run_ours(args):
     import torch
+    ensure_built()
     import dart_b200
 
     world = int(os.environ.get("WORLD_SIZE", "1"))

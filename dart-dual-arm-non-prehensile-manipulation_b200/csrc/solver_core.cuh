@@ -642,7 +642,7 @@ struct Solver {
         tile.sync();
     }
 
-    DART_HD void move_dual(double alpha, double ad, double mu) {
+    DART_HD void move_dual(double alpha, double mu) {
         const double ks = 1e10;
         for (int k = tile.lane(); k < N; k += tile.size()) {
             DART_UNROLL for (int a = 0; a < n; ++a) {      // new multiplier of stage k+1: P_{k+1} dx_{k+1} + p_{k+1}
@@ -746,7 +746,7 @@ struct Solver {
             // the step vanished three times in a row: no restoration phase here -- stop and say so
             tiny = (alpha <= 1e-6) ? tiny + 1 : 0;
             if (tiny >= 3) { st = (pinf > 1e-4) ? ST_INFEASIBLE : ST_MAXITER; ++it; break; }
-            move_dual(alpha, ad, mu);
+            move_dual(alpha, mu);
             eval2(dinf, zs_min, zs_max, lam_sum, z_sum, nact);
         }
         J = f;
