@@ -27,15 +27,17 @@ constexpr int OBS = 520, HID = 64, ACT = 34, N3 = 48;
 constexpr int MT = 128;                 // rows (instances) per tile = UMMA M
 constexpr int BK = 32;                  // fp32 elements per 128-byte swizzle row
 constexpr int NKB = (OBS + BK - 1) / BK;   // 17 K blocks, the last one zero-filled by TMA past column 520
-constexpr int STAGES = 2;                 // x 2 resident CTAs per SM: one streams while the other is in its epilogue
 constexpr int A_BYTES = MT * 128, B_BYTES = HID * 128, W3_BYTES = N3 * 128;
-constexpr int OFF_A = 0;
-constexpr int OFF_B = OFF_A + STAGES * A_BYTES;
-constexpr int OFF_W2 = OFF_B + STAGES * B_BYTES;
-constexpr int OFF_W3 = OFF_W2 + 2 * B_BYTES;
-constexpr int OFF_H = OFF_W3 + 2 * W3_BYTES;
-constexpr int OFF_BAR = OFF_H + 2 * A_BYTES;
-constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;       // + alignment slack
+// shared-memory map for a pipeline of S stages: [A stages | W1 stages | W2 | W3 | H | barriers]
+template <int S> struct Smem {
+    static constexpr int OFF_A = 0;
+    static constexpr int OFF_B = OFF_A + S * A_BYTES;
+    static constexpr int OFF_W2 = OFF_B + S * B_BYTES;
+    static constexpr int OFF_W3 = OFF_W2 + 2 * B_BYTES;
+    static constexpr int OFF_H = OFF_W3 + 2 * W3_BYTES;
+    static constexpr int OFF_BAR = OFF_H + 2 * A_BYTES;
+    static constexpr int BYTES = OFF_BAR + 256 + 1024;       // + alignment slack
+};
 constexpr int NTHREADS = 192;
 constexpr uint32_t TMEM_COLS = 256;
 constexpr uint32_t ACC1 = 0, ACC2 = 64, ACC3 = 128;
@@ -120,13 +122,18 @@ __device__ __forceinline__ void acc_to_hidden(uint32_t tmem_acc, int row, const 
     }
 }
 
-__global__ void __launch_bounds__(NTHREADS, 2)
+// STAGES = 2: two CTAs per SM (one streams while the other is in its epilogue) -- large batches.
+// STAGES = 4: one CTA per SM with a deeper pipeline -- batches of at most one tile per SM, where latency rules.
+template <int STAGES>
+__global__ void __launch_bounds__(NTHREADS, STAGES == 2 ? 2 : 1)
 policy_mlp_kernel(const __grid_constant__ CUtensorMap tm_obs, const __grid_constant__ CUtensorMap tm_w1,
                   const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_w3, const MlpArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int OFF_A = Smem<STAGES>::OFF_A, OFF_B = Smem<STAGES>::OFF_B, OFF_W2 = Smem<STAGES>::OFF_W2,
+                  OFF_W3 = Smem<STAGES>::OFF_W3, OFF_H = Smem<STAGES>::OFF_H, OFF_BAR = Smem<STAGES>::OFF_BAR;
     // barriers: full[S], empty[S], wbar, acc_full[3], h_ready ; then the TMEM base slot
     const uint32_t bar0 = sbase + OFF_BAR;
     auto FULL = [&](int s) { return bar0 + 8 * s; };
@@ -398,7 +405,9 @@ extern "C" int dart_policy_create(dart_policy_handle* out, int device, int32_t o
     if (make_map(&h->tm_w1, h->W1, HID, OBS, HID) || make_map(&h->tm_w2, h->W2, HID, HID, HID) ||
         make_map(&h->tm_w3, h->W3, N3, HID, N3))
         return DART_ERR_CUDA;
-    if (cudaFuncSetAttribute(policy_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) return DART_ERR_CUDA;
+    if (cudaFuncSetAttribute(policy_mlp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<2>::BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(policy_mlp_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<4>::BYTES) != cudaSuccess)
+        return DART_ERR_CUDA;
     *out = h;
     return DART_OK;
 }
@@ -422,8 +431,12 @@ extern "C" int dart_policy_forward(dart_policy_handle h, int32_t B, const float*
     if (rc != DART_OK) return rc;
     MlpArgs a;
     a.B = B; a.ntiles = (B + MT - 1) / MT; a.b1 = h->b1; a.b2 = h->b2; a.b3 = h->b3; a.mean = act_mean;
-    const int grid = a.ntiles < 2 * h->sms ? a.ntiles : 2 * h->sms;     // two persistent CTAs per SM
-    policy_mlp_kernel<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tm_obs, h->tm_w1, h->tm_w2, h->tm_w3, a);
+    if (a.ntiles <= h->sms) {
+        policy_mlp_kernel<4><<<a.ntiles, NTHREADS, Smem<4>::BYTES, (cudaStream_t)stream>>>(tm_obs, h->tm_w1, h->tm_w2, h->tm_w3, a);
+    } else {
+        const int grid = a.ntiles < 2 * h->sms ? a.ntiles : 2 * h->sms;     // two persistent CTAs per SM
+        policy_mlp_kernel<2><<<grid, NTHREADS, Smem<2>::BYTES, (cudaStream_t)stream>>>(tm_obs, h->tm_w1, h->tm_w2, h->tm_w3, a);
+    }
     h->launches += 1;
     return cudaGetLastError() == cudaSuccess ? DART_OK : DART_ERR_CUDA;
 }
