@@ -79,3 +79,52 @@ def lmpc_config4(B=16384, seed=3):
     pvec = np.clip(1.0 + 0.1 * rng.standard_normal((B, 34)), 0.01, 1.9)
     u_prev = np.zeros((B, 2))
     return dict(state=state, target=target, pvec=pvec, u_prev=u_prev)
+
+
+# ----------------------------------------------------------------------------- solver-ready input sets
+def _governor(r_v, target, dr_max=0.01, alpha_rg=0.5):
+    """rob_ctrl.py:346-348."""
+    r_v = r_v.copy()
+    for i in (0, 2):
+        r_v[:, i] = r_v[:, i] + alpha_rg * np.clip(target[:, i] - r_v[:, i], -dr_max, dr_max)
+    return r_v
+
+
+def _ref_traj(r_v, target, N=20, step_fraction=0.2):
+    """np_mpc_adaptive_with_linear_regressor.py:201-210, batched."""
+    B = r_v.shape[0]
+    R = np.zeros((B, N + 1, 4))
+    for i in range(N + 1):
+        w = 1.0 - (1.0 - step_fraction) ** (i + 1)
+        r_i = r_v + w * (target - r_v)
+        R[:, i, 0] = r_i[:, 0]
+        R[:, i, 2] = r_i[:, 2]
+    return R.reshape(B, -1)
+
+
+def pmpc_inputs(states_per_object=4, seed=1):
+    """(config dict, aux [B,4] = per-instance Qp, Qv, R, mu) for dart_solve."""
+    c = pmpc_config2(states_per_object, seed)
+    return c, np.ascontiguousarray(np.stack([c["Qp"], c["Qv"], c["R"], c["mu"]], axis=1))
+
+
+def rmpc_inputs(B=32, seed=2, cold=False):
+    """Mid-episode RMPC solver inputs: friction-like theta_hat, nonzero u_prev, governor-built staged reference."""
+    c = rmpc_config3(B, seed)
+    rng = np.random.default_rng(seed + 100)
+    th = 0.01 * rng.standard_normal((B, 14))
+    if not cold:
+        th[:, 1] -= rng.uniform(0, 0.5, B); th[:, 4] -= rng.uniform(0, 1.0, B)
+        th[:, 10] -= rng.uniform(0, 0.5, B); th[:, 12] -= rng.uniform(0, 1.0, B)
+    up = np.zeros((B, 2)) if cold else rng.uniform(-0.3, 0.3, (B, 2))
+    rv = np.zeros((B, 4)); rv[:, [0, 2]] = c["x0"][:, [0, 2]]
+    rv = _governor(rv, c["target"])
+    ref = _ref_traj(rv, c["target"])
+    return dict(x0=c["x0"], ref=ref, aux=np.concatenate([up, th], axis=1), u_prev=up, theta=th)
+
+
+def lmpc_inputs(B=32, seed=3):
+    c = lmpc_config4(B, seed)
+    rng = np.random.default_rng(seed + 100)
+    up = rng.uniform(-0.2, 0.2, (B, 2))
+    return dict(x0=c["state"], ref=c["target"], aux=np.concatenate([up, c["pvec"]], axis=1), u_prev=up, pvec=c["pvec"])

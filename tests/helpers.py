@@ -37,36 +37,20 @@ class HostEmu:
 
 
 def pmpc_case(states_per_object=4, seed=1):
-    c = dart_b200.workloads.pmpc_config2(states_per_object, seed)
-    aux = np.stack([c["Qp"], c["Qv"], c["R"], c["mu"]], axis=1)
+    c, aux = dart_b200.workloads.pmpc_inputs(states_per_object, seed)
     prob = problems.pmpc_problem(c["state"], c["target"], Qp=c["Qp"], Qv=c["Qv"], R=c["R"], mu=c["mu"])
     return c, aux, prob
 
 
 def rmpc_case(B=32, seed=2, cold=False):
-    """RMPC inputs mid-episode: friction-like theta_hat, nonzero u_prev, governor-built reference."""
-    c = dart_b200.workloads.rmpc_config3(B, seed)
-    rng = np.random.default_rng(seed + 100)
-    th = 0.01 * rng.standard_normal((B, 14))
-    if not cold:
-        th[:, 1] -= rng.uniform(0, 0.5, B); th[:, 4] -= rng.uniform(0, 1.0, B)
-        th[:, 10] -= rng.uniform(0, 0.5, B); th[:, 12] -= rng.uniform(0, 1.0, B)
-    up = np.zeros((B, 2)) if cold else rng.uniform(-0.3, 0.3, (B, 2))
-    rv = np.zeros((B, 4)); rv[:, [0, 2]] = c["x0"][:, [0, 2]]
-    rv = problems.reference_governor(rv, c["target"])
-    ref = problems.build_ref_traj(None, rv, c["target"], 20, 4, 0.2)
-    aux = np.concatenate([up, th], axis=1)
-    prob = problems.rmpc_problem(c["x0"], up, th, ref)
-    return dict(x0=c["x0"], ref=ref, aux=aux, u_prev=up, theta=th), prob
+    """RMPC inputs mid-episode (dart_b200.workloads.rmpc_inputs) + the oracle's problem for them."""
+    d = dart_b200.workloads.rmpc_inputs(B, seed, cold)
+    return d, problems.rmpc_problem(d["x0"], d["u_prev"], d["theta"], d["ref"])
 
 
 def lmpc_case(B=32, seed=3):
-    c = dart_b200.workloads.lmpc_config4(B, seed)
-    rng = np.random.default_rng(seed + 100)
-    up = rng.uniform(-0.2, 0.2, (B, 2))
-    aux = np.concatenate([up, c["pvec"]], axis=1)
-    prob = problems.lmpc_problem(c["state"], up, c["pvec"], c["target"])
-    return dict(x0=c["state"], ref=c["target"], aux=aux), prob
+    d = dart_b200.workloads.lmpc_inputs(B, seed)
+    return d, problems.lmpc_problem(d["x0"], d["u_prev"], d["pvec"], d["ref"])
 
 
 def assert_parity(out, ref, what=""):
