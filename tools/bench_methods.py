@@ -44,7 +44,7 @@ def main():
     peak = dart_b200.measure_fp64_tflops(0)
     print(json.dumps({"fp64_peak_tflops_measured": peak}))
     # config 3: RMPC 4096 instances (mid-episode inputs)
-    d, _ = (W.rmpc_inputs(4096), None)
+    d = W.rmpc_inputs(4096)
     for lanes in ((8, 16, 32) if sweep else (0,)):
         for bt in ((32, 64, 128) if sweep else (0,)):
             try:
@@ -52,7 +52,7 @@ def main():
             except Exception as e:
                 print(json.dumps({"method": "rmpc", "lanes": lanes, "bt": bt, "error": str(e)[:100]}))
     # config 4: LMPC 16384 instances
-    d, _ = (W.lmpc_inputs(16384), None)
+    d = W.lmpc_inputs(16384)
     for lanes in ((4, 8, 16) if sweep else (0,)):
         for bt in ((32, 64, 128) if sweep else (0,)):
             try:

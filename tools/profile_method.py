@@ -2,11 +2,12 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, dart_b200
+W = dart_b200.workloads
 m = sys.argv[1]
 if m == "rmpc":
-    d, _ = (W.rmpc_inputs(4096), None); cfg = dart_b200.rmpc_cfg()
+    d = W.rmpc_inputs(4096); cfg = dart_b200.rmpc_cfg()
 else:
-    d, _ = (W.lmpc_inputs(16384), None); cfg = dart_b200.lmpc_cfg()
+    d = W.lmpc_inputs(16384); cfg = dart_b200.lmpc_cfg()
 eng = dart_b200.NMPCEngine(cfg, 0)
 t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
 x, r, a = t(d["x0"]), t(d["ref"]), t(d["aux"])

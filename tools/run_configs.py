@@ -28,7 +28,7 @@ def config1(steps):
 
 
 def config2_closed_loop(steps):
-    c, aux, _ = (*W.pmpc_inputs(64), None)
+    c, aux = W.pmpc_inputs(64)
     rng = np.random.default_rng(21)
     ep = dart_b200.PMPCEpisodes(c["state"], c["target"], aux, coulomb=rng.uniform(0, 0.02, aux.shape[0]), device=LOCAL)
     a, b = ev(), ev()
@@ -111,9 +111,9 @@ def config5(total):
     S = (n + 17) // 18
     cp = dart_b200.workloads.pmpc_config2(S, seed=seed)
     px, pt = t(cp["state"][:n]), t(cp["target"][:n]); pa = t(np.stack([cp["Qp"], cp["Qv"], cp["R"], cp["mu"]], 1)[:n])
-    rd, _ = (W.rmpc_inputs(n, seed=seed), None)
+    rd = W.rmpc_inputs(n, seed=seed)
     rx, rr, ra = t(rd["x0"]), t(rd["ref"]), t(rd["aux"])
-    ld, _ = (W.lmpc_inputs(n, seed=seed), None)
+    ld = W.lmpc_inputs(n, seed=seed)
     lx, lr, la = t(ld["x0"]), t(ld["ref"]), t(ld["aux"])
     engs = [dart_b200.NMPCEngine(f(), device=LOCAL) for f in (dart_b200.pmpc_cfg, dart_b200.rmpc_cfg, dart_b200.lmpc_cfg)]
     rows = [torch.empty((n, 4), dtype=torch.float64, device=dev) for _ in range(3)]
