@@ -321,35 +321,39 @@ struct LmpcAxis {
 // Solve sub-problem (inst, axis) with the lanes of `tile`; `base` is this tile's workspace.
 // Returns per-problem J/status/iters/kkt; writes X/U of this sub-problem into w_out (reference layout).
 template <class M, class T, int NC = 0>
-DART_HD void solve_one(const T& tile, const KArgs& a, int inst, int axis, double* base, double& J, int32_t& status,
-                       int32_t& iters, double& kkt) {
+DART_HD void solve_one(const T& tile, const KArgs& a, int inst, int axis, bool active, const BlockCtx& bc, double* base,
+                       double& J, int32_t& status, int32_t& iters, double& kkt) {
     constexpr int n = M::NX, m = M::NU, np = M::NP;
     const int N = (NC > 0) ? NC : a.N;
     Workspace<M> w;
     w.bind(base, N);
     typename M::Prm prm;
-    M::load(prm, a, inst, axis);
     double x0[n];
-    M::x0(a, inst, axis, x0);
-    M::load_ref(tile, a, inst, w.REF);
     const int nwf = M::nw(N);
-    const double* warm = a.warm ? a.warm + (long)inst * nwf : nullptr;
     const int uoff = (N + 1) * M::NXF;
     const int ucol = (M::NAXIS > 1) ? axis : 0;
-    for (int k = tile.lane(); k <= N; k += tile.size()) {
-        DART_UNROLL for (int i = 0; i < np; ++i)
-            w.X[k * n + i] = (warm && k > 0) ? warm[k * M::NXF + M::xmap(axis, i)] : x0[i];
-        // carried previous input: u_prev at k = 0, U[k-1] afterwards (so tilt-rate rows start consistent)
-        DART_UNROLL for (int i = np; i < n; ++i)
-            w.X[k * n + i] = (k == 0) ? x0[i] : (warm ? warm[uoff + (k - 1) * 2 + (M::NAXIS > 1 ? ucol : (i - np))] : 0.0);
-        if (k < N) {
-            DART_UNROLL for (int j = 0; j < m; ++j)
-                w.U[k * m + j] = warm ? warm[uoff + k * 2 + (M::NAXIS > 1 ? ucol : j)] : 0.0;
+    if (active) {
+        M::load(prm, a, inst, axis);
+        M::x0(a, inst, axis, x0);
+        M::load_ref(tile, a, inst, w.REF);
+        const double* warm = a.warm ? a.warm + (long)inst * nwf : nullptr;
+        for (int k = tile.lane(); k <= N; k += tile.size()) {
+            DART_UNROLL for (int i = 0; i < np; ++i)
+                w.X[k * n + i] = (warm && k > 0) ? warm[k * M::NXF + M::xmap(axis, i)] : x0[i];
+            // carried previous input: u_prev at k = 0, U[k-1] afterwards (so tilt-rate rows start consistent)
+            DART_UNROLL for (int i = np; i < n; ++i)
+                w.X[k * n + i] = (k == 0) ? x0[i] : (warm ? warm[uoff + (k - 1) * 2 + (M::NAXIS > 1 ? ucol : (i - np))] : 0.0);
+            if (k < N) {
+                DART_UNROLL for (int j = 0; j < m; ++j)
+                    w.U[k * m + j] = warm ? warm[uoff + k * 2 + (M::NAXIS > 1 ? ucol : j)] : 0.0;
+            }
         }
+        tile.sync();
     }
-    tile.sync();
-    Solver<M, T, NC> s(tile, prm, a.o, N, w);
-    s.run(J, status, iters, kkt);
+    // every tile of the block (active or not) takes part in run(): its threads also serve the serial-sweep phase
+    Solver<M, T, NC> s(tile, prm, a.o, N, w, bc);
+    s.run(active, J, status, iters, kkt);
+    if (!active) return;
     if (M::infeasible0(prm, x0) && status != ST_NUMERIC) status = ST_INFEASIBLE;
     if (a.w_out) {
         double* wo = a.w_out + (long)inst * nwf;

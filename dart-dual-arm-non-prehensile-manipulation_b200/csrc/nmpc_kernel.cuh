@@ -19,6 +19,8 @@ struct DevTile {
     __device__ __forceinline__ int lane() const { return ln; }
     __device__ __forceinline__ int size() const { return G; }
     __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+    __device__ __forceinline__ void block_sync() const { __syncthreads(); }
+    __device__ __forceinline__ bool block_any(bool p) const { return __syncthreads_or(p ? 1 : 0) != 0; }
     __device__ __forceinline__ double sum(double v) const {
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o, G);
@@ -36,9 +38,6 @@ struct DevTile {
     }
 };
 
-// Per-tile result slot at the head of each workspace stride (4 doubles).
-constexpr int kSlot = 4;
-
 template <class M, int G, int NC>
 __global__ void __launch_bounds__(256) nmpc_solve_kernel(const KArgs a, const int ws_stride) {
     extern __shared__ double smem[];
@@ -53,7 +52,8 @@ __global__ void __launch_bounds__(256) nmpc_solve_kernel(const KArgs a, const in
     const bool active = inst < a.B;
     double J = 0.0, kkt = 0.0;
     int32_t status = ST_CONVERGED, iters = 0;
-    if (active) solve_one<M, DevTile<G>, NC>(tile, a, inst, axis, slot + kSlot, J, status, iters, kkt);
+    const BlockCtx bc{smem, ws_stride, tpb, (int)threadIdx.x};
+    solve_one<M, DevTile<G>, NC>(tile, a, inst, axis, active, bc, slot + kSlot, J, status, iters, kkt);
     if (NAX == 1) {
         if (active && tile.lane() == 0) {
             a.J[inst] = J;

@@ -48,11 +48,23 @@ struct SolverOpts {
 DART_HD double dmax(double a, double b) { return a > b ? a : b; }
 DART_HD double dmin(double a, double b) { return a < b ? a : b; }
 
-// Host stand-in for a tile of one lane.
+// Per-tile result / hand-shake slot (doubles) at the head of each problem's workspace stride.
+constexpr int kSlot = 4;
+
+// Where the problems of this thread block live in shared memory: problem q's slot is base + q*stride, its workspace
+// follows the slot.  Used by the serial-sweep phase, in which thread `tid` runs the sweeps of problem `tid`.
+struct BlockCtx {
+    double* base;
+    int stride, nprob, tid;
+};
+
+// Host stand-in for a tile of one lane (and a block of one problem).
 struct HostTile {
     DART_HD int lane() const { return 0; }
     DART_HD int size() const { return 1; }
     DART_HD void sync() const {}
+    DART_HD void block_sync() const {}
+    DART_HD bool block_any(bool p) const { return p; }
     DART_HD double sum(double v) const { return v; }
     DART_HD double max(double v) const { return v; }
     DART_HD double min(double v) const { return v; }
@@ -119,9 +131,10 @@ struct Solver {
     const SolverOpts& o;
     const int N;
     W& w;
+    const BlockCtx& bc;
 
-    DART_HD Solver(const T& t, const Prm& p, const SolverOpts& oo, int NN, W& ww)
-        : tile(t), prm(p), o(oo), N(NC > 0 ? NC : NN), w(ww) {}
+    DART_HD Solver(const T& t, const Prm& p, const SolverOpts& oo, int NN, W& ww, const BlockCtx& b)
+        : tile(t), prm(p), o(oo), N(NC > 0 ? NC : NN), w(ww), bc(b) {}
 
     static constexpr int npa = W::npa, npb = W::npb, nps = W::nps, nys = W::nys;
     // packed upper-triangular index of a symmetric d x d matrix
@@ -358,6 +371,13 @@ struct Solver {
                 DART_UNROLL for (int c = i; c < ny; ++c) w.HS[k * nys + sidx(i, c, ny)] = H[i * ny + c];
             DART_UNROLL for (int i = 0; i < ny; ++i) w.GR[k * ny + i] = g[i];
         }
+        if (M::SERIAL_RICCATI && tile.lane() == 0) {
+            // terminal value function P_N, p_N for the serial sweep (which runs without the model parameters)
+            DART_UNROLL for (int i = 0; i < n; ++i) {
+                DART_UNROLL for (int j = i; j < n; ++j) w.PP[N * nps + sidx(i, j, n)] = (i == j) ? 2.0 * M::wT(prm, i) : 0.0;
+                w.PV[N * n + i] = 2.0 * M::wT(prm, i) * (w.X[N * n + i] - M::rT(prm, w.REF, N, i));
+            }
+        }
         tile.sync();
     }
 
@@ -431,20 +451,15 @@ struct Solver {
         }
     }
 
-    // ---- Riccati backward sweep for small problems: every lane runs the whole recursion with P, p and the stage
-    // matrix in REGISTERS (the loop-carried dependency never touches shared memory); stage data loads do not depend
-    // on P, so they are off the critical path.  Lane 0 stores the gains and P_k / p_k for the later phases.
+    // ---- Riccati backward sweep for small problems, run by ONE thread per problem (the serial-sweep phase of run()):
+    // P, p and the stage matrix stay in REGISTERS, so the loop-carried dependency never touches shared memory, and
+    // stage data loads do not depend on P, so they are issued ahead of the dependent chain.  Needs only the workspace
+    // (terminal P_N, p_N were written by prep()).
     DART_HD void backward_serial() {
-        const bool wr = tile.lane() == 0;
         double P[n * n], pv[n];
         DART_UNROLL for (int i = 0; i < n; ++i) {
-            DART_UNROLL for (int j = 0; j < n; ++j) P[i * n + j] = (i == j) ? 2.0 * M::wT(prm, i) : 0.0;
-            pv[i] = 2.0 * M::wT(prm, i) * (w.X[N * n + i] - M::rT(prm, w.REF, N, i));
-        }
-        if (wr) {
-            DART_UNROLL for (int i = 0; i < n; ++i)
-                DART_UNROLL for (int j = i; j < n; ++j) w.PP[N * nps + sidx(i, j, n)] = P[i * n + j];
-            DART_UNROLL for (int i = 0; i < n; ++i) w.PV[N * n + i] = pv[i];
+            DART_UNROLL for (int j = 0; j < n; ++j) P[i * n + j] = Pat(N, i, j);
+            pv[i] = w.PV[N * n + i];
         }
         double Tm[n * nc], HG[ny * nc];
         auto load = [&](int k, double* T_, double* H_) {
@@ -514,32 +529,25 @@ struct Solver {
                     }
                 }
             }
-            if (wr) {
-                DART_UNROLL for (int j = 0; j < m; ++j) {
-                    DART_UNROLL for (int c = 0; c < n; ++c) w.K[k * m * n + j * n + c] = Kt[j * (n + 1) + c];
-                    w.KFF[k * m + j] = Kt[j * (n + 1) + n];
-                }
-                if (k > 0) {
-                    DART_UNROLL for (int i = 0; i < n; ++i)
-                        DART_UNROLL for (int j = i; j < n; ++j) w.PP[k * nps + sidx(i, j, n)] = P[i * n + j];
-                    DART_UNROLL for (int i = 0; i < n; ++i) w.PV[k * n + i] = pv[i];
-                }
+            DART_UNROLL for (int j = 0; j < m; ++j) {
+                DART_UNROLL for (int c = 0; c < n; ++c) w.K[k * m * n + j * n + c] = Kt[j * (n + 1) + c];
+                w.KFF[k * m + j] = Kt[j * (n + 1) + n];
+            }
+            if (k > 0) {
+                DART_UNROLL for (int i = 0; i < n; ++i)
+                    DART_UNROLL for (int j = i; j < n; ++j) w.PP[k * nps + sidx(i, j, n)] = P[i * n + j];
+                DART_UNROLL for (int i = 0; i < n; ++i) w.PV[k * n + i] = pv[i];
             }
             DART_UNROLL for (int i = 0; i < n * nc; ++i) Tm[i] = Tn[i];
             DART_UNROLL for (int i = 0; i < ny * nc; ++i) HG[i] = Hn[i];
         }
-        tile.sync();
     }
 
-    // ---- forward sweep: every lane runs the short affine recurrence in registers (lane 0 stores).  The stage data
-    // of step k+1 is loaded before the dependent arithmetic of step k so shared-memory latency stays off the chain.
+    // ---- forward sweep, ONE thread per problem: the short affine recurrence runs in registers.  The stage data of
+    // step k+1 is loaded before the dependent arithmetic of step k so shared-memory latency stays off the chain.
     DART_HD void forward() {
         double dx[n];
-        DART_UNROLL for (int i = 0; i < n; ++i) dx[i] = 0.0;
-        const bool wr = tile.lane() == 0;
-        if (wr) {
-            DART_UNROLL for (int i = 0; i < n; ++i) w.DX[i] = 0.0;
-        }
+        DART_UNROLL for (int i = 0; i < n; ++i) { dx[i] = 0.0; w.DX[i] = 0.0; }
         double Kc[m * n], kc[m], Ac[n * n], Bc[n * m], dc[n];
         auto load = [&](int k, double* K_, double* k_, double* A_, double* B_, double* d_) {
             DART_UNROLL for (int i = 0; i < m * n; ++i) K_[i] = w.K[k * m * n + i];
@@ -568,10 +576,8 @@ struct Solver {
                 DART_UNROLL for (int j = 0; j < m; ++j) acc += Bc[a * m + j] * du[j];
                 nx[a] = acc;
             }
-            if (wr) {
-                DART_UNROLL for (int j = 0; j < m; ++j) w.DU[k * m + j] = du[j];
-                DART_UNROLL for (int a = 0; a < n; ++a) w.DX[(k + 1) * n + a] = nx[a];
-            }
+            DART_UNROLL for (int j = 0; j < m; ++j) w.DU[k * m + j] = du[j];
+            DART_UNROLL for (int a = 0; a < n; ++a) w.DX[(k + 1) * n + a] = nx[a];
             DART_UNROLL for (int a = 0; a < n; ++a) dx[a] = nx[a];
             DART_UNROLL for (int i = 0; i < m * n; ++i) Kc[i] = Kn[i];
             DART_UNROLL for (int i = 0; i < m; ++i) kc[i] = kn[i];
@@ -579,7 +585,6 @@ struct Solver {
             DART_UNROLL for (int i = 0; i < n * m; ++i) Bc[i] = Bn[i];
             DART_UNROLL for (int i = 0; i < n; ++i) dc[i] = dn[i];
         }
-        tile.sync();
     }
 
     // ---- slack steps, step-length limits, directional derivative, then the dual step z += ad dz (stage-parallel).
@@ -685,38 +690,76 @@ struct Solver {
         }
     }
 
-    // ---- the interior-point loop.  X (all N+1 states, X[0] = x0), U and REF must be set by the caller.
-    DART_HD void run(double& J, int32_t& status, int32_t& iters, double& kkt) {
+    // ---- the interior-point loop.  X (all N+1 states, X[0] = x0), U and REF must be set by the caller when `active`.
+    //
+    // Every iteration has three phases with a phase-dependent mapping of work to threads:
+    //   A (tile = G lanes of this problem): convergence test, barrier update, prep(); tiled Riccati sweep for the
+    //     larger models;
+    //   B (one THREAD per problem of the block): the serial Riccati/forward sweeps -- thread q of the block runs the
+    //     sweeps of problem q out of its shared-memory workspace, so a warp advances 32 problems per instruction
+    //     instead of replicating one recursion in every lane;
+    //   C (tile): slack/dual steps, line search with re-evaluation, multiplier update, KKT residuals.
+    // Two block barriers per iteration separate A|B|C; all tiles of the block (also finished or empty ones) keep
+    // taking part in them until no problem of the block needs another sweep.
+    DART_HD void run(bool active, double& J, int32_t& status, int32_t& iters, double& kkt) {
         double mu = o.mu0;
-        init_rows(mu);
-        double f, L, th, pinf, dinf, zs_min, zs_max, lam_sum, z_sum;
-        int nact;
-        eval1(f, L, th, pinf);
-        eval2(dinf, zs_min, zs_max, lam_sum, z_sum, nact);
-        const double inv_nd = 1.0 / (double)(N * n + 2 * nact), inv_nc = 1.0 / (double)(2 * (nact > 0 ? nact : 1));
+        double f = 0.0, L = 0.0, th = 0.0, pinf = 0.0, dinf = 0.0, zs_min = 0.0, zs_max = 0.0, lam_sum = 0.0, z_sum = 0.0;
+        int nact = 0;
+        double inv_nd = 0.0, inv_nc = 0.0;
+        if (active) {
+            init_rows(mu);
+            eval1(f, L, th, pinf);
+            eval2(dinf, zs_min, zs_max, lam_sum, z_sum, nact);
+            inv_nd = 1.0 / (double)(N * n + 2 * nact);
+            inv_nc = 1.0 / (double)(2 * (nact > 0 ? nact : 1));
+        }
         const double mu_min = o.tol / 10.0;
         int it = 0, tiny = 0;
         int32_t st = ST_MAXITER;
-        double E0 = 0.0;
-        for (;; ++it) {
-            // IPOPT's scaled optimality error; is_d = 1/s_d, is_c = 1/s_c (s_* = max(smax, mean multiplier)/smax)
-            const double is_d = o.smax / dmax(o.smax, (lam_sum + z_sum) * inv_nd);
-            const double is_c = o.smax / dmax(o.smax, z_sum * inv_nc);
-            const double base = dmax(dinf * is_d, pinf);
-            E0 = dmax(base, (nact > 0 ? zs_max : 0.0) * is_c);
-            if (E0 <= o.tol) { st = ST_CONVERGED; break; }
-            if (!(E0 == E0) || E0 > 1e300) { st = ST_NUMERIC; break; }
-            if (it >= o.max_iter) break;
-            for (int q = 0; q < 8; ++q) {
-                double cm = (nact > 0) ? dmax(fabs(zs_max - mu), fabs(zs_min - mu)) : 0.0;
-                double Emu = dmax(base, cm * is_c);
-                if (Emu <= o.kappa_eps * mu && mu > mu_min) mu = dmax(mu_min, dmin(o.kappa_mu * mu, (o.theta_mu == 1.5) ? mu * sqrt(mu) : pow(mu, o.theta_mu)));
-                else break;
+        double E0 = 0.0, is_d = 1.0, is_c = 1.0;
+        bool done = !active;
+        double* myslot = bc.base + (size_t)(bc.tid / tile.size()) * bc.stride;
+        for (;;) {
+            // ---------------- phase A
+            bool need_sweep = false;
+            if (!done) {
+                // IPOPT's scaled optimality error; is_d = 1/s_d, is_c = 1/s_c (s_* = max(smax, mean multiplier)/smax)
+                is_d = o.smax / dmax(o.smax, (lam_sum + z_sum) * inv_nd);
+                is_c = o.smax / dmax(o.smax, z_sum * inv_nc);
+                const double base = dmax(dinf * is_d, pinf);
+                E0 = dmax(base, (nact > 0 ? zs_max : 0.0) * is_c);
+                if (E0 <= o.tol) { st = ST_CONVERGED; done = true; }
+                else if (!(E0 == E0) || E0 > 1e300) { st = ST_NUMERIC; done = true; }
+                else if (it >= o.max_iter) done = true;
+                if (!done) {
+                    for (int q = 0; q < 8; ++q) {
+                        double cm = (nact > 0) ? dmax(fabs(zs_max - mu), fabs(zs_min - mu)) : 0.0;
+                        double Emu = dmax(base, cm * is_c);
+                        if (Emu <= o.kappa_eps * mu && mu > mu_min)
+                            mu = dmax(mu_min, dmin(o.kappa_mu * mu, (o.theta_mu == 1.5) ? mu * sqrt(mu) : pow(mu, o.theta_mu)));
+                        else break;
+                    }
+                    prep(mu);
+                    if (!M::SERIAL_RICCATI) backward(tile);
+                    need_sweep = true;
+                }
             }
-            prep(mu);
-            if (M::SERIAL_RICCATI) backward_serial();
-            else backward(tile);
-            forward();
+            if (tile.lane() == 0) myslot[0] = need_sweep ? 1.0 : 0.0;
+            if (!tile.block_any(need_sweep)) break;        // barrier + vote: phase-A writes are visible past this point
+            // ---------------- phase B: thread q sweeps problem q
+            if (bc.tid < bc.nprob) {
+                double* sl = bc.base + (size_t)bc.tid * bc.stride;
+                if (sl[0] != 0.0) {
+                    W wk;
+                    wk.bind(sl + kSlot, N);
+                    Solver other(tile, prm, o, N, wk, bc);
+                    if (M::SERIAL_RICCATI) other.backward_serial();
+                    other.forward();
+                }
+            }
+            tile.block_sync();
+            if (!need_sweep) continue;
+            // ---------------- phase C
             double ap, ad, dphi;
             post(mu, ap, ad, dphi);
             const double phi0 = f - mu * L, th0 = th;
@@ -727,7 +770,7 @@ struct Solver {
                 applied = alpha;
                 eval1(f, L, th, pinf);
                 const double phit = f - mu * L;
-                // alpha |dphi|^s_phi > delta th0^s_theta, compared in the log domain (only needed when th0 is small)
+                // alpha |dphi|^s_phi > delta th0^s_theta, compared in the log domain (only needed when th0 is small);
                 // single precision is ample for this heuristic test (and keeps three FP64 logs off the serial path)
                 bool switching = false;
                 if (dphi < 0.0 && th0 <= o.theta_small)
@@ -743,9 +786,10 @@ struct Solver {
 #ifdef DART_TRACE
             printf("it %d mu %.3e E0 %.3e dinf %.3e pinf %.3e zsmax %.3e ap %.4f ad %.4f alpha %.5f dphi %.3e th0 %.3e f %.10g\n", it, mu, E0, dinf * is_d, pinf, zs_max * is_c, ap, ad, alpha, dphi, th0, f);
 #endif
+            ++it;
             // the step vanished three times in a row: no restoration phase here -- stop and say so
             tiny = (alpha <= 1e-6) ? tiny + 1 : 0;
-            if (tiny >= 3) { st = (pinf > 1e-4) ? ST_INFEASIBLE : ST_MAXITER; ++it; break; }
+            if (tiny >= 3) { st = (pinf > 1e-4) ? ST_INFEASIBLE : ST_MAXITER; done = true; continue; }
             move_dual(alpha, mu);
             eval2(dinf, zs_min, zs_max, lam_sum, z_sum, nact);
         }

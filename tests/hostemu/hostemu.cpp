@@ -11,7 +11,8 @@ using namespace dart;
 template <class M>
 static void run_all(const KArgs& a) {
     HostTile tile;
-    std::vector<double> ws(Workspace<M>::doubles(a.N) + 8);
+    std::vector<double> ws(Workspace<M>::doubles(a.N) + kSlot + 8);
+    const BlockCtx bc{ws.data(), 0, 1, 0};          // a block of one problem: the same thread runs all three phases
     for (int inst = 0; inst < a.B; ++inst) {
         double Js = 0.0;
         int32_t st = 0, itx = 0;
@@ -19,8 +20,8 @@ static void run_all(const KArgs& a) {
             double J = 0, kkt = 0;
             int32_t s = 0, it = 0;
             // same dispatch as the device launcher: compile-time horizon when it is the reference's
-            if (a.N == M::NDEF) solve_one<M, HostTile, M::NDEF>(tile, a, inst, ax, ws.data(), J, s, it, kkt);
-            else solve_one<M, HostTile, 0>(tile, a, inst, ax, ws.data(), J, s, it, kkt);
+            if (a.N == M::NDEF) solve_one<M, HostTile, M::NDEF>(tile, a, inst, ax, true, bc, ws.data() + kSlot, J, s, it, kkt);
+            else solve_one<M, HostTile, 0>(tile, a, inst, ax, true, bc, ws.data() + kSlot, J, s, it, kkt);
             Js += J;
             st = s > st ? s : st;
             itx = it > itx ? it : itx;

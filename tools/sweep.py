@@ -29,7 +29,7 @@ if __name__ == "__main__":
     for S in (64, 7282):
         c = dart_b200.workloads.pmpc_config2(S)
         for lanes in (2, 4, 8, 16):
-            for bt in (32, 64, 128):
+            for bt in (32, 64, 128, 256):
                 try:
                     ms, ok, lc = timeit(dart_b200.pmpc_cfg(lanes=lanes, block_threads=bt), c, 20 if S == 64 else 3)
                     print(f"B={18*S} lanes={lanes} bt={bt} ms={ms:.4f} solves/s={18*S/ms*1e3:.3e} ok={ok} grid={lc['grid']} smem={lc['smem_bytes']}", flush=True)
