@@ -42,7 +42,6 @@ template <class M, int G, int NC>
 __global__ void __launch_bounds__(256) nmpc_solve_kernel(const KArgs a, const int ws_stride) {
     extern __shared__ double smem[];
     constexpr int NAX = M::NAXIS;
-    static_assert(G * NAX <= 32, "all axes of one instance must share a warp");
     const DevTile<G> tile;
     const int tpb = blockDim.x / G;
     const int tib = threadIdx.x / G;
@@ -66,18 +65,16 @@ __global__ void __launch_bounds__(256) nmpc_solve_kernel(const KArgs a, const in
         }
         return;
     }
-    // combine the axes of one instance (adjacent tiles of the same warp), in a fixed order
+    // combine the axes of one instance (adjacent tiles of the block), in a fixed order.  All tiles of the block leave
+    // the solve loop together (block-uniform exit), so a block barrier orders the slot writes before the reads.
     if (tile.lane() == 0) {
         slot[0] = J;
         slot[1] = (double)status;
         slot[2] = (double)iters;
         slot[3] = kkt;
     }
-    const int l = threadIdx.x & 31;
-    const int gl = l & (G * NAX - 1);
-    const unsigned gmask = (G * NAX == 32) ? 0xffffffffu : (((1u << (G * NAX)) - 1u) << (l - gl));
-    __syncwarp(gmask);
-    if (active && gl == 0) {
+    __syncthreads();
+    if (active && axis == 0 && tile.lane() == 0) {
         double Js = 0.0;
         int32_t st = 0, itx = 0;
         for (int ax = 0; ax < NAX; ++ax) {
@@ -89,7 +86,7 @@ __global__ void __launch_bounds__(256) nmpc_solve_kernel(const KArgs a, const in
         a.J[inst] = Js;
         if (a.status) a.status[inst] = st;
         if (a.iters) a.iters[inst] = itx;
-        if (a.rows) {       // u0 of every axis was stored before the group sync above
+        if (a.rows) {       // u0 of every axis was stored before the barrier above
             double* r = a.rows + (long)inst * 4;
             r[0] = a.u0[(long)inst * 2]; r[1] = a.u0[(long)inst * 2 + 1]; r[2] = Js; r[3] = (double)st;
         }
@@ -117,6 +114,7 @@ static int launch_n(const KArgs& a, int block_threads, cudaStream_t st, LaunchIn
         // block, so shared memory (the occupancy limiter) packs at warp granularity.
         const long probs = (long)a.B * M::NAXIS;
         bt = (probs * G > 148L * 32 * 16) ? 32 : 128;
+        if (bt < 64 && G * M::NAXIS >= 32 && M::NX > 2) bt = 64;     // measured: the larger models prefer 2 warps per block
         if (bt < unit) bt = unit;
     }
     if (bt % 32 != 0 || bt < unit) return DART_ERR_ARG;
@@ -146,9 +144,7 @@ static int launch_g(const KArgs& a, int lanes, int block_threads, cudaStream_t s
         case 4: if constexpr (M::NX <= 5) return launch_t<M, 4>(a, block_threads, st, info); return DART_ERR_ARG;
         case 8: return launch_t<M, 8>(a, block_threads, st, info);
         case 16: return launch_t<M, 16>(a, block_threads, st, info);
-        case 32:
-            if constexpr (M::NAXIS == 1) return launch_t<M, 32>(a, block_threads, st, info);
-            return DART_ERR_ARG;
+        case 32: return launch_t<M, 32>(a, block_threads, st, info);
         default: return DART_ERR_ARG;
     }
 }

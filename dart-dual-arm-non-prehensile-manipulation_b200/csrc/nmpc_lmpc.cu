@@ -3,6 +3,6 @@
 
 namespace dart {
 int launch_solve_lmpc(const KArgs& a, int lanes, int block_threads, cudaStream_t st, LaunchInfo* info) {
-    return launch_g<LmpcAxis>(a, lanes > 0 ? lanes : 16, block_threads, st, info);
+    return launch_g<LmpcAxis>(a, lanes > 0 ? lanes : 32, block_threads, st, info);
 }
 }  // namespace dart

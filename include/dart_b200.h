@@ -70,7 +70,7 @@ typedef struct {
     double tol;          /* [1e-8]  KKT tolerance (IPOPT 'tol')            */
     int32_t max_iter;    /* [PMPC 3000->capped 200, RMPC 200, LMPC 200]     */
     double mu_init;      /* [0.1]   initial barrier parameter               */
-    int32_t lanes;       /* [auto]  lanes of a warp cooperating on one sub-problem: 1,2,4,8,16 (32 where allowed) */
+    int32_t lanes;       /* [auto]  lanes of a warp cooperating on one sub-problem: 2, 4, 8, 16 or 32 */
     int32_t block_threads; /* [auto] threads per block (multiple of 32)     */
 } dart_cfg;
 

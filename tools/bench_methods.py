@@ -53,7 +53,7 @@ def main():
                 print(json.dumps({"method": "rmpc", "lanes": lanes, "bt": bt, "error": str(e)[:100]}))
     # config 4: LMPC 16384 instances
     d = W.lmpc_inputs(16384)
-    for lanes in ((4, 8, 16) if sweep else (0,)):
+    for lanes in ((8, 16, 32) if sweep else (0,)):
         for bt in ((32, 64, 128) if sweep else (0,)):
             try:
                 print(json.dumps(time_solve("lmpc", dart_b200.lmpc_cfg(lanes=lanes, block_threads=bt), d["x0"], d["ref"], d["aux"], reps=3)), flush=True)
