@@ -175,3 +175,55 @@ def test_bitwise_repeatable_under_load(built, method):
     sub = eng.solve(args[0][:37], args[1][:37], aux=kw["aux"][:37], want_w=True)
     for k in ("u0", "J", "w", "status", "iters"):
         assert np.array_equal(first[k][:37], sub[k]), k
+
+
+@pytest.mark.parametrize("N", [5, 30])
+def test_runtime_horizon_kernels(built, N):
+    """Horizons other than the reference's 15/20 take the runtime-N instantiation; parity must hold there too."""
+    c, aux, _ = helpers.pmpc_case(2)
+    out = dart_b200.NMPCEngine(dart_b200.pmpc_cfg(N=N), device=0).solve(c["state"], c["target"], aux=aux)
+    ref = ipm.solve(problems.pmpc_problem(c["state"], c["target"], Qp=c["Qp"], Qv=c["Qv"], R=c["R"], mu=c["mu"], N=N))
+    helpers.assert_parity(out, ref, f"pmpc N={N}")
+    assert out["w"].shape == (36, (N + 1) * 6 + 2 * N)
+    d = dart_b200.workloads.rmpc_inputs(16)
+    rv = np.zeros((16, 4)); rv[:, [0, 2]] = d["x0"][:, [0, 2]]
+    tgt = dart_b200.workloads.rmpc_config3(16)["target"]
+    refN = problems.build_ref_traj(None, problems.reference_governor(rv, tgt), tgt, N, 4, 0.2)
+    out = dart_b200.NMPCEngine(dart_b200.rmpc_cfg(N=N), device=0).solve(d["x0"], refN, aux=d["aux"])
+    ref = ipm.solve(problems.rmpc_problem(d["x0"], d["u_prev"], d["theta"], refN, N=N))
+    helpers.assert_parity(out, ref, f"rmpc N={N}")
+
+
+def test_mpc_worker_queue_protocol(built):
+    """PMPC/main_parallel.py:10-43: items (state, target) / "STOP"; replies (u_cmd, loss, solve_time)."""
+    import queue
+    import threading
+    sq, cq = queue.Queue(), queue.Queue()
+    model, data = dart_b200.GravityModel(-9.81, 0.002), dart_b200.StateHolder()
+    params = {"Ts": 0.002, "nx": 6, "nu": 2, "N": 15, "Qp": 600, "Qv": 5, "R": 0.1, "u_bounds": (-0.6, 0.6), "mu": 0.1}
+    th = threading.Thread(target=dart_b200.mpc_worker, args=((model, data), "cube", params, sq, cq))
+    th.start()
+    c, aux, p = helpers.pmpc_case(1)
+    cube = [i for i in range(p.B) if c["Qp"][i] == 600 and c["mu"][i] == 0.1][:3]
+    for i in cube:
+        sq.put((c["state"][i], c["target"][i]))
+    sq.put("STOP")
+    th.join(timeout=60)
+    assert not th.is_alive()
+    ref = ipm.solve(p)
+    for i in cube:
+        u_cmd, loss, solve_time = cq.get(timeout=5)
+        assert u_cmd.shape == (2,) and loss.shape == (1,) and solve_time > 0
+        assert np.abs(u_cmd - ref["U"][i, 0]).max() <= helpers.TOL_U0
+        assert abs(loss[0] - ref["J"][i]) <= helpers.TOL_J * abs(ref["J"][i])
+
+
+def test_pmpc_class_is_a_dropin(built):
+    model, data = dart_b200.GravityModel(-9.81, 0.002), dart_b200.StateHolder()
+    ctl = dart_b200.PMPC(model, data, Ts=0.002, nx=6, nu=2, N=15, Qp=400, Qv=2, R=0.2, u_bounds=(-0.6, 0.6), mu=0.1)
+    ctl.target_body = "cube"
+    data.body("cube").xpos[:] = [0.0, 0.0, 0.43]
+    assert np.array_equal(ctl.get_state(), [0, 0, 0, 0, 0.43, 0])
+    u0, loss = ctl.solve(np.array([0.1, 0, 0.05, 0, 0.4, 0]))
+    assert u0.shape == (2,) and loss.shape == (1,) and ctl.w0.shape == (126,) and ctl.g == -9.81 and ctl.status == 0
+    assert np.array_equal(ctl.w0[96:98], u0) and np.all(u0 < 0)        # g < 0: +x / +y motion needs negative tilt
