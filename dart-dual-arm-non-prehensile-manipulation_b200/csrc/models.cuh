@@ -77,6 +77,7 @@ DART_HD void rk4_sens(const typename Md::Prm& p, const double* x, const double* 
 struct PmpcAxis {
     static constexpr int NX = 2, NU = 1, NR = 1, NP = 2, NAUG = 0, NAXIS = 2;
     static constexpr bool SERIAL_RICCATI = true;
+    static constexpr int MAX_THREADS = 256, MIN_BLOCKS = 1, BT_LARGE = 64;   // BT_LARGE: block size when the GPU is filled (measured)
     static constexpr int NXF = 6;   // states per stage in the reference's decision vector
     static constexpr int NDEF = 15; // the reference's horizon (compile-time instantiation)
     struct Prm { double Qp, Qv, R, mu, g, Ts, ulo, uhi, rp, rv; };
@@ -136,6 +137,7 @@ struct PmpcAxis {
 struct Rmpc {
     static constexpr int NX = 6, NU = 2, NR = 6, NP = 4, NAUG = 2, NAXIS = 1;
     static constexpr bool SERIAL_RICCATI = false;
+    static constexpr int MAX_THREADS = 256, MIN_BLOCKS = 1, BT_LARGE = 32;
     static constexpr int NXF = 4;
     static constexpr int NDEF = 20;
     struct Prm { double Qp, Qv, Ru, Rdu, gz, Ts, ulo, uhi, dlo, dhi, vmax, inv_eps; double th[14]; };
@@ -212,6 +214,7 @@ struct Rmpc {
 struct LmpcAxis {
     static constexpr int NX = 5, NU = 1, NR = 1, NP = 4, NAUG = 1, NAXIS = 2;
     static constexpr bool SERIAL_RICCATI = false;   // measured: the tiled sweep is 1.3-2x faster than the per-lane one at n = 5
+    static constexpr int MAX_THREADS = 128, MIN_BLOCKS = 3, BT_LARGE = 128;   // 12 warps/SM -> <= 170 registers (shared memory allows 13)
     static constexpr int NXF = 8;
     static constexpr int NDEF = 20;
     struct Prm {

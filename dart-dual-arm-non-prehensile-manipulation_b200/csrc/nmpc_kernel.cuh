@@ -38,8 +38,9 @@ struct DevTile {
     }
 };
 
+// M::MIN_BLOCKS: occupancy hint (blocks of M::MAX_THREADS per SM) that caps registers where shared memory leaves room.
 template <class M, int G, int NC>
-__global__ void __launch_bounds__(256) nmpc_solve_kernel(const KArgs a, const int ws_stride) {
+__global__ void __launch_bounds__(M::MAX_THREADS, M::MIN_BLOCKS) nmpc_solve_kernel(const KArgs a, const int ws_stride) {
     extern __shared__ double smem[];
     constexpr int NAX = M::NAXIS;
     const DevTile<G> tile;
@@ -113,10 +114,10 @@ static int launch_n(const KArgs& a, int block_threads, cudaStream_t st, LaunchIn
         // measured on B200 (tools/sweep.py): few problems -> 4 warps per block; a filled GPU -> one warp per
         // block, so shared memory (the occupancy limiter) packs at warp granularity.
         const long probs = (long)a.B * M::NAXIS;
-        bt = (probs * G > 148L * 32 * 16) ? 32 : 128;
-        if (bt < 64 && G * M::NAXIS >= 32 && M::NX > 2) bt = 64;     // measured: the larger models prefer 2 warps per block
+        bt = (probs * G > 148L * 32 * 16) ? M::BT_LARGE : 128;
         if (bt < unit) bt = unit;
     }
+    if (bt > M::MAX_THREADS) bt = M::MAX_THREADS;
     if (bt % 32 != 0 || bt < unit) return DART_ERR_ARG;
     int tpb = bt / G;
     size_t smem = (size_t)tpb * ws_stride * sizeof(double);
