@@ -82,23 +82,26 @@ struct Workspace {
     static constexpr int n = M::NX, m = M::NU, nr = M::NR, ny = n + m, nc = n + m + 1, np = M::NP;
     // A, Bm: physical NP x NP / NP x NU blocks only (carried-input rows are structural); PP, HS: packed symmetric
     static constexpr int npa = np * np, npb = np * m, nps = n * (n + 1) / 2, nys = ny * (ny + 1) / 2;
+    // per-stage strides (in doubles) of the arrays that lanes index by stage: odd, so that lanes working on
+    // consecutive stages hit distinct shared-memory banks (16 banks of 8 bytes)
+    static constexpr int sA = npa | 1, sB = npb | 1, sH = nys | 1, sG = ny | 1, sK = (m * n) | 1;
     double *X, *U, *A, *Bm, *D, *LAM, *PP, *PV, *K, *KFF, *DX, *DU, *BL;
     double *S, *ZL, *ZU, *ISL, *ISU, *RC, *DS, *MM, *TANU, *HS, *GR, *REF;
 
     DART_HD static int doubles(int N) {
-        return (N + 1) * n + N * m + N * npa + N * npb + N * n + N * n + (N + 1) * nps + (N + 1) * n + N * m * n + N * m +
-               (N + 1) * n + N * m + N * m + 7 * N * nr + ny * nc + N * m + N * nys + N * ny + M::ref_doubles(N);
+        return (N + 1) * n + N * m + N * sA + N * sB + N * n + N * n + (N + 1) * nps + (N + 1) * n + N * sK + N * m +
+               (N + 1) * n + N * m + N * m + 7 * N * nr + ny * nc + N * m + N * sH + N * sG + M::ref_doubles(N);
     }
     DART_HD void bind(double* p, int N) {
         X = p;   p += (N + 1) * n;
         U = p;   p += N * m;
-        A = p;   p += N * npa;
-        Bm = p;  p += N * npb;
+        A = p;   p += N * sA;
+        Bm = p;  p += N * sB;
         D = p;   p += N * n;
         LAM = p; p += N * n;
         PP = p;  p += (N + 1) * nps;
         PV = p;  p += (N + 1) * n;
-        K = p;   p += N * m * n;
+        K = p;   p += N * sK;
         KFF = p; p += N * m;
         DX = p;  p += (N + 1) * n;
         DU = p;  p += N * m;
@@ -112,8 +115,8 @@ struct Workspace {
         DS = p;  p += N * nr;
         MM = p;  p += ny * nc;
         TANU = p; p += N * m;
-        HS = p;  p += N * nys;
-        GR = p;  p += N * ny;
+        HS = p;  p += N * sH;
+        GR = p;  p += N * sG;
         REF = p;
     }
 };
@@ -137,15 +140,16 @@ struct Solver {
         : tile(t), prm(p), o(oo), N(NC > 0 ? NC : NN), w(ww), bc(b) {}
 
     static constexpr int npa = W::npa, npb = W::npb, nps = W::nps, nys = W::nys;
+    static constexpr int sA = W::sA, sB = W::sB, sH = W::sH, sG = W::sG, sK = W::sK;
     // packed upper-triangular index of a symmetric d x d matrix
     DART_HD static constexpr int sidx(int i, int j, int d) {
         return i <= j ? i * d - i * (i - 1) / 2 + (j - i) : j * d - j * (j - 1) / 2 + (i - j);
     }
     // full stage Jacobians from the stored physical blocks (carried-input rows: A = 0, B = identity)
-    DART_HD double Aat(int k, int a, int b) const { return (a < np && b < np) ? w.A[k * npa + a * np + b] : 0.0; }
-    DART_HD double Bat(int k, int a, int j) const { return (a < np) ? w.Bm[k * npb + a * m + j] : ((a - np) == j ? 1.0 : 0.0); }
+    DART_HD double Aat(int k, int a, int b) const { return (a < np && b < np) ? w.A[k * sA + a * np + b] : 0.0; }
+    DART_HD double Bat(int k, int a, int j) const { return (a < np) ? w.Bm[k * sB + a * m + j] : ((a - np) == j ? 1.0 : 0.0); }
     DART_HD double Pat(int k, int a, int b) const { return w.PP[k * nps + sidx(a, b, n)]; }
-    DART_HD double Hat(int k, int i, int c) const { return w.HS[k * nys + sidx(i, c, ny)]; }
+    DART_HD double Hat(int k, int i, int c) const { return w.HS[k * sH + sidx(i, c, ny)]; }
 
     DART_HD double yval(int k, int i) const { return i < n ? w.X[k * n + i] : w.U[k * m + (i - n)]; }
     DART_HD double rowval(int k, int r) const {
@@ -180,8 +184,8 @@ struct Solver {
             double tanu[m];
             M::dyn(prm, x, u, F, Aloc, Bloc, tanu);
             DART_UNROLL for (int j = 0; j < m; ++j) w.TANU[k * m + j] = tanu[j];
-            DART_UNROLL for (int i = 0; i < npa; ++i) w.A[k * npa + i] = Aloc[i];
-            DART_UNROLL for (int i = 0; i < npb; ++i) w.Bm[k * npb + i] = Bloc[i];
+            DART_UNROLL for (int i = 0; i < npa; ++i) w.A[k * sA + i] = Aloc[i];
+            DART_UNROLL for (int i = 0; i < npb; ++i) w.Bm[k * sB + i] = Bloc[i];
             DART_UNROLL for (int a = np; a < n; ++a) F[a] = u[a - np];
             DART_UNROLL for (int a = 0; a < n; ++a) {
                 double d = F[a] - w.X[(k + 1) * n + a];
@@ -241,12 +245,12 @@ struct Solver {
             DART_UNROLL for (int i = 0; i < n; ++i) {
                 double acc = 0.0;
                 DART_UNROLL for (int a = 0; a < np; ++a)
-                    if (i < np) acc += w.A[k * npa + a * np + i] * lam[a];
+                    if (i < np) acc += w.A[k * sA + a * np + i] * lam[a];
                 g[i] += acc - (k >= 1 ? w.LAM[(k - 1) * n + i] : 0.0);
             }
             DART_UNROLL for (int j = 0; j < m; ++j) {
                 double acc = 0.0;
-                DART_UNROLL for (int a = 0; a < np; ++a) acc += w.Bm[k * npb + a * m + j] * lam[a];
+                DART_UNROLL for (int a = 0; a < np; ++a) acc += w.Bm[k * sB + a * m + j] * lam[a];
                 if (M::NAUG > 0) acc += lam[np + j];
                 w.BL[k * m + j] = acc;
                 g[n + j] += acc;
@@ -368,8 +372,8 @@ struct Solver {
             // Lagrangian curvature of the tilt input: -tan(u_j) (B^T lambda)_j
             DART_UNROLL for (int j = 0; j < m; ++j) H[(n + j) * ny + n + j] += -w.TANU[k * m + j] * w.BL[k * m + j];
             DART_UNROLL for (int i = 0; i < ny; ++i)
-                DART_UNROLL for (int c = i; c < ny; ++c) w.HS[k * nys + sidx(i, c, ny)] = H[i * ny + c];
-            DART_UNROLL for (int i = 0; i < ny; ++i) w.GR[k * ny + i] = g[i];
+                DART_UNROLL for (int c = i; c < ny; ++c) w.HS[k * sH + sidx(i, c, ny)] = H[i * ny + c];
+            DART_UNROLL for (int i = 0; i < ny; ++i) w.GR[k * sG + i] = g[i];
         }
         if (M::SERIAL_RICCATI && tile.lane() == 0) {
             // terminal value function P_N, p_N for the serial sweep (which runs without the model parameters)
@@ -408,12 +412,12 @@ struct Solver {
                     ww[a] = acc;
                 }
                 DART_UNROLL for (int i = 0; i < ny; ++i) {
-                    double acc = (c < ny) ? Hat(k, i, c) : w.GR[k * ny + i];
+                    double acc = (c < ny) ? Hat(k, i, c) : w.GR[k * sG + i];
                     if (i < n) {
                         DART_UNROLL for (int a = 0; a < np; ++a)
-                            if (i < np) acc += w.A[k * npa + a * np + i] * ww[a];
+                            if (i < np) acc += w.A[k * sA + a * np + i] * ww[a];
                     } else {
-                        DART_UNROLL for (int a = 0; a < np; ++a) acc += w.Bm[k * npb + a * m + (i - n)] * ww[a];
+                        DART_UNROLL for (int a = 0; a < np; ++a) acc += w.Bm[k * sB + a * m + (i - n)] * ww[a];
                         if (M::NAUG > 0) acc += ww[np + (i - n)];
                     }
                     w.MM[c * ny + i] = acc;
@@ -436,7 +440,7 @@ struct Solver {
                 DART_UNROLL for (int j = 0; j < m; ++j) kt[j] = -w.MM[c * ny + n + j];
                 chol_solve(Lc, kt);
                 DART_UNROLL for (int j = 0; j < m; ++j) {
-                    if (c < n) w.K[k * m * n + j * n + c] = kt[j];
+                    if (c < n) w.K[k * sK + j * n + c] = kt[j];
                     else w.KFF[k * m + j] = kt[j];
                 }
                 if (k == 0) continue;            // P_0 / p_0 are never used (x_0 is fixed)
@@ -470,7 +474,7 @@ struct Solver {
             }
             DART_UNROLL for (int i = 0; i < ny; ++i) {
                 DART_UNROLL for (int c = 0; c < ny; ++c) H_[i * nc + c] = Hat(k, i, c);
-                H_[i * nc + ny] = w.GR[k * ny + i];
+                H_[i * nc + ny] = w.GR[k * sG + i];
             }
         };
         load(N - 1, Tm, HG);
@@ -530,7 +534,7 @@ struct Solver {
                 }
             }
             DART_UNROLL for (int j = 0; j < m; ++j) {
-                DART_UNROLL for (int c = 0; c < n; ++c) w.K[k * m * n + j * n + c] = Kt[j * (n + 1) + c];
+                DART_UNROLL for (int c = 0; c < n; ++c) w.K[k * sK + j * n + c] = Kt[j * (n + 1) + c];
                 w.KFF[k * m + j] = Kt[j * (n + 1) + n];
             }
             if (k > 0) {
@@ -550,7 +554,7 @@ struct Solver {
         DART_UNROLL for (int i = 0; i < n; ++i) { dx[i] = 0.0; w.DX[i] = 0.0; }
         double Kc[m * n], kc[m], Ac[n * n], Bc[n * m], dc[n];
         auto load = [&](int k, double* K_, double* k_, double* A_, double* B_, double* d_) {
-            DART_UNROLL for (int i = 0; i < m * n; ++i) K_[i] = w.K[k * m * n + i];
+            DART_UNROLL for (int i = 0; i < m * n; ++i) K_[i] = w.K[k * sK + i];
             DART_UNROLL for (int i = 0; i < m; ++i) k_[i] = w.KFF[k * m + i];
             DART_UNROLL for (int a = 0; a < n; ++a) {
                 DART_UNROLL for (int b = 0; b < n; ++b) A_[a * n + b] = Aat(k, a, b);
