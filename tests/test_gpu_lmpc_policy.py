@@ -128,3 +128,39 @@ def test_rlmpc_facade(built):
         assert np.array_equal(ctl.views["control"], u)
         u2, _ = ctl.solve(tgt)
         assert np.all(np.isfinite(u2))
+
+
+def test_lmpc_pipeline_end_to_end_within_the_tilt_bar(built):
+    """The TF32 policy feeds the NLP through the parameter update.  17 closed-loop steps (policy updates at steps 0, 8,
+    16) on the GPU against a pipeline that is the oracle end to end (float32 MLP, its own parameters, its own solves):
+    the tilt commands must still agree within the north-star bar of 1e-4 rad (measured: 2e-6).  The parameters are
+    only loosely bounded (2e-3, measured 6e-4): the reference's Welford normaliser divides near-constant channels by a
+    std floor of 1e-6, which amplifies 1e-9 differences between the two state trajectories far more than TF32 does."""
+    import torch
+    B, T = 24, 17
+    c = dart_b200.workloads.lmpc_config4(B, seed=3)
+    dev = torch.device("cuda", 0)
+    weights = dart_b200.init_policy_weights(seed=3)
+    ctl = dart_b200.LMPCBatch(B, c["pvec"], weights=weights, device=0)
+    norm = policy.ObsNormalizer(B)
+    k = c["pvec"].copy(); control = np.zeros((B, 2)); Xw = Uw = None
+    x_gpu = c["state"].copy(); x_ora = c["state"].copy()
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    worst_u = worst_k = 0.0
+    for step in range(T):
+        u_gpu = ctl.step(t(x_gpu), t(c["target"])).cpu().numpy()
+        obs = norm.push(x_ora, c["target"], control, k)
+        a = policy.mlp_forward(obs, weights)
+        if step % 8 == 0:
+            k = policy.write_params(policy.param_update(k, a, 2.0, 0.02, 1e-2), k, 2.0, 1e-2, 0.1, 0.5)
+        prob = problems.lmpc_problem(x_ora, control, k, c["target"])
+        sol = ipm.solve(prob, X0=np.zeros((B, 21, 10)) if Xw is None else Xw, U0=np.zeros((B, 20, 2)) if Uw is None else Uw)
+        assert (sol["status"] == 0).all() and (ctl.status.cpu().numpy() == 0).all()
+        Xw, Uw = sol["X"], sol["U"]
+        control = sol["U"][:, 0].copy()
+        worst_u = max(worst_u, np.abs(u_gpu - control).max())
+        worst_k = max(worst_k, np.abs(ctl.pvec.cpu().numpy() - k).max())
+        x_ora = sol["X"][:, 1, :8].copy()                      # plant = model prediction, each pipeline its own
+        x_gpu = ctl.w.cpu().numpy()[:, 8:16].copy()
+    print(f"end-to-end over {T} steps: max|du0| = {worst_u:.2e} rad, max|dpvec| = {worst_k:.2e}")
+    assert worst_u <= 1e-4 and worst_k <= 2e-3
