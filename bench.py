@@ -318,7 +318,7 @@ def run_ours(args):
                 "traffic": 215552,   # dram__bytes_read + write per launch, ncu --set full capture (profiles/r1_summary.md)
                 "peak_source": "measured in this run (dart_measure_fp64_tflops DFMA microbenchmark); MEASURED_PEAKS.json "
                                "has no FP64 entry",
-                "kernel": "nmpc_solve_kernel<PmpcAxis>", "algorithmic_flops_per_launch": flops,
+                "kernel": "nmpc_solve_kernel<PmpcAxis,16,15>", "algorithmic_flops_per_launch": flops,
                 "mean_iters": iters_sum / B, "note": "latency-bound: 1152 instances occupy a fraction of the SMs; see "
                                                       "throughput_variant for the filled-GPU figure"}
 
