@@ -85,12 +85,13 @@ struct Workspace {
     // per-stage strides (in doubles) of the arrays that lanes index by stage: odd, so that lanes working on
     // consecutive stages hit distinct shared-memory banks (16 banks of 8 bytes)
     static constexpr int sA = npa | 1, sB = npb | 1, sH = nys | 1, sG = ny | 1, sK = (m * n) | 1;
+    static constexpr int sM = ny | 1;     // column stride of the stage-matrix scratch MM (column-lanes store/load it)
     double *X, *U, *A, *Bm, *D, *LAM, *PP, *PV, *K, *KFF, *DX, *DU, *BL;
     double *S, *ZL, *ZU, *ISL, *ISU, *RC, *DS, *MM, *TANU, *HS, *GR, *REF;
 
     DART_HD static int doubles(int N) {
         return (N + 1) * n + N * m + N * sA + N * sB + N * n + N * n + (N + 1) * nps + (N + 1) * n + N * sK + N * m +
-               (N + 1) * n + N * m + N * m + 7 * N * nr + ny * nc + N * m + N * sH + N * sG + M::ref_doubles(N);
+               (N + 1) * n + N * m + N * m + 7 * N * nr + sM * nc + N * m + N * sH + N * sG + M::ref_doubles(N);
     }
     DART_HD void bind(double* p, int N) {
         X = p;   p += (N + 1) * n;
@@ -113,7 +114,7 @@ struct Workspace {
         ISU = p; p += N * nr;
         RC = p;  p += N * nr;
         DS = p;  p += N * nr;
-        MM = p;  p += ny * nc;
+        MM = p;  p += sM * nc;
         TANU = p; p += N * m;
         HS = p;  p += N * sH;
         GR = p;  p += N * sG;
@@ -140,7 +141,7 @@ struct Solver {
         : tile(t), prm(p), o(oo), N(NC > 0 ? NC : NN), w(ww), bc(b) {}
 
     static constexpr int npa = W::npa, npb = W::npb, nps = W::nps, nys = W::nys;
-    static constexpr int sA = W::sA, sB = W::sB, sH = W::sH, sG = W::sG, sK = W::sK;
+    static constexpr int sA = W::sA, sB = W::sB, sH = W::sH, sG = W::sG, sK = W::sK, sM = W::sM;
     // packed upper-triangular index of a symmetric d x d matrix
     DART_HD static constexpr int sidx(int i, int j, int d) {
         return i <= j ? i * d - i * (i - 1) / 2 + (j - i) : j * d - j * (j - 1) / 2 + (i - j);
@@ -420,7 +421,7 @@ struct Solver {
                         DART_UNROLL for (int a = 0; a < np; ++a) acc += w.Bm[k * sB + a * m + (i - n)] * ww[a];
                         if (M::NAUG > 0) acc += ww[np + (i - n)];
                     }
-                    w.MM[c * ny + i] = acc;
+                    w.MM[c * sM + i] = acc;
                 }
             }
             tl.sync();
@@ -430,14 +431,14 @@ struct Solver {
             for (int tries = 0; tries < 40; ++tries) {
                 DART_UNROLL for (int i = 0; i < m; ++i)
                     DART_UNROLL for (int j = 0; j < m; ++j)
-                        Lc[i * m + j] = w.MM[(n + j) * ny + n + i] + (i == j ? shift : 0.0);
+                        Lc[i * m + j] = w.MM[(n + j) * sM + n + i] + (i == j ? shift : 0.0);
                 if (chol(Lc)) break;
                 shift = (shift == 0.0) ? 1e-4 : shift * 8.0;
             }
             for (int c = lane; c < nc; c += G) {
                 if (c >= n && c < ny) continue;
                 double kt[m];
-                DART_UNROLL for (int j = 0; j < m; ++j) kt[j] = -w.MM[c * ny + n + j];
+                DART_UNROLL for (int j = 0; j < m; ++j) kt[j] = -w.MM[c * sM + n + j];
                 chol_solve(Lc, kt);
                 DART_UNROLL for (int j = 0; j < m; ++j) {
                     if (c < n) w.K[k * sK + j * n + c] = kt[j];
@@ -445,8 +446,8 @@ struct Solver {
                 }
                 if (k == 0) continue;            // P_0 / p_0 are never used (x_0 is fixed)
                 DART_UNROLL for (int i = 0; i < n; ++i) {
-                    double v = w.MM[c * ny + i];
-                    DART_UNROLL for (int j = 0; j < m; ++j) v += w.MM[i * ny + n + j] * kt[j];
+                    double v = w.MM[c * sM + i];
+                    DART_UNROLL for (int j = 0; j < m; ++j) v += w.MM[i * sM + n + j] * kt[j];
                     if (c < n) { if (i <= c) w.PP[k * nps + sidx(i, c, n)] = v; }
                     else w.PV[k * n + i] = v;
                 }
