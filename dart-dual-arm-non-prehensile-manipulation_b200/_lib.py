@@ -68,7 +68,7 @@ def lib():
     L.dart_policy_obs_push.argtypes = [C.c_int32, C.c_int32, vp, vp, vp, vp, C.c_int32, vp, vp, vp, vp, vp]
     L.dart_policy_param_update.argtypes = [C.c_int32, vp, vp, C.c_int32] + [C.c_double] * 5 + [vp]
     if hasattr(L, "dart_pmpc_plant_step"):
-        L.dart_pmpc_plant_step.argtypes = [C.c_int32, C.c_double, C.c_double] + [vp] * 5 + [C.c_int32, C.c_double] + [vp] * 3 + [vp]
+        L.dart_pmpc_plant_step.argtypes = [C.c_int32, C.c_double, C.c_double] + [vp] * 6 + [C.c_double] + [vp] * 3 + [vp]
     L.dart_measure_fp64_tflops.argtypes = [C.c_int, dp]
     _lib = L
     return L

@@ -11,10 +11,11 @@
 namespace {
 
 struct PlantArgs {
-    int B, step;
+    int B;
     double Ts, g, tol;
     const double *mu, *coulomb, *u, *target;
     double *state, *conv_time, *effort, *err;
+    int32_t* nsteps;     // per-instance step counter on the device: keeps the launch replayable from a CUDA graph
 };
 
 __device__ __forceinline__ void plant_f(const double* x, double sx, double sy, double vn, double g, double mu, double c,
@@ -38,7 +39,9 @@ __global__ void __launch_bounds__(128) pmpc_plant_step_kernel(const PlantArgs a)
     const double ex = x[0] - a.target[(size_t)b * 6 + 0], ey = x[2] - a.target[(size_t)b * 6 + 2];
     const double e = sqrt(ex * ex + ey * ey);
     a.err[b] = e;
-    if (a.conv_time[b] < 0.0 && e < a.tol) a.conv_time[b] = a.step * a.Ts;
+    const int32_t step = a.nsteps[b];
+    a.nsteps[b] = step + 1;
+    if (a.conv_time[b] < 0.0 && e < a.tol) a.conv_time[b] = step * a.Ts;
     a.effort[b] += sqrt(ux * ux + uy * uy) * a.Ts;
     // RK4, input held
     const double mu = a.mu[b], c = a.coulomb ? a.coulomb[b] : 0.0, Ts = a.Ts, g = a.g;
@@ -61,11 +64,11 @@ __global__ void __launch_bounds__(128) pmpc_plant_step_kernel(const PlantArgs a)
 }  // namespace
 
 extern "C" int dart_pmpc_plant_step(int32_t B, double Ts, double g, const double* mu, const double* coulomb, const double* u,
-                                    const double* target, double* state, int32_t step_index, double tol, double* conv_time,
+                                    const double* target, double* state, int32_t* nsteps, double tol, double* conv_time,
                                     double* effort, double* err, void* stream) {
-    if (B < 0 || !mu || !u || !target || !state || !conv_time || !effort || !err || !(Ts > 0.0)) return DART_ERR_ARG;
+    if (B < 0 || !mu || !u || !target || !state || !nsteps || !conv_time || !effort || !err || !(Ts > 0.0)) return DART_ERR_ARG;
     if (B == 0) return DART_OK;
-    PlantArgs a{B, step_index, Ts, g, tol, mu, coulomb, u, target, state, conv_time, effort, err};
+    PlantArgs a{B, Ts, g, tol, mu, coulomb, u, target, state, conv_time, effort, err, nsteps};
     pmpc_plant_step_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
     return cudaGetLastError() == cudaSuccess ? DART_OK : DART_ERR_CUDA;
 }

@@ -36,8 +36,10 @@ class PMPCEpisodes:
         self.conv_time = torch.full((self.B,), -1.0, dtype=f64, device=self.dev)
         self.effort = torch.zeros((self.B,), dtype=f64, device=self.dev)
         self.err = torch.zeros((self.B,), dtype=f64, device=self.dev)
+        self.nsteps = torch.zeros((self.B,), dtype=torch.int32, device=self.dev)
         self.tol = float(tol)
         self.step_index = 0
+        self._graph = None
         self.not_converged_solves = torch.zeros((), dtype=torch.int64, device=self.dev)
         self.iter_sum = torch.zeros((), dtype=torch.int64, device=self.dev)
 
@@ -50,20 +52,41 @@ class PMPCEpisodes:
         p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
         stream = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
         check(_lib.lib().dart_pmpc_plant_step(self.B, self.cfg.Ts, self.cfg.g, p(self.mu_plant), p(self.coulomb), p(self.u0),
-                                              p(self.target), p(self.state), self.step_index, self.tol, p(self.conv_time),
+                                              p(self.target), p(self.state), p(self.nsteps), self.tol, p(self.conv_time),
                                               p(self.effort), p(self.err), stream), "dart_pmpc_plant_step")
         self.step_index += 1
 
-    def run(self, steps, trace_every=0):
+    def run(self, steps, trace_every=0, graph=False):
         """Run ``steps`` simulated steps; returns the metrics dict (numpy).  ``trace_every`` > 0 records
-        (state, u0, J, iters) of instance 0 every that many steps (config 1's per-step solve trace)."""
+        (state, u0, J, iters) of instance 0 every that many steps (config 1's per-step solve trace).
+        ``graph=True`` captures one step (solve + plant + counters) in a CUDA graph after a warm-up step and replays
+        it: the closed loop is launch-bound at small batch (six launches per simulated step)."""
+        torch = self.torch
         trace = []
-        for k in range(steps):
-            if trace_every and k % trace_every == 0:
-                s0 = self.state[0].cpu().numpy().copy()
-            self.step()
-            if trace_every and k % trace_every == 0:
-                trace.append(np.concatenate([[k * self.cfg.Ts], s0, self.u0[0].cpu().numpy(), [float(self.J[0].item()), float(self.iters[0].item())]]))
+        k0 = 0
+        if graph and not trace_every and steps > 2:
+            if self._graph is None:
+                self.step()                               # warm-up: one real step outside the capture
+                k0 = 1
+                side = torch.cuda.Stream(device=self.dev)
+                side.wait_stream(torch.cuda.current_stream(self.dev))
+                with torch.cuda.stream(side):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=side):
+                        self.step()
+                    self.step_index -= 1                  # the capture itself executed nothing
+                torch.cuda.current_stream(self.dev).wait_stream(side)
+                self._graph = g
+            for k in range(k0, steps):
+                self._graph.replay()
+                self.step_index += 1
+        else:
+            for k in range(steps):
+                if trace_every and k % trace_every == 0:
+                    s0 = self.state[0].cpu().numpy().copy()
+                self.step()
+                if trace_every and k % trace_every == 0:
+                    trace.append(np.concatenate([[k * self.cfg.Ts], s0, self.u0[0].cpu().numpy(), [float(self.J[0].item()), float(self.iters[0].item())]]))
         self.torch.cuda.synchronize()
         T = self.step_index * self.cfg.Ts
         ct = self.conv_time.cpu().numpy()

@@ -172,9 +172,11 @@ int dart_policy_param_update(int32_t B, const float* action, double* pvec, int32
 /* Surrogate closed loop (no MuJoCo): one plant step of the PMPC model (mpc_3d.py:87-104, tilt held over Ts) with
  * per-instance viscous mu [B] and optional unmodelled Coulomb coefficient [B] (NULL = none), plus the episode
  * metrics of PMPC/src/logger.py:155-176 accumulated in place: err [B] = position error of the logged state,
- * conv_time [B] (initialise to -1) = first logged time with err < tol, effort [B] += |u| Ts.  Device pointers. */
+ * conv_time [B] (initialise to -1) = first logged time with err < tol, effort [B] += |u| Ts; nsteps [B] int32
+ * (initialise to 0) is the per-instance step counter, kept on the device so that the launch can be replayed from a
+ * CUDA graph.  Device pointers. */
 int dart_pmpc_plant_step(int32_t B, double Ts, double g, const double* mu, const double* coulomb, const double* u,
-                         const double* target, double* state, int32_t step_index, double tol, double* conv_time,
+                         const double* target, double* state, int32_t* nsteps, double tol, double* conv_time,
                          double* effort, double* err, void* stream);
 
 /* Measured FP64 FMA-pipe peak of the device in TFLOP/s (DFMA microbenchmark, CUDA-event timed): the roofline

@@ -55,3 +55,22 @@ def test_yaml_config_roundtrip():
     assert (c.N, c.Qp, c.R, c.Rdu, c.du_hi, c.vmax) == (20, 80.0, 0.02, 1.0, 0.06, 0.2)
     c = dart_b200.cfg_from_yaml("lmpc")
     assert list(c.Q)[:4] == [200.0, 2.0, 200.0, 2.0] and list(c.Rl) == [0.1, 0.1, 1.0, 1.0] and c.u_hi == 0.4
+
+
+def test_header_is_plain_c99(tmp_path):
+    """include/dart_b200.h is the boundary a C host binds: it must compile as C99 on its own, with no CUDA or C++."""
+    import subprocess
+    src = tmp_path / "use_header.c"
+    src.write_text("""
+#include "dart_b200.h"
+int use(void) {
+    dart_cfg cfg; dart_handle h = 0; double x[6] = {0}, r[6] = {0}, u[2], J[1]; int32_t st[1], it[1];
+    if (dart_default_cfg(DART_PMPC, &cfg) != DART_OK) return 1;
+    if (dart_create(&h, &cfg, 0) != DART_OK) return 2;
+    if (dart_solve_host(h, 1, x, r, 0, 0, 0, u, J, st, it) != DART_OK) return 3;
+    return dart_destroy(h);
+}
+""")
+    r = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr

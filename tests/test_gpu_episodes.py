@@ -39,3 +39,16 @@ def test_config1_episode_settles(built):
     assert tr.shape[1] == 11 and np.all(np.abs(tr[:, 7:9]) <= 0.6 + 1e-12)
     err = np.hypot(tr[:, 1] - 0.1, tr[:, 3] - 0.05)
     assert err[-1] < err[0] * 0.1
+
+
+def test_graph_replay_equals_eager(built):
+    """One closed-loop step captured in a CUDA graph and replayed gives bit-identical episodes."""
+    c, aux, _ = helpers.pmpc_case(2)
+    a = dart_b200.PMPCEpisodes(c["state"], c["target"], aux, device=0)
+    b = dart_b200.PMPCEpisodes(c["state"], c["target"], aux, device=0)
+    ma = a.run(60)
+    mb = b.run(60, graph=True)
+    assert np.array_equal(a.state.cpu().numpy(), b.state.cpu().numpy())
+    assert np.array_equal(ma["control_effort"], mb["control_effort"]) and np.array_equal(ma["convergence_time"], mb["convergence_time"])
+    assert ma["mean_iters"] == mb["mean_iters"] and mb["not_converged_solves"] == 0
+    assert (b.nsteps.cpu().numpy() == 60).all()

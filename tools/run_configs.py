@@ -32,7 +32,7 @@ def config2_closed_loop(steps):
     rng = np.random.default_rng(21)
     ep = dart_b200.PMPCEpisodes(c["state"], c["target"], aux, coulomb=rng.uniform(0, 0.02, aux.shape[0]), device=LOCAL)
     a, b = ev(), ev()
-    a.record(); m = ep.run(steps); b.record(); torch.cuda.synchronize()
+    a.record(); m = ep.run(steps, graph=GRAPH); b.record(); torch.cuda.synchronize()
     sec = a.elapsed_time(b) * 1e-3
     per_obj = []
     objs = dart_b200.workloads.pmpc_objects()
@@ -42,7 +42,7 @@ def config2_closed_loop(steps):
                             convergence_time_s=float(np.median(m["convergence_time"][sl])),
                             steady_state_error_mm=float(np.median(m["steady_state_error"][sl]) * 1e3),
                             control_effort=float(np.median(m["control_effort"][sl]))))
-    return dict(config="2 (closed loop): 18 objects x 64 states, surrogate plant with unmodelled Coulomb term", steps=steps,
+    return dict(config="2 (closed loop): 18 objects x 64 states, surrogate plant with unmodelled Coulomb term", steps=steps, cuda_graph=GRAPH,
                 sim_time_s=m["sim_time"], solves=m["solves"], seconds=sec, solves_per_s=m["solves"] / sec,
                 mean_iters=m["mean_iters"], not_converged_solves=m["not_converged_solves"], per_object=per_obj)
 
@@ -150,7 +150,7 @@ def config5(total):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--quick", action="store_true"); ap.add_argument("--out", default=None); ap.add_argument("--only", default=None)
+    ap.add_argument("--quick", action="store_true"); ap.add_argument("--graph", action="store_true"); ap.add_argument("--out", default=None); ap.add_argument("--only", default=None)
     args = ap.parse_args()
     WORLD = int(os.environ.get("WORLD_SIZE", "1")); RANK = int(os.environ.get("RANK", "0")); LOCAL = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(LOCAL)
@@ -159,6 +159,7 @@ if __name__ == "__main__":
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", LOCAL))
     q = args.quick
+    GRAPH = args.graph
     res = []
     todo = [args.only] if args.only else ["config1", "config2", "config3", "config4", "config5"]
     for name in todo:
