@@ -103,6 +103,8 @@ extern "C" int dart_solve(dart_handle h, int32_t B, const double* x0, const doub
     if (h->cfg.method != DART_PMPC && !aux) return DART_ERR_ARG;
     if (B == 0) return DART_OK;
     if (h->rows && B > h->rows_cap) return DART_ERR_ARG;       // the registered result-row buffer is too small
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess || cur != h->device) return DART_ERR_ARG;   // launch from the handle's device
     KArgs a;
     a.B = B; a.N = h->cfg.N; a.o = h->opts; a.cfg = h->cfg;
     a.x0 = x0; a.ref = ref; a.aux = aux; a.warm = warm_w;

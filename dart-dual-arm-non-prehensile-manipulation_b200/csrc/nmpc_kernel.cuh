@@ -106,13 +106,14 @@ static int launch_n(const KArgs& a, int block_threads, cudaStream_t st, LaunchIn
     while (T > 1 && (ws_stride % 16) != want) ++ws_stride;
     int bt = block_threads > 0 ? block_threads : 0;
     const int unit = G * M::NAXIS;                       // lanes per instance
-    // device limits and the kernel's opt-in shared-memory size are cached: per-launch driver queries cost microseconds
-    static int max_smem = 0;
-    if (max_smem == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    }
+    // device limits and the kernel's opt-in shared-memory size are cached PER DEVICE (a process may hold handles on
+    // several GPUs): per-launch driver queries cost microseconds
+    constexpr int kMaxDev = 64;
+    static int max_smem_dev[kMaxDev] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) return DART_ERR_CUDA;
+    if (max_smem_dev[dev] == 0) cudaDeviceGetAttribute(&max_smem_dev[dev], cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    const int max_smem = max_smem_dev[dev];
     if (bt == 0) {
         // measured on B200 (tools/sweep.py): few problems -> 4 warps per block; a filled GPU -> one warp per
         // block, so shared memory (the occupancy limiter) packs at warp granularity.
@@ -127,10 +128,10 @@ static int launch_n(const KArgs& a, int block_threads, cudaStream_t st, LaunchIn
     while (smem > (size_t)max_smem && bt > 32) { bt -= 32; tpb = bt / G; smem = (size_t)tpb * ws_stride * sizeof(double); }
     if (smem > (size_t)max_smem) return DART_ERR_UNSUPPORTED;
     auto kern = nmpc_solve_kernel<M, G, NC>;
-    static size_t smem_set = 0;          // per instantiation
-    if (smem > smem_set) {
+    static size_t smem_set[kMaxDev] = {0};          // per instantiation and device
+    if (smem > smem_set[dev]) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return DART_ERR_CUDA;
-        smem_set = smem;
+        smem_set[dev] = smem;
     }
     const long probs = (long)a.B * M::NAXIS;
     const int grid = (int)((probs + tpb - 1) / tpb);

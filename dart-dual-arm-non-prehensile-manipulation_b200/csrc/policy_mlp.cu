@@ -379,6 +379,8 @@ struct dart_policy {
     int64_t launches;
 };
 
+extern "C" int dart_policy_destroy(dart_policy_handle h);
+
 extern "C" int dart_policy_create(dart_policy_handle* out, int device, int32_t obs_dim, int32_t hidden, int32_t act_dim,
                                   const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
                                   const float* b3) {
@@ -397,17 +399,22 @@ extern "C" int dart_policy_create(dart_policy_handle* out, int device, int32_t o
     const size_t cap[6] = {n[0], n[1], n[2], n[3], (size_t)N3 * HID, n[5]};   // W3 zero-padded to 48 rows
     const float* src[6] = {W1, b1, W2, b2, W3, b3};
     float** dst[6] = {&h->W1, &h->b1, &h->W2, &h->b2, &h->W3, &h->b3};
-    for (int i = 0; i < 6; ++i) {
-        if (cudaMalloc(dst[i], cap[i] * sizeof(float)) != cudaSuccess) return DART_ERR_ALLOC;
-        if (cudaMemset(*dst[i], 0, cap[i] * sizeof(float)) != cudaSuccess) return DART_ERR_CUDA;
-        if (cudaMemcpy(*dst[i], src[i], n[i] * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return DART_ERR_CUDA;
+    int rc = DART_OK;
+    for (int i = 0; i < 6 && rc == DART_OK; ++i) {
+        if (cudaMalloc(dst[i], cap[i] * sizeof(float)) != cudaSuccess) { *dst[i] = nullptr; rc = DART_ERR_ALLOC; break; }
+        if (cudaMemset(*dst[i], 0, cap[i] * sizeof(float)) != cudaSuccess ||
+            cudaMemcpy(*dst[i], src[i], n[i] * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess)
+            rc = DART_ERR_CUDA;
     }
-    if (make_map(&h->tm_w1, h->W1, HID, OBS, HID) || make_map(&h->tm_w2, h->W2, HID, HID, HID) ||
-        make_map(&h->tm_w3, h->W3, N3, HID, N3))
-        return DART_ERR_CUDA;
+    if (rc == DART_OK && (make_map(&h->tm_w1, h->W1, HID, OBS, HID) || make_map(&h->tm_w2, h->W2, HID, HID, HID) ||
+                          make_map(&h->tm_w3, h->W3, N3, HID, N3)))
+        rc = DART_ERR_CUDA;
+    if (rc != DART_OK) { dart_policy_destroy(h); return rc; }
     if (cudaFuncSetAttribute(policy_mlp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<2>::BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(policy_mlp_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<4>::BYTES) != cudaSuccess)
+        cudaFuncSetAttribute(policy_mlp_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<4>::BYTES) != cudaSuccess) {
+        dart_policy_destroy(h);
         return DART_ERR_CUDA;
+    }
     *out = h;
     return DART_OK;
 }

@@ -143,7 +143,6 @@ class RMPCBatch:
         self.target = t(target)
         self.prev_state = t(x_init)
         self.r_v = torch.zeros((B, 4), dtype=f64, device=self.dev)
-        self.r_v[:, 0] = 0.0
         self.u_prev = torch.zeros((B, 2), dtype=f64, device=self.dev)
         self.theta = torch.zeros((B, 2, 7), dtype=f64, device=self.dev)
         self.P = (torch.eye(7, dtype=f64, device=self.dev) * float(rls_P0)).repeat(B, 2, 1, 1).contiguous()

@@ -99,7 +99,8 @@ int dart_nw(dart_handle h);    /* decision vector size (N+1)*nx + N*2, reference
  *   u0_out  [B, 2]     first tilt command U_opt[0]
  *   J_out   [B]        optimal objective (reference's sol['f'])
  *   status  [B] int32  DART_STATUS_*            iters [B] int32 Newton iterations; either may be NULL
- * Asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default stream). */
+ * Asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default stream).  The calling thread's current
+ * CUDA device must be the handle's device (DART_ERR_ARG otherwise). */
 int dart_solve(dart_handle h, int32_t B, const double* x0, const double* ref, const double* aux,
                const double* warm_w, double* w_out, double* u0_out, double* J_out, int32_t* status,
                int32_t* iters, void* stream);

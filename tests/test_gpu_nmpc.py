@@ -227,3 +227,27 @@ def test_pmpc_class_is_a_dropin(built):
     u0, loss = ctl.solve(np.array([0.1, 0, 0.05, 0, 0.4, 0]))
     assert u0.shape == (2,) and loss.shape == (1,) and ctl.w0.shape == (126,) and ctl.g == -9.81 and ctl.status == 0
     assert np.array_equal(ctl.w0[96:98], u0) and np.all(u0 < 0)        # g < 0: +x / +y motion needs negative tilt
+
+
+def test_two_devices_in_one_process(built):
+    """Handles on different GPUs of one process (kernel attributes are cached per device); wrong current device is refused."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    c, aux, p = helpers.pmpc_case(2)
+    outs = []
+    for dev in (0, 1):
+        torch.cuda.set_device(dev)
+        eng = dart_b200.NMPCEngine(dart_b200.pmpc_cfg(), device=dev)
+        outs.append(eng.solve(c["state"], c["target"], aux=aux, want_w=False))
+        d = torch.device("cuda", dev)
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(d)
+        o = eng.solve_device(t(c["state"]), t(c["target"]), aux=t(aux))
+        torch.cuda.synchronize(d)
+        assert np.array_equal(o["u0"].cpu().numpy(), outs[-1]["u0"])
+        if dev == 1:
+            torch.cuda.set_device(0)
+            with pytest.raises(dart_b200.DartError):
+                eng.solve_device(t(c["state"]), t(c["target"]), aux=t(aux))
+    torch.cuda.set_device(0)
+    assert np.array_equal(outs[0]["u0"], outs[1]["u0"]) and np.array_equal(outs[0]["J"], outs[1]["J"])
