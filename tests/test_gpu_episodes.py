@@ -52,3 +52,14 @@ def test_graph_replay_equals_eager(built):
     assert np.array_equal(ma["control_effort"], mb["control_effort"]) and np.array_equal(ma["convergence_time"], mb["convergence_time"])
     assert ma["mean_iters"] == mb["mean_iters"] and mb["not_converged_solves"] == 0
     assert (b.nsteps.cpu().numpy() == 60).all()
+
+
+def test_reference_main_loop_example(built):
+    """examples/pmpc_main_surrogate.py: the reference's main.py loop with the drop-in class settles the object."""
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("ex", os.path.join(helpers.ROOT, "examples", "pmpc_main_surrogate.py"))
+    ex = importlib.util.module_from_spec(spec); spec.loader.exec_module(ex)
+    log = ex.run([0.1, 0.0, 0.05, 0.0, 0.0, 0.0], friction=0.1, steps=900, verbose=False)
+    assert (log[:, 6] == 0).all()                   # every solve converged
+    assert log[-1, 1] < 0.01 and log[0, 1] > 0.1    # 11 cm -> under 1 cm
+    assert np.abs(log[:, 2:4]).max() <= 0.6 + 1e-12
