@@ -9,6 +9,7 @@ namespace dart {
 
 template <int G>
 struct DevTile {
+    static constexpr int kLanes = G;
     unsigned mask;
     int ln;
     __device__ __forceinline__ DevTile() {

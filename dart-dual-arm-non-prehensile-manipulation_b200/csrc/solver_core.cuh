@@ -35,6 +35,18 @@
 #define DART_UNROLL_N(k)
 #endif
 
+#ifdef DART_PHASE_CLOCK
+#include <cstdio>
+#ifndef DART_PHASE_CLOCK_BLOCK
+#define DART_PHASE_CLOCK_BLOCK (blockIdx.x == 0)
+#endif
+#ifdef __CUDA_ARCH__
+#define DART_CLOCK() clock64()
+#else
+#define DART_CLOCK() 0LL
+#endif
+#endif
+
 namespace dart {
 
 enum Status : int32_t { ST_CONVERGED = 0, ST_MAXITER = 1, ST_INFEASIBLE = 2, ST_NUMERIC = 3 };
@@ -60,6 +72,7 @@ struct BlockCtx {
 
 // Host stand-in for a tile of one lane (and a block of one problem).
 struct HostTile {
+    static constexpr int kLanes = 1;
     DART_HD int lane() const { return 0; }
     DART_HD int size() const { return 1; }
     DART_HD void sync() const {}
@@ -72,6 +85,7 @@ struct HostTile {
 
 // Every lane runs the whole loop redundantly (same values, same addresses): no exchange, no syncs.
 struct SerialTile {
+    static constexpr int kLanes = 1;
     DART_HD int lane() const { return 0; }
     DART_HD int size() const { return 1; }
     DART_HD void sync() const {}
@@ -85,13 +99,17 @@ struct Workspace {
     // per-stage strides (in doubles) of the arrays that lanes index by stage: odd, so that lanes working on
     // consecutive stages hit distinct shared-memory banks (16 banks of 8 bytes)
     static constexpr int sA = npa | 1, sB = npb | 1, sH = nys | 1, sG = ny | 1, sK = (m * n) | 1;
-    static constexpr int sM = ny | 1;     // column stride of the stage-matrix scratch MM (column-lanes store/load it)
+    static constexpr int sM = ny | 1;
+    // stage scratch MM of the tiled Riccati sweep: W = P [A B d] over the nq = np + m variables with computed
+    // curvature (+ gradient column), then the packed upper triangle of the stage matrix (+ gradient column)
+    static constexpr int nq = np + m, nW = n * (nq + 1), nMq = nq * (nq + 1) / 2 + nq;
+    static constexpr int nscr = M::SERIAL_RICCATI ? sM * (ny + 1) : nW + nMq;
     double *X, *U, *A, *Bm, *D, *LAM, *PP, *PV, *K, *KFF, *DX, *DU, *BL;
     double *S, *ZL, *ZU, *ISL, *ISU, *RC, *DS, *MM, *TANU, *HS, *GR, *REF;
 
     DART_HD static int doubles(int N) {
         return (N + 1) * n + N * m + N * sA + N * sB + N * n + N * n + (N + 1) * nps + (N + 1) * n + N * sK + N * m +
-               (N + 1) * n + N * m + N * m + 7 * N * nr + sM * nc + N * m + N * sH + N * sG + M::ref_doubles(N);
+               (N + 1) * n + N * m + N * m + 7 * N * nr + nscr + N * m + N * sH + N * sG + M::ref_doubles(N);
     }
     DART_HD void bind(double* p, int N) {
         X = p;   p += (N + 1) * n;
@@ -114,7 +132,7 @@ struct Workspace {
         ISU = p; p += N * nr;
         RC = p;  p += N * nr;
         DS = p;  p += N * nr;
-        MM = p;  p += sM * nc;
+        MM = p;  p += nscr;
         TANU = p; p += N * m;
         HS = p;  p += N * sH;
         GR = p;  p += N * sG;
@@ -386,11 +404,38 @@ struct Solver {
         tile.sync();
     }
 
-    // ---- Riccati backward sweep; lanes of `tl` own columns of [A B d].  With a SerialTile every lane runs
-    // all columns itself (no exchange, no syncs) -- the faster choice for the 2-state problems.
+    // ---- Riccati backward sweep, one matrix ELEMENT per lane.  Each stage is three rounds separated by tile syncs:
+    //   1. W = P_{k+1} [A B d] + [0 0 p_{k+1}]            n x (nq+1) elements
+    //   2. M = [H g] + [A B]^T W  (upper triangle + g)     nq(nq+1)/2 + nq elements
+    //   3. pivot inverse, gains K, P_k = Mxx + Mxu K       n(n+1)/2 + n elements
+    // with nq = np + m: rows/columns of carried-input states are structural (A = 0, B = I), so their entries of M are
+    // those of [H g] and are read from there.  What a lane reads depends only on its element, not on the stage: the
+    // gather offsets (relative to w.X; the workspace is one allocation) are decoded once, before the stage loop, so the
+    // loop itself is branch-free loads, a short FMA chain and one store per round.
+    struct Gat {
+        int off, ks;                                    // element of stage k: w.X[off + k * ks]
+    };
+    DART_HD int offs(const double* q) const { return (int)(q - w.X); }
+    DART_HD static void tri_decode(int e, int d, int& i, int& c) {   // inverse of sidx(i, c, d) for i <= c
+        i = 0;
+        while (e >= d - i) { e -= d - i; ++i; }
+        c = i + e;
+    }
     template <class TL>
     DART_HD void backward(const TL& tl) {
-        const int lane = tl.lane(), G = tl.size();
+        constexpr int G = TL::kLanes;
+        constexpr int nq = W::nq, ncw = nq + 1, ntri = nq * (nq + 1) / 2;
+        constexpr int nW = W::nW, nM = W::nMq, nPt = n * (n + 1) / 2, nP = nPt + n;
+        constexpr int PW = (nW + G - 1) / G, PM = (nM + G - 1) / G, PQ = (nP + G - 1) / G;
+        constexpr int NZ = (M::NAUG > 0) ? M::NAUG : 1;
+        const int lane = tl.lane();
+        double* const base = w.X;
+        double* const WW = w.MM;
+        double* const MQ = w.MM + nW;
+        const int oA = offs(w.A), oB = offs(w.Bm), oD = offs(w.D), oH = offs(w.HS), oG = offs(w.GR), oMQ = offs(MQ);
+        const int oPP = offs(w.PP), oPV = offs(w.PV), oK = offs(w.K), oKF = offs(w.KFF);
+
+        // terminal value function
         for (int c = lane; c <= n; c += G) {
             if (c < n) {
                 DART_UNROLL for (int i = 0; i < n; ++i)
@@ -400,56 +445,117 @@ struct Solver {
                     w.PV[N * n + i] = 2.0 * M::wT(prm, i) * (w.X[N * n + i] - M::rT(prm, w.REF, N, i));
             }
         }
+
+        // ---- round 1 gathers: element (a, cw), cw < np: state column, cw < nq: input column, cw == nq: d/p column
+        struct DW { int pP[n]; int tOff, tRs, tKs, pv; double ez[NZ]; bool isg, act; };
+        DW dw[PW];
+        DART_UNROLL for (int ps = 0; ps < PW; ++ps) {
+            DW& d = dw[ps];
+            const int e = lane + ps * G;
+            d.act = e < nW;
+            const int ee = d.act ? e : 0;
+            const int a = ee / ncw, cw = ee % ncw;
+            DART_UNROLL for (int b = 0; b < n; ++b) d.pP[b] = oPP + nps + sidx(a, b, n);
+            d.pv = oPV + n + a;
+            d.isg = cw == nq;
+            DART_UNROLL for (int z = 0; z < NZ; ++z) d.ez[z] = (M::NAUG > 0 && cw >= np && cw < nq && cw - np == z) ? 1.0 : 0.0;
+            if (cw < np) { d.tOff = oA + cw; d.tRs = np; d.tKs = sA; }
+            else if (cw < nq) { d.tOff = oB + (cw - np); d.tRs = m; d.tKs = sB; }
+            else { d.tOff = oD; d.tRs = 1; d.tKs = n; }
+        }
+        // ---- round 2 gathers: element (iq, cq) of the upper triangle over the nq active variables, or (iq, g)
+        struct DM { int tOff, tRs, tKs, hOff, hKs, cw, augOff; double augOn; bool act; };
+        DM dm[PM];
+        DART_UNROLL for (int ps = 0; ps < PM; ++ps) {
+            DM& d = dm[ps];
+            const int e = lane + ps * G;
+            d.act = e < nM;
+            const int ee = d.act ? e : 0;
+            int iq, cq;
+            if (ee < ntri) tri_decode(ee, nq, iq, cq); else { iq = ee - ntri; cq = nq; }
+            const int fi = iq < np ? iq : n + (iq - np);              // index among the ny stage variables
+            d.cw = cq;
+            if (iq < np) { d.tOff = oA + iq; d.tRs = np; d.tKs = sA; }
+            else { d.tOff = oB + (iq - np); d.tRs = m; d.tKs = sB; }
+            if (cq < nq) { const int fc = cq < np ? cq : n + (cq - np); d.hOff = oH + sidx(fi, fc, ny); d.hKs = sH; }
+            else { d.hOff = oG + fi; d.hKs = sG; }
+            const bool aug = M::NAUG > 0 && iq >= np;                 // input row: + W[np + j][.] (B = I on carried inputs)
+            d.augOn = aug ? 1.0 : 0.0;
+            d.augOff = (aug ? (np + (iq - np)) * ncw : 0) + cq;
+        }
+        // ---- round 3 gathers: element (i, c) of the upper triangle of P_k, or p_k[i]
+        struct DQ { Gat mu[m], mic, miu[m], st; int kOff, kJs, kKs; bool storeK, act; };
+        DQ dq[PQ];
+        DART_UNROLL for (int ps = 0; ps < PQ; ++ps) {
+            DQ& d = dq[ps];
+            const int e = lane + ps * G;
+            d.act = e < nP;
+            const int ee = d.act ? e : 0;
+            int i, c;
+            if (ee < nPt) tri_decode(ee, n, i, c); else { i = ee - nPt; c = n; }
+            DART_UNROLL for (int j = 0; j < m; ++j) {
+                // M[u_j][c]
+                if (c == n) d.mu[j] = Gat{oMQ + ntri + np + j, 0};
+                else if (c < np) d.mu[j] = Gat{oMQ + sidx(c, np + j, nq), 0};
+                else d.mu[j] = Gat{oH + sidx(c, n + j, ny), sH};
+                // M[i][u_j]
+                if (i < np) d.miu[j] = Gat{oMQ + sidx(i, np + j, nq), 0};
+                else d.miu[j] = Gat{oH + sidx(i, n + j, ny), sH};
+            }
+            if (c == n) d.mic = (i < np) ? Gat{oMQ + ntri + i, 0} : Gat{oG + i, sG};
+            else d.mic = (i < np && c < np) ? Gat{oMQ + sidx(i, c, nq), 0} : Gat{oH + sidx(i, c, ny), sH};
+            d.st = (c == n) ? Gat{oPV + i, n} : Gat{oPP + sidx(i, c, n), nps};
+            d.storeK = d.act && i == 0;
+            if (c == n) { d.kOff = oKF; d.kJs = 1; d.kKs = m; }
+            else { d.kOff = oK + c; d.kJs = n; d.kKs = sK; }
+        }
         tl.sync();
+
         for (int k = N - 1; k >= 0; --k) {
-            const double* pn = w.PV + (k + 1) * n;
-            for (int c = lane; c < nc; c += G) {
-                double t[n], ww[n];
-                DART_UNROLL for (int a = 0; a < n; ++a)
-                    t[a] = (c < n) ? Aat(k, a, c) : (c < ny ? Bat(k, a, c - n) : w.D[k * n + a]);
-                DART_UNROLL for (int a = 0; a < n; ++a) {
-                    double acc = (c == nc - 1) ? pn[a] : 0.0;
-                    DART_UNROLL for (int b = 0; b < n; ++b) acc += Pat(k + 1, a, b) * t[b];
-                    ww[a] = acc;
-                }
-                DART_UNROLL for (int i = 0; i < ny; ++i) {
-                    double acc = (c < ny) ? Hat(k, i, c) : w.GR[k * sG + i];
-                    if (i < n) {
-                        DART_UNROLL for (int a = 0; a < np; ++a)
-                            if (i < np) acc += w.A[k * sA + a * np + i] * ww[a];
-                    } else {
-                        DART_UNROLL for (int a = 0; a < np; ++a) acc += w.Bm[k * sB + a * m + (i - n)] * ww[a];
-                        if (M::NAUG > 0) acc += ww[np + (i - n)];
+            DART_UNROLL for (int ps = 0; ps < PW; ++ps) {
+                const DW& d = dw[ps];
+                double acc = base[d.pv + k * n];
+                acc = d.isg ? acc : 0.0;
+                DART_UNROLL for (int t = 0; t < np; ++t)
+                    acc += base[d.pP[t] + k * nps] * base[d.tOff + t * d.tRs + k * d.tKs];
+                if (M::NAUG > 0) {
+                    DART_UNROLL for (int z = 0; z < M::NAUG; ++z) {
+                        const double dz = w.D[k * n + np + z];
+                        acc += base[d.pP[np + z] + k * nps] * (d.isg ? dz : d.ez[z]);
                     }
-                    w.MM[c * sM + i] = acc;
                 }
+                if (d.act) WW[lane + ps * G] = acc;
             }
             tl.sync();
-            // every lane factors the same m x m block H = M[n.., n..] (+ escalating shift if not PD)
+            DART_UNROLL for (int ps = 0; ps < PM; ++ps) {
+                const DM& d = dm[ps];
+                double acc = base[d.hOff + k * d.hKs];
+                DART_UNROLL for (int a = 0; a < np; ++a)
+                    acc += base[d.tOff + a * d.tRs + k * d.tKs] * WW[a * ncw + d.cw];
+                if (M::NAUG > 0) acc += d.augOn * WW[d.augOff];
+                if (d.act) MQ[lane + ps * G] = acc;
+            }
+            tl.sync();
+            // every lane inverts the same m x m pivot block (+ escalating shift if it is not positive definite)
             double Lc[m * m];
             double shift = 0.0;
             for (int tries = 0; tries < 40; ++tries) {
                 DART_UNROLL for (int i = 0; i < m; ++i)
                     DART_UNROLL for (int j = 0; j < m; ++j)
-                        Lc[i * m + j] = w.MM[(n + j) * sM + n + i] + (i == j ? shift : 0.0);
+                        Lc[i * m + j] = MQ[sidx(np + i, np + j, nq)] + (i == j ? shift : 0.0);
                 if (chol(Lc)) break;
                 shift = (shift == 0.0) ? 1e-4 : shift * 8.0;
             }
-            for (int c = lane; c < nc; c += G) {
-                if (c >= n && c < ny) continue;
+            DART_UNROLL for (int ps = 0; ps < PQ; ++ps) {
+                const DQ& d = dq[ps];
                 double kt[m];
-                DART_UNROLL for (int j = 0; j < m; ++j) kt[j] = -w.MM[c * sM + n + j];
+                DART_UNROLL for (int j = 0; j < m; ++j) kt[j] = -base[d.mu[j].off + k * d.mu[j].ks];
                 chol_solve(Lc, kt);
-                DART_UNROLL for (int j = 0; j < m; ++j) {
-                    if (c < n) w.K[k * sK + j * n + c] = kt[j];
-                    else w.KFF[k * m + j] = kt[j];
-                }
-                if (k == 0) continue;            // P_0 / p_0 are never used (x_0 is fixed)
-                DART_UNROLL for (int i = 0; i < n; ++i) {
-                    double v = w.MM[c * sM + i];
-                    DART_UNROLL for (int j = 0; j < m; ++j) v += w.MM[i * sM + n + j] * kt[j];
-                    if (c < n) { if (i <= c) w.PP[k * nps + sidx(i, c, n)] = v; }
-                    else w.PV[k * n + i] = v;
+                if (d.storeK) { DART_UNROLL for (int j = 0; j < m; ++j) base[d.kOff + j * d.kJs + k * d.kKs] = kt[j]; }
+                if (k > 0) {                         // P_0 / p_0 are never used (x_0 is fixed)
+                    double v = base[d.mic.off + k * d.mic.ks];
+                    DART_UNROLL for (int j = 0; j < m; ++j) v += base[d.miu[j].off + k * d.miu[j].ks] * kt[j];
+                    if (d.act) base[d.st.off + k * d.st.ks] = v;
                 }
             }
             tl.sync();
@@ -724,6 +830,12 @@ struct Solver {
         double E0 = 0.0, is_d = 1.0, is_c = 1.0;
         bool done = !active;
         double* myslot = bc.base + (size_t)(bc.tid / tile.size()) * bc.stride;
+#ifdef DART_PHASE_CLOCK
+        long long ckA = 0, ckB = 0, ckC = 0, ckBb = 0, ckC1 = 0, ckC2 = 0, ckA1 = 0, ckW1 = 0, ckW2 = 0, ck0 = DART_CLOCK();
+#define DART_CK(acc) { long long t_ = DART_CLOCK(); acc += t_ - ck0; ck0 = t_; }
+#else
+#define DART_CK(acc)
+#endif
         for (;;) {
             // ---------------- phase A
             bool need_sweep = false;
@@ -744,29 +856,47 @@ struct Solver {
                             mu = dmax(mu_min, dmin(o.kappa_mu * mu, (o.theta_mu == 1.5) ? mu * sqrt(mu) : pow(mu, o.theta_mu)));
                         else break;
                     }
+                    DART_CK(ckA1)
                     prep(mu);
                     if (!M::SERIAL_RICCATI) backward(tile);
                     need_sweep = true;
                 }
             }
-            if (tile.lane() == 0) myslot[0] = need_sweep ? 1.0 : 0.0;
-            if (!tile.block_any(need_sweep)) break;        // barrier + vote: phase-A writes are visible past this point
-            // ---------------- phase B: thread q sweeps problem q
-            if (bc.tid < bc.nprob) {
-                double* sl = bc.base + (size_t)bc.tid * bc.stride;
-                if (sl[0] != 0.0) {
-                    W wk;
-                    wk.bind(sl + kSlot, N);
-                    Solver other(tile, prm, o, N, wk, bc);
-                    if (M::SERIAL_RICCATI) other.backward_serial();
-                    other.forward();
+            if (M::SERIAL_RICCATI) {
+                if (tile.lane() == 0) myslot[0] = need_sweep ? 1.0 : 0.0;
+                DART_CK(ckA)
+                const bool any_ = tile.block_any(need_sweep);   // barrier + vote: phase-A writes are visible past this point
+                DART_CK(ckW1)
+                if (!any_) break;
+                // ---------------- phase B: thread q sweeps problem q
+                if (bc.tid < bc.nprob) {
+                    double* sl = bc.base + (size_t)bc.tid * bc.stride;
+                    if (sl[0] != 0.0) {
+                        W wk;
+                        wk.bind(sl + kSlot, N);
+                        Solver other(tile, prm, o, N, wk, bc);
+                        other.backward_serial();
+                        DART_CK(ckBb)
+                        other.forward();
+                    }
                 }
+                DART_CK(ckB)
+                tile.block_sync();
+                DART_CK(ckW2)
+                if (!need_sweep) continue;
+            } else {
+                // larger models: the tile swept backwards itself; its problems are independent of the rest of the block,
+                // so no block barrier -- one lane runs the short forward recurrence
+                DART_CK(ckA)
+                if (!need_sweep) break;
+                if (tile.lane() == 0) forward();
+                tile.sync();
+                DART_CK(ckB)
             }
-            tile.block_sync();
-            if (!need_sweep) continue;
             // ---------------- phase C
             double ap, ad, dphi;
             post(mu, ap, ad, dphi);
+            DART_CK(ckC1)
             const double phi0 = f - mu * L, th0 = th;
             const double th_max = 1e4 * dmax(1.0, th0);
             double alpha = ap, applied = 0.0;
@@ -791,13 +921,24 @@ struct Solver {
 #ifdef DART_TRACE
             printf("it %d mu %.3e E0 %.3e dinf %.3e pinf %.3e zsmax %.3e ap %.4f ad %.4f alpha %.5f dphi %.3e th0 %.3e f %.10g\n", it, mu, E0, dinf * is_d, pinf, zs_max * is_c, ap, ad, alpha, dphi, th0, f);
 #endif
+            DART_CK(ckC2)
             ++it;
             // the step vanished three times in a row: no restoration phase here -- stop and say so
             tiny = (alpha <= 1e-6) ? tiny + 1 : 0;
             if (tiny >= 3) { st = (pinf > 1e-4) ? ST_INFEASIBLE : ST_MAXITER; done = true; continue; }
             move_dual(alpha, mu);
             eval2(dinf, zs_min, zs_max, lam_sum, z_sum, nact);
+            DART_CK(ckC)
         }
+#ifdef DART_PHASE_CLOCK
+#ifdef __CUDA_ARCH__
+        if (bc.tid == 0 && DART_PHASE_CLOCK_BLOCK)
+            printf("sub-phases per iter: A.test %lld  B.backward %lld  C.post %lld  C.linesearch %lld\n", ckA1 / (it + 1), ckBb / (it > 0 ? it : 1), ckC1 / (it > 0 ? it : 1), ckC2 / (it > 0 ? it : 1));
+        if (bc.tid == 0 && DART_PHASE_CLOCK_BLOCK)
+            printf("phase clocks: it %d A %lld waitAB %lld B %lld waitBC %lld C %lld (per iter A %lld wAB %lld B %lld wBC %lld C %lld)\n", it, ckA, ckW1, ckB, ckW2,
+                   ckC, ckA / (it + 1), ckW1 / (it + 1), ckB / (it > 0 ? it : 1), ckW2 / (it > 0 ? it : 1), ckC / (it > 0 ? it : 1));
+#endif
+#endif
         J = f;
         status = st;
         iters = it;
