@@ -214,7 +214,7 @@ struct Rmpc {
 struct LmpcAxis {
     static constexpr int NX = 5, NU = 1, NR = 1, NP = 4, NAUG = 1, NAXIS = 2;
     static constexpr bool SERIAL_RICCATI = false;   // measured: the tiled sweep is 1.3-2x faster than the per-lane one at n = 5
-    static constexpr int MAX_THREADS = 128, MIN_BLOCKS = 3, BT_LARGE = 128;   // 12 warps/SM -> <= 170 registers (shared memory allows 13)
+    static constexpr int MAX_THREADS = 128, MIN_BLOCKS = 3, BT_LARGE = 64;    // 12 warps/SM -> <= 170 registers (shared memory allows 13)
     static constexpr int NXF = 8;
     static constexpr int NDEF = 20;
     struct Prm {

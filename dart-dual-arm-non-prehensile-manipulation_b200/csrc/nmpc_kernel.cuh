@@ -22,6 +22,7 @@ struct DevTile {
     __device__ __forceinline__ void sync() const { __syncwarp(mask); }
     __device__ __forceinline__ void block_sync() const { __syncthreads(); }
     __device__ __forceinline__ bool block_any(bool p) const { return __syncthreads_or(p ? 1 : 0) != 0; }
+    __device__ __forceinline__ double shfl(double v, int src) const { return __shfl_sync(mask, v, src, G); }
     __device__ __forceinline__ double sum(double v) const {
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o, G);

@@ -78,6 +78,7 @@ struct HostTile {
     DART_HD void sync() const {}
     DART_HD void block_sync() const {}
     DART_HD bool block_any(bool p) const { return p; }
+    DART_HD double shfl(double v, int) const { return v; }
     DART_HD double sum(double v) const { return v; }
     DART_HD double max(double v) const { return v; }
     DART_HD double min(double v) const { return v; }
@@ -698,6 +699,42 @@ struct Solver {
         }
     }
 
+    // ---- forward sweep across the tile (larger models): every lane keeps dx_k in registers and forms du_k; lane a
+    // forms row a of dx_{k+1} = A dx + B du + d, and the rows are exchanged by shuffles -- per stage one n-deep and one
+    // m-deep FMA chain plus a shuffle instead of the whole stage in one lane.  Needs at least n lanes.
+    template <class TL>
+    DART_HD void forward_tile(const TL& tl) {
+        const int lane = tl.lane();
+        const int a = lane < n ? lane : n - 1;               // lanes >= n shadow the last row (no stores)
+        const int ap = a < np ? a : np - 1;                  // row of the stored physical blocks this lane reads
+        const bool phys = a < np;
+        double dx[n];
+        DART_UNROLL for (int i = 0; i < n; ++i) dx[i] = 0.0;
+        if (lane < n) w.DX[lane] = 0.0;
+        for (int k = 0; k < N; ++k) {
+            double du[m];
+            DART_UNROLL for (int j = 0; j < m; ++j) {
+                double acc = w.KFF[k * m + j];
+                DART_UNROLL for (int i = 0; i < n; ++i) acc += w.K[k * sK + j * n + i] * dx[i];
+                du[j] = acc;
+            }
+            double v = w.D[k * n + a];
+            double vp = v;
+            DART_UNROLL for (int i = 0; i < np; ++i) vp += w.A[k * sA + ap * np + i] * dx[i];
+            DART_UNROLL for (int j = 0; j < m; ++j) vp += w.Bm[k * sB + ap * m + j] * du[j];
+            if (M::NAUG > 0) {                                // carried-input rows: x_{k+1}[np + j] = u_k[j] (+ defect)
+                double va = v;
+                DART_UNROLL for (int j = 0; j < m; ++j) va += (a - np == j) ? du[j] : 0.0;
+                v = phys ? vp : va;
+            } else {
+                v = vp;
+            }
+            if (lane < n) w.DX[(k + 1) * n + lane] = v;
+            if (lane == 0) { DART_UNROLL for (int j = 0; j < m; ++j) w.DU[k * m + j] = du[j]; }
+            DART_UNROLL for (int i = 0; i < n; ++i) dx[i] = tl.shfl(v, i);
+        }
+    }
+
     // ---- slack steps, step-length limits, directional derivative, then the dual step z += ad dz (stage-parallel).
     // dz is recomputed in the second pass instead of being stored; the new equality multipliers are formed in move_dual.
     DART_HD void post(double mu, double& ap, double& ad, double& dphi) {
@@ -889,7 +926,8 @@ struct Solver {
                 // so no block barrier -- one lane runs the short forward recurrence
                 DART_CK(ckA)
                 if (!need_sweep) break;
-                if (tile.lane() == 0) forward();
+                if (T::kLanes >= n) forward_tile(tile);
+                else if (tile.lane() == 0) forward();
                 tile.sync();
                 DART_CK(ckB)
             }
