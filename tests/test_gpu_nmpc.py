@@ -70,7 +70,7 @@ def test_rmpc_parity(built):
     print(f"rmpc: max|du0|={du0:.2e} max rel dJ={dJ:.2e} iters mean={out['iters'].mean():.2f}")
 
 
-@pytest.mark.parametrize("lanes", [8, 32])
+@pytest.mark.parametrize("lanes", [8, 16, 32])
 def test_rmpc_lane_widths_agree(built, lanes):
     d, p = helpers.rmpc_case(64)
     base = dart_b200.NMPCEngine(dart_b200.rmpc_cfg(), device=0).solve(d["x0"], d["ref"], aux=d["aux"])
@@ -97,6 +97,18 @@ def test_lmpc_parity(built):
     ref = ipm.solve(p)
     du0, dJ = helpers.assert_parity(out, ref, "lmpc")
     print(f"lmpc: max|du0|={du0:.2e} max rel dJ={dJ:.2e} iters mean={out['iters'].mean():.2f}")
+
+
+@pytest.mark.parametrize("lanes", [4, 8, 16])
+def test_lmpc_lane_widths_agree(built, lanes):
+    """The element-per-lane Riccati rounds take 1..8 passes depending on the tile width, and with 4 lanes (< nx) one
+    lane runs the forward sweep instead of the tile; all widths must agree."""
+    d, p = helpers.lmpc_case(64)
+    base = dart_b200.NMPCEngine(dart_b200.lmpc_cfg(), device=0).solve(d["x0"], d["ref"], aux=d["aux"])
+    out = dart_b200.NMPCEngine(dart_b200.lmpc_cfg(lanes=lanes), device=0).solve(d["x0"], d["ref"], aux=d["aux"])
+    assert (out["status"] == 0).all()
+    assert np.abs(out["u0"] - base["u0"]).max() < 1e-6
+    assert (np.abs(out["J"] - base["J"]) / np.abs(base["J"])).max() < 1e-8
 
 
 def test_device_pointer_entry_and_quaternion(pmpc_engine):
