@@ -568,6 +568,10 @@ struct Solver {
     // stage data loads do not depend on P, so they are issued ahead of the dependent chain.  Needs only the workspace
     // (terminal P_N, p_N were written by prep()).
     DART_HD void backward_serial() {
+        // structure known at compile time (M::a_kind: 0 general, 1 exact zero, 2 exact one; M::H_DIAG: the stage
+        // Hessian is diagonal) drops loads and FMAs from the single-thread chain; M is formed as its upper triangle
+        auto tkind = [](int b, int c) { return c < n ? M::a_kind(b, c) : 0; };          // entry (b, c) of [A B d]
+        auto hzero = [](int i, int c) { return M::H_DIAG && c < ny && i != c; };
         double P[n * n], pv[n];
         DART_UNROLL for (int i = 0; i < n; ++i) {
             DART_UNROLL for (int j = 0; j < n; ++j) P[i * n + j] = Pat(N, i, j);
@@ -576,12 +580,12 @@ struct Solver {
         double Tm[n * nc], HG[ny * nc];
         auto load = [&](int k, double* T_, double* H_) {
             DART_UNROLL for (int a = 0; a < n; ++a) {
-                DART_UNROLL for (int b = 0; b < n; ++b) T_[a * nc + b] = Aat(k, a, b);
+                DART_UNROLL for (int b = 0; b < n; ++b) T_[a * nc + b] = (tkind(a, b) == 0) ? Aat(k, a, b) : (tkind(a, b) == 2 ? 1.0 : 0.0);
                 DART_UNROLL for (int j = 0; j < m; ++j) T_[a * nc + n + j] = Bat(k, a, j);
                 T_[a * nc + ny] = w.D[k * n + a];
             }
             DART_UNROLL for (int i = 0; i < ny; ++i) {
-                DART_UNROLL for (int c = 0; c < ny; ++c) H_[i * nc + c] = Hat(k, i, c);
+                DART_UNROLL for (int c = i; c < ny; ++c) H_[i * nc + c] = hzero(i, c) ? 0.0 : Hat(k, i, c);
                 H_[i * nc + ny] = w.GR[k * sG + i];
             }
         };
@@ -594,16 +598,36 @@ struct Solver {
             double Wm[n * nc], Mm[ny * nc];
             DART_UNROLL for (int a = 0; a < n; ++a)
                 DART_UNROLL for (int c = 0; c < nc; ++c) {
-                    double acc = (c == nc - 1) ? pv[a] : 0.0;
-                    DART_UNROLL for (int b = 0; b < n; ++b) acc += P[a * n + b] * Tm[b * nc + c];
+                    double acc = 0.0;
+                    bool first = true;
+                    if (c == nc - 1) { acc = pv[a]; first = false; }
+                    DART_UNROLL for (int b = 0; b < n; ++b) {
+                        const int kd = tkind(b, c);
+                        if (kd == 1) continue;
+                        const double term_p = P[a * n + b];
+                        if (first) { acc = (kd == 2) ? term_p : term_p * Tm[b * nc + c]; first = false; }
+                        else if (kd == 2) acc += term_p;
+                        else acc += term_p * Tm[b * nc + c];
+                    }
                     Wm[a * nc + c] = acc;
                 }
             DART_UNROLL for (int i = 0; i < ny; ++i)
                 DART_UNROLL for (int c = 0; c < nc; ++c) {
-                    double acc = HG[i * nc + c];
-                    DART_UNROLL for (int a = 0; a < n; ++a) acc += Tm[a * nc + i] * Wm[a * nc + c];
+                    if (c < ny && c < i) continue;                     // upper triangle (+ gradient column) only
+                    double acc = 0.0;
+                    bool first = hzero(i, c);
+                    if (!first) acc = HG[i * nc + c];
+                    DART_UNROLL for (int a = 0; a < n; ++a) {
+                        const int kd = (i < n) ? tkind(a, i) : 0;
+                        if (kd == 1) continue;
+                        const double wv = Wm[a * nc + c];
+                        if (first) { acc = (kd == 2) ? wv : Tm[a * nc + i] * wv; first = false; }
+                        else if (kd == 2) acc += wv;
+                        else acc += Tm[a * nc + i] * wv;
+                    }
                     Mm[i * nc + c] = acc;
                 }
+            auto Mu = [&](int i, int c) { return (c < ny && c < i) ? Mm[c * nc + i] : Mm[i * nc + c]; };
             double Lc[m * m];
             if (m == 1) {
                 // scalar pivot: reciprocal on the fast path, escalating shift only if it is not positive
@@ -618,7 +642,7 @@ struct Solver {
                 double shift = 0.0;
                 for (int tries = 0; tries < 40; ++tries) {
                     DART_UNROLL for (int i = 0; i < m; ++i)
-                        DART_UNROLL for (int j = 0; j < m; ++j) Lc[i * m + j] = Mm[(n + i) * nc + n + j] + (i == j ? shift : 0.0);
+                        DART_UNROLL for (int j = 0; j < m; ++j) Lc[i * m + j] = Mu(n + i, n + j) + (i == j ? shift : 0.0);
                     if (chol(Lc)) break;
                     shift = (shift == 0.0) ? 1e-4 : shift * 8.0;
                 }
@@ -627,17 +651,17 @@ struct Solver {
             DART_UNROLL for (int c = 0; c <= n; ++c) {
                 double kt[m];
                 const int cc = (c < n) ? c : ny;
-                DART_UNROLL for (int j = 0; j < m; ++j) kt[j] = -Mm[(n + j) * nc + cc];
+                DART_UNROLL for (int j = 0; j < m; ++j) kt[j] = -Mu(n + j, cc);
                 chol_solve(Lc, kt);
                 DART_UNROLL for (int j = 0; j < m; ++j) Kt[j * (n + 1) + c] = kt[j];
             }
             if (k > 0) {
                 DART_UNROLL for (int i = 0; i < n; ++i) {
-                    DART_UNROLL for (int c = 0; c <= n; ++c) {
+                    DART_UNROLL for (int c = i; c <= n; ++c) {
                         const int cc = (c < n) ? c : ny;
                         double v = Mm[i * nc + cc];
                         DART_UNROLL for (int j = 0; j < m; ++j) v += Mm[i * nc + n + j] * Kt[j * (n + 1) + c];
-                        if (c < n) P[i * n + c] = v; else pv[i] = v;
+                        if (c < n) { P[i * n + c] = v; P[c * n + i] = v; } else pv[i] = v;
                     }
                 }
             }
