@@ -47,6 +47,10 @@
 #endif
 #endif
 
+#ifndef DART_SWEEP_UNROLL
+#define DART_SWEEP_UNROLL 3
+#endif
+
 namespace dart {
 
 enum Status : int32_t { ST_CONVERGED = 0, ST_MAXITER = 1, ST_INFEASIBLE = 2, ST_NUMERIC = 3 };
@@ -194,6 +198,19 @@ struct Solver {
         return g;
     }
 
+    // reciprocals of nr positive numbers from ONE division (prefix products); returns their product
+    DART_HD static double batch_inv(const double* v, double* inv) {
+        double pre[nr];
+        double tot = 1.0;
+        DART_UNROLL for (int r = 0; r < nr; ++r) { pre[r] = tot; tot = (r == 0) ? v[0] : tot * v[r]; }
+        double t = 1.0 / tot;
+        DART_UNROLL for (int r = nr - 1; r >= 0; --r) {
+            inv[r] = (r == 0) ? t : t * pre[r];
+            if (r > 0) t *= v[r];
+        }
+        return tot;
+    }
+
     // ---- E1: dynamics, Jacobians, defects, objective, barrier logs, constraint violation (stage-parallel)
     DART_HD void eval1(double& f, double& L, double& th, double& pinf) {
         double f_ = 0.0, L_ = 0.0, th_ = 0.0, pi_ = 0.0;
@@ -223,21 +240,28 @@ struct Solver {
                     f_ += M::wd(prm, j) * e * e;
                 }
             }
+            // rows: one reciprocal and one logarithm per STAGE (of the product of the rows' slack products: at most
+            // nr <= 6 factors >= 1e-24, no underflow), the per-row reciprocals follow from prefix products
+            double sl[nr], su[nr], prod[nr];
             DART_UNROLL for (int r = 0; r < nr; ++r) {
-                if (masked(k, r)) continue;
                 double lo, hi;
                 M::bounds(prm, r, lo, hi);
-                double s = w.S[k * nr + r];
-                double rc = rowval(k, r) - s;
-                double sl = s - lo, su = hi - s;
-                const double prod = sl * su;
-                const double ip = 1.0 / prod;
+                const double s = w.S[k * nr + r];
+                sl[r] = s - lo; su[r] = hi - s;
+                if (masked(k, r)) { prod[r] = 1.0; continue; }
+                const double rc = rowval(k, r) - s;
+                prod[r] = sl[r] * su[r];
                 w.RC[k * nr + r] = rc;
-                w.ISL[k * nr + r] = su * ip;
-                w.ISU[k * nr + r] = sl * ip;
-                L_ += log(prod);
                 th_ += fabs(rc);
                 pi_ = dmax(pi_, fabs(rc));
+            }
+            double ip[nr];
+            const double ptot = batch_inv(prod, ip);
+            L_ += log(ptot);
+            DART_UNROLL for (int r = 0; r < nr; ++r) {
+                if (masked(k, r)) continue;
+                w.ISL[k * nr + r] = su[r] * ip[r];
+                w.ISU[k * nr + r] = sl[r] * ip[r];
             }
         }
         if (tile.lane() == 0) {
@@ -590,7 +614,7 @@ struct Solver {
             }
         };
         load(N - 1, Tm, HG);
-        DART_UNROLL_N(3)
+        DART_UNROLL_N(DART_SWEEP_UNROLL)
         for (int k = N - 1; k >= 0; --k) {
             // next stage's data first: these loads do not depend on P, keep them ahead of the dependent chain
             double Tn[n * nc], Hn[ny * nc];
@@ -689,13 +713,13 @@ struct Solver {
             DART_UNROLL for (int i = 0; i < m * n; ++i) K_[i] = w.K[k * sK + i];
             DART_UNROLL for (int i = 0; i < m; ++i) k_[i] = w.KFF[k * m + i];
             DART_UNROLL for (int a = 0; a < n; ++a) {
-                DART_UNROLL for (int b = 0; b < n; ++b) A_[a * n + b] = Aat(k, a, b);
+                DART_UNROLL for (int b = 0; b < n; ++b) A_[a * n + b] = (M::a_kind(a, b) == 0) ? Aat(k, a, b) : 0.0;
                 DART_UNROLL for (int j = 0; j < m; ++j) B_[a * m + j] = Bat(k, a, j);
             }
             DART_UNROLL for (int i = 0; i < n; ++i) d_[i] = w.D[k * n + i];
         };
         load(0, Kc, kc, Ac, Bc, dc);
-        DART_UNROLL_N(3)
+        DART_UNROLL_N(DART_SWEEP_UNROLL)
         for (int k = 0; k < N; ++k) {
             double Kn[m * n], kn[m], An[n * n], Bn[n * m], dn[n];
             const int kk = (k + 1 < N) ? k + 1 : k;
@@ -708,7 +732,10 @@ struct Solver {
             }
             DART_UNROLL for (int a = 0; a < n; ++a) {
                 double acc = dc[a];
-                DART_UNROLL for (int i = 0; i < n; ++i) acc += Ac[a * n + i] * dx[i];
+                DART_UNROLL for (int i = 0; i < n; ++i) {
+                    if (M::a_kind(a, i) == 1) continue;               // structural zero / one of the sensitivity
+                    if (M::a_kind(a, i) == 2) acc += dx[i]; else acc += Ac[a * n + i] * dx[i];
+                }
                 DART_UNROLL for (int j = 0; j < m; ++j) acc += Bc[a * m + j] * du[j];
                 nx[a] = acc;
             }
@@ -769,8 +796,9 @@ struct Solver {
                 double d = (i < n) ? w.DX[k * n + i] : w.DU[k * m + (i - n)];
                 dp += cost_grad(k, i) * d;
             }
+            double zz[nr], na[nr], nb[nr];                 // z_l z_u and the numerators of -dz_l/z_l, -dz_u/z_u
             DART_UNROLL for (int r = 0; r < nr; ++r) {
-                if (masked(k, r)) { w.DS[k * nr + r] = 0.0; continue; }
+                if (masked(k, r)) { w.DS[k * nr + r] = 0.0; zz[r] = 1.0; na[r] = 0.0; nb[r] = 0.0; continue; }
                 const int ia = M::row_ia(r), ib = M::row_ib(r);
                 double dy = M::row_sa(r) * ((ia < n) ? w.DX[k * n + ia] : w.DU[k * m + (ia - n)]);
                 if (ib >= 0) dy += M::row_sb(r) * ((ib < n) ? w.DX[k * n + ib] : w.DU[k * m + (ib - n)]);
@@ -782,9 +810,11 @@ struct Solver {
                 w.DS[k * nr + r] = ds;
                 dp -= mu * ds * (isl - isu);
                 rp_ = dmax(rp_, dmax(-ds * isl, ds * isu));
-                const double iz = 1.0 / (zl * zu);
-                rd_ = dmax(rd_, dmax(-dzl * zu * iz, -dzu * zl * iz));
+                zz[r] = zl * zu; na[r] = -dzl * zu; nb[r] = -dzu * zl;
             }
+            double iz[nr];
+            batch_inv(zz, iz);                             // one division per stage
+            DART_UNROLL for (int r = 0; r < nr; ++r) rd_ = dmax(rd_, dmax(na[r] * iz[r], nb[r] * iz[r]));
         }
         if (tile.lane() == 0) {
             DART_UNROLL for (int i = 0; i < n; ++i)
@@ -820,7 +850,7 @@ struct Solver {
     }
 
     DART_HD void move_dual(double alpha, double mu) {
-        const double ks = 1e10;
+        const double ks = 1e10, iks = 1e-10;     // safeguard interval [mu/(ks s), ks mu/s]; a product, not a division
         for (int k = tile.lane(); k < N; k += tile.size()) {
             DART_UNROLL for (int a = 0; a < n; ++a) {      // new multiplier of stage k+1: P_{k+1} dx_{k+1} + p_{k+1}
                 double ln = w.PV[(k + 1) * n + a];
@@ -831,8 +861,8 @@ struct Solver {
                 if (masked(k, r)) continue;
                 const double isl = w.ISL[k * nr + r], isu = w.ISU[k * nr + r];   // of the accepted point (eval1)
                 const double zl = w.ZL[k * nr + r], zu = w.ZU[k * nr + r];        // already stepped in post()
-                w.ZL[k * nr + r] = dmin(dmax(zl, mu * isl / ks), ks * mu * isl);
-                w.ZU[k * nr + r] = dmin(dmax(zu, mu * isu / ks), ks * mu * isu);
+                w.ZL[k * nr + r] = dmin(dmax(zl, mu * isl * iks), ks * mu * isl);
+                w.ZU[k * nr + r] = dmin(dmax(zu, mu * isu * iks), ks * mu * isu);
             }
         }
         tile.sync();
@@ -902,8 +932,10 @@ struct Solver {
             bool need_sweep = false;
             if (!done) {
                 // IPOPT's scaled optimality error; is_d = 1/s_d, is_c = 1/s_c (s_* = max(smax, mean multiplier)/smax)
-                is_d = o.smax / dmax(o.smax, (lam_sum + z_sum) * inv_nd);
-                is_c = o.smax / dmax(o.smax, z_sum * inv_nc);
+                // (the scalings are exactly 1 unless the mean multiplier exceeds smax: no division on the usual path)
+                const double md = (lam_sum + z_sum) * inv_nd, mc = z_sum * inv_nc;
+                is_d = (md > o.smax) ? o.smax / md : 1.0;
+                is_c = (mc > o.smax) ? o.smax / mc : 1.0;
                 const double base = dmax(dinf * is_d, pinf);
                 E0 = dmax(base, (nact > 0 ? zs_max : 0.0) * is_c);
                 if (E0 <= o.tol) { st = ST_CONVERGED; done = true; }
