@@ -33,6 +33,24 @@ struct DevTile {
         for (int o = G / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(mask, v, o, G));
         return v;
     }
+    // max of values that are >= 0 (|.|, or maxima seeded with 0): for those the IEEE-754 order is the unsigned integer
+    // order of the bit pattern, so two REDUX instructions replace log2(G) shuffle levels; a NaN still wins the max
+    // (full-warp tiles only: with two sub-warp masks in one warp REDUX measured slower than the shuffle tree)
+    __device__ __forceinline__ double max_nonneg(double v) const {
+        if (G != 32) return max(v);
+        const unsigned hi = (unsigned)__double2hiint(v) & 0x7fffffffu, lo = (unsigned)__double2loint(v);
+        const unsigned mh = __reduce_max_sync(mask, hi);
+        const unsigned ml = __reduce_max_sync(mask, hi == mh ? lo : 0u);
+        return __hiloint2double((int)mh, (int)ml);
+    }
+    // min of positive values (products z * slack of interior iterates), same integer-order argument
+    __device__ __forceinline__ double min_pos(double v) const {
+        if (G != 32) return min(v);
+        const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+        const unsigned mh = __reduce_min_sync(mask, hi);
+        const unsigned ml = __reduce_min_sync(mask, hi == mh ? lo : 0xffffffffu);
+        return __hiloint2double((int)mh, (int)ml);
+    }
     __device__ __forceinline__ double min(double v) const {
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(mask, v, o, G));

@@ -85,6 +85,8 @@ struct HostTile {
     DART_HD double shfl(double v, int) const { return v; }
     DART_HD double sum(double v) const { return v; }
     DART_HD double max(double v) const { return v; }
+    DART_HD double max_nonneg(double v) const { return v; }
+    DART_HD double min_pos(double v) const { return v; }
     DART_HD double min(double v) const { return v; }
 };
 
@@ -273,14 +275,13 @@ struct Solver {
         f = tile.sum(f_);
         L = tile.sum(L_);
         th = tile.sum(th_);
-        pinf = tile.max(pi_);
+        pinf = tile.max_nonneg(pi_);
         tile.sync();
     }
 
     // ---- E2: KKT residuals with the current multipliers (stage-parallel)
-    DART_HD void eval2(double& dinf, double& zs_min, double& zs_max, double& lam_sum, double& z_sum, int& nact) {
+    DART_HD void eval2(double& dinf, double& zs_min, double& zs_max, double& lam_sum, double& z_sum) {
         double di = 0.0, zmn = 1e300, zmx = 0.0, ls = 0.0, zs = 0.0;
-        int na = 0;
         for (int k = tile.lane(); k < N; k += tile.size()) {
             double lam[n];
             DART_UNROLL for (int a = 0; a < n; ++a) { lam[a] = w.LAM[k * n + a]; ls += fabs(lam[a]); }
@@ -312,7 +313,6 @@ struct Solver {
                 zmn = dmin(zmn, dmin(a, b));
                 zmx = dmax(zmx, dmax(a, b));
                 zs += fabs(zl) + fabs(zu);
-                na += 1;
             }
             DART_UNROLL for (int i = 0; i < ny; ++i)
                 if (i >= n || k >= 1) di = dmax(di, fabs(g[i]));
@@ -323,12 +323,11 @@ struct Solver {
                 di = dmax(di, fabs(gT));
             }
         }
-        dinf = tile.max(di);
-        zs_min = tile.min(zmn);
-        zs_max = tile.max(zmx);
+        dinf = tile.max_nonneg(di);
+        zs_min = tile.min_pos(zmn);
+        zs_max = tile.max_nonneg(zmx);
         lam_sum = tile.sum(ls);
         z_sum = tile.sum(zs);
-        nact = (int)(tile.sum((double)na) + 0.5);
         tile.sync();
     }
 
@@ -820,8 +819,8 @@ struct Solver {
             DART_UNROLL for (int i = 0; i < n; ++i)
                 dp += 2.0 * M::wT(prm, i) * (w.X[N * n + i] - M::rT(prm, w.REF, N, i)) * w.DX[N * n + i];
         }
-        rp_ = tile.max(rp_);
-        rd_ = tile.max(rd_);
+        rp_ = tile.max_nonneg(rp_);
+        rd_ = tile.max_nonneg(rd_);
         ap_ = (rp_ > tau) ? tau / rp_ : 1.0;
         ad_ = (rd_ > tau) ? tau / rd_ : 1.0;
         ap = ap_;
@@ -906,12 +905,14 @@ struct Solver {
     DART_HD void run(bool active, double& J, int32_t& status, int32_t& iters, double& kkt) {
         double mu = o.mu0;
         double f = 0.0, L = 0.0, th = 0.0, pinf = 0.0, dinf = 0.0, zs_min = 0.0, zs_max = 0.0, lam_sum = 0.0, z_sum = 0.0;
+        // number of constraint rows of the problem (rows with row_skip0 do not exist at stage 0)
         int nact = 0;
+        DART_UNROLL for (int r = 0; r < nr; ++r) nact += M::row_skip0(r) ? N - 1 : N;
         double inv_nd = 0.0, inv_nc = 0.0;
         if (active) {
             init_rows(mu);
             eval1(f, L, th, pinf);
-            eval2(dinf, zs_min, zs_max, lam_sum, z_sum, nact);
+            eval2(dinf, zs_min, zs_max, lam_sum, z_sum);
             inv_nd = 1.0 / (double)(N * n + 2 * nact);
             inv_nc = 1.0 / (double)(2 * (nact > 0 ? nact : 1));
         }
@@ -1021,7 +1022,7 @@ struct Solver {
             tiny = (alpha <= 1e-6) ? tiny + 1 : 0;
             if (tiny >= 3) { st = (pinf > 1e-4) ? ST_INFEASIBLE : ST_MAXITER; done = true; continue; }
             move_dual(alpha, mu);
-            eval2(dinf, zs_min, zs_max, lam_sum, z_sum, nact);
+            eval2(dinf, zs_min, zs_max, lam_sum, z_sum);
             DART_CK(ckC)
         }
 #ifdef DART_PHASE_CLOCK

@@ -1,10 +1,12 @@
-"""Small driver for ncu: a few solves of one method at its BASELINE batch size (dev tool). usage: profile_method.py rmpc|lmpc"""
+"""Small driver for ncu: a few solves of one method at its BASELINE batch size (dev tool). usage: profile_method.py pmpc|rmpc|lmpc"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, dart_b200
 W = dart_b200.workloads
 m = sys.argv[1]
-if m == "rmpc":
+if m == "pmpc":
+    c, aux = W.pmpc_inputs(64); d = dict(x0=c["state"], ref=c["target"], aux=aux); cfg = dart_b200.pmpc_cfg()
+elif m == "rmpc":
     d = W.rmpc_inputs(4096); cfg = dart_b200.rmpc_cfg()
 else:
     d = W.lmpc_inputs(16384); cfg = dart_b200.lmpc_cfg()
