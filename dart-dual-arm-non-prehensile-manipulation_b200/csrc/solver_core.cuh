@@ -758,30 +758,41 @@ struct Solver {
         const int a = lane < n ? lane : n - 1;               // lanes >= n shadow the last row (no stores)
         const int ap = a < np ? a : np - 1;                  // row of the stored physical blocks this lane reads
         const bool phys = a < np;
+        double sel[m];                                       // carried-input rows: x_{k+1}[np + j] = u_k[j] (+ defect)
+        DART_UNROLL for (int j = 0; j < m; ++j) sel[j] = (M::NAUG > 0 && a - np == j) ? 1.0 : 0.0;
         double dx[n];
         DART_UNROLL for (int i = 0; i < n; ++i) dx[i] = 0.0;
         if (lane < n) w.DX[lane] = 0.0;
+        // stage data is loaded one stage ahead: it does not depend on dx, only the FMA chain and the shuffle do
+        double Kc[m * n], kc[m], Ar[np], Br[m], dc;
+        auto load = [&](int k, double* K_, double* k_, double* A_, double* B_, double& d_) {
+            DART_UNROLL for (int i = 0; i < m * n; ++i) K_[i] = w.K[k * sK + i];
+            DART_UNROLL for (int j = 0; j < m; ++j) k_[j] = w.KFF[k * m + j];
+            DART_UNROLL for (int i = 0; i < np; ++i) A_[i] = w.A[k * sA + ap * np + i];
+            DART_UNROLL for (int j = 0; j < m; ++j) B_[j] = w.Bm[k * sB + ap * m + j];
+            d_ = w.D[k * n + a];
+        };
+        load(0, Kc, kc, Ar, Br, dc);
         for (int k = 0; k < N; ++k) {
+            double Kn[m * n], kn[m], An[np], Bn[m], dn;
+            load(k + 1 < N ? k + 1 : k, Kn, kn, An, Bn, dn);
             double du[m];
             DART_UNROLL for (int j = 0; j < m; ++j) {
-                double acc = w.KFF[k * m + j];
-                DART_UNROLL for (int i = 0; i < n; ++i) acc += w.K[k * sK + j * n + i] * dx[i];
+                double acc = kc[j];
+                DART_UNROLL for (int i = 0; i < n; ++i) acc += Kc[j * n + i] * dx[i];
                 du[j] = acc;
             }
-            double v = w.D[k * n + a];
-            double vp = v;
-            DART_UNROLL for (int i = 0; i < np; ++i) vp += w.A[k * sA + ap * np + i] * dx[i];
-            DART_UNROLL for (int j = 0; j < m; ++j) vp += w.Bm[k * sB + ap * m + j] * du[j];
-            if (M::NAUG > 0) {                                // carried-input rows: x_{k+1}[np + j] = u_k[j] (+ defect)
-                double va = v;
-                DART_UNROLL for (int j = 0; j < m; ++j) va += (a - np == j) ? du[j] : 0.0;
-                v = phys ? vp : va;
-            } else {
-                v = vp;
-            }
+            double vp = dc, va = dc;
+            DART_UNROLL for (int i = 0; i < np; ++i) vp += Ar[i] * dx[i];
+            DART_UNROLL for (int j = 0; j < m; ++j) { vp += Br[j] * du[j]; va += sel[j] * du[j]; }
+            const double v = (M::NAUG > 0 && !phys) ? va : vp;
             if (lane < n) w.DX[(k + 1) * n + lane] = v;
             if (lane == 0) { DART_UNROLL for (int j = 0; j < m; ++j) w.DU[k * m + j] = du[j]; }
             DART_UNROLL for (int i = 0; i < n; ++i) dx[i] = tl.shfl(v, i);
+            DART_UNROLL for (int i = 0; i < m * n; ++i) Kc[i] = Kn[i];
+            DART_UNROLL for (int j = 0; j < m; ++j) { kc[j] = kn[j]; Br[j] = Bn[j]; }
+            DART_UNROLL for (int i = 0; i < np; ++i) Ar[i] = An[i];
+            dc = dn;
         }
     }
 
