@@ -78,8 +78,7 @@ struct PmpcAxis {
     static constexpr int NX = 2, NU = 1, NR = 1, NP = 2, NAUG = 0, NAXIS = 2;
     static constexpr bool SERIAL_RICCATI = true;
     // structure the serial sweep may rely on: the position does not enter the dynamics, so column 0 of the RK4
-    // sensitivity A is exactly e_0; cost and bound rows touch one variable each, so the stage Hessian is diagonal
-    static constexpr bool H_DIAG = true;
+    // sensitivity A is exactly e_0
     DART_HD static constexpr int a_kind(int a, int b) { return b == 0 ? (a == 0 ? 2 : 1) : 0; }
     static constexpr int MAX_THREADS = 256, MIN_BLOCKS = 1, BT_LARGE = 64;   // BT_LARGE: block size when the GPU is filled (measured)
     static constexpr int NXF = 6;   // states per stage in the reference's decision vector
@@ -141,7 +140,6 @@ struct PmpcAxis {
 struct Rmpc {
     static constexpr int NX = 6, NU = 2, NR = 6, NP = 4, NAUG = 2, NAXIS = 1;
     static constexpr bool SERIAL_RICCATI = false;
-    static constexpr bool H_DIAG = false;
     DART_HD static constexpr int a_kind(int, int) { return 0; }
     static constexpr int MAX_THREADS = 256, MIN_BLOCKS = 1, BT_LARGE = 32;
     static constexpr int NXF = 4;
@@ -220,7 +218,6 @@ struct Rmpc {
 struct LmpcAxis {
     static constexpr int NX = 5, NU = 1, NR = 1, NP = 4, NAUG = 1, NAXIS = 2;
     static constexpr bool SERIAL_RICCATI = false;   // measured: the tiled sweep is 1.3-2x faster than the per-lane one at n = 5
-    static constexpr bool H_DIAG = false;
     DART_HD static constexpr int a_kind(int, int) { return 0; }
     static constexpr int MAX_THREADS = 128, MIN_BLOCKS = 3, BT_LARGE = 64;    // 12 warps/SM -> <= 170 registers (shared memory allows 13)
     static constexpr int NXF = 8;

@@ -102,21 +102,36 @@ template <class M>
 struct Workspace {
     static constexpr int n = M::NX, m = M::NU, nr = M::NR, ny = n + m, nc = n + m + 1, np = M::NP;
     // A, Bm: physical NP x NP / NP x NU blocks only (carried-input rows are structural); PP, HS: packed symmetric
-    static constexpr int npa = np * np, npb = np * m, nps = n * (n + 1) / 2, nys = ny * (ny + 1) / 2;
+    static constexpr int npa = np * np, npb = np * m, nps = n * (n + 1) / 2;
+    // stage Hessian: only its structural non-zeros are stored -- the diagonal and, for models with carried inputs,
+    // the (carried input j, input j) pairs that the tilt-rate cost and the tilt-rate rows couple
+    static constexpr int NH = ny + (M::NAUG > 0 ? M::NAUG : 0);
+    DART_HD static constexpr int hslot(int i, int c) {
+        const int lo = i < c ? i : c, hi = i < c ? c : i;
+        if (lo == hi) return lo;
+        if (M::NAUG > 0 && lo >= np && lo < n && hi == n + (lo - np)) return ny + (lo - np);
+        return -1;
+    }
+    DART_HD static constexpr bool rows_fit() {
+        for (int r = 0; r < nr; ++r)
+            if (M::row_ib(r) >= 0 && hslot(M::row_ia(r), M::row_ib(r)) < 0) return false;
+        return true;
+    }
+    static_assert(rows_fit(), "a two-variable constraint row couples variables outside the stored Hessian pattern");
     // per-stage strides (in doubles) of the arrays that lanes index by stage: odd, so that lanes working on
     // consecutive stages hit distinct shared-memory banks (16 banks of 8 bytes)
-    static constexpr int sA = npa | 1, sB = npb | 1, sH = nys | 1, sG = ny | 1, sK = (m * n) | 1;
+    static constexpr int sA = npa | 1, sB = npb | 1, sH = NH | 1, sG = ny | 1, sK = (m * n) | 1;
     static constexpr int sM = ny | 1;
     // stage scratch MM of the tiled Riccati sweep: W = P [A B d] over the nq = np + m variables with computed
     // curvature (+ gradient column), then the packed upper triangle of the stage matrix (+ gradient column)
     static constexpr int nq = np + m, nW = n * (nq + 1), nMq = nq * (nq + 1) / 2 + nq;
     static constexpr int nscr = M::SERIAL_RICCATI ? sM * (ny + 1) : nW + nMq;
     double *X, *U, *A, *Bm, *D, *LAM, *PP, *PV, *K, *KFF, *DX, *DU, *BL;
-    double *S, *ZL, *ZU, *ISL, *ISU, *RC, *DS, *MM, *TANU, *HS, *GR, *REF;
+    double *S, *ZL, *ZU, *ISL, *ISU, *RC, *DS, *MM, *TANU, *HS, *GR, *ZR, *REF;
 
     DART_HD static int doubles(int N) {
         return (N + 1) * n + N * m + N * sA + N * sB + N * n + N * n + (N + 1) * nps + (N + 1) * n + N * sK + N * m +
-               (N + 1) * n + N * m + N * m + 7 * N * nr + nscr + N * m + N * sH + N * sG + M::ref_doubles(N);
+               (N + 1) * n + N * m + N * m + 7 * N * nr + nscr + N * m + N * sH + N * sG + 1 + M::ref_doubles(N);
     }
     DART_HD void bind(double* p, int N) {
         X = p;   p += (N + 1) * n;
@@ -143,6 +158,7 @@ struct Workspace {
         TANU = p; p += N * m;
         HS = p;  p += N * sH;
         GR = p;  p += N * sG;
+        ZR = p;  p += 1;          // a stored 0.0: gather target for structural zeros
         REF = p;
     }
 };
@@ -165,7 +181,7 @@ struct Solver {
     DART_HD Solver(const T& t, const Prm& p, const SolverOpts& oo, int NN, W& ww, const BlockCtx& b)
         : tile(t), prm(p), o(oo), N(NC > 0 ? NC : NN), w(ww), bc(b) {}
 
-    static constexpr int npa = W::npa, npb = W::npb, nps = W::nps, nys = W::nys;
+    static constexpr int npa = W::npa, npb = W::npb, nps = W::nps;
     static constexpr int sA = W::sA, sB = W::sB, sH = W::sH, sG = W::sG, sK = W::sK, sM = W::sM;
     // packed upper-triangular index of a symmetric d x d matrix
     DART_HD static constexpr int sidx(int i, int j, int d) {
@@ -175,7 +191,12 @@ struct Solver {
     DART_HD double Aat(int k, int a, int b) const { return (a < np && b < np) ? w.A[k * sA + a * np + b] : 0.0; }
     DART_HD double Bat(int k, int a, int j) const { return (a < np) ? w.Bm[k * sB + a * m + j] : ((a - np) == j ? 1.0 : 0.0); }
     DART_HD double Pat(int k, int a, int b) const { return w.PP[k * nps + sidx(a, b, n)]; }
-    DART_HD double Hat(int k, int i, int c) const { return w.HS[k * sH + sidx(i, c, ny)]; }
+    DART_HD double Hat(int k, int i, int c) const { return W::hslot(i, c) < 0 ? 0.0 : w.HS[k * sH + (W::hslot(i, c) < 0 ? 0 : W::hslot(i, c))]; }
+    // gather descriptor of H[i][c] (structural zeros read the stored 0.0)
+    DART_HD void hgat(int i, int c, int& off, int& ks) const {
+        const int sl = W::hslot(i, c);
+        if (sl < 0) { off = (int)(w.ZR - w.X); ks = 0; } else { off = (int)(w.HS - w.X) + sl; ks = sH; }
+    }
 
     DART_HD double yval(int k, int i) const { return i < n ? w.X[k * n + i] : w.U[k * m + (i - n)]; }
     DART_HD double rowval(int k, int r) const {
@@ -415,7 +436,8 @@ struct Solver {
             // Lagrangian curvature of the tilt input: -tan(u_j) (B^T lambda)_j
             DART_UNROLL for (int j = 0; j < m; ++j) H[(n + j) * ny + n + j] += -w.TANU[k * m + j] * w.BL[k * m + j];
             DART_UNROLL for (int i = 0; i < ny; ++i)
-                DART_UNROLL for (int c = i; c < ny; ++c) w.HS[k * sH + sidx(i, c, ny)] = H[i * ny + c];
+                DART_UNROLL for (int c = i; c < ny; ++c)
+                    if (W::hslot(i, c) >= 0) w.HS[k * sH + W::hslot(i, c)] = H[i * ny + c];
             DART_UNROLL for (int i = 0; i < ny; ++i) w.GR[k * sG + i] = g[i];
         }
         if (M::SERIAL_RICCATI && tile.lane() == 0) {
@@ -456,7 +478,7 @@ struct Solver {
         double* const base = w.X;
         double* const WW = w.MM;
         double* const MQ = w.MM + nW;
-        const int oA = offs(w.A), oB = offs(w.Bm), oD = offs(w.D), oH = offs(w.HS), oG = offs(w.GR), oMQ = offs(MQ);
+        const int oA = offs(w.A), oB = offs(w.Bm), oD = offs(w.D), oG = offs(w.GR), oMQ = offs(MQ);
         const int oPP = offs(w.PP), oPV = offs(w.PV), oK = offs(w.K), oKF = offs(w.KFF);
 
         // terminal value function
@@ -501,7 +523,7 @@ struct Solver {
             d.cw = cq;
             if (iq < np) { d.tOff = oA + iq; d.tRs = np; d.tKs = sA; }
             else { d.tOff = oB + (iq - np); d.tRs = m; d.tKs = sB; }
-            if (cq < nq) { const int fc = cq < np ? cq : n + (cq - np); d.hOff = oH + sidx(fi, fc, ny); d.hKs = sH; }
+            if (cq < nq) { const int fc = cq < np ? cq : n + (cq - np); hgat(fi, fc, d.hOff, d.hKs); }
             else { d.hOff = oG + fi; d.hKs = sG; }
             const bool aug = M::NAUG > 0 && iq >= np;                 // input row: + W[np + j][.] (B = I on carried inputs)
             d.augOn = aug ? 1.0 : 0.0;
@@ -521,13 +543,14 @@ struct Solver {
                 // M[u_j][c]
                 if (c == n) d.mu[j] = Gat{oMQ + ntri + np + j, 0};
                 else if (c < np) d.mu[j] = Gat{oMQ + sidx(c, np + j, nq), 0};
-                else d.mu[j] = Gat{oH + sidx(c, n + j, ny), sH};
+                else hgat(c, n + j, d.mu[j].off, d.mu[j].ks);
                 // M[i][u_j]
                 if (i < np) d.miu[j] = Gat{oMQ + sidx(i, np + j, nq), 0};
-                else d.miu[j] = Gat{oH + sidx(i, n + j, ny), sH};
+                else hgat(i, n + j, d.miu[j].off, d.miu[j].ks);
             }
             if (c == n) d.mic = (i < np) ? Gat{oMQ + ntri + i, 0} : Gat{oG + i, sG};
-            else d.mic = (i < np && c < np) ? Gat{oMQ + sidx(i, c, nq), 0} : Gat{oH + sidx(i, c, ny), sH};
+            else if (i < np && c < np) d.mic = Gat{oMQ + sidx(i, c, nq), 0};
+            else hgat(i, c, d.mic.off, d.mic.ks);
             d.st = (c == n) ? Gat{oPV + i, n} : Gat{oPP + sidx(i, c, n), nps};
             d.storeK = d.act && i == 0;
             if (c == n) { d.kOff = oKF; d.kJs = 1; d.kKs = m; }
@@ -591,10 +614,10 @@ struct Solver {
     // stage data loads do not depend on P, so they are issued ahead of the dependent chain.  Needs only the workspace
     // (terminal P_N, p_N were written by prep()).
     DART_HD void backward_serial() {
-        // structure known at compile time (M::a_kind: 0 general, 1 exact zero, 2 exact one; M::H_DIAG: the stage
-        // Hessian is diagonal) drops loads and FMAs from the single-thread chain; M is formed as its upper triangle
+        // structure known at compile time (M::a_kind: 0 general, 1 exact zero, 2 exact one; the stage Hessian's
+        // pattern W::hslot) drops loads and FMAs from the single-thread chain; M is formed as its upper triangle
         auto tkind = [](int b, int c) { return c < n ? M::a_kind(b, c) : 0; };          // entry (b, c) of [A B d]
-        auto hzero = [](int i, int c) { return M::H_DIAG && c < ny && i != c; };
+        auto hzero = [](int i, int c) { return c < ny && W::hslot(i, c) < 0; };
         double P[n * n], pv[n];
         DART_UNROLL for (int i = 0; i < n; ++i) {
             DART_UNROLL for (int j = 0; j < n; ++j) P[i * n + j] = Pat(N, i, j);
@@ -880,6 +903,7 @@ struct Solver {
 
     // ---- slack/dual initialisation (IPOPT bound_push / bound_frac; z = mu0 / slack)
     DART_HD void init_rows(double mu) {
+        if (tile.lane() == 0) w.ZR[0] = 0.0;
         for (int k = tile.lane(); k < N; k += tile.size()) {
             DART_UNROLL for (int r = 0; r < nr; ++r) {
                 double lo, hi;
