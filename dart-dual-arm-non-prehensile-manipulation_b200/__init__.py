@@ -5,7 +5,7 @@ through the shim at the repository root (``dart_b200.py``).
 """
 from . import _lib, config, workloads                     # noqa: F401
 from ._lib import (DART_LMPC, DART_PMPC, DART_RMPC, STATUS_CONVERGED, STATUS_INFEASIBLE,  # noqa: F401
-                   STATUS_MAXITER, STATUS_NUMERIC, DartCfg, DartError)
+                   STATUS_MAXITER, STATUS_NUMERIC, STATUS_ACCEPTABLE, DartCfg, DartError)
 from .config import cfg_from_yaml, lmpc_cfg, load_config, pmpc_cfg, rmpc_cfg   # noqa: F401
 from .engine import NMPCEngine, measure_fp64_tflops, tilt_to_quat_device        # noqa: F401
 from .pmpc import PMPC, GravityModel, StateHolder, mpc_worker   # noqa: F401

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DART_B200_LIB") or os.path.join(HERE, "lib", "libdart_b200.so")   # override: A/B builds
 
 DART_PMPC, DART_RMPC, DART_LMPC = 0, 1, 2
-STATUS_CONVERGED, STATUS_MAXITER, STATUS_INFEASIBLE, STATUS_NUMERIC = 0, 1, 2, 3
+STATUS_CONVERGED, STATUS_MAXITER, STATUS_INFEASIBLE, STATUS_NUMERIC, STATUS_ACCEPTABLE = 0, 1, 2, 3, 4
 ERRORS = {0: "ok", -1: "bad argument", -2: "no CUDA device", -3: "CUDA error", -4: "allocation failed", -5: "unsupported configuration"}
 
 
@@ -24,6 +24,7 @@ class DartCfg(C.Structure):
         ("Q", C.c_double * 8), ("Qt", C.c_double * 8), ("Rl", C.c_double * 4),
         ("tol", C.c_double), ("max_iter", C.c_int32), ("mu_init", C.c_double),
         ("lanes", C.c_int32), ("block_threads", C.c_int32),
+        ("acceptable_tol", C.c_double), ("acceptable_iter", C.c_int32),
     ]
 
 

@@ -11,7 +11,11 @@ from ._lib import DART_LMPC, DART_PMPC, DART_RMPC, DartCfg
 
 METHODS = {"pmpc": DART_PMPC, "rmpc": DART_RMPC, "lmpc": DART_LMPC}
 
-_SOLVER_KEYS = ("tol", "max_iter", "mu_init", "lanes", "block_threads")
+_SOLVER_KEYS = ("tol", "max_iter", "mu_init", "lanes", "block_threads", "acceptable_tol", "acceptable_iter")
+
+# The IPOPT options the reference passes for LMPC (rlmpc2.py:484-488; max_cpu_time has no counterpart here).  Not the
+# default: by default every method is solved to tol = 1e-8 so results do not depend on where an early exit lands.
+LMPC_REFERENCE_SOLVER_OPTIONS = dict(tol=1e-4, acceptable_tol=1e-3, acceptable_iter=5, max_iter=50)
 
 
 def pmpc_cfg(Ts=0.002, nx=6, nu=2, N=15, Qp=400.0, Qv=2.0, R=0.2, mu=0.1, u_bounds=(-0.6, 0.6), g=-9.81, **solver):
@@ -61,6 +65,8 @@ def _solver(c, solver):
     c.mu_init = float(solver.pop("mu_init", 0.1))
     c.lanes = int(solver.pop("lanes", 0))
     c.block_threads = int(solver.pop("block_threads", 0))
+    c.acceptable_tol = float(solver.pop("acceptable_tol", 0.0))
+    c.acceptable_iter = int(solver.pop("acceptable_iter", 0))
     # keys of the reference dicts that do not enter the NLP are accepted and ignored
     return c
 

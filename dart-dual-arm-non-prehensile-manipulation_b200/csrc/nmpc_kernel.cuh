@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(M::MAX_THREADS, M::MIN_BLOCKS) nmpc_solve_kern
         for (int ax = 0; ax < NAX; ++ax) {
             const double* s2 = slot + (size_t)ax * ws_stride;
             Js += s2[0];
-            st = max(st, (int32_t)s2[1]);
+            if (status_rank((int32_t)s2[1]) > status_rank(st)) st = (int32_t)s2[1];
             itx = max(itx, (int32_t)s2[2]);
         }
         a.J[inst] = Js;

@@ -12,5 +12,7 @@ inline void fill_opts(const dart_cfg& c, SolverOpts& o) {
     o.gamma_theta = 1e-5; o.gamma_phi = 1e-8; o.theta_small = 1e-4;
     o.max_iter = c.max_iter > 0 ? c.max_iter : 200;
     o.max_backtrack = 12;
+    o.acc_tol = c.acceptable_tol;
+    o.acc_iter = (c.acceptable_iter > 0 && c.acceptable_tol > 0) ? c.acceptable_iter : 0;
 }
 }  // namespace dart

@@ -53,12 +53,17 @@
 
 namespace dart {
 
-enum Status : int32_t { ST_CONVERGED = 0, ST_MAXITER = 1, ST_INFEASIBLE = 2, ST_NUMERIC = 3 };
+enum Status : int32_t { ST_CONVERGED = 0, ST_MAXITER = 1, ST_INFEASIBLE = 2, ST_NUMERIC = 3, ST_ACCEPTABLE = 4 };
+// severity order used when the axes of one instance are combined (acceptable ranks just above converged)
+DART_HD int status_rank(int32_t st) { return st == ST_CONVERGED ? 0 : st == ST_ACCEPTABLE ? 1 : st == ST_MAXITER ? 2 : st == ST_INFEASIBLE ? 3 : 4; }
 
 struct SolverOpts {
     double tol, mu0, kappa_mu, theta_mu, kappa_eps, tau_min, bound_push, eta, smax;
     double s_phi, s_theta, delta_sw, gamma_theta, gamma_phi, theta_small;
     int max_iter, max_backtrack;
+    // IPOPT's acceptable-level termination: acc_iter consecutive iterates with error <= acc_tol (acc_iter = 0: off)
+    double acc_tol;
+    int acc_iter;
 };
 
 DART_HD double dmax(double a, double b) { return a > b ? a : b; }
@@ -952,7 +957,7 @@ struct Solver {
             inv_nc = 1.0 / (double)(2 * (nact > 0 ? nact : 1));
         }
         const double mu_min = o.tol / 10.0;
-        int it = 0, tiny = 0;
+        int it = 0, tiny = 0, nacc = 0;
         int32_t st = ST_MAXITER;
         double E0 = 0.0, is_d = 1.0, is_c = 1.0;
         bool done = !active;
@@ -976,7 +981,11 @@ struct Solver {
                 E0 = dmax(base, (nact > 0 ? zs_max : 0.0) * is_c);
                 if (E0 <= o.tol) { st = ST_CONVERGED; done = true; }
                 else if (!(E0 == E0) || E0 > 1e300) { st = ST_NUMERIC; done = true; }
-                else if (it >= o.max_iter) done = true;
+                else {
+                    nacc = (o.acc_iter > 0 && E0 <= o.acc_tol) ? nacc + 1 : 0;
+                    if (o.acc_iter > 0 && nacc >= o.acc_iter) { st = ST_ACCEPTABLE; done = true; }
+                    else if (it >= o.max_iter) done = true;
+                }
                 if (!done) {
                     for (int q = 0; q < 8; ++q) {
                         double cm = (nact > 0) ? dmax(fabs(zs_max - mu), fabs(zs_min - mu)) : 0.0;

@@ -102,10 +102,18 @@ class PolicyMLP:
 
 
 class LMPCBatch:
-    """B learning-based controllers resident on one GPU (one ``step`` = 3-4 launches)."""
+    """B learning-based controllers resident on one GPU (one ``step`` = 3-4 launches).
+
+    ``warm_start``: True = the previous solution as it is (the reference, rlmpc2.py:492,521), ``"shift"`` = the
+    previous plan advanced by one stage (last stage repeated), False = cold.  ``plan_fallback``: when a solve ends
+    without a usable plan (status other than converged / acceptable) the command is the next entry of the last good
+    plan and that plan stays the warm start -- the reference facade's plan shift (rlmpc2.py:1013-1018), which there
+    covers "the solver process has nothing new yet".  Solver options (``tol``, ``acceptable_tol``, ``acceptable_iter``,
+    ``max_iter``; the reference's are ``config.LMPC_REFERENCE_SOLVER_OPTIONS``) pass through ``cfg_kw``."""
 
     def __init__(self, B, pvec0, weights=None, seed=3, device=0, max_param_abs=2.0, max_delta_abs=0.02, min_k=1e-2,
-                 k_ceiling_margin=None, shm_smooth_alpha=0.5, update_every=8, warm_start=True, **cfg_kw):
+                 k_ceiling_margin=None, shm_smooth_alpha=0.5, update_every=8, warm_start=True, plan_fallback=False,
+                 **cfg_kw):
         torch = _torch()
         self.torch = torch
         self.B = int(B)
@@ -133,6 +141,21 @@ class LMPCBatch:
         self.timestep = 0
         self.count = 0
         self.warm_start = warm_start
+        self.plan_fallback = bool(plan_fallback)
+        N = self.cfg.N
+        self._nxw = 8 * (N + 1)
+        if self.plan_fallback:
+            self.plan_U = torch.zeros((B, N, 2), dtype=f64, device=self.dev)
+            self.plan_pos = torch.zeros((B,), dtype=torch.int64, device=self.dev)
+            self._rows = torch.arange(B, device=self.dev)
+            self.n_fallback = torch.zeros((), dtype=torch.int64, device=self.dev)     # solves replaced by a plan shift
+
+    def _shifted(self, w):
+        """Previous plan advanced by one stage: x_k <- x_{k+1}, u_k <- u_{k+1}, last stage repeated."""
+        torch, N = self.torch, self.cfg.N
+        X = w[:, :self._nxw].view(self.B, N + 1, 8)
+        U = w[:, self._nxw:].view(self.B, N, 2)
+        return torch.cat([X[:, 1:].reshape(self.B, -1), X[:, -1], U[:, 1:].reshape(self.B, -1), U[:, -1]], dim=1)
 
     @property
     def pvec(self):
@@ -157,8 +180,22 @@ class LMPCBatch:
             check(L.dart_policy_param_update(self.B, p(self.action), C.c_void_p(self.aux.data_ptr() + 16), 36, self.k_max,
                                              self.max_delta, self.min_k, self.margin, self.alpha, stream),
                   "dart_policy_param_update")
-        self.engine.solve_device(state, target, aux=self.aux, warm_w=self.w if self.warm_start else None,
+        warm = None
+        if self.warm_start:
+            warm = self._shifted(self.w) if (self.warm_start == "shift" and self.timestep > 0) else self.w
+        self.engine.solve_device(state, target, aux=self.aux, warm_w=warm,
                                  w_out=self.w_next, u0_out=self.u0, J_out=self.J, status=self.status, iters=self.iters)
+        if self.plan_fallback:
+            ok = (self.status == _lib.STATUS_CONVERGED) | (self.status == _lib.STATUS_ACCEPTABLE)
+            if self.timestep == 0:
+                ok = torch.ones_like(ok)                  # nothing to fall back on yet: the reference holds u = 0 / the last iterate
+            N = self.cfg.N
+            U_new = self.w_next[:, self._nxw:].view(self.B, N, 2)
+            self.n_fallback += (~ok).sum()
+            self.plan_U = torch.where(ok[:, None, None], U_new, self.plan_U)
+            self.plan_pos = torch.where(ok, torch.zeros_like(self.plan_pos), torch.clamp(self.plan_pos + 1, max=N - 1))
+            self.u0.copy_(self.plan_U[self._rows, self.plan_pos])
+            self.w_next = torch.where(ok[:, None], self.w_next, self.w)
         self.w, self.w_next = self.w_next, self.w
         self.u_prev.copy_(self.u0)
         self.aux[:, :2] = self.u0
@@ -215,7 +252,8 @@ class RLMPC:
                                 max_param_abs=k_max, max_delta_abs=params.get("max_delta_abs", 0.1), min_k=min_k,
                                 k_ceiling_margin=margin, shm_smooth_alpha=params.get("shm_smooth_alpha", 0.5),
                                 Ts=params["Ts"], N=N, Q=params["Q"], Qt=params["Qt"], R=params["R"],
-                                u_bounds=params["u_bounds"])
+                                u_bounds=params["u_bounds"], plan_fallback=True,
+                                warm_start=params.get("warm_start", True), **dict(params.get("solver_options", {})))
         self.views["model_params"][:] = k0
         self.loss = np.zeros(1)
 

@@ -37,6 +37,8 @@ extern "C" {
 #define DART_STATUS_MAXITER 1     /* iteration cap hit; last iterate returned (reference: silent)  */
 #define DART_STATUS_INFEASIBLE 2  /* x0 violates a stage-0 cap, or the step vanished with violation left   */
 #define DART_STATUS_NUMERIC 3     /* NaN/Inf encountered                                           */
+#define DART_STATUS_ACCEPTABLE 4  /* acceptable_iter consecutive iterates with error <= acceptable_tol (IPOPT's
+                                     "Solved To Acceptable Level"); only when enabled in dart_cfg              */
 
 typedef enum {
     DART_OK = 0,
@@ -72,6 +74,11 @@ typedef struct {
     double mu_init;      /* [0.1]   initial barrier parameter               */
     int32_t lanes;       /* [auto]  lanes of a warp cooperating on one sub-problem: 2, 4, 8, 16 or 32 */
     int32_t block_threads; /* [auto] threads per block (multiple of 32)     */
+    /* IPOPT's acceptable-level termination (rlmpc2.py:486-488 sets tol 1e-4, acceptable_tol 1e-3, acceptable_iter 5,
+     * max_iter 50 for LMPC; PMPC/RMPC leave IPOPT's 1e-6 / 15, which never triggers before tol on this path).
+     * [0 / 0 = off: every solve runs to tol] */
+    double acceptable_tol;
+    int32_t acceptable_iter;
 } dart_cfg;
 
 typedef struct dart_solver* dart_handle;

@@ -31,12 +31,15 @@ STATUS_CONVERGED = 0
 STATUS_MAXITER = 1
 STATUS_INFEASIBLE = 2
 STATUS_NUMERIC = 3
+STATUS_ACCEPTABLE = 4   # IPOPT's acceptable-level termination (rlmpc2.py:486-488), off unless acc_iter > 0
 
 
 @dataclass
 class Options:
     tol: float = 1e-8
     max_iter: int = 200
+    acc_tol: float = 0.0
+    acc_iter: int = 0
     mu0: float = 0.1
     kappa_mu: float = 0.2
     theta_mu: float = 1.5
@@ -120,6 +123,7 @@ def solve(prob: StageProblem, X0=None, U0=None, opts: Options = None, trace=None
     if prob.naug:
         X[:, 1:, n - m:] = U
     status = np.full(B, STATUS_MAXITER, dtype=np.int32)
+    nacc = np.zeros(B, dtype=np.int64)
     infeasible0 = np.zeros(B, dtype=bool)
     for r, row in enumerate(prob.rows):       # rows skipped at k=0 must hold for the given x0
         if row.skip0:
@@ -188,6 +192,11 @@ def solve(prob: StageProblem, X0=None, U0=None, opts: Options = None, trace=None
         bad = (~done) & ~np.isfinite(E0)
         status[bad] = STATUS_NUMERIC
         done |= bad
+        if o.acc_iter > 0:      # consecutive acceptable iterates
+            nacc = np.where((~done) & (E0 <= o.acc_tol), nacc + 1, 0)
+            acc = (~done) & (nacc >= o.acc_iter)
+            status[acc] = STATUS_ACCEPTABLE
+            done |= acc
         if trace is not None:
             trace.append(dict(it=it, E0=E0.copy(), mu=mu.copy(), dual=dual_inf.copy(), prim=prim_inf.copy(),
                               J=prob.objective(X, U), done=done.copy()))

@@ -61,3 +61,30 @@ def test_max_iter_status(hostemu):
     c, aux, _ = helpers.pmpc_case(1)
     out = hostemu.solve(dart_b200.pmpc_cfg(max_iter=2), c["state"], c["target"], aux)
     assert (out["status"] == dart_b200.STATUS_MAXITER).all() and (out["iters"] == 2).all()
+
+
+def test_acceptable_level_termination_matches_oracle(hostemu):
+    """IPOPT's acceptable_tol / acceptable_iter (the reference sets them for LMPC, rlmpc2.py:486-488).  RMPC is one
+    undivided NLP on both sides, so solver and oracle stop at the same iterate."""
+    d, p = helpers.rmpc_case(32)
+    tight = hostemu.solve(dart_b200.rmpc_cfg(), d["x0"], d["ref"], d["aux"])
+    opts = dict(tol=1e-12, acceptable_tol=1e-3, acceptable_iter=3)        # tol out of reach: only the acceptable exit
+    out = hostemu.solve(dart_b200.rmpc_cfg(**opts), d["x0"], d["ref"], d["aux"])
+    ref = ipm.solve(p, opts=ipm.Options(tol=1e-12, acc_tol=1e-3, acc_iter=3))
+    assert (out["status"] == dart_b200.STATUS_ACCEPTABLE).all() and (ref["status"] == ipm.STATUS_ACCEPTABLE).all()
+    assert np.array_equal(out["iters"], ref["iters"])
+    assert np.abs(out["u0"] - ref["U"][:, 0]).max() < 1e-9
+    assert (out["iters"] < tight["iters"]).all()
+    assert np.abs(out["u0"] - tight["u0"]).max() < 5e-3                   # an early exit, not a different optimum
+
+
+def test_reference_lmpc_solver_options(hostemu):
+    """tol 1e-4 / acceptable 1e-3 x 5 / max_iter 50: fewer iterations, same plan to within the early-exit tolerance."""
+    from dart_b200.config import LMPC_REFERENCE_SOLVER_OPTIONS as ro
+    d, p = helpers.lmpc_case(32)
+    tight = hostemu.solve(dart_b200.lmpc_cfg(), d["x0"], d["ref"], d["aux"])
+    out = hostemu.solve(dart_b200.lmpc_cfg(**ro), d["x0"], d["ref"], d["aux"])
+    assert np.isin(out["status"], (dart_b200.STATUS_CONVERGED, dart_b200.STATUS_ACCEPTABLE)).all()
+    assert out["iters"].mean() < tight["iters"].mean() - 1.0
+    assert np.abs(out["u0"] - tight["u0"]).max() < 2e-3
+    assert (np.abs(out["J"] - tight["J"]) / np.abs(tight["J"])).max() < 1e-4

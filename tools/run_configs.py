@@ -78,24 +78,25 @@ def config3(B, T):
                 theta_hat_absmax=float(ctl.theta.abs().max().item()))
 
 
-def config4(B, T):
+def config4(B, T, label="4: LMPC with the policy MLP (random orthogonal init), model-as-plant", **kw):
     c = dart_b200.workloads.lmpc_config4(B, seed=3)
     dev = torch.device("cuda", LOCAL)
-    ctl = dart_b200.LMPCBatch(B, c["pvec"], seed=3, device=LOCAL)
+    ctl = dart_b200.LMPCBatch(B, c["pvec"], seed=3, device=LOCAL, **kw)
     x = torch.from_numpy(c["state"]).to(dev); tg = torch.from_numpy(c["target"]).to(dev)
-    stat = torch.zeros(4, dtype=torch.int64, device=dev); it_sum = torch.zeros((), dtype=torch.int64, device=dev)
+    stat = torch.zeros(5, dtype=torch.int64, device=dev); it_sum = torch.zeros((), dtype=torch.int64, device=dev)
     a, b = ev(), ev()
     a.record()
     for t in range(T):
         ctl.step(x, tg)
-        stat += torch.bincount(ctl.status.long(), minlength=4)
+        stat += torch.bincount(ctl.status.long(), minlength=5)
         it_sum += ctl.iters.sum()
         x = ctl.w[:, 8:16].contiguous()          # plant = the controller's own model: predicted x_1 of the optimal plan
     b.record(); torch.cuda.synchronize()
     sec = a.elapsed_time(b) * 1e-3
     st = stat.cpu().numpy()
-    return dict(config="4: LMPC with the policy MLP (random orthogonal init), model-as-plant", B=B, steps=T, seconds=sec,
-                solves_per_s=B * T / sec, status_counts=dict(converged=int(st[0]), max_iter=int(st[1]), infeasible=int(st[2]), numeric=int(st[3])),
+    return dict(config=label, B=B, steps=T, seconds=sec,
+                solves_per_s=B * T / sec, status_counts=dict(converged=int(st[0]), max_iter=int(st[1]), infeasible=int(st[2]), numeric=int(st[3]), acceptable=int(st[4])),
+                final_pos_err_m=float((x[:, [0, 2]] - tg[:, [0, 2]]).norm(dim=1).median().item()),
                 mean_iters=float(it_sum.item()) / (B * T), policy_launches=ctl.policy.launch_count,
                 pvec_range=[float(ctl.pvec.min().item()), float(ctl.pvec.max().item())])
 
@@ -161,7 +162,7 @@ if __name__ == "__main__":
     q = args.quick
     GRAPH = args.graph
     res = []
-    todo = [args.only] if args.only else ["config1", "config2", "config3", "config4", "config5"]
+    todo = args.only.split(",") if args.only else ["config1", "config2", "config3", "config4", "config4_shift", "config4_refopts", "config5"]
     for name in todo:
         if WORLD > 1 and name != "config5":
             continue
@@ -169,6 +170,10 @@ if __name__ == "__main__":
         elif name == "config2": r = config2_closed_loop(200 if q else 5000)
         elif name == "config3": r = config3(512 if q else 4096, 32 if q else 256)
         elif name == "config4": r = config4(2048 if q else 16384, 8 if q else 64)
+        elif name == "config4_shift": r = config4(2048 if q else 16384, 8 if q else 64, label="4 (f2): shifted-plan warm start", warm_start="shift")
+        elif name == "config4_refopts":
+            from dart_b200.config import LMPC_REFERENCE_SOLVER_OPTIONS as ro
+            r = config4(2048 if q else 16384, 8 if q else 64, label="4 (f2): the reference's IPOPT options (tol 1e-4, acceptable 1e-3 x 5, max_iter 50) + plan-shift fallback", plan_fallback=True, **ro)
         else: r = config5(3 * 2 ** 12 if q else 2 ** 20)
         res.append(r)
         if RANK == 0:
