@@ -13,3 +13,5 @@ from .rmpc import RLS, AdaptiveNPMPCSmooth, RMPCBatch, rls_update_device   # noq
 from .lmpc import RLMPC, LMPCBatch, PolicyMLP, init_policy_weights, load_checkpoint_weights   # noqa: F401
 from .parallel import ShardedSolver, shard_bounds   # noqa: F401
 from .episodes import PMPCEpisodes   # noqa: F401
+from .arm import ARMCONTROL, ArmQPBatch   # noqa: F401
+from . import arm   # noqa: F401

@@ -128,3 +128,23 @@ def lmpc_inputs(B=32, seed=3):
     rng = np.random.default_rng(seed + 100)
     up = rng.uniform(-0.2, 0.2, (B, 2))
     return dict(x0=c["state"], ref=c["target"], aux=np.concatenate([up, c["pvec"]], axis=1), u_prev=up, pvec=c["pvec"])
+
+
+def arm_dynamics(B, seed=0, stress=1.0):
+    """Synthetic but physically shaped inputs of the low-level arm QP (the reference gets them from MuJoCo, arm.py:111-200): SPD mass matrix, full-rank 6x7
+    Jacobian, Mx_inv = J M^-1 J' as in arm.py:139, small pose errors.  ``stress`` scales velocities / errors so that
+    torque and velocity rows become active."""
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((B, 7, 7))
+    M = np.einsum('bij,bkj->bik', A, A) * 0.15 + np.eye(7) * np.array([2.0, 2.0, 1.0, 1.0, 0.5, 0.3, 0.2])
+    jac = rng.standard_normal((B, 6, 7)) * 0.4
+    jacDot = rng.standard_normal((B, 6, 7)) * 0.2 * stress
+    Minv = np.linalg.inv(M)
+    Mx_inv = jac @ Minv @ np.transpose(jac, (0, 2, 1))
+    q = rng.uniform(-1.0, 1.0, (B, 7)); q[:, 3] = rng.uniform(0.2, 2.5, B)
+    ee = rng.uniform(-0.3, 0.3, (B, 3))
+    tau_lim = np.array([50.0, 50, 30, 30, 30, 20, 20])
+    return dict(q=q, qd=rng.standard_normal((B, 7)) * 0.1 * stress, qdd_prev=rng.standard_normal((B, 7)) * 2.0,
+                mocap_pos=ee + 2e-4 * stress * rng.standard_normal((B, 3)), ee_pos=ee,
+                rotvec=rng.standard_normal((B, 3)) * 2e-3 * stress, jac=jac, jacDot=jacDot, M=M,
+                h=rng.uniform(-0.5, 0.5, (B, 7)) * tau_lim * min(1.0, stress), Mx_inv=Mx_inv)

@@ -187,6 +187,19 @@ int dart_pmpc_plant_step(int32_t B, double Ts, double g, const double* mu, const
                          const double* target, double* state, int32_t* nsteps, double tol, double* conv_time,
                          double* effort, double* err, void* stream);
 
+/* Low-level arm controller QP: replaces the per-cycle ca.nlpsol('solver','ipopt',...) construction and call of
+ * ARMCONTROL.solver_worker, PMPC/src/controller/arm.py:337-457, for B arms at once:
+ *     min 0.5 x'Hx + g'x   s.t.  lo <= Cx <= hi,     x = joint accelerations qdd (7),
+ *     C = [0.5 dt^2 I; dt I; M] (21 rows: joint-position, joint-velocity and torque limits, arm.py:399-405).
+ * H [B,7,7] (symmetric positive definite), g [B,7], C [B,21,7], lo/hi [B,21], x0 [B,7] (optional primal start, the
+ * reference's prev_qdd) -> x [B,7], obj [B] = 0.5 x'Hx + g'x, status [B] (DART_STATUS_*), iters [B]; all device pointers,
+ * row-major f64.  tol <= 0 selects 1e-8, max_iter <= 0 selects 100.  The caller forms H, g, lo, hi from the MuJoCo
+ * quantities (dart_b200.arm.build_qp mirrors arm.py:337-405). */
+int dart_arm_qp_solve(int32_t B, const double* H, const double* g, const double* C, const double* lo, const double* hi,
+                      const double* x0, double* x, double* obj, int32_t* status, int32_t* iters, double tol,
+                      int32_t max_iter, void* stream);
+int64_t dart_arm_qp_launch_count(void);
+
 /* Measured FP64 FMA-pipe peak of the device in TFLOP/s (DFMA microbenchmark, CUDA-event timed): the roofline
  * denominator bench.py reports the solver kernels against. */
 int dart_measure_fp64_tflops(int device, double* tflops);
