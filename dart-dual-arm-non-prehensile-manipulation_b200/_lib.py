@@ -74,6 +74,7 @@ def lib():
     if hasattr(L, "dart_arm_qp_solve"):
         L.dart_arm_qp_solve.argtypes = [C.c_int32] + [vp] * 10 + [C.c_double, C.c_int32, vp]
         L.dart_arm_qp_launch_count.restype = C.c_int64
+        L.dart_arm_qp_build.argtypes = [C.c_int32] + [vp] * 7 + [C.c_double] + [vp] * 17 + [vp]
     _lib = L
     return L
 

@@ -93,6 +93,36 @@ def solve_qp_device(H, g, Cm, lo, hi, x0=None, tol=1e-8, max_iter=100, out=None)
     return out
 
 
+_DYN_KEYS = ("q", "qd", "qdd_prev", "mocap_pos", "ee_pos", "rotvec", "jac", "jacDot", "M", "h", "Mx_inv")
+_DYN_SHAPES = {"q": (7,), "qd": (7,), "qdd_prev": (7,), "mocap_pos": (3,), "ee_pos": (3,), "rotvec": (3,), "jac": (6, 7),
+               "jacDot": (6, 7), "M": (7, 7), "h": (7,), "Mx_inv": (6, 6)}
+
+
+def build_qp_device(dyn, params, out=None):
+    """``build_qp`` on the GPU (dart_arm_qp_build): ``dyn`` holds float64 CUDA tensors with a leading batch axis."""
+    import torch
+    B = dyn["q"].shape[0]
+    dev = dyn["q"].device
+    for k in _DYN_KEYS:
+        t = dyn[k]
+        if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and tuple(t.shape) == (B,) + _DYN_SHAPES[k]):
+            raise ValueError(f"dyn['{k}'] must be a contiguous float64 CUDA tensor of shape {(B,) + _DYN_SHAPES[k]}")
+    if out is None:
+        e = lambda *s: torch.empty((B,) + s, dtype=torch.float64, device=dev)
+        out = dict(H=e(NV, NV), g=e(NV), c0=e(), C=e(NR, NV), lo=e(NR), hi=e(NR))
+    hp = lambda a, n: np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(n))
+    host = [hp(params["Wimp"], 36), hp(params["Wpos"], 49), hp(params["Wsmooth"], 49), hp(params["K"], 36), hp(params["K_null"], 49),
+            hp(np.concatenate([params["Qmin"], params["Qdotmin"], params["taumin"]]), 21),
+            hp(np.concatenate([params["Qmax"], params["Qdotmax"], params["taumax"]]), 21)]
+    p = lambda t: C.c_void_p(t.data_ptr())
+    with torch.cuda.device(dev):
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        check(_lib.lib().dart_arm_qp_build(B, *[C.c_void_p(a.ctypes.data) for a in host], float(params["dt"]),
+                                            *[p(dyn[k]) for k in _DYN_KEYS], p(out["H"]), p(out["g"]), p(out["c0"]),
+                                            p(out["C"]), p(out["lo"]), p(out["hi"]), stream), "dart_arm_qp_build")
+    return out
+
+
 class ArmQPBatch:
     """B arm controllers: ``solve(dyn)`` = one cycle of the reference's solver worker for each of them (primal warm start
     from the previous accelerations, arm.py:412-418; IPOPT's dual warm start has no counterpart -- cold duals)."""
@@ -106,20 +136,27 @@ class ArmQPBatch:
         self.prev = None
         self.launches = 0
 
-    def solve(self, dyn):
+    def solve_device(self, dyn):
+        """``dyn``: CUDA tensors.  Two launches (QP build, QP solve) + one batched matrix-vector product for the torque;
+        returns device tensors (tau [B,7], loss [B], qdd [B,7]); ``self.status`` / ``self.iters`` stay on the device."""
         torch = self.torch
-        H, g, c0, Cm, lo, hi = build_qp(dyn, self.params)
-        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(self.dev)
-        x0 = self.prev if (self.warm_start and self.prev is not None and self.prev.shape[0] == H.shape[0]) else None
-        out = solve_qp_device(t(H), t(g), t(Cm), t(lo), t(hi), x0=x0, tol=self.tol, max_iter=self.max_iter)
-        self.launches += 1
+        qp = build_qp_device(dyn, self.params)
+        B = qp["H"].shape[0]
+        x0 = self.prev if (self.warm_start and self.prev is not None and self.prev.shape[0] == B) else None
+        out = solve_qp_device(qp["H"], qp["g"], qp["C"], qp["lo"], qp["hi"], x0=x0, tol=self.tol, max_iter=self.max_iter)
+        self.launches += 2
         self.prev = out["x"]
-        x = out["x"].cpu().numpy()
-        M, h = np.asarray(dyn["M"], float), np.asarray(dyn["h"], float)
-        tau = np.einsum('bij,bj->bi', M, x) + h                                    # arm.py:425
-        loss = out["obj"].cpu().numpy() + c0
-        self.status, self.iters = out["status"].cpu().numpy(), out["iters"].cpu().numpy()
-        return tau, loss, x
+        tau = torch.bmm(dyn["M"], out["x"][:, :, None])[:, :, 0] + dyn["h"]         # arm.py:425
+        self.status, self.iters = out["status"], out["iters"]
+        return tau, out["obj"] + qp["c0"], out["x"]
+
+    def solve(self, dyn):
+        """``dyn``: numpy arrays with a leading batch axis (what compute_dynamics returns, stacked).  Host in, host out."""
+        torch = self.torch
+        d = {k: torch.from_numpy(np.ascontiguousarray(dyn[k], dtype=np.float64)).to(self.dev) for k in _DYN_KEYS}
+        tau, loss, x = self.solve_device(d)
+        self.status, self.iters = self.status.cpu().numpy(), self.iters.cpu().numpy()
+        return tau.cpu().numpy(), loss.cpu().numpy(), x.cpu().numpy()
 
 
 class ARMCONTROL:

@@ -256,3 +256,234 @@ extern "C" int dart_arm_qp_solve(int32_t B, const double* H, const double* g, co
 }
 
 extern "C" int64_t dart_arm_qp_launch_count(void) { return g_arm_qp_launches; }
+
+// =====================================================================================================================
+// QP build on the device: arm.py:337-405 for B arms, from the dictionary ARMCONTROL.compute_dynamics returns.  The
+// reference does this in numpy per cycle (pinv of the mass matrix, inverse or pinv of the task-space inertia, its matrix
+// square root by eigh); here both symmetric eigen-decompositions are cyclic Jacobi iterations run by the 8 lanes of the
+// arm's tile (lane k owns row/column k of the rotation), and every matrix function follows from them:
+//   pinv(M, rcond 1e-6)               = V7 diag(1/w | 0) V7'
+//   Mx = inv(Mx_inv) or pinv(., 1e-3) = V6 diag(1/w | 0) V6'      (arm.py:351-357 picks by |det| > 1e-8)
+//   safe_matrix_sqrt(Mx)              = V6 diag(sqrt|1/w|) V6'    (arm.py:363-366)
+namespace dart {
+namespace {
+
+struct ArmParams {
+    double Wimp[36], Wpos[49], Wsm[49], K[36], Knull[49], lim_lo[21], lim_hi[21], dt;
+};
+
+struct BuildSmem {
+    double A7[49], V7[49], A6[36], V6[36], Mx[36], sMx[36], w7[7], w6[6];
+    double qd[7], q[7], jq[6], jdq[6], v1[7], v2[6], F[6], e0[6], beta[7], we0[6];
+};
+constexpr int kBuildDoubles = sizeof(BuildSmem) / sizeof(double) | 1;
+
+// Cyclic Jacobi for a symmetric n x n matrix in shared memory (full storage).  On return the diagonal of A holds the
+// eigenvalues and the columns of V the eigenvectors.  Lane k (< n) owns row k in the column update and column k in the
+// row update; lanes >= n idle through the same syncs.
+template <int n>
+__device__ __forceinline__ void jacobi_eig(double* A, double* V, int lane, unsigned mask) {
+    if (lane < n) {
+        for (int c = 0; c < n; ++c) V[lane * n + c] = (lane == c) ? 1.0 : 0.0;
+        for (int c = lane + 1; c < n; ++c) {                 // symmetrise from both triangles
+            const double a = 0.5 * (A[lane * n + c] + A[c * n + lane]);
+            A[lane * n + c] = a; A[c * n + lane] = a;
+        }
+    }
+    __syncwarp(mask);
+    for (int sweep = 0; sweep < 12; ++sweep) {
+        double off = 0.0, dia = 0.0;
+        for (int i = 0; i < n; ++i)
+            for (int k = 0; k < n; ++k) { const double a = A[i * n + k]; if (i == k) dia += a * a; else off += a * a; }
+        if (off <= 1e-32 * dia) break;                       // tile-uniform: every lane read the same matrix
+        for (int p = 0; p < n - 1; ++p) {
+            for (int q = p + 1; q < n; ++q) {
+                const double apq = A[p * n + q];
+                if (fabs(apq) < 1e-300) continue;            // uniform
+                const double app = A[p * n + p], aqq = A[q * n + q];
+                const double theta = (aqq - app) / (2.0 * apq);
+                const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                __syncwarp(mask);                            // all lanes have read app, aqq, apq
+                if (lane < n) {                              // columns p, q of row `lane`; eigenvector row `lane`
+                    const double akp = A[lane * n + p], akq = A[lane * n + q];
+                    A[lane * n + p] = c * akp - s * akq; A[lane * n + q] = s * akp + c * akq;
+                    const double vkp = V[lane * n + p], vkq = V[lane * n + q];
+                    V[lane * n + p] = c * vkp - s * vkq; V[lane * n + q] = s * vkp + c * vkq;
+                }
+                __syncwarp(mask);
+                if (lane < n) {                              // rows p, q of column `lane`
+                    const double apk = A[p * n + lane], aqk = A[q * n + lane];
+                    A[p * n + lane] = c * apk - s * aqk; A[q * n + lane] = s * apk + c * aqk;
+                }
+                __syncwarp(mask);
+            }
+        }
+    }
+    __syncwarp(mask);
+}
+
+__global__ void __launch_bounds__(128) arm_qp_build_kernel(int B, ArmParams P, const double* __restrict__ q_, const double* __restrict__ qd_,
+                                                            const double* __restrict__ qddp_, const double* __restrict__ mocap_,
+                                                            const double* __restrict__ ee_, const double* __restrict__ rotvec_,
+                                                            const double* __restrict__ jac_, const double* __restrict__ jacDot_,
+                                                            const double* __restrict__ M_, const double* __restrict__ h_,
+                                                            const double* __restrict__ Mxinv_, double* __restrict__ Hout,
+                                                            double* __restrict__ gout, double* __restrict__ c0out,
+                                                            double* __restrict__ Cout, double* __restrict__ loout,
+                                                            double* __restrict__ hiout) {
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & (G - 1);
+    const unsigned mask = 0xffu << ((threadIdx.x & 31) - lane);
+    const int qib = threadIdx.x / G;
+    const long b = (long)blockIdx.x * (blockDim.x / G) + qib;
+    if (b >= B) return;
+    BuildSmem& S = *reinterpret_cast<BuildSmem*>(smem + (size_t)qib * kBuildDoubles);
+    const double* jac = jac_ + b * 42;
+    const double* jacDot = jacDot_ + b * 42;
+    const double* Mg = M_ + b * 49;
+    const double* Mxi = Mxinv_ + b * 36;
+    for (int i = lane; i < 49; i += G) S.A7[i] = Mg[i];
+    for (int i = lane; i < 36; i += G) S.A6[i] = Mxi[i];
+    if (lane < 7) { S.qd[lane] = qd_[b * 7 + lane]; S.q[lane] = q_[b * 7 + lane]; }
+    __syncwarp(mask);
+    jacobi_eig<7>(S.A7, S.V7, lane, mask);
+    jacobi_eig<6>(S.A6, S.V6, lane, mask);
+    // ---- spectra -> reciprocal spectra (pinv thresholds on singular values = |eigenvalues|)
+    {
+        double m7 = 0.0, m6 = 0.0, det = 1.0;
+        for (int k = 0; k < 7; ++k) m7 = fmax(m7, fabs(S.A7[k * 7 + k]));
+        for (int k = 0; k < 6; ++k) { m6 = fmax(m6, fabs(S.A6[k * 6 + k])); det *= S.A6[k * 6 + k]; }
+        const bool regular = fabs(det) > 1e-8;
+        __syncwarp(mask);
+        if (lane < 7) { const double w = S.A7[lane * 7 + lane]; S.w7[lane] = (fabs(w) > 1e-6 * m7) ? 1.0 / w : 0.0; }
+        if (lane < 6) { const double w = S.A6[lane * 6 + lane]; S.w6[lane] = (regular || fabs(w) > 1e-3 * m6) ? 1.0 / w : 0.0; }
+    }
+    __syncwarp(mask);
+    // ---- Mx, sqrt(Mx) (column `lane`), v1 = pinv(M) h, J qd, Jdot qd
+    if (lane < 6) {
+        for (int i = 0; i < 6; ++i) {
+            double a = 0.0, r = 0.0;
+            for (int k = 0; k < 6; ++k) {
+                const double vv = S.V6[i * 6 + k] * S.V6[lane * 6 + k];
+                a += vv * S.w6[k]; r += vv * sqrt(fabs(S.w6[k]));
+            }
+            S.Mx[i * 6 + lane] = a; S.sMx[i * 6 + lane] = r;
+        }
+        double a = 0.0, d = 0.0;
+        for (int v = 0; v < 7; ++v) { a += jac[lane * 7 + v] * S.qd[v]; d += jacDot[lane * 7 + v] * S.qd[v]; }
+        S.jq[lane] = a; S.jdq[lane] = d;
+    }
+    if (lane < 7) {
+        double acc = 0.0;                                    // (V diag(w) V' h)_lane
+        for (int k = 0; k < 7; ++k) {
+            double vh = 0.0;
+            for (int i = 0; i < 7; ++i) vh += S.V7[i * 7 + k] * h_[b * 7 + i];
+            acc += S.V7[lane * 7 + k] * S.w7[k] * vh;
+        }
+        S.v1[lane] = acc;
+        double be = 2.0 * sqrt(P.Knull[lane * 7 + lane]) * (-S.qd[lane]);
+        for (int v = 0; v < 7; ++v) be += P.Knull[lane * 7 + v] * (-S.q[v]);
+        S.beta[lane] = be;
+    }
+    __syncwarp(mask);
+    if (lane < 6) {
+        double a = S.jdq[lane];
+        for (int v = 0; v < 7; ++v) a += jac[lane * 7 + v] * S.v1[v];
+        S.v2[lane] = a;
+    }
+    __syncwarp(mask);
+    // ---- F = -D (J qd) + K twist + Mx v2,  D = sqrt(Mx) sqrt(K) + sqrt(K) sqrt(Mx)  (sqrt(K) elementwise, arm.py:368)
+    if (lane < 6) {
+        double f = 0.0;
+        for (int c = 0; c < 6; ++c) {
+            double d = 0.0;
+            for (int k = 0; k < 6; ++k) d += S.sMx[lane * 6 + k] * sqrt(P.K[k * 6 + c]) + sqrt(P.K[lane * 6 + k]) * S.sMx[k * 6 + c];
+            const double tw = (c < 3) ? (mocap_[b * 3 + c] - ee_[b * 3 + c]) : rotvec_[b * 3 + (c - 3)];
+            f += -d * S.jq[c] + P.K[lane * 6 + c] * tw + S.Mx[lane * 6 + c] * S.v2[c];
+        }
+        S.F[lane] = f;
+    }
+    __syncwarp(mask);
+    if (lane < 6) {
+        double e = S.jdq[lane];
+        for (int c = 0; c < 6; ++c) e -= Mxi[lane * 6 + c] * S.F[c];
+        S.e0[lane] = e;
+    }
+    __syncwarp(mask);
+    if (lane < 6) {
+        double a = 0.0;
+        for (int c = 0; c < 6; ++c) a += P.Wimp[lane * 6 + c] * S.e0[c];
+        S.we0[lane] = a;
+    }
+    __syncwarp(mask);
+    // ---- H column `lane`, g, bounds, C; c0 by reduction
+    double c0p = 0.0;
+    if (lane < 7) {
+        double wj[6];                                        // (Wimp J)[:, lane]
+        for (int r = 0; r < 6; ++r) { double a = 0.0; for (int c = 0; c < 6; ++c) a += P.Wimp[r * 6 + c] * jac[c * 7 + lane]; wj[r] = a; }
+        for (int i = 0; i < 7; ++i) {
+            double a = 0.0, at = 0.0;                        // J'WJ [i][lane] and its transpose entry (Wimp may be non-symmetric)
+            for (int r = 0; r < 6; ++r) a += jac[r * 7 + i] * wj[r];
+            for (int r = 0; r < 6; ++r) { double w2 = 0.0; for (int c = 0; c < 6; ++c) w2 += P.Wimp[r * 6 + c] * jac[c * 7 + i]; at += jac[r * 7 + lane] * w2; }
+            const double hij = 2.0 * (a + P.Wpos[i * 7 + lane] + P.Wsm[i * 7 + lane]);
+            const double hji = 2.0 * (at + P.Wpos[lane * 7 + i] + P.Wsm[lane * 7 + i]);
+            Hout[b * 49 + i * 7 + lane] = 0.5 * (hij + hji);
+        }
+        double gg = 0.0, wb = 0.0, ws = 0.0;
+        for (int r = 0; r < 6; ++r) gg += jac[r * 7 + lane] * S.we0[r];
+        for (int v = 0; v < 7; ++v) { wb += P.Wpos[lane * 7 + v] * S.beta[v]; ws += P.Wsm[lane * 7 + v] * qddp_[b * 7 + v]; }
+        gout[b * 7 + lane] = 2.0 * (gg - wb - ws);
+        c0p = S.beta[lane] * wb + qddp_[b * 7 + lane] * ws;
+        const double qd = S.qd[lane], q = S.q[lane], hh = h_[b * 7 + lane];
+        const double off[3] = {qd * P.dt + q, qd, hh};
+        for (int t = 0; t < 3; ++t) {
+            loout[b * 21 + t * 7 + lane] = P.lim_lo[t * 7 + lane] - off[t];
+            hiout[b * 21 + t * 7 + lane] = P.lim_hi[t * 7 + lane] - off[t];
+        }
+        for (int v = 0; v < 7; ++v) {
+            Cout[b * 147 + lane * 7 + v] = (v == lane) ? 0.5 * P.dt * P.dt : 0.0;
+            Cout[b * 147 + (7 + lane) * 7 + v] = (v == lane) ? P.dt : 0.0;
+            Cout[b * 147 + (14 + lane) * 7 + v] = Mg[lane * 7 + v];
+        }
+    }
+    if (lane < 6) c0p += S.e0[lane] * S.we0[lane];
+    c0p = tsum(c0p, mask);
+    if (lane == 0) c0out[b] = c0p;
+}
+
+}  // namespace
+}  // namespace dart
+
+extern "C" int dart_arm_qp_build(int32_t B, const double* Wimp, const double* Wpos, const double* Wsmooth, const double* K,
+                                 const double* K_null, const double* limits_lo, const double* limits_hi, double dt,
+                                 const double* q, const double* qd, const double* qdd_prev, const double* mocap_pos,
+                                 const double* ee_pos, const double* rotvec, const double* jac, const double* jacDot,
+                                 const double* M, const double* h, const double* Mx_inv, double* H, double* g, double* c0,
+                                 double* C, double* lo, double* hi, void* stream) {
+    if (B < 0 || !Wimp || !Wpos || !Wsmooth || !K || !K_null || !limits_lo || !limits_hi || !(dt > 0) || !q || !qd || !qdd_prev ||
+        !mocap_pos || !ee_pos || !rotvec || !jac || !jacDot || !M || !h || !Mx_inv || !H || !g || !c0 || !C || !lo || !hi)
+        return DART_ERR_ARG;
+    if (B == 0) return DART_OK;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return DART_ERR_NO_DEVICE;
+    dart::ArmParams P;
+    for (int i = 0; i < 36; ++i) { P.Wimp[i] = Wimp[i]; P.K[i] = K[i]; }
+    for (int i = 0; i < 49; ++i) { P.Wpos[i] = Wpos[i]; P.Wsm[i] = Wsmooth[i] / (dt * dt); P.Knull[i] = K_null[i]; }
+    for (int i = 0; i < 21; ++i) { P.lim_lo[i] = limits_lo[i]; P.lim_hi[i] = limits_hi[i]; }
+    P.dt = dt;
+    const int threads = 128, qpb = threads / dart::G;
+    const size_t smem = (size_t)qpb * dart::kBuildDoubles * sizeof(double);
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return DART_ERR_CUDA;
+    if (!attr_set[dev]) {
+        if (cudaFuncSetAttribute(dart::arm_qp_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return DART_ERR_CUDA;
+        attr_set[dev] = true;
+    }
+    dart::arm_qp_build_kernel<<<(B + qpb - 1) / qpb, threads, smem, (cudaStream_t)stream>>>(
+        B, P, q, qd, qdd_prev, mocap_pos, ee_pos, rotvec, jac, jacDot, M, h, Mx_inv, H, g, c0, C, lo, hi);
+    ++g_arm_qp_launches;
+    return cudaGetLastError() == cudaSuccess ? DART_OK : DART_ERR_CUDA;
+}

@@ -198,6 +198,18 @@ int dart_pmpc_plant_step(int32_t B, double Ts, double g, const double* mu, const
 int dart_arm_qp_solve(int32_t B, const double* H, const double* g, const double* C, const double* lo, const double* hi,
                       const double* x0, double* x, double* obj, int32_t* status, int32_t* iters, double tol,
                       int32_t max_iter, void* stream);
+/* Forms the QP data above on the device from what ARMCONTROL.compute_dynamics returns (arm.py:186-200) and the controller
+ * parameters (arm.py:495-519) -- the numpy block arm.py:337-405: pinv(M), inv/pinv of the task-space inertia Mx_inv, its
+ * matrix square root, damping D, impedance force F, null-space target beta.  Parameters are HOST pointers (row-major:
+ * Wimp, K [6,6]; Wpos, Wsmooth, K_null [7,7]; limits_lo/hi [21] = [Qmin|Qdotmin|taumin], [Qmax|Qdotmax|taumax]); per-arm
+ * inputs and outputs are DEVICE pointers: q, qd, qdd_prev, h [B,7]; mocap_pos, ee_pos, rotvec [B,3]; jac, jacDot [B,6,7];
+ * M [B,7,7]; Mx_inv [B,6,6] -> H, g, c0 [B] (cost = 0.5 x'Hx + g'x + c0 = the reference's loss), C, lo, hi. */
+int dart_arm_qp_build(int32_t B, const double* Wimp, const double* Wpos, const double* Wsmooth, const double* K,
+                      const double* K_null, const double* limits_lo, const double* limits_hi, double dt,
+                      const double* q, const double* qd, const double* qdd_prev, const double* mocap_pos,
+                      const double* ee_pos, const double* rotvec, const double* jac, const double* jacDot,
+                      const double* M, const double* h, const double* Mx_inv, double* H, double* g, double* c0,
+                      double* C, double* lo, double* hi, void* stream);
 int64_t dart_arm_qp_launch_count(void);
 
 /* Measured FP64 FMA-pipe peak of the device in TFLOP/s (DFMA microbenchmark, CUDA-event timed): the roofline

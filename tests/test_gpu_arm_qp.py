@@ -66,7 +66,7 @@ def test_batch_wrapper_returns_torque_and_reference_loss(built):
     assert (tau <= P["taumax"] + 1e-6).all() and (tau >= P["taumin"] - 1e-6).all()      # torque limits hold (arm.py:401-405)
     # second cycle: warm start from the previous accelerations
     tau2, loss2, x2 = ctl.solve(dyn)
-    assert np.abs(x2 - x).max() < 1e-6 * (1 + np.abs(x).max()) and ctl.launches == 2
+    assert np.abs(x2 - x).max() < 1e-6 * (1 + np.abs(x).max()) and ctl.launches == 4      # QP build + QP solve per cycle
 
 
 def test_facade_single_arm(built):
@@ -79,3 +79,25 @@ def test_facade_single_arm(built):
     ref = arm_qp.solve_qp(H, g, C, lo, hi)
     assert np.abs(tau - (dyn["M"][0] @ ref["x"][0] + dyn["h"][0])).max() < 1e-5
     assert abs(loss - (ref["obj"][0] + c0[0])) <= 1e-8 * (1 + abs(loss))
+
+
+@pytest.mark.parametrize("stress", [0.3, 3.0])
+def test_device_qp_build_matches_literal_restatement(built, stress):
+    """dart_arm_qp_build (Jacobi eigen-decompositions on the GPU) against the per-instance numpy restatement of arm.py:337-405."""
+    import torch
+    P = parm.default_params()
+    P["Wsmooth"] = np.eye(7) * 1e-7
+    dyn = dart_b200.workloads.arm_dynamics(200, seed=21, stress=stress)
+    dyn["Mx_inv"][3] *= 1e-3                      # |det| < 1e-8: the pinv(rcond=1e-3) branch of arm.py:351-357
+    dyn["Mx_inv"][5] = dyn["Mx_inv"][5] @ np.diag([1, 1, 1, 1, 1, 1e-9]) ; dyn["Mx_inv"][5] = 0.5 * (dyn["Mx_inv"][5] + dyn["Mx_inv"][5].T)
+    Pref = arm_qp.default_params(); Pref["Wsmooth"] = P["Wsmooth"]
+    ref = arm_qp.build_qp(dyn, Pref)
+    d = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in dyn.items()}
+    out = parm.build_qp_device(d, P)
+    torch.cuda.synchronize()
+    for name, b in zip(("H", "g", "c0", "C", "lo", "hi"), ref):
+        a = out[name].cpu().numpy()
+        scale = np.abs(b).reshape(b.shape[0], -1).max(axis=1) + 1.0
+        err = (np.abs(a - b).reshape(b.shape[0], -1).max(axis=1) / scale).max()
+        print(f"{name}: max rel err {err:.2e}")
+        assert err < 1e-9, name
