@@ -11,6 +11,7 @@
 // (lane-local, 147 FMAs) -> every lane factors the 7x7 system from shared memory in registers (no exchange) ->
 // lane-local step lengths -> tile reductions by shuffle.
 #include <cuda_runtime.h>
+#include <cmath>
 #include <cstdint>
 
 #include "../../include/dart_b200.h"
@@ -269,61 +270,74 @@ namespace dart {
 namespace {
 
 struct ArmParams {
-    double Wimp[36], Wpos[49], Wsm[49], K[36], Knull[49], lim_lo[21], lim_hi[21], dt;
+    double Wimp[36], Wpos[49], Wsm[49], K[36], sK[36], Knull[49], lim_lo[21], lim_hi[21], dt;      // sK = sqrt(K) elementwise
 };
 
 struct BuildSmem {
-    double A7[49], V7[49], A6[36], V6[36], Mx[36], sMx[36], w7[7], w6[6];
+    double A7[49], V7[49], A6[36], V6[36], Mx[36], sMx[36], w7[7], w6[6], sw6[6];
     double qd[7], q[7], jq[6], jdq[6], v1[7], v2[6], F[6], e0[6], beta[7], we0[6];
 };
 constexpr int kBuildDoubles = sizeof(BuildSmem) / sizeof(double) | 1;
 
-// Cyclic Jacobi for a symmetric n x n matrix in shared memory (full storage).  On return the diagonal of A holds the
-// eigenvalues and the columns of V the eigenvectors.  Lane k (< n) owns row k in the column update and column k in the
-// row update; lanes >= n idle through the same syncs.
+// Cyclic Jacobi eigen-decomposition of a symmetric n x n matrix, ONE THREAD per matrix: the upper triangle lives in
+// registers (all indices are compile-time after unrolling), the eigenvector matrix V in the thread's shared-memory
+// block.  A warp thus advances 32 arms per instruction and needs no synchronisation -- the 8-lanes-per-arm version of
+// this routine spent 60 % of the build kernel in rotation arithmetic replicated across lanes and in tile syncs.
+// On return the diagonal of A (shared memory) holds the eigenvalues and the columns of V the eigenvectors.
 template <int n>
-__device__ __forceinline__ void jacobi_eig(double* A, double* V, int lane, unsigned mask) {
-    if (lane < n) {
-        for (int c = 0; c < n; ++c) V[lane * n + c] = (lane == c) ? 1.0 : 0.0;
-        for (int c = lane + 1; c < n; ++c) {                 // symmetrise from both triangles
-            const double a = 0.5 * (A[lane * n + c] + A[c * n + lane]);
-            A[lane * n + c] = a; A[c * n + lane] = a;
-        }
-    }
-    __syncwarp(mask);
+__device__ __forceinline__ void jacobi_serial(double* A, double* V) {
+    double a[n * n];                                         // a[i * n + j], i <= j used
+#pragma unroll
+    for (int i = 0; i < n; ++i)
+#pragma unroll
+        for (int j = i; j < n; ++j) a[i * n + j] = (i == j) ? A[i * n + i] : 0.5 * (A[i * n + j] + A[j * n + i]);
+#pragma unroll
+    for (int i = 0; i < n; ++i)
+#pragma unroll
+        for (int j = 0; j < n; ++j) V[i * n + j] = (i == j) ? 1.0 : 0.0;
+#pragma unroll 1
     for (int sweep = 0; sweep < 12; ++sweep) {
         double off = 0.0, dia = 0.0;
+#pragma unroll
         for (int i = 0; i < n; ++i)
-            for (int k = 0; k < n; ++k) { const double a = A[i * n + k]; if (i == k) dia += a * a; else off += a * a; }
-        if (off <= 1e-32 * dia) break;                       // tile-uniform: every lane read the same matrix
+#pragma unroll
+            for (int j = i; j < n; ++j) { if (i == j) dia += a[i * n + j] * a[i * n + j]; else off += a[i * n + j] * a[i * n + j]; }
+        if (2.0 * off <= 1e-32 * dia) break;
+#pragma unroll
         for (int p = 0; p < n - 1; ++p) {
+#pragma unroll
             for (int q = p + 1; q < n; ++q) {
-                const double apq = A[p * n + q];
-                if (fabs(apq) < 1e-300) continue;            // uniform
-                const double app = A[p * n + p], aqq = A[q * n + q];
-                const double theta = (aqq - app) / (2.0 * apq);
-                const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-                __syncwarp(mask);                            // all lanes have read app, aqq, apq
-                if (lane < n) {                              // columns p, q of row `lane`; eigenvector row `lane`
-                    const double akp = A[lane * n + p], akq = A[lane * n + q];
-                    A[lane * n + p] = c * akp - s * akq; A[lane * n + q] = s * akp + c * akq;
-                    const double vkp = V[lane * n + p], vkq = V[lane * n + q];
-                    V[lane * n + p] = c * vkp - s * vkq; V[lane * n + q] = s * vkp + c * vkq;
+                const double apq = a[p * n + q];
+                if (fabs(apq) > 1e-300) {
+                    const double d = a[q * n + q] - a[p * n + p], b2 = 2.0 * apq;
+                    const double t = (d >= 0.0 ? b2 : -b2) / (fabs(d) + sqrt(d * d + b2 * b2));
+                    const double c = rsqrt(t * t + 1.0), s = t * c;
+                    a[p * n + p] -= t * apq;
+                    a[q * n + q] += t * apq;
+                    a[p * n + q] = 0.0;
+#pragma unroll
+                    for (int k = 0; k < n; ++k) {
+                        if (k == p || k == q) continue;
+                        const int ip = (k < p) ? k * n + p : p * n + k, iq = (k < q) ? k * n + q : q * n + k;
+                        const double akp = a[ip], akq = a[iq];
+                        a[ip] = c * akp - s * akq;
+                        a[iq] = s * akp + c * akq;
+                    }
+#pragma unroll
+                    for (int k = 0; k < n; ++k) {
+                        const double vkp = V[k * n + p], vkq = V[k * n + q];
+                        V[k * n + p] = c * vkp - s * vkq;
+                        V[k * n + q] = s * vkp + c * vkq;
+                    }
                 }
-                __syncwarp(mask);
-                if (lane < n) {                              // rows p, q of column `lane`
-                    const double apk = A[p * n + lane], aqk = A[q * n + lane];
-                    A[p * n + lane] = c * apk - s * aqk; A[q * n + lane] = s * apk + c * aqk;
-                }
-                __syncwarp(mask);
             }
         }
     }
-    __syncwarp(mask);
+#pragma unroll
+    for (int i = 0; i < n; ++i) A[i * n + i] = a[i * n + i];
 }
 
-__global__ void __launch_bounds__(128) arm_qp_build_kernel(int B, ArmParams P, const double* __restrict__ q_, const double* __restrict__ qd_,
+__global__ void __launch_bounds__(256) arm_qp_build_kernel(int B, ArmParams P, const double* __restrict__ q_, const double* __restrict__ qd_,
                                                             const double* __restrict__ qddp_, const double* __restrict__ mocap_,
                                                             const double* __restrict__ ee_, const double* __restrict__ rotvec_,
                                                             const double* __restrict__ jac_, const double* __restrict__ jacDot_,
@@ -336,19 +350,32 @@ __global__ void __launch_bounds__(128) arm_qp_build_kernel(int B, ArmParams P, c
     const int lane = threadIdx.x & (G - 1);
     const unsigned mask = 0xffu << ((threadIdx.x & 31) - lane);
     const int qib = threadIdx.x / G;
-    const long b = (long)blockIdx.x * (blockDim.x / G) + qib;
-    if (b >= B) return;
+    const int apb = blockDim.x / G;                          // arms per block (32)
+    const long b0 = (long)blockIdx.x * apb;
+    const long b = b0 + qib;
+    const bool active = b < B;
     BuildSmem& S = *reinterpret_cast<BuildSmem*>(smem + (size_t)qib * kBuildDoubles);
     const double* jac = jac_ + b * 42;
     const double* jacDot = jacDot_ + b * 42;
     const double* Mg = M_ + b * 49;
     const double* Mxi = Mxinv_ + b * 36;
-    for (int i = lane; i < 49; i += G) S.A7[i] = Mg[i];
-    for (int i = lane; i < 36; i += G) S.A6[i] = Mxi[i];
-    if (lane < 7) { S.qd[lane] = qd_[b * 7 + lane]; S.q[lane] = q_[b * 7 + lane]; }
-    __syncwarp(mask);
-    jacobi_eig<7>(S.A7, S.V7, lane, mask);
-    jacobi_eig<6>(S.A6, S.V6, lane, mask);
+    if (active) {
+        for (int i = lane; i < 49; i += G) S.A7[i] = Mg[i];
+        for (int i = lane; i < 36; i += G) S.A6[i] = Mxi[i];
+        if (lane < 7) { S.qd[lane] = qd_[b * 7 + lane]; S.q[lane] = q_[b * 7 + lane]; }
+    }
+    __syncthreads();
+    // ---- eigen-decompositions, one thread per matrix: warp 0 takes the mass matrices, warp 1 the task-space inertias
+    if (threadIdx.x < 2 * apb) {
+        const int arm = threadIdx.x % apb;
+        if (b0 + arm < B) {
+            BuildSmem& T = *reinterpret_cast<BuildSmem*>(smem + (size_t)arm * kBuildDoubles);
+            if (threadIdx.x < apb) jacobi_serial<7>(T.A7, T.V7);
+            else jacobi_serial<6>(T.A6, T.V6);
+        }
+    }
+    __syncthreads();
+    if (!active) return;
     // ---- spectra -> reciprocal spectra (pinv thresholds on singular values = |eigenvalues|)
     {
         double m7 = 0.0, m6 = 0.0, det = 1.0;
@@ -357,7 +384,11 @@ __global__ void __launch_bounds__(128) arm_qp_build_kernel(int B, ArmParams P, c
         const bool regular = fabs(det) > 1e-8;
         __syncwarp(mask);
         if (lane < 7) { const double w = S.A7[lane * 7 + lane]; S.w7[lane] = (fabs(w) > 1e-6 * m7) ? 1.0 / w : 0.0; }
-        if (lane < 6) { const double w = S.A6[lane * 6 + lane]; S.w6[lane] = (regular || fabs(w) > 1e-3 * m6) ? 1.0 / w : 0.0; }
+        if (lane < 6) {
+            const double w = S.A6[lane * 6 + lane];
+            const double iw = (regular || fabs(w) > 1e-3 * m6) ? 1.0 / w : 0.0;
+            S.w6[lane] = iw; S.sw6[lane] = sqrt(fabs(iw));
+        }
     }
     __syncwarp(mask);
     // ---- Mx, sqrt(Mx) (column `lane`), v1 = pinv(M) h, J qd, Jdot qd
@@ -366,7 +397,7 @@ __global__ void __launch_bounds__(128) arm_qp_build_kernel(int B, ArmParams P, c
             double a = 0.0, r = 0.0;
             for (int k = 0; k < 6; ++k) {
                 const double vv = S.V6[i * 6 + k] * S.V6[lane * 6 + k];
-                a += vv * S.w6[k]; r += vv * sqrt(fabs(S.w6[k]));
+                a += vv * S.w6[k]; r += vv * S.sw6[k];
             }
             S.Mx[i * 6 + lane] = a; S.sMx[i * 6 + lane] = r;
         }
@@ -398,7 +429,7 @@ __global__ void __launch_bounds__(128) arm_qp_build_kernel(int B, ArmParams P, c
         double f = 0.0;
         for (int c = 0; c < 6; ++c) {
             double d = 0.0;
-            for (int k = 0; k < 6; ++k) d += S.sMx[lane * 6 + k] * sqrt(P.K[k * 6 + c]) + sqrt(P.K[lane * 6 + k]) * S.sMx[k * 6 + c];
+            for (int k = 0; k < 6; ++k) d += S.sMx[lane * 6 + k] * P.sK[k * 6 + c] + P.sK[lane * 6 + k] * S.sMx[k * 6 + c];
             const double tw = (c < 3) ? (mocap_[b * 3 + c] - ee_[b * 3 + c]) : rotvec_[b * 3 + (c - 3)];
             f += -d * S.jq[c] + P.K[lane * 6 + c] * tw + S.Mx[lane * 6 + c] * S.v2[c];
         }
@@ -468,11 +499,11 @@ extern "C" int dart_arm_qp_build(int32_t B, const double* Wimp, const double* Wp
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return DART_ERR_NO_DEVICE;
     dart::ArmParams P;
-    for (int i = 0; i < 36; ++i) { P.Wimp[i] = Wimp[i]; P.K[i] = K[i]; }
+    for (int i = 0; i < 36; ++i) { P.Wimp[i] = Wimp[i]; P.K[i] = K[i]; P.sK[i] = sqrt(K[i]); }
     for (int i = 0; i < 49; ++i) { P.Wpos[i] = Wpos[i]; P.Wsm[i] = Wsmooth[i] / (dt * dt); P.Knull[i] = K_null[i]; }
     for (int i = 0; i < 21; ++i) { P.lim_lo[i] = limits_lo[i]; P.lim_hi[i] = limits_hi[i]; }
     P.dt = dt;
-    const int threads = 128, qpb = threads / dart::G;
+    const int threads = 256, qpb = threads / dart::G;
     const size_t smem = (size_t)qpb * dart::kBuildDoubles * sizeof(double);
     static bool attr_set[64] = {false};
     int dev = 0;
