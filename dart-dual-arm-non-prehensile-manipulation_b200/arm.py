@@ -150,13 +150,40 @@ class ArmQPBatch:
         self.status, self.iters = out["status"], out["iters"]
         return tau, out["obj"] + qp["c0"], out["x"]
 
+    def _staging(self, B):
+        """One pinned host buffer / one device buffer holding all eleven inputs back to back (contiguous per key), and
+        one pair for the outputs [tau | loss | qdd | status | iters]: a control cycle costs one H2D and one D2H copy."""
+        torch = self.torch
+        if getattr(self, "_stage_B", None) != B:
+            sizes = [int(np.prod(_DYN_SHAPES[k])) for k in _DYN_KEYS]
+            self._offs = np.concatenate([[0], np.cumsum([B * sz for sz in sizes])])
+            self._pin_in = torch.empty(int(self._offs[-1]), dtype=torch.float64).pin_memory()
+            self._dev_in = torch.empty(int(self._offs[-1]), dtype=torch.float64, device=self.dev)
+            self._np_in = self._pin_in.numpy()
+            self._dev_out = torch.empty((B, 17), dtype=torch.float64, device=self.dev)
+            self._pin_out = torch.empty((B, 17), dtype=torch.float64).pin_memory()
+            self._stage_B = B
+        return self._offs
+
     def solve(self, dyn):
         """``dyn``: numpy arrays with a leading batch axis (what compute_dynamics returns, stacked).  Host in, host out."""
         torch = self.torch
-        d = {k: torch.from_numpy(np.ascontiguousarray(dyn[k], dtype=np.float64)).to(self.dev) for k in _DYN_KEYS}
+        B = np.asarray(dyn["q"]).shape[0]
+        offs = self._staging(B)
+        d = {}
+        for i, k in enumerate(_DYN_KEYS):
+            self._np_in[offs[i]:offs[i + 1]] = np.asarray(dyn[k], dtype=np.float64).reshape(-1)
+        self._dev_in.copy_(self._pin_in, non_blocking=True)
+        for i, k in enumerate(_DYN_KEYS):
+            d[k] = self._dev_in[offs[i]:offs[i + 1]].view((B,) + _DYN_SHAPES[k])
         tau, loss, x = self.solve_device(d)
-        self.status, self.iters = self.status.cpu().numpy(), self.iters.cpu().numpy()
-        return tau.cpu().numpy(), loss.cpu().numpy(), x.cpu().numpy()
+        o = self._dev_out
+        o[:, 0:7] = tau; o[:, 7] = loss; o[:, 8:15] = x; o[:, 15] = self.status; o[:, 16] = self.iters
+        self._pin_out.copy_(o, non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
+        h = self._pin_out.numpy()
+        self.status, self.iters = h[:, 15].astype(np.int32), h[:, 16].astype(np.int32)
+        return h[:, 0:7].copy(), h[:, 7].copy(), h[:, 8:15].copy()
 
 
 class ARMCONTROL:
