@@ -54,6 +54,8 @@ def lib():
     L.dart_solve_host.argtypes = [vp, C.c_int32] + [vp] * 9
     if hasattr(L, "dart_set_result_rows"):          # absent only in older A/B builds loaded through DART_B200_LIB
         L.dart_set_result_rows.argtypes = [vp, vp, C.c_int32]
+    if hasattr(L, "dart_set_mu_init"):
+        L.dart_set_mu_init.argtypes = [vp, C.c_double]
     L.dart_launch_count.argtypes = [vp]
     L.dart_launch_count.restype = C.c_int64
     L.dart_last_launch_config.argtypes = [vp, ip, ip, ip, ip]

@@ -91,6 +91,13 @@ extern "C" int dart_destroy(dart_handle h) {
     return DART_OK;
 }
 
+extern "C" int dart_set_mu_init(dart_handle h, double mu_init) {
+    if (!h || !(mu_init >= 0.0)) return DART_ERR_ARG;
+    h->cfg.mu_init = mu_init;                  // 0 selects the default (0.1)
+    fill_opts(h->cfg, h->opts);
+    return DART_OK;
+}
+
 extern "C" int dart_nx(dart_handle h) { int a, b, c, d; if (!h || sizes(h->cfg, a, b, c, d)) return DART_ERR_ARG; return a; }
 extern "C" int dart_nref(dart_handle h) { int a, b, c, d; if (!h || sizes(h->cfg, a, b, c, d)) return DART_ERR_ARG; return b; }
 extern "C" int dart_naux(dart_handle h) { int a, b, c, d; if (!h || sizes(h->cfg, a, b, c, d)) return DART_ERR_ARG; return c; }

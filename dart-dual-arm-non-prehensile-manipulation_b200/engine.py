@@ -39,6 +39,10 @@ class NMPCEngine:
         self.nw = self._lib.dart_nw(self._h)
         self.N = cfg.N
 
+    def set_mu_init(self, mu_init):
+        """Initial barrier parameter of the following solves (0 = default 0.1); see dart_set_mu_init."""
+        check(self._lib.dart_set_mu_init(self._h, float(mu_init)), "dart_set_mu_init")
+
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
             self._lib.dart_destroy(self._h)

@@ -15,7 +15,12 @@ from .engine import NMPCEngine
 
 
 class PMPCEpisodes:
-    def __init__(self, state, target, params, mu_plant=None, coulomb=None, device=0, tol=0.01, **cfg_kw):
+    """``warm_start=False`` is the reference: every PMPC solve starts cold from ``tile(state)`` / zeros (mpc_3d.py:123).
+    ``warm_start=True`` reuses the previous plan as the initial point and starts the barrier of every solve after the
+    first at ``warm_mu`` -- the same optimum to the solver tolerance in roughly half the iterations."""
+
+    def __init__(self, state, target, params, mu_plant=None, coulomb=None, device=0, tol=0.01, warm_start=False,
+                 warm_mu=1e-4, **cfg_kw):
         import torch
         if not torch.cuda.is_available():
             raise _lib.DartError("dart_b200 episodes need a CUDA device (no CPU fallback)")
@@ -39,14 +44,25 @@ class PMPCEpisodes:
         self.nsteps = torch.zeros((self.B,), dtype=torch.int32, device=self.dev)
         self.tol = float(tol)
         self.step_index = 0
+        self.warm_start, self.warm_mu = bool(warm_start), warm_mu
+        if self.warm_start:
+            self.w = torch.zeros((self.B, self.engine.nw), dtype=f64, device=self.dev)
+            self.w_next = torch.empty_like(self.w)
         self._graph = None
         self.not_converged_solves = torch.zeros((), dtype=torch.int64, device=self.dev)
         self.iter_sum = torch.zeros((), dtype=torch.int64, device=self.dev)
 
     def step(self):
         torch = self.torch
-        self.engine.solve_device(self.state, self.target, aux=self.params, u0_out=self.u0, J_out=self.J,
-                                 status=self.status, iters=self.iters)
+        if self.warm_start:
+            if self.step_index == 1 and self.warm_mu:
+                self.engine.set_mu_init(self.warm_mu)
+            self.engine.solve_device(self.state, self.target, aux=self.params, warm_w=self.w if self.step_index > 0 else None,
+                                     w_out=self.w_next, u0_out=self.u0, J_out=self.J, status=self.status, iters=self.iters)
+            self.w, self.w_next = self.w_next, self.w
+        else:
+            self.engine.solve_device(self.state, self.target, aux=self.params, u0_out=self.u0, J_out=self.J,
+                                     status=self.status, iters=self.iters)
         self.not_converged_solves += (self.status != 0).sum()
         self.iter_sum += self.iters.sum()
         p = lambda t: None if t is None else C.c_void_p(t.data_ptr())

@@ -109,11 +109,12 @@ class LMPCBatch:
     without a usable plan (status other than converged / acceptable) the command is the next entry of the last good
     plan and that plan stays the warm start -- the reference facade's plan shift (rlmpc2.py:1013-1018), which there
     covers "the solver process has nothing new yet".  Solver options (``tol``, ``acceptable_tol``, ``acceptable_iter``,
-    ``max_iter``; the reference's are ``config.LMPC_REFERENCE_SOLVER_OPTIONS``) pass through ``cfg_kw``."""
+    ``max_iter``; the reference's are ``config.LMPC_REFERENCE_SOLVER_OPTIONS``) pass through ``cfg_kw``.  ``warm_mu``: initial
+    barrier parameter of the warm-started solves (every step after the first); None keeps the cold value 0.1."""
 
     def __init__(self, B, pvec0, weights=None, seed=3, device=0, max_param_abs=2.0, max_delta_abs=0.02, min_k=1e-2,
                  k_ceiling_margin=None, shm_smooth_alpha=0.5, update_every=8, warm_start=True, plan_fallback=False,
-                 **cfg_kw):
+                 warm_mu=1e-4, **cfg_kw):
         torch = _torch()
         self.torch = torch
         self.B = int(B)
@@ -141,6 +142,7 @@ class LMPCBatch:
         self.timestep = 0
         self.count = 0
         self.warm_start = warm_start
+        self.warm_mu = warm_mu if warm_start else None
         self.plan_fallback = bool(plan_fallback)
         N = self.cfg.N
         self._nxw = 8 * (N + 1)
@@ -183,6 +185,8 @@ class LMPCBatch:
         warm = None
         if self.warm_start:
             warm = self._shifted(self.w) if (self.warm_start == "shift" and self.timestep > 0) else self.w
+        if self.timestep == 1 and self.warm_mu:
+            self.engine.set_mu_init(self.warm_mu)
         self.engine.solve_device(state, target, aux=self.aux, warm_w=warm,
                                  w_out=self.w_next, u0_out=self.u0, J_out=self.J, status=self.status, iters=self.iters)
         if self.plan_fallback:

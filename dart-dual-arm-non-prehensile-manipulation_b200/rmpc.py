@@ -129,7 +129,7 @@ class RMPCBatch:
     virtual reference r_v, previous state and command, primal warm start."""
 
     def __init__(self, B, target, x_init, device=0, rls_P0=1e3, rls_lam=0.995, dr_max=0.01, alpha_rg=0.5,
-                 step_fraction=0.2, warm_start=True, **cfg_kw):
+                 step_fraction=0.2, warm_start=True, warm_mu=1e-4, **cfg_kw):
         torch = _torch()
         self.torch = torch
         self.B = int(B)
@@ -155,6 +155,9 @@ class RMPCBatch:
         self.status = torch.empty((B,), dtype=torch.int32, device=self.dev)
         self.iters = torch.empty((B,), dtype=torch.int32, device=self.dev)
         self.warm_start = warm_start
+        # initial barrier parameter of the warm-started solves (every step after the first); None keeps 0.1
+        self.warm_mu = warm_mu if warm_start else None
+        self.steps = 0
 
     def set_virtual_reference(self, r_v):
         self.r_v.copy_(self.torch.from_numpy(np.ascontiguousarray(r_v, dtype=np.float64)).to(self.dev))
@@ -169,8 +172,11 @@ class RMPCBatch:
                                             self.step_fraction, p(xk), p(self.prev_state), p(self.target), p(self.u_prev),
                                             p(self.r_v), p(self.theta), p(self.P), p(self.ref), p(self.aux), stream),
               "dart_rmpc_prologue")
+        if self.steps == 1 and self.warm_mu:
+            self.engine.set_mu_init(self.warm_mu)
         self.engine.solve_device(xk, self.ref, aux=self.aux, warm_w=self.w if self.warm_start else None,
                                  w_out=self.w_next, u0_out=self.u0, J_out=self.J, status=self.status, iters=self.iters)
+        self.steps += 1
         self.w, self.w_next = self.w_next, self.w
         self.prev_state.copy_(xk)
         self.u_prev.copy_(self.u0)

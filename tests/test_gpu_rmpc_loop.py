@@ -83,7 +83,8 @@ def test_closed_loop_matches_oracle_loop(built):
             X0 = np.zeros((B, 21, 6)); U0 = np.zeros((B, 20, 2))        # reference: w0 = zeros at the first call
         else:
             X0, U0 = Xw, Uw
-        sol = ipm.solve(prob, X0=X0, U0=U0)
+        # warm-started solves start the barrier at RMPCBatch's warm_mu (1e-4), the first one at 0.1
+        sol = ipm.solve(prob, X0=X0, U0=U0, opts=ipm.Options(mu0=0.1 if t == 0 else ctl.warm_mu))
         assert (sol["status"] == 0).all()
         Xw, Uw = sol["X"], sol["U"]
         u_o = sol["U"][:, 0]

@@ -80,3 +80,15 @@ def test_plan_shift_fallback(built):
         assert np.array_equal(u, plan[:, k])
     assert int(ctl.n_fallback.item()) == 3 * B
     assert np.array_equal(ctl.w[:, 8 * 21:].view(B, 20, 2).cpu().numpy(), plan)        # the good plan stays the warm start
+
+
+def test_pmpc_episode_warm_start_same_metrics(built):
+    """Warm start + warm-started barrier change the iteration path only: same episode to the solver tolerance."""
+    c, aux = dart_b200.workloads.pmpc_inputs(2)
+    cold = dart_b200.PMPCEpisodes(c["state"], c["target"], aux, device=0)
+    warm = dart_b200.PMPCEpisodes(c["state"], c["target"], aux, device=0, warm_start=True)
+    a, b = cold.run(60), warm.run(60)
+    assert a["not_converged_solves"] == 0 and b["not_converged_solves"] == 0
+    assert np.abs(cold.state.cpu().numpy() - warm.state.cpu().numpy()).max() < 1e-6
+    assert b["mean_iters"] < 0.75 * a["mean_iters"]
+    print(f"mean iterations per solve: cold {a['mean_iters']:.2f}, warm {b['mean_iters']:.2f}")

@@ -27,10 +27,10 @@ def config1(steps):
                 mean_iters=m["mean_iters"], not_converged_solves=m["not_converged_solves"], trace=m["trace"].tolist())
 
 
-def config2_closed_loop(steps):
+def config2_closed_loop(steps, label="2 (closed loop): 18 objects x 64 states, surrogate plant with unmodelled Coulomb term", **kw):
     c, aux = W.pmpc_inputs(64)
     rng = np.random.default_rng(21)
-    ep = dart_b200.PMPCEpisodes(c["state"], c["target"], aux, coulomb=rng.uniform(0, 0.02, aux.shape[0]), device=LOCAL)
+    ep = dart_b200.PMPCEpisodes(c["state"], c["target"], aux, coulomb=rng.uniform(0, 0.02, aux.shape[0]), device=LOCAL, **kw)
     a, b = ev(), ev()
     a.record(); m = ep.run(steps, graph=GRAPH); b.record(); torch.cuda.synchronize()
     sec = a.elapsed_time(b) * 1e-3
@@ -42,7 +42,7 @@ def config2_closed_loop(steps):
                             convergence_time_s=float(np.median(m["convergence_time"][sl])),
                             steady_state_error_mm=float(np.median(m["steady_state_error"][sl]) * 1e3),
                             control_effort=float(np.median(m["control_effort"][sl]))))
-    return dict(config="2 (closed loop): 18 objects x 64 states, surrogate plant with unmodelled Coulomb term", steps=steps, cuda_graph=GRAPH,
+    return dict(config=label, steps=steps, cuda_graph=GRAPH,
                 sim_time_s=m["sim_time"], solves=m["solves"], seconds=sec, solves_per_s=m["solves"] / sec,
                 mean_iters=m["mean_iters"], not_converged_solves=m["not_converged_solves"], per_object=per_obj)
 
@@ -162,12 +162,13 @@ if __name__ == "__main__":
     q = args.quick
     GRAPH = args.graph
     res = []
-    todo = args.only.split(",") if args.only else ["config1", "config2", "config3", "config4", "config4_shift", "config4_refopts", "config5"]
+    todo = args.only.split(",") if args.only else ["config1", "config2", "config2_warm", "config3", "config4", "config4_shift", "config4_refopts", "config5"]
     for name in todo:
         if WORLD > 1 and name != "config5":
             continue
         if name == "config1": r = config1(500 if q else 5000)
         elif name == "config2": r = config2_closed_loop(200 if q else 5000)
+        elif name == "config2_warm": r = config2_closed_loop(200 if q else 5000, label="2 (f2): closed loop with primal warm start + warm-started barrier (not the reference's cold start)", warm_start=True)
         elif name == "config3": r = config3(512 if q else 4096, 32 if q else 256)
         elif name == "config4": r = config4(2048 if q else 16384, 8 if q else 64)
         elif name == "config4_shift": r = config4(2048 if q else 16384, 8 if q else 64, label="4 (f2): shifted-plan warm start", warm_start="shift")
