@@ -59,7 +59,7 @@ class PMPCEpisodes:
                 self.engine.set_mu_init(self.warm_mu)
             self.engine.solve_device(self.state, self.target, aux=self.params, warm_w=self.w if self.step_index > 0 else None,
                                      w_out=self.w_next, u0_out=self.u0, J_out=self.J, status=self.status, iters=self.iters)
-            self.w, self.w_next = self.w_next, self.w
+            self.w.copy_(self.w_next)                 # a copy, not a pointer swap: the step may be replayed from a CUDA graph
         else:
             self.engine.solve_device(self.state, self.target, aux=self.params, u0_out=self.u0, J_out=self.J,
                                      status=self.status, iters=self.iters)
