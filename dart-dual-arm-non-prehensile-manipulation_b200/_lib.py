@@ -56,6 +56,9 @@ def lib():
         L.dart_set_result_rows.argtypes = [vp, vp, C.c_int32]
     if hasattr(L, "dart_set_mu_init"):
         L.dart_set_mu_init.argtypes = [vp, C.c_double]
+    if hasattr(L, "dart_set_dual_state"):
+        L.dart_set_dual_state.argtypes = [vp, vp, C.c_int32]
+        L.dart_ndual.argtypes = [vp]
     L.dart_launch_count.argtypes = [vp]
     L.dart_launch_count.restype = C.c_int64
     L.dart_last_launch_config.argtypes = [vp, ip, ip, ip, ip]

@@ -20,6 +20,8 @@ struct dart_solver {
     void* dev;   size_t dev_bytes;
     double* rows;      // dart_set_result_rows
     int32_t rows_cap;
+    double* dual;      // dart_set_dual_state
+    int32_t dual_cap;
 };
 
 extern "C" int dart_default_cfg(int32_t method, dart_cfg* c) {
@@ -75,7 +77,7 @@ extern "C" int dart_create(dart_handle* out, const dart_cfg* cfg, int device) {
     fill_opts(*cfg, h->opts);
     h->launches = 0;
     memset(&h->last, 0, sizeof(h->last));
-    h->pin = nullptr; h->pin_bytes = 0; h->dev = nullptr; h->dev_bytes = 0; h->rows = nullptr; h->rows_cap = 0;
+    h->pin = nullptr; h->pin_bytes = 0; h->dev = nullptr; h->dev_bytes = 0; h->rows = nullptr; h->rows_cap = 0; h->dual = nullptr; h->dual_cap = 0;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return DART_ERR_CUDA; }
     *out = h;
     return DART_OK;
@@ -88,6 +90,24 @@ extern "C" int dart_destroy(dart_handle h) {
     if (h->dev) cudaFree(h->dev);
     cudaStreamDestroy(h->stream);
     delete h;
+    return DART_OK;
+}
+
+static int dual_doubles(const dart_cfg& c) {
+    switch (c.method) {
+        case DART_PMPC: return PmpcAxis::NAXIS * Solver<PmpcAxis, HostTile, 0>::dual_doubles(c.N);
+        case DART_RMPC: return Rmpc::NAXIS * Solver<Rmpc, HostTile, 0>::dual_doubles(c.N);
+        case DART_LMPC: return LmpcAxis::NAXIS * Solver<LmpcAxis, HostTile, 0>::dual_doubles(c.N);
+    }
+    return -1;
+}
+
+extern "C" int dart_ndual(dart_handle h) { return h ? dual_doubles(h->cfg) : DART_ERR_ARG; }
+
+extern "C" int dart_set_dual_state(dart_handle h, double* dual, int32_t capacity_rows) {
+    if (!h || (dual && capacity_rows <= 0)) return DART_ERR_ARG;
+    h->dual = dual;
+    h->dual_cap = dual ? capacity_rows : 0;
     return DART_OK;
 }
 
@@ -110,12 +130,13 @@ extern "C" int dart_solve(dart_handle h, int32_t B, const double* x0, const doub
     if (h->cfg.method != DART_PMPC && !aux) return DART_ERR_ARG;
     if (B == 0) return DART_OK;
     if (h->rows && B > h->rows_cap) return DART_ERR_ARG;       // the registered result-row buffer is too small
+    if (h->dual && B > h->dual_cap) return DART_ERR_ARG;       // the registered dual-state buffer is too small
     int cur = -1;
     if (cudaGetDevice(&cur) != cudaSuccess || cur != h->device) return DART_ERR_ARG;   // launch from the handle's device
     KArgs a;
     a.B = B; a.N = h->cfg.N; a.o = h->opts; a.cfg = h->cfg;
     a.x0 = x0; a.ref = ref; a.aux = aux; a.warm = warm_w;
-    a.w_out = w_out; a.u0 = u0_out; a.J = J_out; a.status = status; a.iters = iters; a.rows = h->rows;
+    a.w_out = w_out; a.u0 = u0_out; a.J = J_out; a.status = status; a.iters = iters; a.rows = h->rows; a.dual = h->dual;
     cudaStream_t st = (cudaStream_t)stream;
     int rc = launch_solve(a, h->cfg.lanes, h->cfg.block_threads, st, &h->last);
     if (rc != DART_OK) return rc;

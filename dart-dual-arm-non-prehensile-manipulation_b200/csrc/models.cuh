@@ -27,6 +27,7 @@ struct KArgs {
     double *w_out, *u0, *J;
     int32_t *status, *iters;
     double* rows;      // optional packed result rows [B,4] = [u0x, u0y, J, status] for the multi-GPU gather
+    double* dual;      // optional dual-state blocks [B, NAXIS * dual_doubles(N)] (read when warm is given, always written)
 };
 
 // Generic RK4 step with forward sensitivities.  Md::deriv(prm, x, u, f, fx, fu) gives xdot and its
@@ -340,11 +341,9 @@ DART_HD void solve_one(const T& tile, const KArgs& a, int inst, int axis, bool a
     const int nwf = M::nw(N);
     const int uoff = (N + 1) * M::NXF;
     const int ucol = (M::NAXIS > 1) ? axis : 0;
-    if (active) {
-        M::load(prm, a, inst, axis);
-        M::x0(a, inst, axis, x0);
-        M::load_ref(tile, a, inst, w.REF);
-        const double* warm = a.warm ? a.warm + (long)inst * nwf : nullptr;
+    const double* warm = (active && a.warm) ? a.warm + (long)inst * nwf : nullptr;
+    // the starting point: the caller's plan (warm) or x0 held over the horizon with zero inputs (mpc_3d.py:123)
+    auto load_start = [&]() {
         for (int k = tile.lane(); k <= N; k += tile.size()) {
             DART_UNROLL for (int i = 0; i < np; ++i)
                 w.X[k * n + i] = (warm && k > 0) ? warm[k * M::NXF + M::xmap(axis, i)] : x0[i];
@@ -357,12 +356,22 @@ DART_HD void solve_one(const T& tile, const KArgs& a, int inst, int axis, bool a
             }
         }
         tile.sync();
+    };
+    if (active) {
+        M::load(prm, a, inst, axis);
+        M::x0(a, inst, axis, x0);
+        M::load_ref(tile, a, inst, w.REF);
+        load_start();
     }
     // every tile of the block (active or not) takes part in run(): its threads also serve the serial-sweep phase
     Solver<M, T, NC> s(tile, prm, a.o, N, w, bc);
-    s.run(active, J, status, iters, kkt);
+    double* dblk = (active && a.dual) ? a.dual + ((long)inst * M::NAXIS + axis) * Solver<M, T, NC>::dual_doubles(N) : nullptr;
+    s.run(active, J, status, iters, kkt, a.warm ? dblk : nullptr, dblk);
     if (!active) return;
     if (M::infeasible0(prm, x0) && status != ST_NUMERIC) status = ST_INFEASIBLE;
+    // a solve that ran into NaN/Inf hands back its starting point, not the broken iterate: a closed loop that feeds
+    // plans and commands back in must not be poisoned by one failed solve
+    if (status == ST_NUMERIC) load_start();
     if (a.w_out) {
         double* wo = a.w_out + (long)inst * nwf;
         for (int k = tile.lane(); k <= N; k += tile.size()) {

@@ -931,6 +931,51 @@ struct Solver {
         }
     }
 
+    // ---- dual warm start: per-problem block [valid | LAM (N n) | S (N nr) | ZL | ZU] in global memory.
+    // The previous optimum's slacks sit within ~1e-9 of their active bounds; they are pushed 1e-6 of the row's range
+    // into the interior, and the bound multipliers are kept from falling below IPOPT's safeguard for the new mu.
+    DART_HD static int dual_doubles(int N_) { return 1 + N_ * n + 3 * N_ * nr; }
+    DART_HD void load_duals(const double* blk, double mu) {
+        const double* lam = blk + 1;
+        const double* sp = lam + N * n;
+        const double* zlp = sp + N * nr;
+        const double* zup = zlp + N * nr;
+        const double ks = 1e10;
+        for (int k = tile.lane(); k < N; k += tile.size()) {
+            DART_UNROLL for (int r = 0; r < nr; ++r) {
+                if (masked(k, r)) continue;
+                double lo, hi;
+                M::bounds(prm, r, lo, hi);
+                const double push = 1e-6 * (hi - lo);
+                const double sv = dmin(dmax(sp[k * nr + r], lo + push), hi - push);
+                if (M::row_ib(r) < 0 && M::row_ia(r) >= n) w.U[k * m + (M::row_ia(r) - n)] = sv / M::row_sa(r);
+                w.S[k * nr + r] = sv;
+                w.ZL[k * nr + r] = dmax(zlp[k * nr + r], mu / (ks * (sv - lo)));
+                w.ZU[k * nr + r] = dmax(zup[k * nr + r], mu / (ks * (hi - sv)));
+            }
+            DART_UNROLL for (int a = 0; a < n; ++a) w.LAM[k * n + a] = lam[k * n + a];
+        }
+        tile.sync();
+        if (M::NAUG > 0) {
+            for (int k = tile.lane(); k < N; k += tile.size())
+                DART_UNROLL for (int j = 0; j < m; ++j) w.X[(k + 1) * n + np + j] = w.U[k * m + j];
+            tile.sync();
+        }
+    }
+    DART_HD void store_duals(double* blk, bool usable) {
+        double* lam = blk + 1;
+        double* sp = lam + N * n;
+        double* zlp = sp + N * nr;
+        double* zup = zlp + N * nr;
+        for (int k = tile.lane(); k < N; k += tile.size()) {
+            DART_UNROLL for (int r = 0; r < nr; ++r) {
+                sp[k * nr + r] = w.S[k * nr + r]; zlp[k * nr + r] = w.ZL[k * nr + r]; zup[k * nr + r] = w.ZU[k * nr + r];
+            }
+            DART_UNROLL for (int a = 0; a < n; ++a) lam[k * n + a] = w.LAM[k * n + a];
+        }
+        if (tile.lane() == 0) blk[0] = usable ? 1.0 : 0.0;
+    }
+
     // ---- the interior-point loop.  X (all N+1 states, X[0] = x0), U and REF must be set by the caller when `active`.
     //
     // Every iteration has three phases with a phase-dependent mapping of work to threads:
@@ -942,8 +987,14 @@ struct Solver {
     //   C (tile): slack/dual steps, line search with re-evaluation, multiplier update, KKT residuals.
     // Two block barriers per iteration separate A|B|C; all tiles of the block (also finished or empty ones) keep
     // taking part in them until no problem of the block needs another sweep.
-    DART_HD void run(bool active, double& J, int32_t& status, int32_t& iters, double& kkt) {
+    // dual_in: block to start from (nullptr or not valid: default initialisation; an instance without a valid
+    // block never starts below mu = 1e-4, the value that suits a primal-only warm start); dual_out: where to leave the
+    // final slacks and multipliers.
+    DART_HD void run(bool active, double& J, int32_t& status, int32_t& iters, double& kkt, const double* dual_in = nullptr,
+                     double* dual_out = nullptr) {
         double mu = o.mu0;
+        const bool dualwarm = active && dual_in != nullptr && dual_in[0] == 1.0;
+        if (active && dual_out != nullptr && !dualwarm) mu = dmax(mu, 1e-4);
         double f = 0.0, L = 0.0, th = 0.0, pinf = 0.0, dinf = 0.0, zs_min = 0.0, zs_max = 0.0, lam_sum = 0.0, z_sum = 0.0;
         // number of constraint rows of the problem (rows with row_skip0 do not exist at stage 0)
         int nact = 0;
@@ -951,6 +1002,7 @@ struct Solver {
         double inv_nd = 0.0, inv_nc = 0.0;
         if (active) {
             init_rows(mu);
+            if (dualwarm) load_duals(dual_in, mu);
             eval1(f, L, th, pinf);
             eval2(dinf, zs_min, zs_max, lam_sum, z_sum);
             inv_nd = 1.0 / (double)(N * n + 2 * nact);
@@ -1082,6 +1134,7 @@ struct Solver {
         status = st;
         iters = it;
         kkt = E0;
+        if (active && dual_out != nullptr) store_duals(dual_out, st == ST_CONVERGED || st == ST_ACCEPTABLE);
     }
 };
 

@@ -43,6 +43,23 @@ class NMPCEngine:
         """Initial barrier parameter of the following solves (0 = default 0.1); see dart_set_mu_init."""
         check(self._lib.dart_set_mu_init(self._h, float(mu_init)), "dart_set_mu_init")
 
+    @property
+    def ndual(self):
+        return self._lib.dart_ndual(self._h)
+
+    def set_dual_state(self, dual):
+        """Register a zero-initialised float64 CUDA tensor [B, ndual] as the dual warm-start state (None unregisters);
+        see dart_set_dual_state.  The tensor must outlive the registration."""
+        if dual is None:
+            check(self._lib.dart_set_dual_state(self._h, None, 0), "dart_set_dual_state")
+            self._dual = None
+            return
+        import torch
+        if not (dual.is_cuda and dual.dtype == torch.float64 and dual.is_contiguous() and dual.dim() == 2 and dual.shape[1] == self.ndual):
+            raise ValueError(f"dual state must be a contiguous float64 CUDA tensor [B, {self.ndual}]")
+        check(self._lib.dart_set_dual_state(self._h, C.c_void_p(dual.data_ptr()), int(dual.shape[0])), "dart_set_dual_state")
+        self._dual = dual
+
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
             self._lib.dart_destroy(self._h)

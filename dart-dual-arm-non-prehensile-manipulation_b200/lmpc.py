@@ -114,7 +114,7 @@ class LMPCBatch:
 
     def __init__(self, B, pvec0, weights=None, seed=3, device=0, max_param_abs=2.0, max_delta_abs=0.02, min_k=1e-2,
                  k_ceiling_margin=None, shm_smooth_alpha=0.5, update_every=8, warm_start=True, plan_fallback=False,
-                 warm_mu=1e-4, **cfg_kw):
+                 warm_mu=1e-4, dual_warm=False, **cfg_kw):
         torch = _torch()
         self.torch = torch
         self.B = int(B)
@@ -143,6 +143,11 @@ class LMPCBatch:
         self.count = 0
         self.warm_start = warm_start
         self.warm_mu = warm_mu if warm_start else None
+        self.dual = None
+        if dual_warm and warm_start:             # dart_set_dual_state: previous slacks and multipliers, barrier from 1e-6
+            self.dual = torch.zeros((B, self.engine.ndual), dtype=f64, device=self.dev)
+            self.engine.set_dual_state(self.dual)
+            self.warm_mu = 1e-6
         self.plan_fallback = bool(plan_fallback)
         N = self.cfg.N
         self._nxw = 8 * (N + 1)

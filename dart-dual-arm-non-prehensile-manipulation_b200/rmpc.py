@@ -129,7 +129,7 @@ class RMPCBatch:
     virtual reference r_v, previous state and command, primal warm start."""
 
     def __init__(self, B, target, x_init, device=0, rls_P0=1e3, rls_lam=0.995, dr_max=0.01, alpha_rg=0.5,
-                 step_fraction=0.2, warm_start=True, warm_mu=1e-4, **cfg_kw):
+                 step_fraction=0.2, warm_start=True, warm_mu=1e-4, dual_warm=False, **cfg_kw):
         torch = _torch()
         self.torch = torch
         self.B = int(B)
@@ -158,6 +158,12 @@ class RMPCBatch:
         # initial barrier parameter of the warm-started solves (every step after the first); None keeps 0.1
         self.warm_mu = warm_mu if warm_start else None
         self.steps = 0
+        # dual warm start (dart_set_dual_state): slacks and multipliers of the previous solve, barrier from 1e-6
+        self.dual = None
+        if dual_warm and warm_start:
+            self.dual = torch.zeros((B, self.engine.ndual), dtype=f64, device=self.dev)
+            self.engine.set_dual_state(self.dual)
+            self.warm_mu = 1e-6
 
     def set_virtual_reference(self, r_v):
         self.r_v.copy_(self.torch.from_numpy(np.ascontiguousarray(r_v, dtype=np.float64)).to(self.dev))

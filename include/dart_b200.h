@@ -89,6 +89,16 @@ typedef struct dart_solver* dart_handle;
  * IPOPT's mu_init (arm.py:306 sets it for its warm-started worker). */
 int dart_set_mu_init(dart_handle h, double mu_init);
 
+/* Dual warm start for closed loops (IPOPT's warm_start_init_point with lam_x0 / lam_g0, which the reference passes
+ * for its arm worker at arm.py:420-424 but not for the tray controllers).  `dual` is a DEVICE buffer of
+ * [capacity_rows, dart_ndual(h)] doubles that the caller zero-initialises once and then leaves alone: every dart_solve
+ * (a) starts instance i from the equality multipliers, slacks and bound multipliers stored in row i -- if that row was
+ * written by a solve that ended converged/acceptable and warm_w is given; such a solve starts its barrier at mu_init
+ * (use dart_set_mu_init(h, 1e-6)), any other instance never below 1e-4 -- and (b) writes its final slacks and multipliers
+ * back to row i.  NULL unregisters.  Rows belong to instances by position, like warm_w. */
+int dart_ndual(dart_handle h);
+int dart_set_dual_state(dart_handle h, double* dual, int32_t capacity_rows);
+
 /* Fill cfg with the reference's defaults for a method (values cited above). */
 int dart_default_cfg(int32_t method, dart_cfg* cfg);
 

@@ -106,8 +106,12 @@ def cost_grad_hess(prob: StageProblem, X, U):
     return gy, gT, H, HT
 
 
-def solve(prob: StageProblem, X0=None, U0=None, opts: Options = None, trace=None):
-    """Solve every instance of ``prob``. Returns dict(X, U, J, status, iters, lam, zl, zu, s, kkt)."""
+def solve(prob: StageProblem, X0=None, U0=None, opts: Options = None, trace=None, warm=None):
+    """Solve every instance of ``prob``. Returns dict(X, U, J, status, iters, lam, zl, zu, s, kkt).
+
+    ``warm``: dict(lam, s, zl, zu, valid[B]) of a previous solve -- the dual warm start of dart_set_dual_state: where
+    ``valid``, slacks are taken from it (pushed 1e-6 of the row range into the interior), bound multipliers kept above
+    mu/(1e10 slack), equality multipliers as they are; elsewhere the default start, with mu not below 1e-4."""
     o = opts or Options()
     n, m, N, B = prob.n, prob.m, prob.N, prob.B
     nr = len(prob.rows)
@@ -143,6 +147,22 @@ def solve(prob: StageProblem, X0=None, U0=None, opts: Options = None, trace=None
     zl = (mu[:, None, None] / (s - lo)) * msk
     zu = (mu[:, None, None] / (hi - s)) * msk
     lam = np.zeros((B, N, n))                 # lam[:,k] multiplies F(x_k,u_k) - x_{k+1}
+    if warm is not None:
+        v = np.asarray(warm["valid"], dtype=bool)
+        mu = np.where(v, mu, np.maximum(mu, 1e-4))
+        zl = np.where(v[:, None, None], zl, (mu[:, None, None] / (s - lo)) * msk)
+        zu = np.where(v[:, None, None], zu, (mu[:, None, None] / (hi - s)) * msk)
+        p2 = 1e-6 * (hi - lo)
+        sw = np.clip(warm["s"], lo + p2, hi - p2)
+        s = np.where(v[:, None, None] & (msk > 0), sw, s)
+        for r, row in enumerate(prob.rows):
+            if row.ib < 0 and row.ia >= n:
+                U[:, :, row.ia - n] = np.where(v[:, None], s[:, :, r] / row.sa, U[:, :, row.ia - n])
+        if prob.naug:
+            X[:, 1:, n - m:] = U
+        zl = np.where(v[:, None, None], np.maximum(warm["zl"], mu[:, None, None] / (1e10 * (s - lo))) * msk, zl)
+        zu = np.where(v[:, None, None], np.maximum(warm["zu"], mu[:, None, None] / (1e10 * (hi - s))) * msk, zu)
+        lam = np.where(v[:, None, None], warm["lam"], lam)
     iters = np.zeros(B, dtype=np.int32)
     tiny = np.zeros(B, dtype=np.int32)
     done = np.zeros(B, dtype=bool)

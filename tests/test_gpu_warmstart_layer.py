@@ -92,3 +92,63 @@ def test_pmpc_episode_warm_start_same_metrics(built):
     assert np.abs(cold.state.cpu().numpy() - warm.state.cpu().numpy()).max() < 1e-6
     assert b["mean_iters"] < 0.75 * a["mean_iters"]
     print(f"mean iterations per solve: cold {a['mean_iters']:.2f}, warm {b['mean_iters']:.2f}")
+
+
+def test_dual_warm_start_rmpc_loop_matches_oracle(built):
+    """RMPCBatch(dual_warm=True) against the oracle doing the same dual warm start: same iterates, same commands."""
+    import torch
+    from oracle import problems, rls
+    from tests.test_gpu_rmpc_loop import _plant_step
+    B, T = 16, 8
+    c = dart_b200.workloads.rmpc_config3(B, seed=2)
+    x = c["x0"].copy(); x[:, [1, 3]] *= 0.5
+    P0 = 1.0
+    ctl = dart_b200.RMPCBatch(B, c["target"], x, device=0, rls_P0=P0, dual_warm=True)
+    ref_ctl = dart_b200.RMPCBatch(B, c["target"], x, device=0, rls_P0=P0)
+    rv0 = np.zeros((B, 4)); rv0[:, [0, 2]] = x[:, [0, 2]]
+    ctl.set_virtual_reference(rv0); ref_ctl.set_virtual_reference(rv0)
+    th = np.zeros((B, 2, 7)); P = np.tile(np.eye(7) * P0, (B, 2, 1, 1))
+    r_v = rv0.copy(); prev = x.copy(); u_prev = np.zeros((B, 2)); sol = None
+    x_o = x.copy(); x_r = x.copy()
+    it_dual = it_ref = 0
+    for t in range(T):
+        u_gpu = ctl.step(torch.from_numpy(x).cuda()).cpu().numpy()
+        u_ref = ref_ctl.step(torch.from_numpy(x_r).cuda()).cpu().numpy()
+        phi = rls.regressor(prev, 0.1); y = rls.accel_measurement(x_o, prev, 0.002)
+        th, P = rls.rls_update_batch(th, P, phi, y, 0.995)
+        r_v = problems.reference_governor(r_v, c["target"])
+        ref = problems.build_ref_traj(x_o, r_v, c["target"], 20, 4, 0.2)
+        prob = problems.rmpc_problem(x_o, u_prev, th.reshape(B, 14), ref)
+        if sol is None:
+            new = ipm.solve(prob, X0=np.zeros((B, 21, 6)), U0=np.zeros((B, 20, 2)))
+        else:
+            warm = dict(lam=sol["lam"], s=sol["s"], zl=sol["zl"], zu=sol["zu"], valid=np.isin(sol["status"], (0, 4)))
+            new = ipm.solve(prob, X0=sol["X"], U0=sol["U"], opts=ipm.Options(mu0=1e-6), warm=warm)
+        sol = new
+        assert (sol["status"] == 0).all() and (ctl.status.cpu().numpy() == 0).all()
+        assert np.abs(u_gpu - sol["U"][:, 0]).max() <= helpers.TOL_U0, (t, np.abs(u_gpu - sol["U"][:, 0]).max())
+        assert np.abs(ctl.iters.cpu().numpy() - sol["iters"]).max() <= 1, (t, ctl.iters.cpu().numpy(), sol["iters"])
+        if t > 0:
+            it_dual += int(ctl.iters.sum().item()); it_ref += int(ref_ctl.iters.sum().item())
+        prev = x_o.copy(); u_prev = sol["U"][:, 0].copy()
+        x_o = _plant_step(x_o, sol["U"][:, 0], c["mu_plant"], c["c_plant"])
+        x = _plant_step(x, u_gpu, c["mu_plant"], c["c_plant"])
+        x_r = _plant_step(x_r, u_ref, c["mu_plant"], c["c_plant"])
+    print(f"iterations per warm solve: dual {it_dual / (B * (T - 1)):.2f}, primal + mu {it_ref / (B * (T - 1)):.2f}")
+    assert np.abs(x - x_r).max() < 1e-6                  # same closed loop as without the dual warm start
+    assert it_dual < it_ref
+
+
+def test_dual_warm_start_lmpc_loop(built):
+    ca, ua, ia = _closed_loop(64, 12)
+    cb, ub, ib = _closed_loop(64, 12, dual_warm=True)
+    assert (cb.status.cpu().numpy() == 0).all()
+    assert np.abs(ua - ub).max() < 1e-5
+    print(f"LMPC mean iterations: primal + mu {ia:.2f}, dual {ib:.2f}")
+    assert ib < ia
+    # a row whose solve failed is not reused: invalidate by hand and solve again
+    cb.dual[:, 0] = 0.0
+    import torch
+    c = dart_b200.workloads.lmpc_config4(64, seed=3)
+    cb.step(cb.w[:, 8:16].contiguous(), torch.from_numpy(c["target"]).cuda())
+    assert (cb.status.cpu().numpy() == 0).all()

@@ -47,11 +47,11 @@ def config2_closed_loop(steps, label="2 (closed loop): 18 objects x 64 states, s
                 mean_iters=m["mean_iters"], not_converged_solves=m["not_converged_solves"], per_object=per_obj)
 
 
-def config3(B, T):
+def config3(B, T, label="3: RMPC + per-instance RLS closed loop", **kw):
     c = dart_b200.workloads.rmpc_config3(B, seed=2)
     dev = torch.device("cuda", LOCAL)
     x = torch.from_numpy(c["x0"]).to(dev)
-    ctl = dart_b200.RMPCBatch(B, c["target"], c["x0"], device=LOCAL)
+    ctl = dart_b200.RMPCBatch(B, c["target"], c["x0"], device=LOCAL, **kw)
     rv0 = np.zeros((B, 4)); rv0[:, [0, 2]] = c["x0"][:, [0, 2]]
     ctl.set_virtual_reference(rv0)
     mu = torch.from_numpy(c["mu_plant"]).to(dev); cp = torch.from_numpy(c["c_plant"]).to(dev)
@@ -72,7 +72,7 @@ def config3(B, T):
     sec = a.elapsed_time(b) * 1e-3
     st = stat.cpu().numpy()
     err = (x[:, [0, 2]] - ctl.target[:, [0, 2]]).norm(dim=1)
-    return dict(config="3: RMPC + per-instance RLS closed loop", B=B, steps=T, seconds=sec, solves_per_s=B * T / sec,
+    return dict(config=label, B=B, steps=T, seconds=sec, solves_per_s=B * T / sec,
                 status_counts=dict(converged=int(st[0]), max_iter=int(st[1]), infeasible=int(st[2]), numeric=int(st[3])),
                 mean_iters=float(it_sum.item()) / (B * T), median_pos_err_m=float(err.median().item()),
                 theta_hat_absmax=float(ctl.theta.abs().max().item()))
@@ -162,7 +162,7 @@ if __name__ == "__main__":
     q = args.quick
     GRAPH = args.graph
     res = []
-    todo = args.only.split(",") if args.only else ["config1", "config2", "config2_warm", "config3", "config4", "config4_shift", "config4_refopts", "config5"]
+    todo = args.only.split(",") if args.only else ["config1", "config2", "config2_warm", "config3", "config3_dual", "config4", "config4_dual", "config4_shift", "config4_refopts", "config5"]
     for name in todo:
         if WORLD > 1 and name != "config5":
             continue
@@ -170,7 +170,9 @@ if __name__ == "__main__":
         elif name == "config2": r = config2_closed_loop(200 if q else 5000)
         elif name == "config2_warm": r = config2_closed_loop(200 if q else 5000, label="2 (f2): closed loop with primal warm start + warm-started barrier (not the reference's cold start)", warm_start=True)
         elif name == "config3": r = config3(512 if q else 4096, 32 if q else 256)
+        elif name == "config3_dual": r = config3(512 if q else 4096, 32 if q else 256, label="3 (f2): dual warm start", dual_warm=True)
         elif name == "config4": r = config4(2048 if q else 16384, 8 if q else 64)
+        elif name == "config4_dual": r = config4(2048 if q else 16384, 8 if q else 64, label="4 (f2): dual warm start", dual_warm=True)
         elif name == "config4_shift": r = config4(2048 if q else 16384, 8 if q else 64, label="4 (f2): shifted-plan warm start", warm_start="shift")
         elif name == "config4_refopts":
             from dart_b200.config import LMPC_REFERENCE_SOLVER_OPTIONS as ro
