@@ -76,6 +76,8 @@ def lib():
     if hasattr(L, "dart_pmpc_plant_step"):
         L.dart_pmpc_plant_step.argtypes = [C.c_int32, C.c_double, C.c_double] + [vp] * 6 + [C.c_double] + [vp] * 3 + [vp]
     L.dart_measure_fp64_tflops.argtypes = [C.c_int, dp]
+    if hasattr(L, "dart_pmpc_episode"):
+        L.dart_pmpc_episode.argtypes = [vp, C.c_int32, C.c_int32] + [vp] * 5 + [C.c_double] + [vp] * 9 + [vp]
     if hasattr(L, "dart_arm_qp_solve"):
         L.dart_arm_qp_solve.argtypes = [C.c_int32] + [vp] * 10 + [C.c_double, C.c_int32, vp]
         L.dart_arm_qp_launch_count.restype = C.c_int64

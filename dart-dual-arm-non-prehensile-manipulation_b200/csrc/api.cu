@@ -210,6 +210,28 @@ extern "C" int dart_solve_host(dart_handle h, int32_t B, const double* x0, const
     return DART_OK;
 }
 
+extern "C" int dart_pmpc_episode(dart_handle h, int32_t B, int32_t T, double* state, const double* target, const double* aux,
+                                 const double* mu_plant, const double* coulomb, double tol, int32_t* nsteps,
+                                 double* conv_time, double* effort, double* err, double* u0, double* J, int32_t* status,
+                                 int32_t* iters, uint64_t* counters, void* stream) {
+    if (!h || h->cfg.method != DART_PMPC || B < 0 || T < 0 || !state || !target || !mu_plant || !nsteps || !conv_time || !effort ||
+        !err || !u0 || !J || !status || !iters || !counters)
+        return DART_ERR_ARG;
+    if (B == 0 || T == 0) return DART_OK;
+    if (h->rows || h->dual) return DART_ERR_UNSUPPORTED;     // the episode kernel keeps no result rows / dual state
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess || cur != h->device) return DART_ERR_ARG;
+    KArgs a;
+    a.B = B; a.N = h->cfg.N; a.o = h->opts; a.cfg = h->cfg;
+    a.x0 = state; a.ref = target; a.aux = aux; a.warm = nullptr;
+    a.w_out = nullptr; a.u0 = u0; a.J = J; a.status = status; a.iters = iters; a.rows = nullptr; a.dual = nullptr;
+    PlantArgs pl{B, h->cfg.Ts, h->cfg.g, tol, mu_plant, coulomb, u0, target, state, conv_time, effort, err, nsteps};
+    int rc = launch_episode_pmpc(a, T, pl, (unsigned long long*)counters, h->cfg.lanes, (cudaStream_t)stream, &h->last);
+    if (rc != DART_OK) return rc;
+    h->launches += 1;
+    return DART_OK;
+}
+
 extern "C" int dart_set_result_rows(dart_handle h, double* rows, int32_t capacity_rows) {
     if (!h || (rows && capacity_rows <= 0)) return DART_ERR_ARG;
     h->rows = rows;

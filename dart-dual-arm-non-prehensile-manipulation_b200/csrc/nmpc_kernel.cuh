@@ -4,6 +4,7 @@
 
 #include "models.cuh"
 #include "launch.h"
+#include "plant.cuh"
 
 namespace dart {
 
@@ -59,9 +60,9 @@ struct DevTile {
 };
 
 // M::MIN_BLOCKS: occupancy hint (blocks of M::MAX_THREADS per SM) that caps registers where shared memory leaves room.
+// One batch solve by this block: every tile solves its sub-problem, then the axes of an instance are combined.
 template <class M, int G, int NC>
-__global__ void __launch_bounds__(M::MAX_THREADS, M::MIN_BLOCKS) nmpc_solve_kernel(const KArgs a, const int ws_stride) {
-    extern __shared__ double smem[];
+__device__ __forceinline__ void solve_block(const KArgs& a, const int ws_stride, double* smem) {
     constexpr int NAX = M::NAXIS;
     const DevTile<G> tile;
     const int tpb = blockDim.x / G;
@@ -115,7 +116,41 @@ __global__ void __launch_bounds__(M::MAX_THREADS, M::MIN_BLOCKS) nmpc_solve_kern
 }
 
 template <class M, int G, int NC>
-static int launch_n(const KArgs& a, int block_threads, cudaStream_t st, LaunchInfo* info) {
+__global__ void __launch_bounds__(M::MAX_THREADS, M::MIN_BLOCKS) nmpc_solve_kernel(const KArgs a, const int ws_stride) {
+    extern __shared__ double smem[];
+    solve_block<M, G, NC>(a, ws_stride, smem);
+}
+
+// Persistent closed-loop episode: T times { solve the block's instances, advance their surrogate plant,
+// update the episode metrics } in ONE launch.  Instances are independent, so blocks never synchronise with each other;
+// inside a block the state written by the plant thread is visible to the solving tiles after the block barrier.
+struct EpisodeArgs {
+    int T;
+    PlantArgs plant;                       // plant.u = a.u0, plant.state = a.x0, plant.target = a.ref
+    unsigned long long* counters;          // [0] += iterations of every solve, [1] += solves that did not converge
+};
+
+template <class M, int G, int NC>
+__global__ void __launch_bounds__(M::MAX_THREADS, M::MIN_BLOCKS) nmpc_episode_kernel(const KArgs a, const int ws_stride,
+                                                                                     const EpisodeArgs e) {
+    extern __shared__ double smem[];
+    const int ipb = (blockDim.x / G) / M::NAXIS;                 // instances of this block
+    const int inst = blockIdx.x * ipb + (int)threadIdx.x;        // the plant thread's instance
+    const bool plant_thread = (int)threadIdx.x < ipb && inst < a.B;
+    for (int step = 0; step < e.T; ++step) {
+        solve_block<M, G, NC>(a, ws_stride, smem);
+        __syncthreads();                                         // u0 / status / iters of this block's instances are written
+        if (plant_thread) {
+            atomicAdd(&e.counters[0], (unsigned long long)a.iters[inst]);
+            if (a.status[inst] != ST_CONVERGED) atomicAdd(&e.counters[1], 1ull);
+            plant_step_one(e.plant, inst);
+        }
+        __syncthreads();                                         // the new states are visible to the solving tiles
+    }
+}
+
+template <class M, int G, int NC>
+static int launch_n(const KArgs& a, int block_threads, cudaStream_t st, LaunchInfo* info, const EpisodeArgs* ep = nullptr) {
     const int ws = Workspace<M>::doubles(a.N) + kSlot;
     // Shared memory has 16 banks of 8 bytes.  In the serial sweeps all lanes of a tile read the same address and the
     // 32/G tiles of a warp differ by the workspace stride, so the stride is padded to make them land on distinct
@@ -147,15 +182,26 @@ static int launch_n(const KArgs& a, int block_threads, cudaStream_t st, LaunchIn
     size_t smem = (size_t)tpb * ws_stride * sizeof(double);
     while (smem > (size_t)max_smem && bt > 32) { bt -= 32; tpb = bt / G; smem = (size_t)tpb * ws_stride * sizeof(double); }
     if (smem > (size_t)max_smem) return DART_ERR_UNSUPPORTED;
-    auto kern = nmpc_solve_kernel<M, G, NC>;
-    static size_t smem_set[kMaxDev] = {0};          // per instantiation and device
-    if (smem > smem_set[dev]) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return DART_ERR_CUDA;
-        smem_set[dev] = smem;
-    }
     const long probs = (long)a.B * M::NAXIS;
     const int grid = (int)((probs + tpb - 1) / tpb);
-    kern<<<grid, bt, smem, st>>>(a, ws_stride);
+    if (ep) {
+        if (tpb % M::NAXIS != 0) return DART_ERR_ARG;   // the axes of an instance must share a block
+        auto kern = nmpc_episode_kernel<M, G, NC>;
+        static size_t smem_set_ep[kMaxDev] = {0};
+        if (smem > smem_set_ep[dev]) {
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return DART_ERR_CUDA;
+            smem_set_ep[dev] = smem;
+        }
+        kern<<<grid, bt, smem, st>>>(a, ws_stride, *ep);
+    } else {
+        auto kern = nmpc_solve_kernel<M, G, NC>;
+        static size_t smem_set[kMaxDev] = {0};          // per instantiation and device
+        if (smem > smem_set[dev]) {
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return DART_ERR_CUDA;
+            smem_set[dev] = smem;
+        }
+        kern<<<grid, bt, smem, st>>>(a, ws_stride);
+    }
     if (info) { info->lanes = G; info->block_threads = bt; info->grid = grid; info->smem_bytes = (int)smem; }
     return cudaGetLastError() == cudaSuccess ? DART_OK : DART_ERR_CUDA;
 }
@@ -164,6 +210,15 @@ template <class M, int G>
 static int launch_t(const KArgs& a, int block_threads, cudaStream_t st, LaunchInfo* info) {
     if (a.N == M::NDEF) return launch_n<M, G, M::NDEF>(a, block_threads, st, info);
     return launch_n<M, G, 0>(a, block_threads, st, info);
+}
+
+// Persistent episode: the reference horizon and the two tile widths the batch launcher picks for PMPC.
+template <class M>
+static int launch_episode(const KArgs& a, const EpisodeArgs& ep, int lanes, cudaStream_t st, LaunchInfo* info) {
+    if (a.N != M::NDEF) return DART_ERR_UNSUPPORTED;
+    if (lanes == 8) return launch_n<M, 8, M::NDEF>(a, 0, st, info, &ep);
+    if (lanes == 16) return launch_n<M, 16, M::NDEF>(a, 0, st, info, &ep);
+    return DART_ERR_UNSUPPORTED;
 }
 
 template <class M>

@@ -72,15 +72,29 @@ class PMPCEpisodes:
                                               p(self.effort), p(self.err), stream), "dart_pmpc_plant_step")
         self.step_index += 1
 
-    def run(self, steps, trace_every=0, graph=False):
+    def run(self, steps, trace_every=0, graph=False, persistent=False):
         """Run ``steps`` simulated steps; returns the metrics dict (numpy).  ``trace_every`` > 0 records
         (state, u0, J, iters) of instance 0 every that many steps (config 1's per-step solve trace).
         ``graph=True`` captures one step (solve + plant + counters) in a CUDA graph after a warm-up step and replays
-        it: the closed loop is launch-bound at small batch (six launches per simulated step)."""
+        it: the closed loop is launch-bound at small batch (six launches per simulated step).
+        ``persistent=True`` runs all ``steps`` in ONE launch (dart_pmpc_episode; cold start only): the same arithmetic,
+        bit-identical states and metrics, no launch gaps."""
         torch = self.torch
         trace = []
         k0 = 0
-        if graph and not trace_every and steps > 2:
+        if persistent and not trace_every and not self.warm_start and steps > 0:
+            p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+            counters = torch.zeros(2, dtype=torch.int64, device=self.dev)
+            stream = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+            with torch.cuda.device(self.dev):
+                check(_lib.lib().dart_pmpc_episode(self.engine._h, self.B, int(steps), p(self.state), p(self.target), p(self.params),
+                                                   p(self.mu_plant), p(self.coulomb), self.tol, p(self.nsteps), p(self.conv_time),
+                                                   p(self.effort), p(self.err), p(self.u0), p(self.J), p(self.status), p(self.iters),
+                                                   p(counters), stream), "dart_pmpc_episode")
+            self.iter_sum += counters[0]
+            self.not_converged_solves += counters[1]
+            self.step_index += int(steps)
+        elif graph and not trace_every and steps > 2:
             if self._graph is None:
                 self.step()                               # warm-up: one real step outside the capture
                 k0 = 1

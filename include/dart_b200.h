@@ -228,6 +228,16 @@ int dart_arm_qp_build(int32_t B, const double* Wimp, const double* Wpos, const d
                       double* C, double* lo, double* hi, void* stream);
 int64_t dart_arm_qp_launch_count(void);
 
+/* T closed-loop steps of B PMPC instances in ONE launch: each step = dart_solve (cold start, as the reference) followed by
+ * dart_pmpc_plant_step, with the state fed back on the device.  Same arithmetic as calling the two T times (bit-identical
+ * states and metrics); removes the per-step launch gaps that bound the small-batch closed loop.  `state` [B,6] is read and
+ * advanced in place; u0/J/status/iters hold the last step's solve; counters[0] += Newton iterations of all solves,
+ * counters[1] += solves that did not end converged (uint64, device).  PMPC handles with the reference horizon only. */
+int dart_pmpc_episode(dart_handle h, int32_t B, int32_t T, double* state, const double* target, const double* aux,
+                      const double* mu_plant, const double* coulomb, double tol, int32_t* nsteps, double* conv_time,
+                      double* effort, double* err, double* u0, double* J, int32_t* status, int32_t* iters,
+                      uint64_t* counters, void* stream);
+
 /* Measured FP64 FMA-pipe peak of the device in TFLOP/s (DFMA microbenchmark, CUDA-event timed): the roofline
  * denominator bench.py reports the solver kernels against. */
 int dart_measure_fp64_tflops(int device, double* tflops);

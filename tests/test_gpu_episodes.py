@@ -63,3 +63,22 @@ def test_reference_main_loop_example(built):
     assert (log[:, 6] == 0).all()                   # every solve converged
     assert log[-1, 1] < 0.01 and log[0, 1] > 0.1    # 11 cm -> under 1 cm
     assert np.abs(log[:, 2:4]).max() <= 0.6 + 1e-12
+
+
+def test_persistent_episode_is_bit_identical_to_stepwise(built):
+    """dart_pmpc_episode (all steps in one launch) against solve + plant launched step by step."""
+    c, aux = dart_b200.workloads.pmpc_inputs(4)
+    rng = np.random.default_rng(3)
+    cou = rng.uniform(0, 0.02, aux.shape[0])
+    a = dart_b200.PMPCEpisodes(c["state"], c["target"], aux, coulomb=cou, device=0)
+    b = dart_b200.PMPCEpisodes(c["state"], c["target"], aux, coulomb=cou, device=0)
+    ma = a.run(150)
+    mb = b.run(150, persistent=True)
+    assert np.array_equal(a.state.cpu().numpy(), b.state.cpu().numpy())
+    for k in ("steady_state_error", "convergence_time", "control_effort"):
+        assert np.array_equal(ma[k], mb[k]), k
+    assert ma["mean_iters"] == mb["mean_iters"] and ma["not_converged_solves"] == mb["not_converged_solves"] == 0
+    assert np.array_equal(a.u0.cpu().numpy(), b.u0.cpu().numpy())
+    # a second call continues the same episode
+    a.run(20); b.run(20, persistent=True)
+    assert np.array_equal(a.state.cpu().numpy(), b.state.cpu().numpy()) and a.step_index == b.step_index == 170

@@ -16,23 +16,28 @@ def ev():
     return torch.cuda.Event(enable_timing=True)
 
 
-def config1(steps):
+def config1(steps, persistent=False):
     c1 = dart_b200.workloads.pmpc_config1()
     aux = np.stack([c1["Qp"], c1["Qv"], c1["R"], c1["mu"]], axis=1)
     ep = dart_b200.PMPCEpisodes(c1["state"], c1["target"], aux, device=LOCAL)
-    t0 = time.perf_counter(); m = ep.run(steps, trace_every=max(1, steps // 100)); dt = time.perf_counter() - t0
-    return dict(config="1: PMPC single episode (cube, mu=0.10, model-as-plant)", steps=steps, wall_s=dt, solves_per_s=steps / dt,
+    if persistent:
+        dart_b200.PMPCEpisodes(c1["state"], c1["target"], aux, device=LOCAL).run(10, persistent=True)       # first-launch costs
+        t0 = time.perf_counter(); m = ep.run(steps, persistent=True); dt = time.perf_counter() - t0
+        m["trace"] = np.zeros((0,))
+    else:
+        t0 = time.perf_counter(); m = ep.run(steps, trace_every=max(1, steps // 100)); dt = time.perf_counter() - t0
+    return dict(config="1: PMPC single episode (cube, mu=0.10, model-as-plant)" + (", all steps in one launch" if persistent else ""), steps=steps, wall_s=dt, solves_per_s=steps / dt,
                 ms_per_solve=dt / steps * 1e3, convergence_time_s=float(m["convergence_time"][0]),
                 steady_state_error_m=float(m["steady_state_error"][0]), control_effort=float(m["control_effort"][0]),
                 mean_iters=m["mean_iters"], not_converged_solves=m["not_converged_solves"], trace=m["trace"].tolist())
 
 
-def config2_closed_loop(steps, label="2 (closed loop): 18 objects x 64 states, surrogate plant with unmodelled Coulomb term", **kw):
+def config2_closed_loop(steps, label="2 (closed loop): 18 objects x 64 states, surrogate plant with unmodelled Coulomb term", persistent=False, **kw):
     c, aux = W.pmpc_inputs(64)
     rng = np.random.default_rng(21)
     ep = dart_b200.PMPCEpisodes(c["state"], c["target"], aux, coulomb=rng.uniform(0, 0.02, aux.shape[0]), device=LOCAL, **kw)
     a, b = ev(), ev()
-    a.record(); m = ep.run(steps, graph=GRAPH); b.record(); torch.cuda.synchronize()
+    a.record(); m = ep.run(steps, graph=GRAPH, persistent=persistent); b.record(); torch.cuda.synchronize()
     sec = a.elapsed_time(b) * 1e-3
     per_obj = []
     objs = dart_b200.workloads.pmpc_objects()
@@ -162,11 +167,13 @@ if __name__ == "__main__":
     q = args.quick
     GRAPH = args.graph
     res = []
-    todo = args.only.split(",") if args.only else ["config1", "config2", "config2_warm", "config3", "config3_dual", "config4", "config4_dual", "config4_shift", "config4_refopts", "config5"]
+    todo = args.only.split(",") if args.only else ["config1", "config1_persistent", "config2", "config2_persistent", "config2_warm", "config3", "config3_dual", "config4", "config4_dual", "config4_shift", "config4_refopts", "config5"]
     for name in todo:
         if WORLD > 1 and name != "config5":
             continue
         if name == "config1": r = config1(500 if q else 5000)
+        elif name == "config1_persistent": r = config1(500 if q else 5000, persistent=True)
+        elif name == "config2_persistent": r = config2_closed_loop(200 if q else 5000, label="2 (f1): closed loop, all 5000 steps in one launch (dart_pmpc_episode)", persistent=True)
         elif name == "config2": r = config2_closed_loop(200 if q else 5000)
         elif name == "config2_warm": r = config2_closed_loop(200 if q else 5000, label="2 (f2): closed loop with primal warm start + warm-started barrier (not the reference's cold start)", warm_start=True)
         elif name == "config3": r = config3(512 if q else 4096, 32 if q else 256)
