@@ -22,8 +22,13 @@ class HostEmu:
     def __init__(self):
         self.lib = C.CDLL(os.path.join(ROOT, "tests", "hostemu", "_build", "libhostemu.so"))
         self.lib.hostemu_solve.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 9
+        self.lib.hostemu_solve_dual.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 10
+        self.lib.hostemu_ndual.argtypes = [C.c_void_p]
 
-    def solve(self, cfg, x0, ref, aux=None, warm=None):
+    def ndual(self, cfg):
+        return self.lib.hostemu_ndual(C.byref(cfg))
+
+    def solve(self, cfg, x0, ref, aux=None, warm=None, dual=None):
         x0 = np.ascontiguousarray(np.atleast_2d(x0), dtype=np.float64)
         B, N = x0.shape[0], cfg.N
         nw = (N + 1) * NXF[cfg.method] + 2 * N
@@ -31,7 +36,11 @@ class HostEmu:
         w = np.zeros((B, nw)); u0 = np.zeros((B, 2)); J = np.zeros(B)
         st = np.zeros(B, np.int32); it = np.zeros(B, np.int32)
         p = lambda a: None if a is None else C.c_void_p(a.ctypes.data)
-        rc = self.lib.hostemu_solve(C.byref(cfg), B, *[p(a) for a in arrs], p(w), p(u0), p(J), p(st), p(it))
+        if dual is None:
+            rc = self.lib.hostemu_solve(C.byref(cfg), B, *[p(a) for a in arrs], p(w), p(u0), p(J), p(st), p(it))
+        else:       # dual: float64 [B, ndual] array, read and updated in place (dart_set_dual_state semantics)
+            assert dual.dtype == np.float64 and dual.flags.c_contiguous and dual.shape == (B, self.ndual(cfg))
+            rc = self.lib.hostemu_solve_dual(C.byref(cfg), B, *[p(a) for a in arrs], p(w), p(u0), p(J), p(st), p(it), p(dual))
         assert rc == 0
         return dict(w=w, u0=u0, J=J, status=st, iters=it)
 

@@ -33,12 +33,36 @@ static void run_all(const KArgs& a) {
     }
 }
 
+static int solve_impl(const dart_cfg* cfg, int B, const double* x0, const double* ref, const double* aux,
+                      const double* warm, double* w_out, double* u0, double* J, int32_t* status, int32_t* iters, double* dual);
+
 extern "C" int hostemu_solve(const dart_cfg* cfg, int B, const double* x0, const double* ref, const double* aux,
                              const double* warm, double* w_out, double* u0, double* J, int32_t* status, int32_t* iters) {
+    return solve_impl(cfg, B, x0, ref, aux, warm, w_out, u0, J, status, iters, nullptr);
+}
+
+// with a dual-state buffer [B, hostemu_ndual(cfg)] (dart_set_dual_state semantics)
+extern "C" int hostemu_solve_dual(const dart_cfg* cfg, int B, const double* x0, const double* ref, const double* aux,
+                                  const double* warm, double* w_out, double* u0, double* J, int32_t* status, int32_t* iters,
+                                  double* dual) {
+    return solve_impl(cfg, B, x0, ref, aux, warm, w_out, u0, J, status, iters, dual);
+}
+
+extern "C" int hostemu_ndual(const dart_cfg* cfg) {
+    switch (cfg->method) {
+        case DART_PMPC: return PmpcAxis::NAXIS * Solver<PmpcAxis, HostTile, 0>::dual_doubles(cfg->N);
+        case DART_RMPC: return Rmpc::NAXIS * Solver<Rmpc, HostTile, 0>::dual_doubles(cfg->N);
+        case DART_LMPC: return LmpcAxis::NAXIS * Solver<LmpcAxis, HostTile, 0>::dual_doubles(cfg->N);
+    }
+    return -1;
+}
+
+static int solve_impl(const dart_cfg* cfg, int B, const double* x0, const double* ref, const double* aux,
+                      const double* warm, double* w_out, double* u0, double* J, int32_t* status, int32_t* iters, double* dual) {
     KArgs a;
     a.B = B; a.N = cfg->N; a.cfg = *cfg;
     fill_opts(*cfg, a.o);
-    a.x0 = x0; a.ref = ref; a.aux = aux; a.warm = warm; a.w_out = w_out; a.u0 = u0; a.J = J; a.status = status; a.iters = iters; a.rows = nullptr; a.dual = nullptr;
+    a.x0 = x0; a.ref = ref; a.aux = aux; a.warm = warm; a.w_out = w_out; a.u0 = u0; a.J = J; a.status = status; a.iters = iters; a.rows = nullptr; a.dual = dual;
     switch (cfg->method) {
         case DART_PMPC: run_all<PmpcAxis>(a); return 0;
         case DART_RMPC: run_all<Rmpc>(a); return 0;

@@ -88,3 +88,29 @@ def test_reference_lmpc_solver_options(hostemu):
     assert out["iters"].mean() < tight["iters"].mean() - 1.0
     assert np.abs(out["u0"] - tight["u0"]).max() < 2e-3
     assert (np.abs(out["J"] - tight["J"]) / np.abs(tight["J"])).max() < 1e-4
+
+
+def test_dual_warm_start_matches_oracle(hostemu):
+    """dart_set_dual_state semantics on the host build of the solver: second solve of a slightly moved RMPC problem,
+    started from the first one's plan, slacks and multipliers, against the oracle given the same state."""
+    d, p = helpers.rmpc_case(16)
+    cfg = dart_b200.rmpc_cfg()
+    dual = np.zeros((16, hostemu.ndual(cfg)))
+    a = hostemu.solve(cfg, d["x0"], d["ref"], d["aux"], dual=dual)
+    ra = ipm.solve(p)
+    assert (a["status"] == 0).all() and (dual[:, 0] == 1.0).all()
+    # the next control cycle: state advanced by a little, previous command as u_prev
+    x1 = d["x0"] + 0.002 * np.stack([d["x0"][:, 1], 0 * d["x0"][:, 1], d["x0"][:, 3], 0 * d["x0"][:, 3]], axis=1)
+    aux1 = d["aux"].copy(); aux1[:, :2] = a["u0"]
+    from oracle import problems
+    p1 = problems.rmpc_problem(x1, a["u0"], d["theta"], d["ref"])
+    warm = dict(lam=ra["lam"], s=ra["s"], zl=ra["zl"], zu=ra["zu"], valid=ra["status"] == 0)
+    rb = ipm.solve(p1, X0=ra["X"], U0=ra["U"], opts=ipm.Options(mu0=1e-6), warm=warm)
+    dual[3, 0] = 0.0; warm["valid"][3] = False            # one instance without a usable dual state: mu not below 1e-4
+    rb = ipm.solve(p1, X0=ra["X"], U0=ra["U"], opts=ipm.Options(mu0=1e-6), warm=warm)
+    b = hostemu.solve(dart_b200.rmpc_cfg(mu_init=1e-6), x1, d["ref"], aux1, warm=a["w"], dual=dual)
+    plain = hostemu.solve(dart_b200.rmpc_cfg(mu_init=1e-4), x1, d["ref"], aux1, warm=a["w"])
+    assert (b["status"] == 0).all() and (rb["status"] == 0).all()
+    assert np.abs(b["iters"] - rb["iters"]).max() <= 1
+    assert np.abs(b["u0"] - rb["U"][:, 0]).max() < 1e-8
+    assert np.abs(b["u0"] - plain["u0"]).max() < 1e-6 and b["iters"].sum() < plain["iters"].sum()
