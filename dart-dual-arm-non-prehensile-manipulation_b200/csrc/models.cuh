@@ -341,9 +341,9 @@ DART_HD void solve_one(const T& tile, const KArgs& a, int inst, int axis, bool a
     const int nwf = M::nw(N);
     const int uoff = (N + 1) * M::NXF;
     const int ucol = (M::NAXIS > 1) ? axis : 0;
-    const double* warm = (active && a.warm) ? a.warm + (long)inst * nwf : nullptr;
     // the starting point: the caller's plan (warm) or x0 held over the horizon with zero inputs (mpc_3d.py:123)
     auto load_start = [&]() {
+        const double* warm = a.warm ? a.warm + (long)inst * nwf : nullptr;     // re-derived, not kept live across the solve
         for (int k = tile.lane(); k <= N; k += tile.size()) {
             DART_UNROLL for (int i = 0; i < np; ++i)
                 w.X[k * n + i] = (warm && k > 0) ? warm[k * M::NXF + M::xmap(axis, i)] : x0[i];
@@ -365,24 +365,45 @@ DART_HD void solve_one(const T& tile, const KArgs& a, int inst, int axis, bool a
     }
     // every tile of the block (active or not) takes part in run(): its threads also serve the serial-sweep phase
     Solver<M, T, NC> s(tile, prm, a.o, N, w, bc);
-    double* dblk = (active && a.dual) ? a.dual + ((long)inst * M::NAXIS + axis) * Solver<M, T, NC>::dual_doubles(N) : nullptr;
-    s.run(active, J, status, iters, kkt, a.warm ? dblk : nullptr, dblk);
+    // dual warm start (dart_set_dual_state): the block pointer is re-derived where it is needed so that it does not
+    // occupy registers across the solve
+    auto dual_block = [&]() { return a.dual + ((long)inst * M::NAXIS + axis) * Solver<M, T, NC>::dual_doubles(N); };
+    double mu0 = a.o.mu0;
+    if (active) {
+        const bool dualwarm = a.dual != nullptr && a.warm != nullptr && dual_block()[0] == 1.0;
+        if (a.dual != nullptr && !dualwarm) mu0 = dmax(mu0, 1e-4);     // no usable dual state: never below the primal-warm value
+        s.init_rows(mu0);
+        if (dualwarm) s.load_duals(dual_block(), mu0);
+    }
+    s.run(active, mu0, J, status, iters, kkt);
+    if (active && a.dual != nullptr) s.store_duals(dual_block(), status == ST_CONVERGED || status == ST_ACCEPTABLE);
     if (!active) return;
     if (M::infeasible0(prm, x0) && status != ST_NUMERIC) status = ST_INFEASIBLE;
     // a solve that ran into NaN/Inf hands back its starting point, not the broken iterate: a closed loop that feeds
-    // plans and commands back in must not be poisoned by one failed solve
-    if (status == ST_NUMERIC) load_start();
+    // plans and commands back in must not be poisoned by one failed solve (selected at the output, so that the cold
+    // path adds nothing to the solve's register budget)
+    const bool bad = status == ST_NUMERIC;
+    const double* warm = a.warm ? a.warm + (long)inst * nwf : nullptr;
     if (a.w_out) {
         double* wo = a.w_out + (long)inst * nwf;
         for (int k = tile.lane(); k <= N; k += tile.size()) {
-            DART_UNROLL for (int i = 0; i < np; ++i) wo[k * M::NXF + M::xmap(axis, i)] = w.X[k * n + i];
+            DART_UNROLL for (int i = 0; i < np; ++i) {
+                const int io = k * M::NXF + M::xmap(axis, i);
+                wo[io] = bad ? ((warm && k > 0) ? warm[io] : x0[i]) : w.X[k * n + i];
+            }
             if (k < N) {
-                DART_UNROLL for (int j = 0; j < m; ++j) wo[uoff + k * 2 + (M::NAXIS > 1 ? ucol : j)] = w.U[k * m + j];
+                DART_UNROLL for (int j = 0; j < m; ++j) {
+                    const int io = uoff + k * 2 + (M::NAXIS > 1 ? ucol : j);
+                    wo[io] = bad ? (warm ? warm[io] : 0.0) : w.U[k * m + j];
+                }
             }
         }
     }
     if (tile.lane() == 0) {
-        DART_UNROLL for (int j = 0; j < m; ++j) a.u0[(long)inst * 2 + (M::NAXIS > 1 ? ucol : j)] = w.U[j];
+        DART_UNROLL for (int j = 0; j < m; ++j) {
+            const int jo = (M::NAXIS > 1 ? ucol : j);
+            a.u0[(long)inst * 2 + jo] = bad ? (warm ? warm[uoff + jo] : 0.0) : w.U[j];
+        }
     }
 }
 

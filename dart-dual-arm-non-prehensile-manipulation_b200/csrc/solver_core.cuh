@@ -987,22 +987,15 @@ struct Solver {
     //   C (tile): slack/dual steps, line search with re-evaluation, multiplier update, KKT residuals.
     // Two block barriers per iteration separate A|B|C; all tiles of the block (also finished or empty ones) keep
     // taking part in them until no problem of the block needs another sweep.
-    // dual_in: block to start from (nullptr or not valid: default initialisation; an instance without a valid
-    // block never starts below mu = 1e-4, the value that suits a primal-only warm start); dual_out: where to leave the
-    // final slacks and multipliers.
-    DART_HD void run(bool active, double& J, int32_t& status, int32_t& iters, double& kkt, const double* dual_in = nullptr,
-                     double* dual_out = nullptr) {
-        double mu = o.mu0;
-        const bool dualwarm = active && dual_in != nullptr && dual_in[0] == 1.0;
-        if (active && dual_out != nullptr && !dualwarm) mu = dmax(mu, 1e-4);
+    // The caller has initialised slacks and multipliers (init_rows, optionally load_duals) for barrier parameter mu0.
+    DART_HD void run(bool active, double mu0, double& J, int32_t& status, int32_t& iters, double& kkt) {
+        double mu = mu0;
         double f = 0.0, L = 0.0, th = 0.0, pinf = 0.0, dinf = 0.0, zs_min = 0.0, zs_max = 0.0, lam_sum = 0.0, z_sum = 0.0;
         // number of constraint rows of the problem (rows with row_skip0 do not exist at stage 0)
         int nact = 0;
         DART_UNROLL for (int r = 0; r < nr; ++r) nact += M::row_skip0(r) ? N - 1 : N;
         double inv_nd = 0.0, inv_nc = 0.0;
         if (active) {
-            init_rows(mu);
-            if (dualwarm) load_duals(dual_in, mu);
             eval1(f, L, th, pinf);
             eval2(dinf, zs_min, zs_max, lam_sum, z_sum);
             inv_nd = 1.0 / (double)(N * n + 2 * nact);
@@ -1134,7 +1127,6 @@ struct Solver {
         status = st;
         iters = it;
         kkt = E0;
-        if (active && dual_out != nullptr) store_duals(dual_out, st == ST_CONVERGED || st == ST_ACCEPTABLE);
     }
 };
 
