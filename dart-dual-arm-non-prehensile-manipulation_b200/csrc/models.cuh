@@ -220,7 +220,10 @@ struct LmpcAxis {
     static constexpr int NX = 5, NU = 1, NR = 1, NP = 4, NAUG = 1, NAXIS = 2;
     static constexpr bool SERIAL_RICCATI = false;   // measured: the tiled sweep is 1.3-2x faster than the per-lane one at n = 5
     DART_HD static constexpr int a_kind(int, int) { return 0; }
-    static constexpr int MAX_THREADS = 128, MIN_BLOCKS = 3, BT_LARGE = 64;    // 12 warps/SM -> <= 170 registers (shared memory allows 13)
+    // one instance (two axis tiles) per block; 168 registers -> 6 blocks = 12 warps per SM (shared memory allows 14).
+    // Measured at 16 384 instances: bounds (64,5) 7.06 ms, (128,3) 7.58 ms (same register count, worse schedule),
+    // (64,4) / (128,2) with 255 registers and 8 warps 7.30 ms, (64,7) with 128 registers 8.2 ms
+    static constexpr int MAX_THREADS = 64, MIN_BLOCKS = 5, BT_LARGE = 64;
     static constexpr int NXF = 8;
     static constexpr int NDEF = 20;
     struct Prm {
