@@ -82,6 +82,25 @@ def lib():
         L.dart_arm_qp_solve.argtypes = [C.c_int32] + [vp] * 10 + [C.c_double, C.c_int32, vp]
         L.dart_arm_qp_launch_count.restype = C.c_int64
         L.dart_arm_qp_build.argtypes = [C.c_int32] + [vp] * 7 + [C.c_double] + [vp] * 17 + [vp]
+    if hasattr(L, "dart_lmpc_plant_step"):
+        L.dart_lmpc_plant_step.argtypes = [C.c_int32, C.c_double, vp, vp, vp, vp, vp]
+    if hasattr(L, "dart_ppo_create"):
+        L.dart_ppo_default_cfg.argtypes = [vp]
+        L.dart_ppo_default_reward_cfg.argtypes = [vp]
+        L.dart_ppo_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp]
+        L.dart_ppo_destroy.argtypes = [vp]
+        L.dart_ppo_get_state.argtypes = [vp, vp, vp, vp, C.POINTER(C.c_int64)]
+        L.dart_ppo_set_state.argtypes = [vp, vp, vp, vp, C.c_int64]
+        L.dart_ppo_get_grad.argtypes = [vp, vp]
+        L.dart_ppo_params_dev.argtypes = [vp]
+        L.dart_ppo_params_dev.restype = vp
+        L.dart_ppo_launch_count.argtypes = [vp]
+        L.dart_ppo_launch_count.restype = C.c_int64
+        L.dart_ppo_act.argtypes = [vp, C.c_int32] + [vp] * 6 + [vp]
+        L.dart_ppo_reward.argtypes = [C.c_int32] + [vp] * 11 + [vp]
+        L.dart_ppo_gae.argtypes = [C.c_int32, C.c_int32] + [vp] * 4 + [C.c_double, C.c_double, vp, vp, vp]
+        L.dart_ppo_normalize.argtypes = [C.c_int64, vp, C.c_int32, vp]
+        L.dart_ppo_update.argtypes = [vp, C.c_int32] + [vp] * 6 + [C.c_int32, vp, vp]
     _lib = L
     return L
 

@@ -1,0 +1,694 @@
+// PPO training path of the LMPC parameter-adaptation policy, batched over instances.
+//
+// Replaces, for B instances at once, what RLMPC._rl_worker does with torch autograd for one instance
+// (LMPC/src/controller/rlmpc2.py):
+//   ppo_sample_kernel     rollout-time action:  a = mean + std * eps, log-probability, value        (:670-699)
+//   ppo_reward_kernel     proximity reward, penalties, bonuses, termination                            (:598-601, 701-735)
+//   ppo_gae_kernel        generalised advantage estimation along each instance's rollout, returns     (:589-596, 783-784)
+//   ppo_normalize_kernel  (x - mean) / (std + 1e-8) over the pooled rollout (numpy std for returns :785, torch std :792)
+//   ppo_gather_kernel     minibatch gather by a permutation                                            (:795-800)
+//   gemm_kernel           FP32 SIMT tiled GEMM, grouped over the actor/critic pair: forward (bias + tanh), data
+//                         gradient (fused tanh'), weight gradient (split over the minibatch, partials summed in a
+//                         fixed order => bitwise repeatable)                                           (:801, :815)
+//   ppo_loss_kernel       clipped surrogate + value MSE + entropy bonus and their gradients w.r.t. mean/value/log_std (:802-813)
+//   ppo_grad_reduce_kernel, ppo_adam_kernel   clip_grad_norm_(0.5) and Adam with L2 weight decay       (:561, :814-817)
+//
+// Arithmetic is FP32 like the reference's torch modules (per-sample scalars and all reductions in FP64).  This is the
+// first correct device path of the training step: the GEMMs run on the FP32 CUDA-core pipe, not on tcgen05, so that the
+// gradients match torch's FP32 autograd (TF32 would not).  The reference's rollout buffer swaps reward and value
+// (`buf.add(..., value, reward, ...)` against `add(o, a, logp, r, v, done)`, :744 vs :93); that bug is not reproduced.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+#include <math.h>
+#include <new>
+
+#include "../../include/dart_b200.h"
+
+namespace {
+
+constexpr int OBS = 520, HID = 64, ACT = 34, H2W = 2 * HID;
+// flat parameter vector (float32): every weight matrix is followed by its bias, torch layout [out, in]
+constexpr int OFF_W1 = 0;                          // [128,520] rows 0-63 mean_net.0.weight, rows 64-127 value_net.0.weight
+constexpr int OFF_B1 = OFF_W1 + H2W * OBS;         // [128]
+constexpr int OFF_W2A = OFF_B1 + H2W;              // mean_net.2.weight [64,64]
+constexpr int OFF_B2A = OFF_W2A + HID * HID;
+constexpr int OFF_W2C = OFF_B2A + HID;             // value_net.2.weight [64,64]
+constexpr int OFF_B2C = OFF_W2C + HID * HID;
+constexpr int OFF_W3A = OFF_B2C + HID;             // mean_net.4.weight [34,64]
+constexpr int OFF_B3A = OFF_W3A + ACT * HID;
+constexpr int OFF_W3C = OFF_B3A + ACT;             // value_net.4.weight [1,64]
+constexpr int OFF_B3C = OFF_W3C + HID;
+constexpr int OFF_LS = OFF_B3C + 1;                // log_std [34]
+constexpr int NPW = OFF_LS;                        // weights + biases
+constexpr int NP = OFF_LS + ACT;                   // 77 317 parameters
+
+constexpr int BM = 64, BN = 64, BK = 16, PAD = 4, GT = 256;
+constexpr int LOSS_T = 128, LOSS_W = 3 + ACT;      // per-block partials: policy sum, value sq. sum, unused, dlog_std[34]
+constexpr int MAX_SPLITS = 64;
+constexpr double HALF_LOG_2PI = 0.91893853320467274178;
+
+// One GEMM of a grouped launch:  C[m,n] = epilogue( sum_k A(m,k) B(k,n) ).
+struct GemmProb {
+    const float* A; int lda; int ta;      // A(m,k) = ta ? A[k*lda + m] : A[m*lda + k]
+    const float* B; int ldb; int tb;      // B(k,n) = tb ? B[n*ldb + k] : B[k*ldb + n]
+    float* C; int ldc;
+    int M, N, K;
+    int mode;                             // 0 store, 1 tanh(acc + bias[n]), 2 acc + bias[n], 3 acc * (1 - H[m,n]^2)
+    const float* bias;
+    const float* H; int ldh;
+    float* rowsum;                        // split mode: partial sums over k of A(m,k) (the bias gradient), or nullptr
+};
+struct GemmGroup {
+    GemmProb p[2];
+    int count, splits, kchunk;
+    long split_stride;                    // floats between the outputs of consecutive splits
+};
+
+__global__ void __launch_bounds__(GT) gemm_kernel(const GemmGroup g) {
+    const int pi = blockIdx.z / g.splits, split = blockIdx.z % g.splits;
+    const GemmProb& P = g.p[pi];
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    if (m0 >= P.M || n0 >= P.N) return;
+    __shared__ __align__(16) float As[BK][BM + PAD];
+    __shared__ __align__(16) float Bs[BK][BN + PAD];
+    const int t = threadIdx.x, ty = t / 16, tx = t % 16;
+    const int k_begin = split * g.kchunk;
+    const int k_end = min(P.K, k_begin + g.kchunk);
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    float rs[4] = {0.f, 0.f, 0.f, 0.f};
+    const bool want_rs = P.rowsum != nullptr && blockIdx.x == 0 && tx == 0;
+    for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+#pragma unroll
+        for (int i = 0; i < (BM * BK) / GT; ++i) {
+            const int e = t + i * GT;
+            int m, k;
+            if (P.ta) { k = e / BM; m = e % BM; } else { m = e / BK; k = e % BK; }
+            const int gm = m0 + m, gk = k0 + k;
+            float v = 0.f;
+            if (gm < P.M && gk < k_end) v = P.ta ? P.A[(size_t)gk * P.lda + gm] : P.A[(size_t)gm * P.lda + gk];
+            As[k][m] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < (BN * BK) / GT; ++i) {
+            const int e = t + i * GT;
+            int n, k;
+            if (P.tb) { n = e / BK; k = e % BK; } else { k = e / BN; n = e % BN; }
+            const int gn = n0 + n, gk = k0 + k;
+            float v = 0.f;
+            if (gn < P.N && gk < k_end) v = P.tb ? P.B[(size_t)gn * P.ldb + gk] : P.B[(size_t)gk * P.ldb + gn];
+            Bs[k][n] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+            if (want_rs) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) rs[i] += av[i];
+            }
+        }
+        __syncthreads();
+    }
+    float* C = P.C + (size_t)split * g.split_stride;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= P.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= P.N) continue;
+            float v = acc[i][j];
+            if (P.mode == 1) v = tanhf(v + P.bias[n]);
+            else if (P.mode == 2) v = v + P.bias[n];
+            else if (P.mode == 3) { const float h = P.H[(size_t)m * P.ldh + n]; v = v * (1.f - h * h); }
+            C[(size_t)m * P.ldc + n] = v;
+        }
+        if (want_rs) P.rowsum[(size_t)split * g.split_stride + m] = rs[i];
+    }
+}
+
+// ---- rollout-time sampling (rlmpc2.py:670-699): a = mean + std * eps, logp = sum_j log N(a_j; mean_j, std_j) ----
+__global__ void ppo_sample_kernel(int B, const float* __restrict__ mean, const float* __restrict__ log_std, float ls_min,
+                                  float ls_max, const float* __restrict__ eps, float* __restrict__ action,
+                                  float* __restrict__ logp) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double lp = 0.0;
+    for (int j = 0; j < ACT; ++j) {
+        const float ls = fminf(fmaxf(log_std[j], ls_min), ls_max);
+        const float sd = fmaxf(expf(ls), 1e-6f);
+        const float e = eps ? eps[(size_t)b * ACT + j] : 0.f;
+        const float mu = mean[(size_t)b * ACT + j];
+        const float a = fmaf(sd, e, mu);
+        action[(size_t)b * ACT + j] = a;
+        const double z = ((double)a - (double)mu) / (double)sd;
+        lp += -0.5 * z * z - (double)logf(sd) - HALF_LOG_2PI;
+    }
+    logp[b] = (float)lp;
+}
+
+// ---- reward and termination (rlmpc2.py:598-601, 701-735) ----
+struct RewardArgs {
+    int B;
+    const double *state, *target, *control, *in_contact;   // [B,8] [B,8] [B,2] [B] (nullable: in contact)
+    double* prev_cmd;                                        // [B,2] in/out
+    const float* action;                                     // [B,34] raw action
+    int32_t* episode_step;                                   // [B] in/out
+    double* time_penalty;                                    // [B] in/out
+    float *reward, *done;                                    // [B]
+    dart_ppo_reward_cfg c;
+};
+__global__ void ppo_reward_kernel(const RewardArgs a) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    const double* s = a.state + (size_t)b * 8;
+    const double* tg = a.target + (size_t)b * 8;
+    const double ex = fabs(tg[0] - s[0]), ey = fabs(tg[2] - s[2]);
+    const double pos_err = sqrt(ex * ex + ey * ey), vel_err = sqrt(s[1] * s[1] + s[3] * s[3]);
+    double n2 = 0.0;
+    const double dz = a.c.max_delta * a.c.action_scale;
+    for (int j = 0; j < ACT; ++j) { const double d = (double)(a.action[(size_t)b * ACT + j] * (float)dz); n2 += d * d; }
+    double change = sqrt(n2);
+    const double rms = change / sqrt((double)ACT);
+    if (rms > a.c.max_per_dim_rms) change *= (double)(float)(a.c.max_per_dim_rms / (rms + 1e-12));
+    const double c0 = a.control[2 * b], c1 = a.control[2 * b + 1];
+    const double rate = fabs(c0 - a.prev_cmd[2 * b]) + fabs(c1 - a.prev_cmd[2 * b + 1]);
+    a.prev_cmd[2 * b] = c0; a.prev_cmd[2 * b + 1] = c1;
+    const double pt = exp(-(pos_err * pos_err) / (2.0 * a.c.sigma_pos * a.c.sigma_pos));
+    const double vt = exp(-(vel_err * vel_err) / (2.0 * a.c.sigma_vel * a.c.sigma_vel));
+    const double tp = a.time_penalty[b];
+    double r = a.c.w_pos * pt + a.c.w_vel * pt * vt - a.c.w_change * change - a.c.w_d_ctrl * rate - tp;
+    if (pos_err < a.c.success_tol && vel_err < a.c.success_tol) r += a.c.success_bonus;
+    bool done = false;
+    const int step = a.episode_step[b] + 1;
+    if (fabs(s[0]) > a.c.tray_limit[0] || fabs(s[2]) > a.c.tray_limit[1]) { r -= a.c.oob_penalty; done = true; }
+    if (a.in_contact && a.in_contact[b] == 0.0) r -= a.c.no_contact_penalty;
+    if (step >= a.c.max_episode_steps) done = true;
+    a.reward[b] = (float)r;
+    a.done[b] = done ? 1.f : 0.f;
+    a.episode_step[b] = done ? 0 : step;
+    a.time_penalty[b] = done ? 0.0 : tp + a.c.time_penalty_inc;
+}
+
+// ---- GAE (rlmpc2.py:589-596), arrays [T,B], one thread per instance ----
+__global__ void ppo_gae_kernel(int B, int T, const float* __restrict__ rew, const float* __restrict__ val,
+                               const float* __restrict__ done, const float* __restrict__ last_value, double gamma,
+                               double lam, float* __restrict__ adv, float* __restrict__ ret) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double gae = 0.0, vnext = (double)last_value[b];
+    for (int t = T - 1; t >= 0; --t) {
+        const size_t i = (size_t)t * B + b;
+        const double nd = 1.0 - (double)done[i], v = (double)val[i];
+        const double delta = (double)rew[i] + gamma * vnext * nd - v;
+        gae = delta + gamma * lam * nd * gae;
+        adv[i] = (float)gae;
+        ret[i] = (float)(gae + v);
+        vnext = v;
+    }
+}
+
+__device__ double block_sum(double v, double* sh) {   // fixed-order tree: the same result on every launch
+    const int t = threadIdx.x;
+    sh[t] = v;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (t < s) sh[t] += sh[t + s];
+        __syncthreads();
+    }
+    const double r = sh[0];
+    __syncthreads();
+    return r;
+}
+
+// ---- in-place (x - mean) / (std + 1e-8), std with `ddof` delta degrees of freedom; single CTA ----
+__global__ void __launch_bounds__(1024) ppo_normalize_kernel(long n, float* x, int ddof) {
+    __shared__ double sh[1024];
+    double s = 0.0;
+    for (long i = threadIdx.x; i < n; i += blockDim.x) s += (double)x[i];
+    const double mean = block_sum(s, sh) / (double)n;
+    double q = 0.0;
+    for (long i = threadIdx.x; i < n; i += blockDim.x) { const double d = (double)x[i] - mean; q += d * d; }
+    const double denom = (double)(n - ddof);
+    const double sd = sqrt(block_sum(q, sh) / (denom > 0.0 ? denom : 1.0));
+    const double inv = 1.0 / (sd + 1e-8);
+    for (long i = threadIdx.x; i < n; i += blockDim.x) x[i] = (float)(((double)x[i] - mean) * inv);
+}
+
+// ---- minibatch gather ----
+struct GatherArgs {
+    int M;
+    const int64_t* idx;
+    const float *obs, *act, *logp, *adv, *ret;
+    float *o_obs, *o_act, *o_logp, *o_adv, *o_ret;
+};
+__global__ void ppo_gather_kernel(const GatherArgs a) {
+    const int m = blockIdx.x;
+    const int64_t src = a.idx[m];
+    const float4* s4 = reinterpret_cast<const float4*>(a.obs + (size_t)src * OBS);   // 2080-byte rows: 16-byte aligned
+    float4* d4 = reinterpret_cast<float4*>(a.o_obs + (size_t)m * OBS);
+    for (int i = threadIdx.x; i < OBS / 4; i += blockDim.x) d4[i] = s4[i];
+    for (int i = threadIdx.x; i < ACT; i += blockDim.x) a.o_act[(size_t)m * ACT + i] = a.act[(size_t)src * ACT + i];
+    if (threadIdx.x == 0) { a.o_logp[m] = a.logp[src]; a.o_adv[m] = a.adv[src]; a.o_ret[m] = a.ret[src]; }
+}
+
+// ---- loss and its gradient w.r.t. the network outputs (rlmpc2.py:802-813) ----
+struct LossArgs {
+    int M;
+    const float *mean, *value, *act, *old_logp, *adv, *ret, *log_std;
+    float ls_min, ls_max, clip_eps, vf_coef;
+    float *dmean, *dvalue;
+    double* part;                      // [nblocks, LOSS_W]
+};
+__global__ void __launch_bounds__(LOSS_T) ppo_loss_kernel(const LossArgs a) {
+    __shared__ double sh[LOSS_T];
+    __shared__ float s_sd[ACT], s_in[ACT], s_ls[ACT];
+    if (threadIdx.x < ACT) {
+        const float raw = a.log_std[threadIdx.x];
+        const float ls = fminf(fmaxf(raw, a.ls_min), a.ls_max);
+        s_ls[threadIdx.x] = ls;
+        s_sd[threadIdx.x] = fmaxf(expf(ls), 1e-6f);
+        s_in[threadIdx.x] = (raw >= a.ls_min && raw <= a.ls_max) ? 1.f : 0.f;    // clamp passes the gradient inside its range
+    }
+    __syncthreads();
+    const int m = blockIdx.x * LOSS_T + threadIdx.x;
+    const bool on = m < a.M;
+    double pl = 0.0, vl = 0.0, g = 0.0;
+    float z[ACT];
+    if (on) {
+        double lp = 0.0;
+#pragma unroll
+        for (int j = 0; j < ACT; ++j) {
+            const float d = a.act[(size_t)m * ACT + j] - a.mean[(size_t)m * ACT + j];
+            z[j] = d / s_sd[j];
+            lp += -0.5 * (double)z[j] * (double)z[j] - (double)s_ls[j] - HALF_LOG_2PI;
+        }
+        const double A = (double)a.adv[m];
+        const double ratio = exp((double)(float)lp - (double)a.old_logp[m]);
+        const double lo = 1.0 - (double)a.clip_eps, hi = 1.0 + (double)a.clip_eps;
+        const double s1 = ratio * A, s2 = fmin(fmax(ratio, lo), hi) * A;
+        pl = -fmin(s1, s2);
+        g = (s1 <= s2) ? -A * ratio / (double)a.M : 0.0;        // dL/dlogp (torch.min ties split, both halves reach ratio)
+        const double dv = (double)a.value[m] - (double)a.ret[m];
+        vl = dv * dv;
+        a.dvalue[m] = (float)((double)a.vf_coef * 2.0 * dv / (double)a.M);
+#pragma unroll
+        for (int j = 0; j < ACT; ++j) a.dmean[(size_t)m * ACT + j] = (float)(g * (double)z[j] / (double)s_sd[j]);
+    }
+    double* out = a.part + (size_t)blockIdx.x * LOSS_W;
+    double r = block_sum(pl, sh);
+    if (threadIdx.x == 0) out[0] = r;
+    r = block_sum(vl, sh);
+    if (threadIdx.x == 0) { out[1] = r; out[2] = 0.0; }
+#pragma unroll 1
+    for (int j = 0; j < ACT; ++j) {
+        const double zj = on ? (double)z[j] : 0.0;
+        r = block_sum(on ? g * (zj * zj - 1.0) * (double)s_in[j] : 0.0, sh);
+        if (threadIdx.x == 0) out[3 + j] = r;
+    }
+}
+
+// ---- sum the split partials into the flat gradient, per-block sum of squares for the global norm ----
+struct ReduceArgs {
+    int splits, loss_blocks, M;
+    const float* part;       // [splits, NPW]
+    const double* loss_part; // [loss_blocks, LOSS_W]
+    const float* log_std;
+    float ls_min, ls_max, ent_coef, vf_coef;
+    float* grad;             // [NP]
+    double* normpart;        // [gridDim.x]
+    float* stats;            // [4] policy loss, value loss, entropy, (grad norm: written by the Adam kernel)
+};
+__global__ void __launch_bounds__(256) ppo_grad_reduce_kernel(const ReduceArgs a) {
+    __shared__ double sh[256];
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    float g = 0.f;
+    if (j < NPW) {
+        for (int s = 0; s < a.splits; ++s) g += a.part[(size_t)s * NPW + j];
+    } else if (j < NP) {
+        const int jj = j - NPW;
+        double d = 0.0;
+        for (int b = 0; b < a.loss_blocks; ++b) d += a.loss_part[(size_t)b * LOSS_W + 3 + jj];
+        const float raw = a.log_std[jj];
+        if (raw >= a.ls_min && raw <= a.ls_max) d -= (double)a.ent_coef;     // d(-ent_coef * entropy)/dlog_std
+        g = (float)d;
+    }
+    if (j < NP) a.grad[j] = g;
+    const double ss = block_sum(j < NP ? (double)g * (double)g : 0.0, sh);
+    if (threadIdx.x == 0) a.normpart[blockIdx.x] = ss;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.stats) {
+        double pl = 0.0, vl = 0.0, ent = 0.0;
+        for (int b = 0; b < a.loss_blocks; ++b) { pl += a.loss_part[(size_t)b * LOSS_W]; vl += a.loss_part[(size_t)b * LOSS_W + 1]; }
+        for (int q = 0; q < ACT; ++q) ent += 0.5 + HALF_LOG_2PI + (double)fminf(fmaxf(a.log_std[q], a.ls_min), a.ls_max);
+        a.stats[0] = (float)(pl / a.M);
+        a.stats[1] = (float)(vl / a.M);
+        a.stats[2] = (float)ent;
+    }
+}
+
+// ---- clip_grad_norm_ + Adam with L2 weight decay (torch.optim.Adam, rlmpc2.py:561, 816-817) ----
+struct AdamArgs {
+    int nparts;
+    const double* normpart;
+    const float* grad;
+    float *param, *m, *v;
+    float max_norm, wd, beta1, beta2, eps, step_size, bc2_sqrt;
+    float* stats;
+};
+__global__ void __launch_bounds__(256) ppo_adam_kernel(const AdamArgs a) {
+    __shared__ double sh[256];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < a.nparts; i += 256) s += a.normpart[i];
+    const float gnorm = (float)sqrt(block_sum(s, sh));
+    const float coef = fminf(a.max_norm / (gnorm + 1e-6f), 1.f);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.stats) a.stats[3] = gnorm;
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= NP) return;
+    const float p = a.param[j];
+    const float g = fmaf(a.wd, p, a.grad[j] * coef);
+    const float m = a.m[j] + (g - a.m[j]) * (1.f - a.beta1);
+    const float v = fmaf(1.f - a.beta2, g * g, a.v[j] * a.beta2);
+    a.m[j] = m;
+    a.v[j] = v;
+    const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
+    a.param[j] = p - a.step_size * (m / denom);
+}
+
+}  // namespace
+
+struct dart_ppo {
+    int device, capacity, splits_cap, loss_blocks_cap;
+    dart_ppo_cfg cfg;
+    float *param, *grad, *m, *v;         // [NP]
+    float *h1, *h2, *dz1, *dz2;          // [capacity, 128]
+    float *mean, *value, *dmean, *dvalue;
+    float *mb_obs, *mb_act, *mb_logp, *mb_adv, *mb_ret;
+    float* part;                         // [MAX_SPLITS, NPW]
+    double *loss_part, *normpart;
+    int64_t step, launches;
+};
+
+namespace {
+
+int launch_group(dart_ppo* h, GemmGroup& g, int maxM, int maxN, cudaStream_t st) {
+    dim3 grid((maxN + BN - 1) / BN, (maxM + BM - 1) / BM, g.count * g.splits);
+    gemm_kernel<<<grid, GT, 0, st>>>(g);
+    h->launches += 1;
+    return cudaGetLastError() == cudaSuccess ? DART_OK : DART_ERR_CUDA;
+}
+
+GemmProb fwd_prob(const float* X, int ldx, const float* W, const float* b, float* Y, int ldy, int M, int N, int K, int mode) {
+    GemmProb p;
+    memset(&p, 0, sizeof(p));
+    p.A = X; p.lda = ldx; p.ta = 0;
+    p.B = W; p.ldb = K; p.tb = 1;          // B(k,n) = W[n*K + k]
+    p.C = Y; p.ldc = ldy; p.M = M; p.N = N; p.K = K; p.mode = mode; p.bias = b;
+    return p;
+}
+
+// Both networks' forward pass for M rows of `obs`: h1, h2 [M,128] (actor columns 0-63, critic 64-127), mean [M,34], value [M].
+int forward(dart_ppo* h, int M, const float* obs, cudaStream_t st) {
+    const float* P = h->param;
+    GemmGroup g;
+    memset(&g, 0, sizeof(g));
+    g.count = 1; g.splits = 1; g.kchunk = OBS; g.split_stride = 0;
+    g.p[0] = fwd_prob(obs, OBS, P + OFF_W1, P + OFF_B1, h->h1, H2W, M, H2W, OBS, 1);
+    int rc = launch_group(h, g, M, H2W, st);
+    if (rc != DART_OK) return rc;
+    g.count = 2; g.kchunk = HID;
+    g.p[0] = fwd_prob(h->h1, H2W, P + OFF_W2A, P + OFF_B2A, h->h2, H2W, M, HID, HID, 1);
+    g.p[1] = fwd_prob(h->h1 + HID, H2W, P + OFF_W2C, P + OFF_B2C, h->h2 + HID, H2W, M, HID, HID, 1);
+    rc = launch_group(h, g, M, HID, st);
+    if (rc != DART_OK) return rc;
+    g.p[0] = fwd_prob(h->h2, H2W, P + OFF_W3A, P + OFF_B3A, h->mean, ACT, M, ACT, HID, 2);
+    g.p[1] = fwd_prob(h->h2 + HID, H2W, P + OFF_W3C, P + OFF_B3C, h->value, 1, M, 1, HID, 2);
+    return launch_group(h, g, M, ACT, st);
+}
+
+// dW[N,K] (+ db[N]) = dY^T X over the minibatch, split into g.splits chunks of samples
+GemmProb wgrad_prob(const float* dY, int lddy, const float* X, int ldx, float* part, int off, int M, int N, int K) {
+    GemmProb p;
+    memset(&p, 0, sizeof(p));
+    p.A = dY; p.lda = lddy; p.ta = 1;      // A(n, sample) = dY[sample*lddy + n]
+    p.B = X; p.ldb = ldx; p.tb = 0;        // B(sample, k) = X[sample*ldx + k]
+    p.C = part + off; p.ldc = K; p.M = N; p.N = K; p.K = M; p.mode = 0;
+    p.rowsum = part + off + N * K;          // the bias follows its weight matrix in the flat layout
+    return p;
+}
+
+// dX[M,K] = (dY[M,N] W[N,K]) * (1 - Hprev^2)
+GemmProb dgrad_prob(const float* dY, int lddy, const float* W, float* dX, int lddx, const float* Hprev, int ldh, int M, int N, int K) {
+    GemmProb p;
+    memset(&p, 0, sizeof(p));
+    p.A = dY; p.lda = lddy; p.ta = 0;
+    p.B = W; p.ldb = K; p.tb = 0;          // B(n,k) = W[n*K + k]
+    p.C = dX; p.ldc = lddx; p.M = M; p.N = K; p.K = N; p.mode = 3; p.H = Hprev; p.ldh = ldh;
+    return p;
+}
+
+void free_all(dart_ppo* h) {
+    void* p[] = {h->param, h->grad, h->m, h->v, h->h1, h->h2, h->dz1, h->dz2, h->mean, h->value, h->dmean, h->dvalue,
+                 h->mb_obs, h->mb_act, h->mb_logp, h->mb_adv, h->mb_ret, h->part, h->loss_part, h->normpart};
+    for (void* q : p) if (q) cudaFree(q);
+}
+
+}  // namespace
+
+extern "C" int dart_ppo_default_cfg(dart_ppo_cfg* c) {
+    if (!c) return DART_ERR_ARG;
+    // rlmpc2.py:202-226 packet defaults, torch.optim.Adam defaults, Policy log_std range (:57-61)
+    c->lr = 3e-4; c->weight_decay = 1e-5; c->beta1 = 0.9; c->beta2 = 0.999; c->adam_eps = 1e-8;
+    c->clip_eps = 0.2; c->vf_coef = 0.25; c->ent_coef = 0.01; c->max_grad_norm = 0.5;
+    c->log_std_min = log(1e-2); c->log_std_max = log(2.0);
+    return DART_OK;
+}
+
+extern "C" int dart_ppo_default_reward_cfg(dart_ppo_reward_cfg* c) {
+    if (!c) return DART_ERR_ARG;
+    // rlmpc2.py:701-735 with the defaults of the packet.get(...) calls there
+    c->max_delta = 0.1; c->action_scale = 1.0; c->max_per_dim_rms = 0.5;
+    c->sigma_pos = 0.02; c->sigma_vel = 0.02; c->w_pos = 60.0; c->w_vel = 30.0; c->w_change = 1e-3; c->w_d_ctrl = 5.0;
+    c->success_tol = 0.01; c->success_bonus = 20.0; c->oob_penalty = 20.0; c->no_contact_penalty = 10.0;
+    c->tray_limit[0] = 0.2; c->tray_limit[1] = 0.15; c->max_episode_steps = 1000; c->time_penalty_inc = 1e-4;
+    return DART_OK;
+}
+
+extern "C" int dart_ppo_nparams(void) { return NP; }
+
+extern "C" int dart_ppo_destroy(dart_ppo_handle h) {
+    if (!h) return DART_ERR_ARG;
+    cudaSetDevice(h->device);
+    free_all(h);
+    delete h;
+    return DART_OK;
+}
+
+extern "C" int dart_ppo_create(dart_ppo_handle* out, int device, int32_t obs_dim, int32_t hidden, int32_t act_dim,
+                               int32_t capacity, const float* params_host, const dart_ppo_cfg* cfg) {
+    if (!out || !params_host || !cfg || capacity < 1) return DART_ERR_ARG;
+    if (obs_dim != OBS || hidden != HID || act_dim != ACT) return DART_ERR_UNSUPPORTED;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return DART_ERR_NO_DEVICE; }
+    if (device < 0 || device >= ndev) return DART_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return DART_ERR_CUDA;
+    dart_ppo* h = new (std::nothrow) dart_ppo();
+    if (!h) return DART_ERR_ALLOC;
+    memset(h, 0, sizeof(*h));
+    h->device = device; h->capacity = capacity; h->cfg = *cfg;
+    h->loss_blocks_cap = (capacity + LOSS_T - 1) / LOSS_T;
+    const size_t cap = (size_t)capacity;
+    struct { void** p; size_t bytes; } al[] = {
+        {(void**)&h->param, NP * sizeof(float)}, {(void**)&h->grad, NP * sizeof(float)},
+        {(void**)&h->m, NP * sizeof(float)}, {(void**)&h->v, NP * sizeof(float)},
+        {(void**)&h->h1, cap * H2W * sizeof(float)}, {(void**)&h->h2, cap * H2W * sizeof(float)},
+        {(void**)&h->dz1, cap * H2W * sizeof(float)}, {(void**)&h->dz2, cap * H2W * sizeof(float)},
+        {(void**)&h->mean, cap * ACT * sizeof(float)}, {(void**)&h->value, cap * sizeof(float)},
+        {(void**)&h->dmean, cap * ACT * sizeof(float)}, {(void**)&h->dvalue, cap * sizeof(float)},
+        {(void**)&h->mb_obs, cap * OBS * sizeof(float)}, {(void**)&h->mb_act, cap * ACT * sizeof(float)},
+        {(void**)&h->mb_logp, cap * sizeof(float)}, {(void**)&h->mb_adv, cap * sizeof(float)},
+        {(void**)&h->mb_ret, cap * sizeof(float)}, {(void**)&h->part, (size_t)MAX_SPLITS * NPW * sizeof(float)},
+        {(void**)&h->loss_part, (size_t)h->loss_blocks_cap * LOSS_W * sizeof(double)},
+        {(void**)&h->normpart, (size_t)((NP + 255) / 256) * sizeof(double)}};
+    int rc = DART_OK;
+    for (auto& a : al) {
+        if (cudaMalloc(a.p, a.bytes) != cudaSuccess) { *a.p = nullptr; rc = DART_ERR_ALLOC; break; }
+        if (cudaMemset(*a.p, 0, a.bytes) != cudaSuccess) { rc = DART_ERR_CUDA; break; }
+    }
+    if (rc == DART_OK && cudaMemcpy(h->param, params_host, NP * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess)
+        rc = DART_ERR_CUDA;
+    if (rc != DART_OK) { cudaGetLastError(); free_all(h); delete h; return rc; }
+    *out = h;
+    return DART_OK;
+}
+
+extern "C" int dart_ppo_get_state(dart_ppo_handle h, float* params_host, float* m_host, float* v_host, int64_t* step) {
+    if (!h) return DART_ERR_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) return DART_ERR_CUDA;
+    if (cudaDeviceSynchronize() != cudaSuccess) return DART_ERR_CUDA;
+    const size_t n = NP * sizeof(float);
+    if ((params_host && cudaMemcpy(params_host, h->param, n, cudaMemcpyDeviceToHost) != cudaSuccess) ||
+        (m_host && cudaMemcpy(m_host, h->m, n, cudaMemcpyDeviceToHost) != cudaSuccess) ||
+        (v_host && cudaMemcpy(v_host, h->v, n, cudaMemcpyDeviceToHost) != cudaSuccess))
+        return DART_ERR_CUDA;
+    if (step) *step = h->step;
+    return DART_OK;
+}
+
+extern "C" int dart_ppo_set_state(dart_ppo_handle h, const float* params_host, const float* m_host, const float* v_host,
+                                  int64_t step) {
+    if (!h || step < 0) return DART_ERR_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) return DART_ERR_CUDA;
+    if (cudaDeviceSynchronize() != cudaSuccess) return DART_ERR_CUDA;
+    const size_t n = NP * sizeof(float);
+    if ((params_host && cudaMemcpy(h->param, params_host, n, cudaMemcpyHostToDevice) != cudaSuccess) ||
+        (m_host && cudaMemcpy(h->m, m_host, n, cudaMemcpyHostToDevice) != cudaSuccess) ||
+        (v_host && cudaMemcpy(h->v, v_host, n, cudaMemcpyHostToDevice) != cudaSuccess))
+        return DART_ERR_CUDA;
+    h->step = step;
+    return DART_OK;
+}
+
+extern "C" int dart_ppo_get_grad(dart_ppo_handle h, float* grad_host) {
+    if (!h || !grad_host) return DART_ERR_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) return DART_ERR_CUDA;
+    return cudaMemcpy(grad_host, h->grad, NP * sizeof(float), cudaMemcpyDeviceToHost) == cudaSuccess ? DART_OK : DART_ERR_CUDA;
+}
+
+extern "C" const float* dart_ppo_params_dev(dart_ppo_handle h) { return h ? h->param : nullptr; }
+extern "C" int64_t dart_ppo_launch_count(dart_ppo_handle h) { return h ? h->launches : -1; }
+
+extern "C" int dart_ppo_act(dart_ppo_handle h, int32_t B, const float* obs, const float* eps, float* action, float* logp,
+                            float* value, float* mean, void* stream) {
+    if (!h || B < 0 || B > h->capacity || !obs || !action || !logp || !value) return DART_ERR_ARG;
+    if (B == 0) return DART_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = forward(h, B, obs, st);
+    if (rc != DART_OK) return rc;
+    ppo_sample_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, h->mean, h->param + OFF_LS, (float)h->cfg.log_std_min,
+                                                      (float)h->cfg.log_std_max, eps, action, logp);
+    h->launches += 1;
+    if (cudaMemcpyAsync(value, h->value, (size_t)B * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess ||
+        (mean && cudaMemcpyAsync(mean, h->mean, (size_t)B * ACT * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess))
+        return DART_ERR_CUDA;
+    return cudaGetLastError() == cudaSuccess ? DART_OK : DART_ERR_CUDA;
+}
+
+extern "C" int dart_ppo_reward(int32_t B, const dart_ppo_reward_cfg* cfg, const double* state, const double* target,
+                               const double* control, double* prev_cmd, const float* action, const double* in_contact,
+                               int32_t* episode_step, double* time_penalty, float* reward, float* done, void* stream) {
+    if (B < 0 || !cfg || !state || !target || !control || !prev_cmd || !action || !episode_step || !time_penalty || !reward || !done)
+        return DART_ERR_ARG;
+    if (B == 0) return DART_OK;
+    RewardArgs a;
+    a.B = B; a.state = state; a.target = target; a.control = control; a.in_contact = in_contact; a.prev_cmd = prev_cmd;
+    a.action = action; a.episode_step = episode_step; a.time_penalty = time_penalty; a.reward = reward; a.done = done;
+    a.c = *cfg;
+    ppo_reward_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
+    return cudaGetLastError() == cudaSuccess ? DART_OK : DART_ERR_CUDA;
+}
+
+extern "C" int dart_ppo_gae(int32_t B, int32_t T, const float* rewards, const float* values, const float* dones,
+                            const float* last_value, double gamma, double lam, float* adv, float* ret, void* stream) {
+    if (B < 0 || T < 0 || !rewards || !values || !dones || !last_value || !adv || !ret) return DART_ERR_ARG;
+    if (B == 0 || T == 0) return DART_OK;
+    ppo_gae_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(B, T, rewards, values, dones, last_value, gamma, lam, adv, ret);
+    return cudaGetLastError() == cudaSuccess ? DART_OK : DART_ERR_CUDA;
+}
+
+extern "C" int dart_ppo_normalize(int64_t n, float* x, int32_t ddof, void* stream) {
+    if (n < 0 || !x || ddof < 0 || ddof > 1) return DART_ERR_ARG;
+    if (n == 0) return DART_OK;
+    ppo_normalize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>((long)n, x, ddof);
+    return cudaGetLastError() == cudaSuccess ? DART_OK : DART_ERR_CUDA;
+}
+
+extern "C" int dart_ppo_update(dart_ppo_handle h, int32_t M, const int64_t* idx, const float* obs, const float* act,
+                               const float* old_logp, const float* adv, const float* ret, int32_t apply, float* stats,
+                               void* stream) {
+    if (!h || M < 1 || M > h->capacity || !obs || !act || !old_logp || !adv || !ret) return DART_ERR_ARG;
+    if ((reinterpret_cast<uintptr_t>(obs) & 15) != 0) return DART_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const dart_ppo_cfg& c = h->cfg;
+    if (idx) {
+        GatherArgs ga{M, idx, obs, act, old_logp, adv, ret, h->mb_obs, h->mb_act, h->mb_logp, h->mb_adv, h->mb_ret};
+        ppo_gather_kernel<<<M, 128, 0, st>>>(ga);
+        h->launches += 1;
+        obs = h->mb_obs; act = h->mb_act; old_logp = h->mb_logp; adv = h->mb_adv; ret = h->mb_ret;
+    }
+    int rc = forward(h, M, obs, st);
+    if (rc != DART_OK) return rc;
+    const float* P = h->param;
+    const int loss_blocks = (M + LOSS_T - 1) / LOSS_T;
+    LossArgs la;
+    la.M = M; la.mean = h->mean; la.value = h->value; la.act = act; la.old_logp = old_logp; la.adv = adv; la.ret = ret;
+    la.log_std = P + OFF_LS; la.ls_min = (float)c.log_std_min; la.ls_max = (float)c.log_std_max;
+    la.clip_eps = (float)c.clip_eps; la.vf_coef = (float)c.vf_coef; la.dmean = h->dmean; la.dvalue = h->dvalue;
+    la.part = h->loss_part;
+    ppo_loss_kernel<<<loss_blocks, LOSS_T, 0, st>>>(la);
+    h->launches += 1;
+    if (cudaGetLastError() != cudaSuccess) return DART_ERR_CUDA;
+
+    // backward: weight gradients split over the minibatch, data gradients with the fused tanh'
+    int splits = (M + 255) / 256;
+    if (splits > MAX_SPLITS) splits = MAX_SPLITS;
+    int kchunk = (M + splits - 1) / splits;
+    kchunk = (kchunk + BK - 1) / BK * BK;
+    GemmGroup gw;
+    memset(&gw, 0, sizeof(gw));
+    gw.count = 2; gw.splits = splits; gw.kchunk = kchunk; gw.split_stride = NPW;
+    GemmGroup gd;
+    memset(&gd, 0, sizeof(gd));
+    gd.count = 2; gd.splits = 1; gd.split_stride = 0;
+    // layer 3
+    gw.p[0] = wgrad_prob(h->dmean, ACT, h->h2, H2W, h->part, OFF_W3A, M, ACT, HID);
+    gw.p[1] = wgrad_prob(h->dvalue, 1, h->h2 + HID, H2W, h->part, OFF_W3C, M, 1, HID);
+    if ((rc = launch_group(h, gw, ACT, HID, st)) != DART_OK) return rc;
+    gd.kchunk = ACT;
+    gd.p[0] = dgrad_prob(h->dmean, ACT, P + OFF_W3A, h->dz2, H2W, h->h2, H2W, M, ACT, HID);
+    gd.p[1] = dgrad_prob(h->dvalue, 1, P + OFF_W3C, h->dz2 + HID, H2W, h->h2 + HID, H2W, M, 1, HID);
+    if ((rc = launch_group(h, gd, M, HID, st)) != DART_OK) return rc;
+    // layer 2
+    gw.p[0] = wgrad_prob(h->dz2, H2W, h->h1, H2W, h->part, OFF_W2A, M, HID, HID);
+    gw.p[1] = wgrad_prob(h->dz2 + HID, H2W, h->h1 + HID, H2W, h->part, OFF_W2C, M, HID, HID);
+    if ((rc = launch_group(h, gw, HID, HID, st)) != DART_OK) return rc;
+    gd.kchunk = HID;
+    gd.p[0] = dgrad_prob(h->dz2, H2W, P + OFF_W2A, h->dz1, H2W, h->h1, H2W, M, HID, HID);
+    gd.p[1] = dgrad_prob(h->dz2 + HID, H2W, P + OFF_W2C, h->dz1 + HID, H2W, h->h1 + HID, H2W, M, HID, HID);
+    if ((rc = launch_group(h, gd, M, HID, st)) != DART_OK) return rc;
+    // layer 1 (both networks at once: dz1 is [M,128])
+    gw.count = 1;
+    gw.p[0] = wgrad_prob(h->dz1, H2W, obs, OBS, h->part, OFF_W1, M, H2W, OBS);
+    if ((rc = launch_group(h, gw, H2W, OBS, st)) != DART_OK) return rc;
+
+    const int nred = (NP + 255) / 256;
+    ReduceArgs ra;
+    ra.splits = splits; ra.loss_blocks = loss_blocks; ra.M = M; ra.part = h->part; ra.loss_part = h->loss_part;
+    ra.log_std = P + OFF_LS; ra.ls_min = la.ls_min; ra.ls_max = la.ls_max; ra.ent_coef = (float)c.ent_coef;
+    ra.vf_coef = la.vf_coef; ra.grad = h->grad; ra.normpart = h->normpart; ra.stats = stats;
+    ppo_grad_reduce_kernel<<<nred, 256, 0, st>>>(ra);
+    h->launches += 1;
+    if (cudaGetLastError() != cudaSuccess) return DART_ERR_CUDA;
+    if (!apply) return DART_OK;
+
+    h->step += 1;
+    const double bc1 = 1.0 - pow(c.beta1, (double)h->step), bc2 = 1.0 - pow(c.beta2, (double)h->step);
+    AdamArgs aa;
+    aa.nparts = nred; aa.normpart = h->normpart; aa.grad = h->grad; aa.param = h->param; aa.m = h->m; aa.v = h->v;
+    aa.max_norm = (float)c.max_grad_norm; aa.wd = (float)c.weight_decay; aa.beta1 = (float)c.beta1; aa.beta2 = (float)c.beta2;
+    aa.eps = (float)c.adam_eps; aa.step_size = (float)(c.lr / bc1); aa.bc2_sqrt = (float)sqrt(bc2); aa.stats = stats;
+    ppo_adam_kernel<<<nred, 256, 0, st>>>(aa);
+    h->launches += 1;
+    return cudaGetLastError() == cudaSuccess ? DART_OK : DART_ERR_CUDA;
+}

@@ -5,7 +5,8 @@ Mirrors LMPC/src/controller/rlmpc2.py: ``Policy.mean_net`` (:33-46, :71-80), the
 :606-616) and the ``RLMPC`` facade (:110-226, :986-1065).  The reference runs the solver and the policy in two
 unsynchronised daemon processes over shared-memory mailboxes; here one ``step`` does, in order and on the
 device: observation push -> policy forward -> (every ``update_every``-th step) parameter update -> NLP solve
-warm-started from the previous solution.  Training (PPO) is out of scope; the action is the policy mean.
+warm-started from the previous solution.  In evaluation the action is the policy mean; PPO training (``ppo.py``)
+plugs in through ``LMPCBatch.action_source``.
 """
 import ctypes as C
 import os
@@ -141,6 +142,7 @@ class LMPCBatch:
         self.iters = torch.empty((B,), dtype=torch.int32, device=self.dev)
         self.timestep = 0
         self.count = 0
+        self.action_source = None
         self.warm_start = warm_start
         self.warm_mu = warm_mu if warm_start else None
         self.dual = None
@@ -182,7 +184,10 @@ class LMPCBatch:
         check(L.dart_policy_obs_push(self.B, self.count, p(state), p(target), p(self.u_prev), C.c_void_p(self.aux.data_ptr() + 16),
                                      36, p(self.mean), p(self.M2), p(obs_in), p(obs_out), stream), "dart_policy_obs_push")
         self.obs = [obs_out, obs_in]
-        self.policy.forward(obs_out, self.action)
+        if self.action_source is None:
+            self.policy.forward(obs_out, self.action)          # evaluation: the policy mean (tcgen05 kernel)
+        else:
+            self.action_source(obs_out, self.action)           # training: sampled by the PPO learner (ppo.LMPCTrainer)
         if self.timestep % self.update_every == 0:
             check(L.dart_policy_param_update(self.B, p(self.action), C.c_void_p(self.aux.data_ptr() + 16), 36, self.k_max,
                                              self.max_delta, self.min_k, self.margin, self.alpha, stream),
@@ -210,6 +215,22 @@ class LMPCBatch:
         self.aux[:, :2] = self.u0
         self.timestep += 1
         return self.u0
+
+
+def lmpc_plant_step(state, u, true_aux, Ts=0.002, out=None):
+    """One surrogate-plant step (``dart_lmpc_plant_step``): the LMPC model with per-instance true parameters ``true_aux``
+    [B,36] (columns 2: are the 34 parameters).  state [B,8], u [B,2] float64 CUDA tensors -> next state [B,8]."""
+    torch = _torch()
+    B = state.shape[0]
+    for t, shape in ((state, (B, 8)), (u, (B, 2)), (true_aux, (B, 36))):
+        if t.dtype != torch.float64 or not t.is_cuda or not t.is_contiguous() or tuple(t.shape) != shape:
+            raise ValueError(f"lmpc_plant_step: need contiguous float64 CUDA tensors, got {t.dtype} {tuple(t.shape)} for {shape}")
+    if out is None:
+        out = torch.empty_like(state)
+    stream = C.c_void_p(torch.cuda.current_stream(state.device).cuda_stream)
+    check(_lib.lib().dart_lmpc_plant_step(B, float(Ts), C.c_void_p(true_aux.data_ptr()), C.c_void_p(u.data_ptr()),
+                                          C.c_void_p(state.data_ptr()), C.c_void_p(out.data_ptr()), stream), "dart_lmpc_plant_step")
+    return out
 
 
 class _Event:

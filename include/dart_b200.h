@@ -238,6 +238,74 @@ int dart_pmpc_episode(dart_handle h, int32_t B, int32_t T, double* state, const 
                       double* effort, double* err, double* u0, double* J, int32_t* status, int32_t* iters,
                       uint64_t* counters, void* stream);
 
+/* LMPC surrogate plant: one RK4 step (tilt u [B,2] held over Ts) of the 8-state model of
+ * rlmpc2.py:260-436 with per-instance TRUE parameters: true_aux [B,36] has the layout of the LMPC solver's aux rows
+ * ([u_prev(2), pvec(34)]; the first two columns are ignored).  state [B,8] -> state_out [B,8] (may alias).  With
+ * true_aux equal to the controller's aux the result is the controller's own one-step prediction, bit for bit. */
+int dart_lmpc_plant_step(int32_t B, double Ts, const double* true_aux, const double* u, const double* state,
+                         double* state_out, void* stream);
+
+/* ---- PPO training of the LMPC policy (RLMPC._rl_worker, LMPC/src/controller/rlmpc2.py:536-935) ----
+ * The reference trains one instance's policy with torch autograd on whatever device torch finds; these entry points run the
+ * same arithmetic (FP32 networks, Adam, clipped surrogate) for B instances that share one policy, without torch.
+ * Flat parameter vector, float32, dart_ppo_nparams() = 77 317 entries, torch layout [out,in] per matrix:
+ *   [W1 (128x520: rows 0-63 mean_net.0.weight, rows 64-127 value_net.0.weight) | b1 (128) |
+ *    mean_net.2.weight (64x64) | .bias (64) | value_net.2.weight (64x64) | .bias (64) |
+ *    mean_net.4.weight (34x64) | .bias (34) | value_net.4.weight (1x64) | .bias (1) | log_std (34)]            */
+typedef struct dart_ppo* dart_ppo_handle;
+
+typedef struct dart_ppo_cfg {
+    double lr, weight_decay, beta1, beta2, adam_eps;      /* optim.Adam(lr, weight_decay=1e-5)        rlmpc2.py:561     */
+    double clip_eps, vf_coef, ent_coef, max_grad_norm;    /* loss and clip_grad_norm_(0.5)            rlmpc2.py:806-816 */
+    double log_std_min, log_std_max;                      /* Policy.forward clamp                     rlmpc2.py:60-61,76 */
+} dart_ppo_cfg;
+
+typedef struct dart_ppo_reward_cfg {                      /* rlmpc2.py:598-601, 701-735                                  */
+    double max_delta, action_scale, max_per_dim_rms;      /* delta_z = a * max_delta * action_scale, damped above the rms */
+    double sigma_pos, sigma_vel, w_pos, w_vel, w_change, w_d_ctrl;
+    double success_tol, success_bonus, oob_penalty, no_contact_penalty;
+    double tray_limit[2];
+    int32_t max_episode_steps;
+    double time_penalty_inc;
+} dart_ppo_reward_cfg;
+
+int dart_ppo_default_cfg(dart_ppo_cfg* cfg);
+int dart_ppo_default_reward_cfg(dart_ppo_reward_cfg* cfg);
+int dart_ppo_nparams(void);
+/* capacity = largest B of dart_ppo_act and largest minibatch of dart_ppo_update.  params_host: the flat vector above. */
+int dart_ppo_create(dart_ppo_handle* out, int device, int32_t obs_dim, int32_t hidden, int32_t act_dim, int32_t capacity,
+                    const float* params_host, const dart_ppo_cfg* cfg);
+int dart_ppo_destroy(dart_ppo_handle h);
+/* Checkpointing (torch.save({"model", "optimizer", ...}), rlmpc2.py:920-922): parameters, Adam moments (host pointers,
+ * each nullable) and the optimiser step count.  Both calls synchronise the device. */
+int dart_ppo_get_state(dart_ppo_handle h, float* params_host, float* m_host, float* v_host, int64_t* step);
+int dart_ppo_set_state(dart_ppo_handle h, const float* params_host, const float* m_host, const float* v_host, int64_t step);
+int dart_ppo_get_grad(dart_ppo_handle h, float* grad_host);          /* last dart_ppo_update's gradient, before clipping */
+const float* dart_ppo_params_dev(dart_ppo_handle h);                 /* device pointer of the live parameters           */
+int64_t dart_ppo_launch_count(dart_ppo_handle h);
+/* Rollout-time policy call (rlmpc2.py:670-699): mean, std, value = policy(obs); action = mean + std * eps (eps [B,34]
+ * standard normal draws supplied by the caller, NULL = the mean action), logp = sum_j log N(action_j).  obs [B,520],
+ * action/mean [B,34] (mean nullable), logp/value [B]; float32 device pointers. */
+int dart_ppo_act(dart_ppo_handle h, int32_t B, const float* obs, const float* eps, float* action, float* logp,
+                 float* value, float* mean, void* stream);
+/* Reward and termination of one control step for B instances (rlmpc2.py:701-735).  state/target [B,8], control [B,2],
+ * prev_cmd [B,2] (in/out), in_contact [B] (nullable = in contact) f64; action [B,34] f32 (the raw action);
+ * episode_step [B] int32 and time_penalty [B] f64 are advanced in place and reset where done; reward/done [B] f32. */
+int dart_ppo_reward(int32_t B, const dart_ppo_reward_cfg* cfg, const double* state, const double* target,
+                    const double* control, double* prev_cmd, const float* action, const double* in_contact,
+                    int32_t* episode_step, double* time_penalty, float* reward, float* done, void* stream);
+/* GAE along each instance's rollout (compute_gae, rlmpc2.py:589-596) and returns = adv + values (:784).  Arrays [T,B] f32. */
+int dart_ppo_gae(int32_t B, int32_t T, const float* rewards, const float* values, const float* dones,
+                 const float* last_value, double gamma, double lam, float* adv, float* ret, void* stream);
+/* In place x = (x - mean) / (std + 1e-8) over n values; ddof 0 = numpy std (returns, :785), 1 = torch std (advantages, :792). */
+int dart_ppo_normalize(int64_t n, float* x, int32_t ddof, void* stream);
+/* One minibatch step (rlmpc2.py:797-817): forward of both networks, clipped-surrogate + vf_coef * MSE - ent_coef * entropy,
+ * backward, clip_grad_norm_, Adam.  idx [M] int64 (nullable) gathers the minibatch rows from obs [*,520] (16-byte
+ * aligned), act [*,34], old_logp, adv, ret [*].  apply = 0 computes the gradient only.  stats [4] (nullable, device) =
+ * policy loss, value loss, entropy, gradient norm before clipping.  Results are bitwise repeatable. */
+int dart_ppo_update(dart_ppo_handle h, int32_t M, const int64_t* idx, const float* obs, const float* act,
+                    const float* old_logp, const float* adv, const float* ret, int32_t apply, float* stats, void* stream);
+
 /* Measured FP64 FMA-pipe peak of the device in TFLOP/s (DFMA microbenchmark, CUDA-event timed): the roofline
  * denominator bench.py reports the solver kernels against. */
 int dart_measure_fp64_tflops(int device, double* tflops);

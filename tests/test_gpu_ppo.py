@@ -1,0 +1,226 @@
+"""PPO training path (csrc/ppo.cu through the C ABI) against torch autograd + torch.optim.Adam on the CPU (oracle/ppo.py).
+
+Tolerances (FP32 arithmetic on both sides, different summation orders):
+  forward mean / value, log-probability      |d| <= 2e-5 * max(1, |ref|)
+  gradient (before clipping)                 |d| <= 1e-6 + 2e-4 * max|g| of the tensor (FP32 accumulation over up to 16 384 samples)
+                                             and ||d||_2 <= 1e-4 ||g||_2 per tensor
+  one optimiser step from the same state     98 % of the elements within 1 % of lr, 99.5 % within lr / 4, all within 2 lr (an Adam step is
+                                             lr * g / (|g| + 1e-8): elements whose clipped gradient is at the 1e-8 floor turn FP32
+                                             summation-order noise into a fraction of one step)
+  GAE / reward / normalisation               1e-5 relative
+"""
+import numpy as np
+import pytest
+
+import dart_b200
+from oracle import ppo as oppo
+
+pytestmark = pytest.mark.gpu
+
+
+def _rollout(M, seed, policy):
+    """Synthetic minibatch: observations, actions sampled near the policy, old log-probabilities off by a little, advantages, returns."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    obs = torch.randn(M, 520, generator=g)
+    eps = torch.randn(M, 34, generator=g)
+    action, logp, value, mean = oppo.act(policy, obs, eps)
+    old_logp = logp + 0.3 * torch.randn(M, generator=g)          # ratios on both sides of the clip range
+    adv = torch.randn(M, generator=g)
+    ret = value + torch.randn(M, generator=g)
+    return obs, eps, action, logp, value, mean, old_logp, adv, ret
+
+
+def _perturbed_policy(seed=3):
+    import torch
+    pol = oppo.make_policy(seed)
+    g = torch.Generator().manual_seed(seed + 100)
+    with torch.no_grad():
+        for p in pol.parameters():                              # non-zero biases, log_std off its initial value
+            if p.ndim == 1:
+                p.add_(0.05 * torch.randn(p.shape, generator=g))
+    return pol
+
+
+@pytest.mark.parametrize("B", [1, 63, 200, 4096])
+def test_act_matches_torch(built, B):
+    import torch
+    pol = _perturbed_policy()
+    obs, eps, action, logp, value, mean, *_ = _rollout(B, B, pol)
+    tr = dart_b200.PPOTrainer(capacity=B, state_dict=pol.state_dict())
+    a, lp, v, mu = tr.act(obs.cuda(), eps.cuda())
+    tol = lambda ref: 2e-5 * max(1.0, float(ref.abs().max()))
+    assert (mu.cpu() - mean).abs().max() <= tol(mean)
+    assert (v.cpu() - value).abs().max() <= tol(value)
+    assert (a.cpu() - action).abs().max() <= tol(action)
+    assert (lp.cpu() - logp).abs().max() <= tol(logp)
+    a0, lp0, _, _ = tr.act(obs.cuda(), None)                       # evaluation: the mean action
+    assert torch.equal(a0.cpu(), mu.cpu())
+    tr.close()
+
+
+@pytest.mark.parametrize("M", [1, 64, 257, 1000, 16384])
+def test_gradient_matches_autograd(built, M):
+    import torch
+    pol = _perturbed_policy()
+    obs, eps, action, logp, value, mean, old_logp, adv, ret = _rollout(M, M + 7, pol)
+    opt = oppo.make_optimizer(pol)
+    pl, vl, ent, gn = oppo.minibatch_step(pol, opt, obs, action, old_logp, adv, ret, apply=False)
+    tr = dart_b200.PPOTrainer(capacity=M, state_dict=pol.state_dict())
+    stats = tr.update_minibatch(obs.cuda(), action.cuda(), old_logp.cuda(), adv.cuda(), ret.cuda(), apply=False).cpu().numpy()
+    grad = tr.gradient()
+    # log-probabilities are ~30 in FP32 (ulp 2e-6, 34-term sums): the ratio exp(logp - old) carries ~3e-5 relative noise on both sides
+    assert abs(stats[0] - pl) <= 1e-4 * max(1.0, abs(pl)) and abs(stats[1] - vl) <= 1e-5 * max(1.0, abs(vl))
+    assert abs(stats[2] - ent) <= 1e-5 * abs(ent)
+    for k, p in pol.named_parameters():
+        ref = p.grad.numpy()
+        assert grad[k].shape == ref.shape
+        err = np.abs(grad[k] - ref).max()
+        assert err <= 1e-6 + 2e-4 * np.abs(ref).max(), (k, err, np.abs(ref).max())
+        rel2 = np.linalg.norm((grad[k] - ref).astype(np.float64)) / max(np.linalg.norm(ref.astype(np.float64)), 1e-30)
+        assert rel2 <= 1e-4, (k, rel2)                                   # no structured error hiding under the element-wise bound
+    before = tr.state_dict()
+    assert all(np.array_equal(before[k], v.detach().numpy()) for k, v in pol.state_dict().items())   # apply=False leaves the parameters alone
+    tr.close()
+
+
+@pytest.mark.parametrize("M,steps", [(64, 6), (1000, 4)])
+def test_optimizer_steps_match_torch_adam(built, M, steps):
+    """Step by step from the same state (parameters, Adam moments, step count).  A free-running comparison is ill-conditioned:
+    std = 0.1 amplifies parameter differences 10x into the log-probabilities, and an Adam step is lr * g / (|g| + 1e-8), so the
+    0.3-0.5 % of elements whose clipped gradient is below 1e-7 turn FP32 summation-order noise into O(lr) differences."""
+    import torch
+    lr = 3e-4
+    pol = _perturbed_policy()
+    opt = oppo.make_optimizer(pol, lr=lr, weight_decay=1e-5)
+    tr = dart_b200.PPOTrainer(capacity=M, state_dict=pol.state_dict(), lr=lr, weight_decay=1e-5)
+    names = [k for k, _ in pol.named_parameters()]
+    for s in range(steps):
+        obs, eps, action, logp, value, mean, old_logp, adv, ret = _rollout(M, 1000 + s, pol)
+        before = {k: v.detach().clone().numpy() for k, v in pol.state_dict().items()}
+        if s > 0:
+            st = opt.state_dict()["state"]
+            tr.set_state(before, {k: st[i]["exp_avg"] for i, k in enumerate(names)},
+                         {k: st[i]["exp_avg_sq"] for i, k in enumerate(names)}, step=s)
+        pl, vl, ent, gn = oppo.minibatch_step(pol, opt, obs, action, old_logp, adv, ret)
+        stats = tr.update_minibatch(obs.cuda(), action.cuda(), old_logp.cuda(), adv.cuda(), ret.cuda()).cpu().numpy()
+        assert abs(stats[3] - gn) <= 5e-5 * gn, (s, stats[3], gn)
+        assert abs(stats[0] - pl) <= 1e-4 * max(1.0, abs(pl)), (s, stats[0], pl)
+        sd = tr.state_dict()
+        for k, p in pol.state_dict().items():
+            d_ref, d_gpu = p.numpy() - before[k], sd[k] - before[k]
+            err = np.abs(d_gpu - d_ref)
+            assert err.max() <= 1e-7 + 2 * lr, (s, k, err.max())         # a sign flip of a noise-floor gradient is the worst case
+            assert np.mean(err <= 1e-7 + 0.25 * lr) >= 0.995, (s, k, np.mean(err <= 1e-7 + 0.25 * lr))
+            assert np.mean(err <= 1e-7 + 1e-2 * lr) >= 0.98, (s, k, np.mean(err <= 1e-7 + 1e-2 * lr))
+            assert np.abs(d_gpu).max() > 0.1 * lr, (s, k)               # the parameters did move
+    tr.close()
+
+
+def test_minibatch_gather_and_repeatability(built):
+    import torch
+    pol = _perturbed_policy()
+    S, M = 3000, 512
+    obs, eps, action, logp, value, mean, old_logp, adv, ret = _rollout(S, 11, pol)
+    idx = torch.randperm(S, generator=torch.Generator().manual_seed(5))[:M]
+    d = [t.cuda() for t in (obs, action, old_logp, adv, ret)]
+    outs = []
+    for rep in range(3):
+        tr = dart_b200.PPOTrainer(capacity=M, state_dict=pol.state_dict())
+        if rep < 2:
+            tr.update_minibatch(*d, idx=idx.cuda())
+        else:                                                   # gathered on the host instead
+            tr.update_minibatch(*[t[idx].contiguous().cuda() for t in (obs, action, old_logp, adv, ret)])
+        outs.append(tr.state_dict())
+        tr.close()
+    for k in outs[0]:
+        assert np.array_equal(outs[0][k], outs[1][k]), k          # bitwise repeatable
+        assert np.array_equal(outs[0][k], outs[2][k]), k          # device gather == host gather
+
+
+def test_gae_reward_normalise(built):
+    import torch
+    rng = np.random.default_rng(4)
+    T, B = 37, 301
+    rew = rng.standard_normal((T, B)).astype(np.float32)
+    val = rng.standard_normal((T, B)).astype(np.float32)
+    done = (rng.random((T, B)) < 0.05).astype(np.float32)
+    last = rng.standard_normal(B).astype(np.float32)
+    tr = dart_b200.PPOTrainer(capacity=64, gamma=0.99, gae_lambda=0.95)
+    adv, ret = tr.gae(*[torch.from_numpy(a).cuda() for a in (rew, val, done, last)])
+    for b in (0, 17, 300):
+        ref = np.array(oppo.compute_gae(rew[:, b].astype(float).tolist(), val[:, b].astype(float).tolist(),
+                                        done[:, b].astype(float).tolist(), float(last[b]), 0.99, 0.95))
+        assert np.abs(adv[:, b].cpu().numpy() - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())
+        assert np.abs(ret[:, b].cpu().numpy() - (ref + val[:, b])).max() <= 1e-5 * max(1.0, np.abs(ref).max())
+    a_np, r_np = adv.cpu().numpy().reshape(-1).copy(), ret.cpu().numpy().reshape(-1).copy()
+    tr.normalize_(ret, 0)
+    tr.normalize_(adv, 1)
+    assert np.abs(ret.cpu().numpy().reshape(-1) - oppo.normalise_returns(r_np)).max() <= 1e-5
+    assert np.abs(adv.cpu().numpy().reshape(-1) - oppo.normalise_advantages(a_np).numpy()).max() <= 1e-5
+
+    # reward: near the target, far away, out of bounds, lost contact, episode cap
+    Bn = 64
+    state = np.zeros((Bn, 8)); target = np.zeros((Bn, 8))
+    state[:, 0] = rng.uniform(-0.25, 0.25, Bn); state[:, 2] = rng.uniform(-0.18, 0.18, Bn)
+    state[:, 1] = rng.uniform(-0.1, 0.1, Bn); state[:, 3] = rng.uniform(-0.1, 0.1, Bn)
+    target[:, 0] = rng.uniform(-0.1, 0.1, Bn); target[:, 2] = rng.uniform(-0.1, 0.1, Bn)
+    state[:8, :4] = target[:8, :4] + 1e-3                           # success bonus
+    control = rng.uniform(-0.4, 0.4, (Bn, 2)); prev = rng.uniform(-0.4, 0.4, (Bn, 2))
+    action = (rng.standard_normal((Bn, 34)) * np.where(np.arange(Bn)[:, None] % 4 == 0, 40.0, 1.0)).astype(np.float32)   # some damped
+    contact = (rng.random(Bn) > 0.2).astype(np.float64)
+    step = rng.integers(0, 1000, Bn).astype(np.int32); step[-3:] = 999
+    tpen = rng.uniform(0, 0.1, Bn)
+    t = lambda a: torch.from_numpy(a.copy()).cuda()
+    prev_d, step_d, tpen_d = t(prev), t(step), t(tpen)
+    r, dn = tr.reward(t(state), t(target), t(control), prev_d, t(action), step_d, tpen_d, in_contact=t(contact))
+    for b in range(Bn):
+        rr, dd, s2, tp2 = oppo.reward(state[b], target[b], control[b], prev[b], action[b], contact[b], int(step[b]), float(tpen[b]))
+        assert abs(float(r[b]) - rr) <= 1e-5 * max(1.0, abs(rr)), b
+        assert bool(dn[b]) == dd and int(step_d[b]) == s2 and abs(float(tpen_d[b]) - tp2) < 1e-12, b
+    assert torch.equal(prev_d.cpu(), torch.from_numpy(control))
+    tr.close()
+
+
+def test_train_rollout_improves_surrogate_and_checkpoint_roundtrip(built, tmp_path):
+    """End to end on a synthetic pooled rollout: after the reference's epochs x minibatches the value loss has dropped, the
+    checkpoint loads into the reference's Policy class (oracle restatement, same state_dict keys) and back into a trainer."""
+    import torch
+    T, B = 16, 256
+    g = torch.Generator(device="cuda").manual_seed(0)
+    tr = dart_b200.PPOTrainer(capacity=1024, epochs=4, mini_batch_size=1024, lr=1e-3)
+    obs = torch.randn(T, B, 520, device="cuda", generator=g)
+    eps = torch.randn(T, B, 34, device="cuda", generator=g)
+    act, logp, val, _ = tr.act(obs.reshape(-1, 520)[:1024], eps.reshape(-1, 34)[:1024])
+    acts, logps, vals = [], [], []
+    for s in range(0, T * B, 1024):
+        a, lp, v, _ = tr.act(obs.reshape(-1, 520)[s:s + 1024], eps.reshape(-1, 34)[s:s + 1024])
+        acts.append(a); logps.append(lp); vals.append(v)
+    act, logp, val = torch.cat(acts).view(T, B, 34), torch.cat(logps).view(T, B), torch.cat(vals).view(T, B)
+    rew = obs[:, :, 0].contiguous() + 0.1 * torch.randn(T, B, device="cuda", generator=g)      # learnable from the observation
+    done = torch.zeros(T, B, device="cuda")
+    last = torch.zeros(B, device="cuda")
+    adv, ret = tr.gae(rew, val, done, last)
+    tr.normalize_(ret, 0); tr.normalize_(adv, 1)
+    flat = (obs.reshape(-1, 520), act.reshape(-1, 34), logp.reshape(-1), adv.reshape(-1), ret.reshape(-1))
+    v0 = float(tr.update_minibatch(*[f[:1024].contiguous() for f in flat], apply=False)[1])
+    steps = tr.train_rollout(obs, act, logp, rew, val, done, last, generator=g)
+    assert steps == 4 * (T * B // 1024) and tr.launch_count > steps * 10
+    v1 = float(tr.update_minibatch(*[f[:1024].contiguous() for f in flat], apply=False)[1])
+    assert v1 < 0.8 * v0, (v0, v1)
+    path = str(tmp_path / "best_agent.pth")
+    tr.save(path, episode=3)
+    ck = torch.load(path, map_location="cpu", weights_only=True)
+    pol = oppo.Policy()
+    pol.load_state_dict(ck["model"])                               # the reference's keys and shapes
+    mean_ref = oppo.act(pol, obs[0, :8].cpu(), torch.zeros(8, 34))[3]
+    tr2 = dart_b200.PPOTrainer(capacity=64)
+    extra = tr2.load(path)
+    assert extra["episode"] == 3
+    mean2 = tr2.act(obs[0, :8].contiguous(), None)[3].cpu()
+    assert (mean2 - mean_ref).abs().max() <= 2e-5
+    sd1, sd2 = tr.state_dict(), tr2.state_dict()
+    assert all(np.array_equal(sd1[k], sd2[k]) for k in sd1)
+    pm = dart_b200.PolicyMLP(tr.actor_weights())                   # the trained actor feeds the tcgen05 inference kernel
+    assert (pm.forward(obs[0, :8].contiguous()).cpu() - mean_ref).abs().max() <= 8e-3
+    tr.close(); tr2.close(); pm.close()
