@@ -224,3 +224,53 @@ def test_train_rollout_improves_surrogate_and_checkpoint_roundtrip(built, tmp_pa
     pm = dart_b200.PolicyMLP(tr.actor_weights())                   # the trained actor feeds the tcgen05 inference kernel
     assert (pm.forward(obs[0, :8].contiguous()).cpu() - mean_ref).abs().max() <= 8e-3
     tr.close(); tr2.close(); pm.close()
+
+
+def test_lmpc_plant_step_matches_oracle_model(built):
+    """dart_lmpc_plant_step = one RK4 step of the reference's 8-state ODE (oracle/models.lmpc_step, rlmpc2.py:260-436)."""
+    import torch
+    from oracle import models
+    rng = np.random.default_rng(9)
+    B = 257
+    x = rng.uniform(-0.1, 0.1, (B, 8))
+    u = rng.uniform(-0.4, 0.4, (B, 2))
+    pvec = np.clip(1.0 + 0.3 * rng.standard_normal((B, 34)), 0.01, 1.9)
+    aux = np.concatenate([np.zeros((B, 2)), pvec], axis=1)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    out = dart_b200.lmpc_plant_step(t(x), t(u), t(aux)).cpu().numpy()
+    ref = np.stack([np.asarray(models.lmpc_step(x[b], u[b], pvec[b], 0.002)).reshape(-1) for b in range(B)])
+    assert np.abs(out - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
+
+
+def test_closed_loop_training_runs_and_matches_step_semantics(built):
+    """LMPCTrainer on the surrogate plant: transitions are recorded every 8th step, a rollout of T transitions triggers
+    epochs x minibatches optimiser steps, actions are the learner's samples, rewards equal the oracle's on the logged states."""
+    import torch
+    B, T = 64, 4
+    c = dart_b200.workloads.lmpc_config4(B, seed=3)
+    rng = np.random.default_rng(1)
+    true_aux = torch.from_numpy(np.concatenate([np.zeros((B, 2)), np.clip(c["pvec"] + 0.2 * rng.standard_normal((B, 34)), 0.05, 1.8)], axis=1)).cuda()
+    ctl = dart_b200.LMPCBatch(B, c["pvec"], seed=3)
+    ppo = dart_b200.PPOTrainer(capacity=256, epochs=2, mini_batch_size=128, reward_cfg=dict(max_delta=0.02, w_pos=40.0))
+    g = torch.Generator(device="cuda").manual_seed(7)
+    tr = dart_b200.LMPCTrainer(ctl, ppo, rollout_len=T, record_every=8, generator=g)
+    x = torch.from_numpy(c["state"]).cuda(); tg = torch.from_numpy(c["target"]).cuda()
+    p0 = ppo.state_dict()
+    steps = 8 * T
+    for k in range(steps):
+        ctrl_before, prev_before = ctl.u_prev.cpu().numpy().copy(), tr.prev_cmd.cpu().numpy().copy()
+        es, tp = tr.episode_step.cpu().numpy().copy(), tr.time_penalty.cpu().numpy().copy()
+        u0, rew, done = tr.step(x, tg)
+        a = tr._last[1].cpu().numpy()
+        for b in (0, 31):
+            rr, dd, _, _ = oppo.reward(x[b].cpu().numpy(), tg[b].cpu().numpy(), ctrl_before[b], prev_before[b], a[b], 1.0,
+                                       int(es[b]), float(tp[b]), max_delta=0.02, w_pos=40.0)
+            assert abs(float(rew[b]) - rr) <= 1e-5 * max(1.0, abs(rr)) and bool(done[b]) == dd
+        assert torch.equal(ctl.action, tr._last[1])                 # the sampled action is what updated the model parameters
+        assert tr.k == ((k // 8 + 1) % T if k % 8 == 0 else tr.k)
+        x = dart_b200.lmpc_plant_step(x, u0, true_aux)
+    assert tr.updates == 2 * (T * B // 128) and len(tr.mean_reward) == 1 and tr.k == 0
+    p1 = ppo.state_dict()
+    assert all(np.abs(p1[k] - p0[k]).max() > 0 for k in p0)         # every tensor was trained
+    assert np.isfinite(x.cpu().numpy()).all() and (ctl.status.cpu().numpy() != dart_b200.STATUS_NUMERIC).all()
+    ctl.engine.close(); ctl.policy.close(); ppo.close()
