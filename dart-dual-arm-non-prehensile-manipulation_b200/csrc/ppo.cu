@@ -45,7 +45,11 @@ constexpr int NP = OFF_LS + ACT;                   // 77 317 parameters
 
 constexpr int BM = 64, BN = 64, BK = 16, PAD = 4, GT = 256;
 constexpr int LOSS_T = 128, LOSS_W = 3 + ACT;      // per-block partials: policy sum, value sq. sum, unused, dlog_std[34]
-constexpr int MAX_SPLITS = 64;
+constexpr int MAX_SPLITS = 64;                     // layer-1 weight gradient: chunks of >= 256 samples
+constexpr int MAX_SPLITS_SMALL = 256;              // layers 2-3: chunks of >= 64 samples (more CTAs in flight for these latency-bound GEMMs)
+constexpr int NPB = OFF_W2A;                       // layer-1 block of the flat vector (W1 | b1)
+constexpr int NPS = NPW - OFF_W2A;                 // layers 2-3 block
+constexpr int BIG_MIN_ROWS = 512;                  // minibatches from here on use the 128x128 kernel for the layer-1 GEMMs
 constexpr double HALF_LOG_2PI = 0.91893853320467274178;
 
 // One GEMM of a grouped launch:  C[m,n] = epilogue( sum_k A(m,k) B(k,n) ).
@@ -136,6 +140,113 @@ __global__ void __launch_bounds__(GT) gemm_kernel(const GemmGroup g) {
             C[(size_t)m * P.ldc + n] = v;
         }
         if (want_rs) P.rowsum[(size_t)split * g.split_stride + m] = rs[i];
+    }
+}
+
+// The two layer-1 GEMMs (forward [M,520]x[520,128] and weight gradient [128,M]x[M,520]) carry 81 % of the step's flops:
+// 128x128 tiles, BK = 8, 8x8 register micro-tile per thread (as 2x2 blocks of 4x4 so that the shared-memory reads are
+// conflict-free float4s), 16-byte global loads, next tile prefetched into registers while the current one is multiplied
+// (two shared-memory buffers, one barrier per k-step).  Same operand conventions, epilogues and split/rowsum outputs
+// as gemm_kernel; requires 16-byte aligned operands with leading dimensions that are multiples of 4.
+constexpr int TM = 128, TN = 128, TK = 8, TP = 4;
+__device__ __forceinline__ void load_tile(const float* __restrict__ X, int ld, bool trans_rows_contig, int r0, int R, int k0,
+                                          int k_end, int t, float (&v)[4], int& r, int& k) {
+    // trans_rows_contig: X(r,k) = X[k*ld + r] (r contiguous) else X[r*ld + k] (k contiguous); returns 4 elements:
+    // rows r..r+3 at column k (contiguous r) or row r at columns k..k+3 (contiguous k)
+    if (trans_rows_contig) { k = t / 32; r = (t % 32) * 4; } else { r = t / 2; k = (t % 2) * 4; }
+    const int gr = r0 + r, gk = k0 + k;
+    v[0] = v[1] = v[2] = v[3] = 0.f;
+    if (trans_rows_contig) {
+        if (gk < k_end) {
+            const float* src = X + (size_t)gk * ld + gr;
+            if (gr + 3 < R) { const float4 q = *reinterpret_cast<const float4*>(src); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+            else { for (int i = 0; i < 4; ++i) if (gr + i < R) v[i] = src[i]; }
+        }
+    } else {
+        if (gr < R) {
+            const float* src = X + (size_t)gr * ld + gk;
+            if (gk + 3 < k_end) { const float4 q = *reinterpret_cast<const float4*>(src); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+            else { for (int i = 0; i < 4; ++i) if (gk + i < k_end) v[i] = src[i]; }
+        }
+    }
+}
+__device__ __forceinline__ void store_tile(float (*S)[TM + TP], bool rows_contig, int r, int k, const float (&v)[4]) {
+    if (rows_contig) *reinterpret_cast<float4*>(&S[k][r]) = make_float4(v[0], v[1], v[2], v[3]);
+    else { S[k][r] = v[0]; S[k + 1][r] = v[1]; S[k + 2][r] = v[2]; S[k + 3][r] = v[3]; }
+}
+
+__global__ void __launch_bounds__(GT, 2) gemm128_kernel(const GemmProb P, const int splits, const int kchunk, const long split_stride) {
+    const int split = blockIdx.z;
+    const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+    __shared__ __align__(16) float As[2][TK][TM + TP];
+    __shared__ __align__(16) float Bs[2][TK][TN + TP];
+    const int t = threadIdx.x, ty = t / 16, tx = t % 16;
+    const int k_begin = split * kchunk;
+    const int k_end = min(P.K, k_begin + kchunk);
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    float rs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const bool want_rs = P.rowsum != nullptr && blockIdx.x == 0 && tx == 0;
+    const bool a_rc = P.ta != 0, b_rc = P.tb == 0;      // "rows contiguous": A(m,k) with m contiguous / B(k,n) with n contiguous
+    float va[4], vb[4];
+    int ar, ak, br, bk;
+    int buf = 0;
+    if (k_begin < k_end) {
+        load_tile(P.A, P.lda, a_rc, m0, P.M, k_begin, k_end, t, va, ar, ak);
+        load_tile(P.B, P.ldb, b_rc, n0, P.N, k_begin, k_end, t, vb, br, bk);
+        store_tile(As[0], a_rc, ar, ak, va);
+        store_tile(Bs[0], b_rc, br, bk, vb);
+    }
+    __syncthreads();
+    for (int k0 = k_begin; k0 < k_end; k0 += TK) {
+        const bool more = k0 + TK < k_end;
+        if (more) {
+            load_tile(P.A, P.lda, a_rc, m0, P.M, k0 + TK, k_end, t, va, ar, ak);
+            load_tile(P.B, P.ldb, b_rc, n0, P.N, k0 + TK, k_end, t, vb, br, bk);
+        }
+#pragma unroll
+        for (int k = 0; k < TK; ++k) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+            if (want_rs) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) rs[i] += av[i];
+            }
+        }
+        if (more) {
+            store_tile(As[buf ^ 1], a_rc, ar, ak, va);
+            store_tile(Bs[buf ^ 1], b_rc, br, bk, vb);
+        }
+        __syncthreads();
+        buf ^= 1;
+    }
+    float* C = P.C + (size_t)split * split_stride;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+        if (m >= P.M) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+            if (n >= P.N) continue;
+            float v = acc[i][j];
+            if (P.mode == 1) v = tanhf(v + P.bias[n]);
+            else if (P.mode == 2) v = v + P.bias[n];
+            else if (P.mode == 3) { const float h = P.H[(size_t)m * P.ldh + n]; v = v * (1.f - h * h); }
+            C[(size_t)m * P.ldc + n] = v;
+        }
+        if (want_rs) P.rowsum[(size_t)split * split_stride + m] = rs[i];
     }
 }
 
@@ -273,7 +384,6 @@ struct LossArgs {
     double* part;                      // [nblocks, LOSS_W]
 };
 __global__ void __launch_bounds__(LOSS_T) ppo_loss_kernel(const LossArgs a) {
-    __shared__ double sh[LOSS_T];
     __shared__ float s_sd[ACT], s_in[ACT], s_ls[ACT];
     if (threadIdx.x < ACT) {
         const float raw = a.log_std[threadIdx.x];
@@ -307,23 +417,34 @@ __global__ void __launch_bounds__(LOSS_T) ppo_loss_kernel(const LossArgs a) {
 #pragma unroll
         for (int j = 0; j < ACT; ++j) a.dmean[(size_t)m * ACT + j] = (float)(g * (double)z[j] / (double)s_sd[j]);
     }
-    double* out = a.part + (size_t)blockIdx.x * LOSS_W;
-    double r = block_sum(pl, sh);
-    if (threadIdx.x == 0) out[0] = r;
-    r = block_sum(vl, sh);
-    if (threadIdx.x == 0) { out[1] = r; out[2] = 0.0; }
+    // block reduction of the 3 + 34 per-sample terms: shuffle tree inside each warp, then the 4 warp sums in a fixed order
+    __shared__ double wsum[LOSS_T / 32][LOSS_W];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll 1
-    for (int j = 0; j < ACT; ++j) {
-        const double zj = on ? (double)z[j] : 0.0;
-        r = block_sum(on ? g * (zj * zj - 1.0) * (double)s_in[j] : 0.0, sh);
-        if (threadIdx.x == 0) out[3 + j] = r;
+    for (int q = 0; q < LOSS_W; ++q) {
+        double v;
+        if (q == 0) v = pl;
+        else if (q == 1) v = vl;
+        else if (q == 2) v = 0.0;
+        else { const double zj = on ? (double)z[q - 3] : 0.0; v = on ? g * (zj * zj - 1.0) * (double)s_in[q - 3] : 0.0; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) wsum[warp][q] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < LOSS_W) {
+        double r = 0.0;
+#pragma unroll
+        for (int w = 0; w < LOSS_T / 32; ++w) r += wsum[w][threadIdx.x];
+        a.part[(size_t)blockIdx.x * LOSS_W + threadIdx.x] = r;
     }
 }
 
 // ---- sum the split partials into the flat gradient, per-block sum of squares for the global norm ----
 struct ReduceArgs {
-    int splits, loss_blocks, M;
-    const float* part;       // [splits, NPW]
+    int splits, splits_small, loss_blocks, M;
+    const float* part;       // [splits, NPB]
+    const float* part_small; // [splits_small, NPS]
     const double* loss_part; // [loss_blocks, LOSS_W]
     const float* log_std;
     float ls_min, ls_max, ent_coef, vf_coef;
@@ -335,8 +456,10 @@ __global__ void __launch_bounds__(256) ppo_grad_reduce_kernel(const ReduceArgs a
     __shared__ double sh[256];
     const int j = blockIdx.x * 256 + threadIdx.x;
     float g = 0.f;
-    if (j < NPW) {
-        for (int s = 0; s < a.splits; ++s) g += a.part[(size_t)s * NPW + j];
+    if (j < NPB) {
+        for (int s = 0; s < a.splits; ++s) g += a.part[(size_t)s * NPB + j];
+    } else if (j < NPW) {
+        for (int s = 0; s < a.splits_small; ++s) g += a.part_small[(size_t)s * NPS + (j - NPB)];
     } else if (j < NP) {
         const int jj = j - NPW;
         double d = 0.0;
@@ -395,7 +518,7 @@ struct dart_ppo {
     float *h1, *h2, *dz1, *dz2;          // [capacity, 128]
     float *mean, *value, *dmean, *dvalue;
     float *mb_obs, *mb_act, *mb_logp, *mb_adv, *mb_ret;
-    float* part;                         // [MAX_SPLITS, NPW]
+    float *part, *part_small;            // [MAX_SPLITS, NPB], [MAX_SPLITS_SMALL, NPS]
     double *loss_part, *normpart;
     int64_t step, launches;
 };
@@ -405,6 +528,13 @@ namespace {
 int launch_group(dart_ppo* h, GemmGroup& g, int maxM, int maxN, cudaStream_t st) {
     dim3 grid((maxN + BN - 1) / BN, (maxM + BM - 1) / BM, g.count * g.splits);
     gemm_kernel<<<grid, GT, 0, st>>>(g);
+    h->launches += 1;
+    return cudaGetLastError() == cudaSuccess ? DART_OK : DART_ERR_CUDA;
+}
+
+int launch_big(dart_ppo* h, const GemmProb& p, int splits, int kchunk, long split_stride, cudaStream_t st) {
+    dim3 grid((p.N + TN - 1) / TN, (p.M + TM - 1) / TM, splits);
+    gemm128_kernel<<<grid, GT, 0, st>>>(p, splits, kchunk, split_stride);
     h->launches += 1;
     return cudaGetLastError() == cudaSuccess ? DART_OK : DART_ERR_CUDA;
 }
@@ -425,7 +555,7 @@ int forward(dart_ppo* h, int M, const float* obs, cudaStream_t st) {
     memset(&g, 0, sizeof(g));
     g.count = 1; g.splits = 1; g.kchunk = OBS; g.split_stride = 0;
     g.p[0] = fwd_prob(obs, OBS, P + OFF_W1, P + OFF_B1, h->h1, H2W, M, H2W, OBS, 1);
-    int rc = launch_group(h, g, M, H2W, st);
+    int rc = M >= BIG_MIN_ROWS ? launch_big(h, g.p[0], 1, OBS, 0, st) : launch_group(h, g, M, H2W, st);
     if (rc != DART_OK) return rc;
     g.count = 2; g.kchunk = HID;
     g.p[0] = fwd_prob(h->h1, H2W, P + OFF_W2A, P + OFF_B2A, h->h2, H2W, M, HID, HID, 1);
@@ -460,7 +590,7 @@ GemmProb dgrad_prob(const float* dY, int lddy, const float* W, float* dX, int ld
 
 void free_all(dart_ppo* h) {
     void* p[] = {h->param, h->grad, h->m, h->v, h->h1, h->h2, h->dz1, h->dz2, h->mean, h->value, h->dmean, h->dvalue,
-                 h->mb_obs, h->mb_act, h->mb_logp, h->mb_adv, h->mb_ret, h->part, h->loss_part, h->normpart};
+                 h->mb_obs, h->mb_act, h->mb_logp, h->mb_adv, h->mb_ret, h->part, h->part_small, h->loss_part, h->normpart};
     for (void* q : p) if (q) cudaFree(q);
 }
 
@@ -518,7 +648,8 @@ extern "C" int dart_ppo_create(dart_ppo_handle* out, int device, int32_t obs_dim
         {(void**)&h->dmean, cap * ACT * sizeof(float)}, {(void**)&h->dvalue, cap * sizeof(float)},
         {(void**)&h->mb_obs, cap * OBS * sizeof(float)}, {(void**)&h->mb_act, cap * ACT * sizeof(float)},
         {(void**)&h->mb_logp, cap * sizeof(float)}, {(void**)&h->mb_adv, cap * sizeof(float)},
-        {(void**)&h->mb_ret, cap * sizeof(float)}, {(void**)&h->part, (size_t)MAX_SPLITS * NPW * sizeof(float)},
+        {(void**)&h->mb_ret, cap * sizeof(float)}, {(void**)&h->part, (size_t)MAX_SPLITS * NPB * sizeof(float)},
+        {(void**)&h->part_small, (size_t)MAX_SPLITS_SMALL * NPS * sizeof(float)},
         {(void**)&h->loss_part, (size_t)h->loss_blocks_cap * LOSS_W * sizeof(double)},
         {(void**)&h->normpart, (size_t)((NP + 255) / 256) * sizeof(double)}};
     int rc = DART_OK;
@@ -645,36 +776,43 @@ extern "C" int dart_ppo_update(dart_ppo_handle h, int32_t M, const int64_t* idx,
     if (splits > MAX_SPLITS) splits = MAX_SPLITS;
     int kchunk = (M + splits - 1) / splits;
     kchunk = (kchunk + BK - 1) / BK * BK;
+    int splits_small = (M + 63) / 64;
+    if (splits_small > MAX_SPLITS_SMALL) splits_small = MAX_SPLITS_SMALL;
+    int kchunk_small = (M + splits_small - 1) / splits_small;
+    kchunk_small = (kchunk_small + BK - 1) / BK * BK;
+    float* ps = h->part_small;                        // layers 2-3 block: flat offsets relative to NPB
     GemmGroup gw;
     memset(&gw, 0, sizeof(gw));
-    gw.count = 2; gw.splits = splits; gw.kchunk = kchunk; gw.split_stride = NPW;
+    gw.count = 2; gw.splits = splits_small; gw.kchunk = kchunk_small; gw.split_stride = NPS;
     GemmGroup gd;
     memset(&gd, 0, sizeof(gd));
     gd.count = 2; gd.splits = 1; gd.split_stride = 0;
     // layer 3
-    gw.p[0] = wgrad_prob(h->dmean, ACT, h->h2, H2W, h->part, OFF_W3A, M, ACT, HID);
-    gw.p[1] = wgrad_prob(h->dvalue, 1, h->h2 + HID, H2W, h->part, OFF_W3C, M, 1, HID);
+    gw.p[0] = wgrad_prob(h->dmean, ACT, h->h2, H2W, ps, OFF_W3A - NPB, M, ACT, HID);
+    gw.p[1] = wgrad_prob(h->dvalue, 1, h->h2 + HID, H2W, ps, OFF_W3C - NPB, M, 1, HID);
     if ((rc = launch_group(h, gw, ACT, HID, st)) != DART_OK) return rc;
     gd.kchunk = ACT;
     gd.p[0] = dgrad_prob(h->dmean, ACT, P + OFF_W3A, h->dz2, H2W, h->h2, H2W, M, ACT, HID);
     gd.p[1] = dgrad_prob(h->dvalue, 1, P + OFF_W3C, h->dz2 + HID, H2W, h->h2 + HID, H2W, M, 1, HID);
     if ((rc = launch_group(h, gd, M, HID, st)) != DART_OK) return rc;
     // layer 2
-    gw.p[0] = wgrad_prob(h->dz2, H2W, h->h1, H2W, h->part, OFF_W2A, M, HID, HID);
-    gw.p[1] = wgrad_prob(h->dz2 + HID, H2W, h->h1 + HID, H2W, h->part, OFF_W2C, M, HID, HID);
+    gw.p[0] = wgrad_prob(h->dz2, H2W, h->h1, H2W, ps, OFF_W2A - NPB, M, HID, HID);
+    gw.p[1] = wgrad_prob(h->dz2 + HID, H2W, h->h1 + HID, H2W, ps, OFF_W2C - NPB, M, HID, HID);
     if ((rc = launch_group(h, gw, HID, HID, st)) != DART_OK) return rc;
     gd.kchunk = HID;
     gd.p[0] = dgrad_prob(h->dz2, H2W, P + OFF_W2A, h->dz1, H2W, h->h1, H2W, M, HID, HID);
     gd.p[1] = dgrad_prob(h->dz2 + HID, H2W, P + OFF_W2C, h->dz1 + HID, H2W, h->h1 + HID, H2W, M, HID, HID);
     if ((rc = launch_group(h, gd, M, HID, st)) != DART_OK) return rc;
     // layer 1 (both networks at once: dz1 is [M,128])
-    gw.count = 1;
+    gw.count = 1; gw.splits = splits; gw.kchunk = kchunk; gw.split_stride = NPB;
     gw.p[0] = wgrad_prob(h->dz1, H2W, obs, OBS, h->part, OFF_W1, M, H2W, OBS);
-    if ((rc = launch_group(h, gw, H2W, OBS, st)) != DART_OK) return rc;
+    rc = M >= BIG_MIN_ROWS ? launch_big(h, gw.p[0], splits, kchunk, NPB, st) : launch_group(h, gw, H2W, OBS, st);
+    if (rc != DART_OK) return rc;
 
     const int nred = (NP + 255) / 256;
     ReduceArgs ra;
-    ra.splits = splits; ra.loss_blocks = loss_blocks; ra.M = M; ra.part = h->part; ra.loss_part = h->loss_part;
+    ra.splits = splits; ra.splits_small = splits_small; ra.loss_blocks = loss_blocks; ra.M = M; ra.part = h->part;
+    ra.part_small = h->part_small; ra.loss_part = h->loss_part;
     ra.log_std = P + OFF_LS; ra.ls_min = la.ls_min; ra.ls_max = la.ls_max; ra.ent_coef = (float)c.ent_coef;
     ra.vf_coef = la.vf_coef; ra.grad = h->grad; ra.normpart = h->normpart; ra.stats = stats;
     ppo_grad_reduce_kernel<<<nred, 256, 0, st>>>(ra);

@@ -13,7 +13,9 @@ from oracle import ppo as oppo
 FLOP_PER_SAMPLE = 2 * (520 * 128 + 2 * 64 * 64 + 64 * 35) * 2 + 2 * (2 * 64 * 64 + 64 * 35)
 dev = torch.device("cuda", 0)
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-for M in (64, 1024, 16384, 65536):
+SIZES = [int(a) for a in sys.argv[1:] if a.isdigit()] or [64, 1024, 16384, 65536]
+NOCPU = "nocpu" in sys.argv
+for M in SIZES:
     g = torch.Generator().manual_seed(M)
     pol = oppo.make_policy(3)
     obs, eps = torch.randn(M, 520, generator=g), torch.randn(M, 34, generator=g)
@@ -40,13 +42,15 @@ for M in (64, 1024, 16384, 65536):
     b.record(); torch.cuda.synchronize()
     ms_b2b = a.elapsed_time(b) / 20
     # the reference's path: torch autograd + Adam on the host cores
-    opt = oppo.make_optimizer(pol)
-    n_cpu = 3 if M >= 16384 else 10
-    oppo.minibatch_step(pol, opt, obs, act, old, adv, ret)
-    t0 = time.perf_counter()
-    for _ in range(n_cpu):
+    cpu_ms = float("nan")
+    if not NOCPU:
+        opt = oppo.make_optimizer(pol)
+        n_cpu = 3 if M >= 16384 else 10
         oppo.minibatch_step(pol, opt, obs, act, old, adv, ret)
-    cpu_ms = (time.perf_counter() - t0) / n_cpu * 1e3
+        t0 = time.perf_counter()
+        for _ in range(n_cpu):
+            oppo.minibatch_step(pol, opt, obs, act, old, adv, ret)
+        cpu_ms = (time.perf_counter() - t0) / n_cpu * 1e3
     print(json.dumps(dict(kernel="dart_ppo_update", M=M, ms_flushed=round(ms, 4), ms_back_to_back=round(ms_b2b, 4), launches_per_step=launches,
                           samples_per_s=M / ms_b2b * 1e3, fp32_tflops=FLOP_PER_SAMPLE * M / ms_b2b * 1e-9,
                           hbm_GBps=M * (2 * 2080 + 148) / ms_b2b * 1e-6, torch_cpu_ms=round(cpu_ms, 3), torch_cpu_threads=torch.get_num_threads(),
@@ -54,6 +58,8 @@ for M in (64, 1024, 16384, 65536):
     tr.close()
 
 # rollout-time policy call (actor + critic forward + sampling) for 16 384 instances
+if NOCPU:
+    sys.exit(0)
 B = 16384
 tr = dart_b200.PPOTrainer(capacity=B)
 obs, eps = torch.randn(B, 520, device=dev), torch.randn(B, 34, device=dev)
