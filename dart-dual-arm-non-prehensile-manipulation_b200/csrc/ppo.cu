@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string.h>
+#include <stdlib.h>
 #include <math.h>
 #include <new>
 
@@ -49,6 +50,7 @@ constexpr int MAX_SPLITS = 64;                     // layer-1 weight gradient: c
 constexpr int MAX_SPLITS_SMALL = 256;              // layers 2-3: chunks of >= 64 samples (more CTAs in flight for these latency-bound GEMMs)
 constexpr int NPB = OFF_W2A;                       // layer-1 block of the flat vector (W1 | b1)
 constexpr int NPS = NPW - OFF_W2A;                 // layers 2-3 block
+constexpr int NPS_LD = (NPS + 3) / 4 * 4;          // row stride of its partial buffer (16-byte aligned rows)
 constexpr int BIG_MIN_ROWS = 512;                  // minibatches from here on use the 128x128 kernel for the layer-1 GEMMs
 constexpr double HALF_LOG_2PI = 0.91893853320467274178;
 
@@ -440,11 +442,293 @@ __global__ void __launch_bounds__(LOSS_T) ppo_loss_kernel(const LossArgs a) {
     }
 }
 
+// ---- layers 2-3, loss and their gradients for a tile of 64 samples in ONE kernel ----
+// Everything between the two layer-1 GEMMs: h2 = tanh(h1 W2' + b2), mean / value, the per-sample loss terms, dmean / dvalue,
+// dz2 = (dOut W3)(1 - h2^2), dz1 = (dz2 W2)(1 - h1^2) (written for the layer-1 weight-gradient GEMM) and this tile's
+// partial weight/bias gradients of layers 2-3 (one row of part_small per CTA, summed in CTA order by the reduce kernel).
+// The h1 tile, both weight orientations and all intermediates stay in shared memory (189 kB, one CTA per SM); replaces six
+// grouped-GEMM launches + the loss kernel and the [M,128] h2 / dz2 round trips through HBM.  backward = 0 is the
+// rollout-time forward (mean and value only).
+constexpr int MS = 64, LDH = 132, LDW = 68, LDO = 36;
+constexpr int SM_H1 = 0, SM_H2 = SM_H1 + MS * LDH, SM_D2 = SM_H2 + MS * LDH, SM_W2 = SM_D2 + MS * LDH,
+              SM_W2T = SM_W2 + H2W * LDW, SM_W3 = SM_W2T + HID * LDH, SM_OUT = SM_W3 + 36 * LDW, SM_B = SM_OUT + MS * LDO,
+              SM_FLOATS = SM_B + H2W + 36 + 3 * 36;
+constexpr int MID_SMEM = SM_FLOATS * 4 + 2 * LOSS_W * 8;
+// offsets inside a part_small row (flat layout relative to NPB)
+constexpr int RS_W2A = OFF_W2A - NPB, RS_B2A = OFF_B2A - NPB, RS_W2C = OFF_W2C - NPB, RS_B2C = OFF_B2C - NPB,
+              RS_W3A = OFF_W3A - NPB, RS_B3A = OFF_B3A - NPB, RS_W3C = OFF_W3C - NPB, RS_B3C = OFF_B3C - NPB;
+struct MidArgs {
+    int M, backward;
+    const float *h1, *P, *act, *old_logp, *adv, *ret;
+    float ls_min, ls_max, clip_eps, vf_coef;
+    float *mean, *value, *dz1, *part_small;
+    double* loss_part;
+};
+
+__global__ void __launch_bounds__(GT, 1) ppo_mid_kernel(const MidArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    float* sH1 = sm + SM_H1; float* sH2 = sm + SM_H2; float* sD2 = sm + SM_D2; float* sW2 = sm + SM_W2;
+    float* sW2T = sm + SM_W2T; float* sW3 = sm + SM_W3; float* sOut = sm + SM_OUT; float* sB2 = sm + SM_B;
+    float* sB3 = sB2 + H2W; float* s_sd = sB3 + 36; float* s_ls = s_sd + 36; float* s_in = s_ls + 36;
+    double* sLoss = reinterpret_cast<double*>(sm + SM_FLOATS);            // [2][LOSS_W]
+    const int t = threadIdx.x, ty = t / 16, tx = t % 16;
+    const int s0 = blockIdx.x * MS;
+    const float* P = a.P;
+    // ---- P0: stage the h1 tile (rows past M zero-filled), W2 in both orientations, W3, biases, std ----
+    for (int e = t; e < MS * (H2W / 4); e += GT) {
+        const int s = e / (H2W / 4), c4 = (e % (H2W / 4)) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (s0 + s < a.M) v = *reinterpret_cast<const float4*>(a.h1 + (size_t)(s0 + s) * H2W + c4);
+        *reinterpret_cast<float4*>(&sH1[s * LDH + c4]) = v;
+    }
+    for (int e = t; e < H2W * HID; e += GT) {                              // e = c*64 + k over [W2A; W2C]
+        const int c = e / HID, k = e % HID;
+        const float w = (c < HID) ? P[OFF_W2A + c * HID + k] : P[OFF_W2C + (c - HID) * HID + k];
+        sW2[c * LDW + k] = w;
+        sW2T[k * LDH + c] = w;
+    }
+    for (int e = t; e < 36 * HID; e += GT) {
+        const int j = e / HID, k = e % HID;
+        sW3[j * LDW + k] = (j < ACT) ? P[OFF_W3A + j * HID + k] : (j == ACT ? P[OFF_W3C + k] : 0.f);
+    }
+    if (t < H2W) sB2[t] = (t < HID) ? P[OFF_B2A + t] : P[OFF_B2C + t - HID];
+    if (t < 36) {
+        sB3[t] = (t < ACT) ? P[OFF_B3A + t] : (t == ACT ? P[OFF_B3C] : 0.f);
+        const float raw = (t < ACT) ? P[OFF_LS + t] : 0.f;
+        const float ls = fminf(fmaxf(raw, a.ls_min), a.ls_max);
+        s_ls[t] = ls; s_sd[t] = fmaxf(expf(ls), 1e-6f);
+        s_in[t] = (raw >= a.ls_min && raw <= a.ls_max) ? 1.f : 0.f;
+    }
+    __syncthreads();
+    // ---- P1: h2[s][c] = tanh(b2[c] + sum_k h1[s][k] W2[c][k]); thread: samples ty*4+i, columns tx*4+j of both networks ----
+    {
+        float acA[4][4], acC[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { acA[i][j] = 0.f; acC[i][j] = 0.f; }
+#pragma unroll 4
+        for (int k = 0; k < HID; ++k) {
+            const float4 wa = *reinterpret_cast<const float4*>(&sW2T[k * LDH + tx * 4]);
+            const float4 wc = *reinterpret_cast<const float4*>(&sW2T[k * LDH + HID + tx * 4]);
+            const float wav[4] = {wa.x, wa.y, wa.z, wa.w}, wcv[4] = {wc.x, wc.y, wc.z, wc.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float ha = sH1[(ty * 4 + i) * LDH + k], hc = sH1[(ty * 4 + i) * LDH + HID + k];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { acA[i][j] = fmaf(ha, wav[j], acA[i][j]); acC[i][j] = fmaf(hc, wcv[j], acC[i][j]); }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                sH2[(ty * 4 + i) * LDH + tx * 4 + j] = tanhf(acA[i][j] + sB2[tx * 4 + j]);
+                sH2[(ty * 4 + i) * LDH + HID + tx * 4 + j] = tanhf(acC[i][j] + sB2[HID + tx * 4 + j]);
+            }
+    }
+    __syncthreads();
+    // ---- P2: mean[s][j] (j < 34) and value[s] (j = 34); thread: sample t/4, columns (t%4) + 4i ----
+    {
+        const int s = t / 4, q = t % 4;
+        float o[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) o[i] = 0.f;
+        for (int k = 0; k < HID; ++k) {
+            const float ha = sH2[s * LDH + k], hc = sH2[s * LDH + HID + k];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                const int j = q + 4 * i;
+                o[i] = fmaf(j == ACT ? hc : ha, sW3[j * LDW + k], o[i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            const int j = q + 4 * i;
+            const float v = o[i] + sB3[j];
+            sOut[s * LDO + j] = v;
+            if (s0 + s < a.M) {
+                if (j < ACT) a.mean[(size_t)(s0 + s) * ACT + j] = v;
+                else if (j == ACT) a.value[s0 + s] = v;
+            }
+        }
+    }
+    if (!a.backward) return;
+    __syncthreads();
+    // ---- P3: per-sample loss terms and d(loss)/d(mean, value) (threads 0-63, one sample each); sOut becomes dOut ----
+    if (t < MS) {
+        const int m = s0 + t;
+        const bool on = m < a.M;
+        double pl = 0.0, vl = 0.0, g = 0.0;
+        float z[ACT];
+        if (on) {
+            double lp = 0.0;
+#pragma unroll
+            for (int j = 0; j < ACT; ++j) {
+                const float d = a.act[(size_t)m * ACT + j] - sOut[t * LDO + j];
+                z[j] = d / s_sd[j];
+                lp += -0.5 * (double)z[j] * (double)z[j] - (double)s_ls[j] - HALF_LOG_2PI;
+            }
+            const double A = (double)a.adv[m];
+            const double ratio = exp((double)(float)lp - (double)a.old_logp[m]);
+            const double lo = 1.0 - (double)a.clip_eps, hi = 1.0 + (double)a.clip_eps;
+            const double s1 = ratio * A, s2 = fmin(fmax(ratio, lo), hi) * A;
+            pl = -fmin(s1, s2);
+            g = (s1 <= s2) ? -A * ratio / (double)a.M : 0.0;
+            const double dv = (double)sOut[t * LDO + ACT] - (double)a.ret[m];
+            vl = dv * dv;
+#pragma unroll
+            for (int j = 0; j < ACT; ++j) sOut[t * LDO + j] = (float)(g * (double)z[j] / (double)s_sd[j]);
+            sOut[t * LDO + ACT] = (float)((double)a.vf_coef * 2.0 * dv / (double)a.M);
+        } else {
+#pragma unroll
+            for (int j = 0; j <= ACT; ++j) sOut[t * LDO + j] = 0.f;
+#pragma unroll
+            for (int j = 0; j < ACT; ++j) z[j] = 0.f;
+        }
+        const int lane = t & 31, warp = t >> 5;
+#pragma unroll 1
+        for (int q = 0; q < LOSS_W; ++q) {
+            double v;
+            if (q == 0) v = pl;
+            else if (q == 1) v = vl;
+            else if (q == 2) v = 0.0;
+            else { const double zj = (double)z[q - 3]; v = on ? g * (zj * zj - 1.0) * (double)s_in[q - 3] : 0.0; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+            if (lane == 0) sLoss[warp * LOSS_W + q] = v;
+        }
+    }
+    __syncthreads();
+    if (t < LOSS_W) a.loss_part[(size_t)blockIdx.x * LOSS_W + t] = sLoss[t] + sLoss[LOSS_W + t];
+    // ---- P4: dz2[s][c] = (sum_j dOut[s][j] W3[j][c]) (1 - h2^2) ----
+    {
+        float acA[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acA[i][j] = 0.f;
+        for (int j = 0; j < ACT; ++j) {
+            const float4 w = *reinterpret_cast<const float4*>(&sW3[j * LDW + tx * 4]);
+            const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float d = sOut[(ty * 4 + i) * LDO + j];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) acA[i][jj] = fmaf(d, wv[jj], acA[i][jj]);
+            }
+        }
+        const float4 wc4 = *reinterpret_cast<const float4*>(&sW3[ACT * LDW + tx * 4]);
+        const float wcv[4] = {wc4.x, wc4.y, wc4.z, wc4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float dvv = sOut[(ty * 4 + i) * LDO + ACT];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float ha = sH2[(ty * 4 + i) * LDH + tx * 4 + j], hc = sH2[(ty * 4 + i) * LDH + HID + tx * 4 + j];
+                sD2[(ty * 4 + i) * LDH + tx * 4 + j] = acA[i][j] * (1.f - ha * ha);
+                sD2[(ty * 4 + i) * LDH + HID + tx * 4 + j] = dvv * wcv[j] * (1.f - hc * hc);
+            }
+        }
+    }
+    __syncthreads();
+    // ---- P5: dz1[s][k] = (sum_c dz2[s][c] W2[c][k]) (1 - h1^2)  -> HBM ----
+    {
+        float acA[4][4], acC[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { acA[i][j] = 0.f; acC[i][j] = 0.f; }
+#pragma unroll 4
+        for (int c = 0; c < HID; ++c) {
+            const float4 wa = *reinterpret_cast<const float4*>(&sW2[c * LDW + tx * 4]);
+            const float4 wc = *reinterpret_cast<const float4*>(&sW2[(HID + c) * LDW + tx * 4]);
+            const float wav[4] = {wa.x, wa.y, wa.z, wa.w}, wcv[4] = {wc.x, wc.y, wc.z, wc.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float da = sD2[(ty * 4 + i) * LDH + c], dc = sD2[(ty * 4 + i) * LDH + HID + c];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { acA[i][j] = fmaf(da, wav[j], acA[i][j]); acC[i][j] = fmaf(dc, wcv[j], acC[i][j]); }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int s = ty * 4 + i;
+            if (s0 + s >= a.M) continue;
+            float oa[4], oc[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float ha = sH1[s * LDH + tx * 4 + j], hc = sH1[s * LDH + HID + tx * 4 + j];
+                oa[j] = acA[i][j] * (1.f - ha * ha);
+                oc[j] = acC[i][j] * (1.f - hc * hc);
+            }
+            *reinterpret_cast<float4*>(a.dz1 + (size_t)(s0 + s) * H2W + tx * 4) = make_float4(oa[0], oa[1], oa[2], oa[3]);
+            *reinterpret_cast<float4*>(a.dz1 + (size_t)(s0 + s) * H2W + HID + tx * 4) = make_float4(oc[0], oc[1], oc[2], oc[3]);
+        }
+    }
+    // ---- P6: this tile's weight / bias gradient partials of layers 2-3 ----
+    float* row = a.part_small + (size_t)blockIdx.x * NPS_LD;
+    {   // dW2[c][k] = sum_s dz2[s][c] h1[s][k]; thread: c = ty*4+i, k = tx*4+j, both networks
+        float acA[4][4], acC[4][4], ba[4] = {0.f, 0.f, 0.f, 0.f}, bc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { acA[i][j] = 0.f; acC[i][j] = 0.f; }
+#pragma unroll 2
+        for (int s = 0; s < MS; ++s) {
+            const float4 da = *reinterpret_cast<const float4*>(&sD2[s * LDH + ty * 4]);
+            const float4 dc = *reinterpret_cast<const float4*>(&sD2[s * LDH + HID + ty * 4]);
+            const float4 ha = *reinterpret_cast<const float4*>(&sH1[s * LDH + tx * 4]);
+            const float4 hc = *reinterpret_cast<const float4*>(&sH1[s * LDH + HID + tx * 4]);
+            const float dav[4] = {da.x, da.y, da.z, da.w}, dcv[4] = {dc.x, dc.y, dc.z, dc.w};
+            const float hav[4] = {ha.x, ha.y, ha.z, ha.w}, hcv[4] = {hc.x, hc.y, hc.z, hc.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                ba[i] += dav[i]; bc[i] += dcv[i];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { acA[i][j] = fmaf(dav[i], hav[j], acA[i][j]); acC[i][j] = fmaf(dcv[i], hcv[j], acC[i][j]); }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c = ty * 4 + i;
+            *reinterpret_cast<float4*>(row + RS_W2A + c * HID + tx * 4) = make_float4(acA[i][0], acA[i][1], acA[i][2], acA[i][3]);
+            *reinterpret_cast<float4*>(row + RS_W2C + c * HID + tx * 4) = make_float4(acC[i][0], acC[i][1], acC[i][2], acC[i][3]);
+            if (tx == 0) { row[RS_B2A + c] = ba[i]; row[RS_B2C + c] = bc[i]; }
+        }
+    }
+    {   // dW3[j][k] = sum_s dOut[s][j] h2[s][k]; thread: k = t%64, rows j = t/64 + 4i (j = 34: the critic's row on its own h2 half)
+        const int k = t % HID, q = t / HID;
+        float o[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) o[i] = 0.f;
+        for (int s = 0; s < MS; ++s) {
+            const float ha = sH2[s * LDH + k], hc = sH2[s * LDH + HID + k];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                const int j = q + 4 * i;
+                o[i] = fmaf(sOut[s * LDO + j], j == ACT ? hc : ha, o[i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            const int j = q + 4 * i;
+            if (j < ACT) row[RS_W3A + j * HID + k] = o[i];
+            else if (j == ACT) row[RS_W3C + k] = o[i];
+        }
+        if (t <= ACT) {
+            float b = 0.f;
+            for (int s = 0; s < MS; ++s) b += sOut[s * LDO + t];
+            if (t < ACT) row[RS_B3A + t] = b; else row[RS_B3C] = b;
+        }
+    }
+}
+
 // ---- sum the split partials into the flat gradient, per-block sum of squares for the global norm ----
 struct ReduceArgs {
     int splits, splits_small, loss_blocks, M;
     const float* part;       // [splits, NPB]
-    const float* part_small; // [splits_small, NPS]
+    const float* part_small; // [splits_small, NPS_LD]
     const double* loss_part; // [loss_blocks, LOSS_W]
     const float* log_std;
     float ls_min, ls_max, ent_coef, vf_coef;
@@ -459,7 +743,7 @@ __global__ void __launch_bounds__(256) ppo_grad_reduce_kernel(const ReduceArgs a
     if (j < NPB) {
         for (int s = 0; s < a.splits; ++s) g += a.part[(size_t)s * NPB + j];
     } else if (j < NPW) {
-        for (int s = 0; s < a.splits_small; ++s) g += a.part_small[(size_t)s * NPS + (j - NPB)];
+        for (int s = 0; s < a.splits_small; ++s) g += a.part_small[(size_t)s * NPS_LD + (j - NPB)];
     } else if (j < NP) {
         const int jj = j - NPW;
         double d = 0.0;
@@ -512,7 +796,7 @@ __global__ void __launch_bounds__(256) ppo_adam_kernel(const AdamArgs a) {
 }  // namespace
 
 struct dart_ppo {
-    int device, capacity, splits_cap, loss_blocks_cap;
+    int device, capacity, splits_cap, loss_blocks_cap, fused;
     dart_ppo_cfg cfg;
     float *param, *grad, *m, *v;         // [NP]
     float *h1, *h2, *dz1, *dz2;          // [capacity, 128]
@@ -549,7 +833,7 @@ GemmProb fwd_prob(const float* X, int ldx, const float* W, const float* b, float
 }
 
 // Both networks' forward pass for M rows of `obs`: h1, h2 [M,128] (actor columns 0-63, critic 64-127), mean [M,34], value [M].
-int forward(dart_ppo* h, int M, const float* obs, cudaStream_t st) {
+int forward(dart_ppo* h, int M, const float* obs, cudaStream_t st, bool with_tail = true) {
     const float* P = h->param;
     GemmGroup g;
     memset(&g, 0, sizeof(g));
@@ -557,6 +841,16 @@ int forward(dart_ppo* h, int M, const float* obs, cudaStream_t st) {
     g.p[0] = fwd_prob(obs, OBS, P + OFF_W1, P + OFF_B1, h->h1, H2W, M, H2W, OBS, 1);
     int rc = M >= BIG_MIN_ROWS ? launch_big(h, g.p[0], 1, OBS, 0, st) : launch_group(h, g, M, H2W, st);
     if (rc != DART_OK) return rc;
+    if (h->fused) {
+        if (!with_tail) return DART_OK;
+        MidArgs ma;
+        memset(&ma, 0, sizeof(ma));
+        ma.M = M; ma.backward = 0; ma.h1 = h->h1; ma.P = P; ma.mean = h->mean; ma.value = h->value;
+        ma.ls_min = (float)h->cfg.log_std_min; ma.ls_max = (float)h->cfg.log_std_max;
+        ppo_mid_kernel<<<(M + MS - 1) / MS, GT, MID_SMEM, st>>>(ma);
+        h->launches += 1;
+        return cudaGetLastError() == cudaSuccess ? DART_OK : DART_ERR_CUDA;
+    }
     g.count = 2; g.kchunk = HID;
     g.p[0] = fwd_prob(h->h1, H2W, P + OFF_W2A, P + OFF_B2A, h->h2, H2W, M, HID, HID, 1);
     g.p[1] = fwd_prob(h->h1 + HID, H2W, P + OFF_W2C, P + OFF_B2C, h->h2 + HID, H2W, M, HID, HID, 1);
@@ -586,6 +880,54 @@ GemmProb dgrad_prob(const float* dY, int lddy, const float* W, float* dX, int ld
     p.B = W; p.ldb = K; p.tb = 0;          // B(n,k) = W[n*K + k]
     p.C = dX; p.ldc = lddx; p.M = M; p.N = K; p.K = N; p.mode = 3; p.H = Hprev; p.ldh = ldh;
     return p;
+}
+
+// The first (unfused) kernel chain for layers 2-3 and the loss: kept as the A/B reference of ppo_mid_kernel (DART_PPO_UNFUSED=1).
+int backward_unfused(dart_ppo* h, int M, const float* act, const float* old_logp, const float* adv, const float* ret,
+                     cudaStream_t st, int* loss_blocks_out, int* splits_small_out) {
+    int rc;
+    const dart_ppo_cfg& c = h->cfg;
+    const float* P = h->param;
+    const int loss_blocks = (M + LOSS_T - 1) / LOSS_T;
+    LossArgs la;
+    la.M = M; la.mean = h->mean; la.value = h->value; la.act = act; la.old_logp = old_logp; la.adv = adv; la.ret = ret;
+    la.log_std = P + OFF_LS; la.ls_min = (float)c.log_std_min; la.ls_max = (float)c.log_std_max;
+    la.clip_eps = (float)c.clip_eps; la.vf_coef = (float)c.vf_coef; la.dmean = h->dmean; la.dvalue = h->dvalue;
+    la.part = h->loss_part;
+    ppo_loss_kernel<<<loss_blocks, LOSS_T, 0, st>>>(la);
+    h->launches += 1;
+    if (cudaGetLastError() != cudaSuccess) return DART_ERR_CUDA;
+
+    // backward: weight gradients split over the minibatch, data gradients with the fused tanh'
+    int splits_small = (M + 63) / 64;
+    if (splits_small > MAX_SPLITS_SMALL) splits_small = MAX_SPLITS_SMALL;
+    int kchunk_small = (M + splits_small - 1) / splits_small;
+    kchunk_small = (kchunk_small + BK - 1) / BK * BK;
+    float* ps = h->part_small;                        // layers 2-3 block: flat offsets relative to NPB
+    GemmGroup gw;
+    memset(&gw, 0, sizeof(gw));
+    gw.count = 2; gw.splits = splits_small; gw.kchunk = kchunk_small; gw.split_stride = NPS_LD;
+    GemmGroup gd;
+    memset(&gd, 0, sizeof(gd));
+    gd.count = 2; gd.splits = 1; gd.split_stride = 0;
+    // layer 3
+    gw.p[0] = wgrad_prob(h->dmean, ACT, h->h2, H2W, ps, OFF_W3A - NPB, M, ACT, HID);
+    gw.p[1] = wgrad_prob(h->dvalue, 1, h->h2 + HID, H2W, ps, OFF_W3C - NPB, M, 1, HID);
+    if ((rc = launch_group(h, gw, ACT, HID, st)) != DART_OK) return rc;
+    gd.kchunk = ACT;
+    gd.p[0] = dgrad_prob(h->dmean, ACT, P + OFF_W3A, h->dz2, H2W, h->h2, H2W, M, ACT, HID);
+    gd.p[1] = dgrad_prob(h->dvalue, 1, P + OFF_W3C, h->dz2 + HID, H2W, h->h2 + HID, H2W, M, 1, HID);
+    if ((rc = launch_group(h, gd, M, HID, st)) != DART_OK) return rc;
+    // layer 2
+    gw.p[0] = wgrad_prob(h->dz2, H2W, h->h1, H2W, ps, OFF_W2A - NPB, M, HID, HID);
+    gw.p[1] = wgrad_prob(h->dz2 + HID, H2W, h->h1 + HID, H2W, ps, OFF_W2C - NPB, M, HID, HID);
+    if ((rc = launch_group(h, gw, HID, HID, st)) != DART_OK) return rc;
+    gd.kchunk = HID;
+    gd.p[0] = dgrad_prob(h->dz2, H2W, P + OFF_W2A, h->dz1, H2W, h->h1, H2W, M, HID, HID);
+    gd.p[1] = dgrad_prob(h->dz2 + HID, H2W, P + OFF_W2C, h->dz1 + HID, H2W, h->h1 + HID, H2W, M, HID, HID);
+    if ((rc = launch_group(h, gd, M, HID, st)) != DART_OK) return rc;
+    *loss_blocks_out = loss_blocks; *splits_small_out = splits_small;
+    return DART_OK;
 }
 
 void free_all(dart_ppo* h) {
@@ -637,7 +979,8 @@ extern "C" int dart_ppo_create(dart_ppo_handle* out, int device, int32_t obs_dim
     if (!h) return DART_ERR_ALLOC;
     memset(h, 0, sizeof(*h));
     h->device = device; h->capacity = capacity; h->cfg = *cfg;
-    h->loss_blocks_cap = (capacity + LOSS_T - 1) / LOSS_T;
+    h->loss_blocks_cap = (capacity + MS - 1) / MS;          // the fused path has one loss row per 64-sample tile
+    h->fused = getenv("DART_PPO_UNFUSED") ? 0 : 1;         // A/B switch: the first, unfused kernel chain
     const size_t cap = (size_t)capacity;
     struct { void** p; size_t bytes; } al[] = {
         {(void**)&h->param, NP * sizeof(float)}, {(void**)&h->grad, NP * sizeof(float)},
@@ -649,7 +992,7 @@ extern "C" int dart_ppo_create(dart_ppo_handle* out, int device, int32_t obs_dim
         {(void**)&h->mb_obs, cap * OBS * sizeof(float)}, {(void**)&h->mb_act, cap * ACT * sizeof(float)},
         {(void**)&h->mb_logp, cap * sizeof(float)}, {(void**)&h->mb_adv, cap * sizeof(float)},
         {(void**)&h->mb_ret, cap * sizeof(float)}, {(void**)&h->part, (size_t)MAX_SPLITS * NPB * sizeof(float)},
-        {(void**)&h->part_small, (size_t)MAX_SPLITS_SMALL * NPS * sizeof(float)},
+        {(void**)&h->part_small, (size_t)(h->loss_blocks_cap > MAX_SPLITS_SMALL ? h->loss_blocks_cap : MAX_SPLITS_SMALL) * NPS_LD * sizeof(float)},
         {(void**)&h->loss_part, (size_t)h->loss_blocks_cap * LOSS_W * sizeof(double)},
         {(void**)&h->normpart, (size_t)((NP + 255) / 256) * sizeof(double)}};
     int rc = DART_OK;
@@ -658,6 +1001,8 @@ extern "C" int dart_ppo_create(dart_ppo_handle* out, int device, int32_t obs_dim
         if (cudaMemset(*a.p, 0, a.bytes) != cudaSuccess) { rc = DART_ERR_CUDA; break; }
     }
     if (rc == DART_OK && cudaMemcpy(h->param, params_host, NP * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess)
+        rc = DART_ERR_CUDA;
+    if (rc == DART_OK && cudaFuncSetAttribute(ppo_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MID_SMEM) != cudaSuccess)
         rc = DART_ERR_CUDA;
     if (rc != DART_OK) { cudaGetLastError(); free_all(h); delete h; return rc; }
     *out = h;
@@ -758,56 +1103,40 @@ extern "C" int dart_ppo_update(dart_ppo_handle h, int32_t M, const int64_t* idx,
         h->launches += 1;
         obs = h->mb_obs; act = h->mb_act; old_logp = h->mb_logp; adv = h->mb_adv; ret = h->mb_ret;
     }
-    int rc = forward(h, M, obs, st);
+    int rc = forward(h, M, obs, st, /*with_tail=*/!h->fused);
     if (rc != DART_OK) return rc;
     const float* P = h->param;
-    const int loss_blocks = (M + LOSS_T - 1) / LOSS_T;
-    LossArgs la;
-    la.M = M; la.mean = h->mean; la.value = h->value; la.act = act; la.old_logp = old_logp; la.adv = adv; la.ret = ret;
-    la.log_std = P + OFF_LS; la.ls_min = (float)c.log_std_min; la.ls_max = (float)c.log_std_max;
-    la.clip_eps = (float)c.clip_eps; la.vf_coef = (float)c.vf_coef; la.dmean = h->dmean; la.dvalue = h->dvalue;
-    la.part = h->loss_part;
-    ppo_loss_kernel<<<loss_blocks, LOSS_T, 0, st>>>(la);
-    h->launches += 1;
-    if (cudaGetLastError() != cudaSuccess) return DART_ERR_CUDA;
-
-    // backward: weight gradients split over the minibatch, data gradients with the fused tanh'
-    int splits = (M + 255) / 256;
+    int loss_blocks, splits, kchunk, splits_small;
+    splits = (M + 255) / 256;
     if (splits > MAX_SPLITS) splits = MAX_SPLITS;
-    int kchunk = (M + splits - 1) / splits;
+    kchunk = (M + splits - 1) / splits;
     kchunk = (kchunk + BK - 1) / BK * BK;
-    int splits_small = (M + 63) / 64;
-    if (splits_small > MAX_SPLITS_SMALL) splits_small = MAX_SPLITS_SMALL;
-    int kchunk_small = (M + splits_small - 1) / splits_small;
-    kchunk_small = (kchunk_small + BK - 1) / BK * BK;
-    float* ps = h->part_small;                        // layers 2-3 block: flat offsets relative to NPB
-    GemmGroup gw;
-    memset(&gw, 0, sizeof(gw));
-    gw.count = 2; gw.splits = splits_small; gw.kchunk = kchunk_small; gw.split_stride = NPS;
-    GemmGroup gd;
-    memset(&gd, 0, sizeof(gd));
-    gd.count = 2; gd.splits = 1; gd.split_stride = 0;
-    // layer 3
-    gw.p[0] = wgrad_prob(h->dmean, ACT, h->h2, H2W, ps, OFF_W3A - NPB, M, ACT, HID);
-    gw.p[1] = wgrad_prob(h->dvalue, 1, h->h2 + HID, H2W, ps, OFF_W3C - NPB, M, 1, HID);
-    if ((rc = launch_group(h, gw, ACT, HID, st)) != DART_OK) return rc;
-    gd.kchunk = ACT;
-    gd.p[0] = dgrad_prob(h->dmean, ACT, P + OFF_W3A, h->dz2, H2W, h->h2, H2W, M, ACT, HID);
-    gd.p[1] = dgrad_prob(h->dvalue, 1, P + OFF_W3C, h->dz2 + HID, H2W, h->h2 + HID, H2W, M, 1, HID);
-    if ((rc = launch_group(h, gd, M, HID, st)) != DART_OK) return rc;
-    // layer 2
-    gw.p[0] = wgrad_prob(h->dz2, H2W, h->h1, H2W, ps, OFF_W2A - NPB, M, HID, HID);
-    gw.p[1] = wgrad_prob(h->dz2 + HID, H2W, h->h1 + HID, H2W, ps, OFF_W2C - NPB, M, HID, HID);
-    if ((rc = launch_group(h, gw, HID, HID, st)) != DART_OK) return rc;
-    gd.kchunk = HID;
-    gd.p[0] = dgrad_prob(h->dz2, H2W, P + OFF_W2A, h->dz1, H2W, h->h1, H2W, M, HID, HID);
-    gd.p[1] = dgrad_prob(h->dz2 + HID, H2W, P + OFF_W2C, h->dz1 + HID, H2W, h->h1 + HID, H2W, M, HID, HID);
-    if ((rc = launch_group(h, gd, M, HID, st)) != DART_OK) return rc;
-    // layer 1 (both networks at once: dz1 is [M,128])
-    gw.count = 1; gw.splits = splits; gw.kchunk = kchunk; gw.split_stride = NPB;
-    gw.p[0] = wgrad_prob(h->dz1, H2W, obs, OBS, h->part, OFF_W1, M, H2W, OBS);
-    rc = M >= BIG_MIN_ROWS ? launch_big(h, gw.p[0], splits, kchunk, NPB, st) : launch_group(h, gw, H2W, OBS, st);
-    if (rc != DART_OK) return rc;
+    const float ls_min = (float)c.log_std_min, ls_max = (float)c.log_std_max;
+    if (h->fused) {
+        const int tiles = (M + MS - 1) / MS;
+        MidArgs ma;
+        memset(&ma, 0, sizeof(ma));
+        ma.M = M; ma.backward = 1; ma.h1 = h->h1; ma.P = P; ma.act = act; ma.old_logp = old_logp; ma.adv = adv; ma.ret = ret;
+        ma.ls_min = ls_min; ma.ls_max = ls_max; ma.clip_eps = (float)c.clip_eps; ma.vf_coef = (float)c.vf_coef;
+        ma.mean = h->mean; ma.value = h->value; ma.dz1 = h->dz1; ma.part_small = h->part_small; ma.loss_part = h->loss_part;
+        ppo_mid_kernel<<<tiles, GT, MID_SMEM, st>>>(ma);
+        h->launches += 1;
+        if (cudaGetLastError() != cudaSuccess) return DART_ERR_CUDA;
+        loss_blocks = tiles; splits_small = tiles;
+    } else {
+        rc = backward_unfused(h, M, act, old_logp, adv, ret, st, &loss_blocks, &splits_small);
+        if (rc != DART_OK) return rc;
+    }
+    {   // layer 1 (both networks at once: dz1 is [M,128])
+        GemmGroup gw;
+        memset(&gw, 0, sizeof(gw));
+        gw.count = 1; gw.splits = splits; gw.kchunk = kchunk; gw.split_stride = NPB;
+        gw.p[0] = wgrad_prob(h->dz1, H2W, obs, OBS, h->part, OFF_W1, M, H2W, OBS);
+        rc = M >= BIG_MIN_ROWS ? launch_big(h, gw.p[0], splits, kchunk, NPB, st) : launch_group(h, gw, H2W, OBS, st);
+        if (rc != DART_OK) return rc;
+    }
+    LossArgs la;            // (only the clamp bounds are read below)
+    la.ls_min = ls_min; la.ls_max = ls_max; la.vf_coef = (float)c.vf_coef;
 
     const int nred = (NP + 255) / 256;
     ReduceArgs ra;

@@ -205,7 +205,7 @@ def test_train_rollout_improves_surrogate_and_checkpoint_roundtrip(built, tmp_pa
     flat = (obs.reshape(-1, 520), act.reshape(-1, 34), logp.reshape(-1), adv.reshape(-1), ret.reshape(-1))
     v0 = float(tr.update_minibatch(*[f[:1024].contiguous() for f in flat], apply=False)[1])
     steps = tr.train_rollout(obs, act, logp, rew, val, done, last, generator=g)
-    assert steps == 4 * (T * B // 1024) and tr.launch_count > steps * 10
+    assert steps == 4 * (T * B // 1024) and tr.launch_count >= steps * 5   # gather + 5 kernels per step
     v1 = float(tr.update_minibatch(*[f[:1024].contiguous() for f in flat], apply=False)[1])
     assert v1 < 0.8 * v0, (v0, v1)
     path = str(tmp_path / "best_agent.pth")
@@ -274,3 +274,26 @@ def test_closed_loop_training_runs_and_matches_step_semantics(built):
     assert all(np.abs(p1[k] - p0[k]).max() > 0 for k in p0)         # every tensor was trained
     assert np.isfinite(x.cpu().numpy()).all() and (ctl.status.cpu().numpy() != dart_b200.STATUS_NUMERIC).all()
     ctl.engine.close(); ctl.policy.close(); ppo.close()
+
+
+@pytest.mark.parametrize("M", [37, 1000])
+def test_fused_tile_kernel_matches_unfused_chain(built, M, monkeypatch):
+    """ppo_mid_kernel (layers 2-3 + loss + gradients per 64-sample tile) against the first, unfused GEMM chain
+    (DART_PPO_UNFUSED=1): same arithmetic per element, different summation grouping over the samples."""
+    pol = _perturbed_policy()
+    obs, eps, action, logp, value, mean, old_logp, adv, ret = _rollout(M, M + 3, pol)
+    d = [t.cuda() for t in (obs, action, old_logp, adv, ret)]
+    grads, stats = [], []
+    for unfused in (False, True):
+        if unfused:
+            monkeypatch.setenv("DART_PPO_UNFUSED", "1")
+        else:
+            monkeypatch.delenv("DART_PPO_UNFUSED", raising=False)
+        tr = dart_b200.PPOTrainer(capacity=M, state_dict=pol.state_dict())
+        stats.append(tr.update_minibatch(*d, apply=False).cpu().numpy().copy())
+        grads.append(tr.gradient())
+        tr.close()
+    assert np.abs(stats[0][:3] - stats[1][:3]).max() <= 1e-6 * max(1.0, np.abs(stats[1][:3]).max())
+    for k in grads[0]:
+        ref = grads[1][k]
+        assert np.abs(grads[0][k] - ref).max() <= 1e-7 + 2e-5 * np.abs(ref).max(), k
