@@ -796,7 +796,7 @@ __global__ void __launch_bounds__(256) ppo_adam_kernel(const AdamArgs a) {
 }  // namespace
 
 struct dart_ppo {
-    int device, capacity, splits_cap, loss_blocks_cap, fused;
+    int device, capacity, splits_cap, loss_blocks_cap, fused, sms;
     dart_ppo_cfg cfg;
     float *param, *grad, *m, *v;         // [NP]
     float *h1, *h2, *dz1, *dz2;          // [capacity, 128]
@@ -980,6 +980,7 @@ extern "C" int dart_ppo_create(dart_ppo_handle* out, int device, int32_t obs_dim
     memset(h, 0, sizeof(*h));
     h->device = device; h->capacity = capacity; h->cfg = *cfg;
     h->loss_blocks_cap = (capacity + MS - 1) / MS;          // the fused path has one loss row per 64-sample tile
+    cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, device);
     h->fused = getenv("DART_PPO_UNFUSED") ? 0 : 1;         // A/B switch: the first, unfused kernel chain
     const size_t cap = (size_t)capacity;
     struct { void** p; size_t bytes; } al[] = {
@@ -1108,9 +1109,15 @@ extern "C" int dart_ppo_update(dart_ppo_handle h, int32_t M, const int64_t* idx,
     const float* P = h->param;
     int loss_blocks, splits, kchunk, splits_small;
     splits = (M + 255) / 256;
-    if (splits > MAX_SPLITS) splits = MAX_SPLITS;
+    int max_splits = MAX_SPLITS;
+    if (M >= BIG_MIN_ROWS) {              // 5 column tiles x splits CTAs, two per SM: keep them to a single wave
+        const int fit = (2 * h->sms) / ((OBS + TN - 1) / TN);
+        if (fit >= 1 && fit < max_splits) max_splits = fit;
+    }
+    if (splits > max_splits) splits = max_splits;
     kchunk = (M + splits - 1) / splits;
     kchunk = (kchunk + BK - 1) / BK * BK;
+    splits = (M + kchunk - 1) / kchunk;
     const float ls_min = (float)c.log_std_min, ls_max = (float)c.log_std_max;
     if (h->fused) {
         const int tiles = (M + MS - 1) / MS;
