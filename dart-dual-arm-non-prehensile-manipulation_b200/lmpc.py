@@ -286,6 +286,30 @@ class RLMPC:
                                 warm_start=params.get("warm_start", True), **dict(params.get("solver_options", {})))
         self.views["model_params"][:] = k0
         self.loss = np.zeros(1)
+        # Training mode (rlmpc2.py:563-578, train=True is the packet default): the RL worker's PPO learner runs on the device and
+        # the action applied to the model parameters is its sample, not the mean.  With train=False and no checkpoint the
+        # reference silently switches to training; here that case evaluates the freshly initialised policy (deterministic).
+        self.training = bool(params.get("train", True))
+        self._trainer = self._ppo = None
+        self.episode_return, self.episode_count, self.best_return = 0.0, 0, -float("inf")
+        self.views["in_contact"][:] = 1.0
+        if self.training:
+            from .ppo import LMPCTrainer, PPOTrainer
+            torch = _torch()
+            pk = lambda k, d: params.get(k, d)
+            tl = pk("tray_limit", [0.2, 0.15])
+            self._ppo = PPOTrainer(capacity=max(1, int(pk("mini_batch_size", 64))), seed=pk("policy_seed", 3), device=device,
+                                   lr=pk("lr", pk("learning_rate", 3e-4)), weight_decay=pk("weight_decay", 1e-5),
+                                   clip_eps=pk("clip_eps", 0.2), vf_coef=pk("vf_coef", 0.25), ent_coef=pk("ent_coef", 0.01),
+                                   epochs=pk("epochs", 8), mini_batch_size=pk("mini_batch_size", 64), gamma=pk("gamma", 0.99),
+                                   gae_lambda=pk("gae_lambda", 0.95), policy_std_init=pk("policy_std_init", 0.1),
+                                   reward_cfg=dict(max_delta=pk("max_delta_abs", 0.1), action_scale=pk("action_scale", 1.0),
+                                                   max_per_dim_rms=pk("max_per_dim_rms", 0.5), w_pos=pk("w_pos", 1.0), w_vel=pk("w_vel", 0.1),
+                                                   w_change=pk("w_change", 1e-3), w_d_ctrl=pk("w_d_ctrl", 5.0), tray_limit=tl,
+                                                   max_episode_steps=int(pk("max_episode_steps", 10000))))
+            gen = torch.Generator(device=self._batch.dev)
+            gen.manual_seed(int(pk("seed", 0) or 0))
+            self._trainer = LMPCTrainer(self._batch, self._ppo, rollout_len=int(pk("rollout_len", 2048)), record_every=8, generator=gen)
 
     def rebind(self, model, data):
         self.setup(model, data, self.params)
@@ -317,7 +341,14 @@ class RLMPC:
         self.views["target"][:] = target
         dev = self._batch.dev
         t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)[None, :]).to(dev)
-        u0 = self._batch.step(t(state), t(target)).cpu().numpy()[0]
+        if self._trainer is not None:
+            u0_t, rew, done = self._trainer.step(t(state), t(target), in_contact=torch.from_numpy(self.views["in_contact"].copy()).to(dev))
+            u0 = u0_t.cpu().numpy()[0]
+            self.episode_return += float(rew[0])
+            if bool(done[0]):
+                self._episode_end()
+        else:
+            u0 = self._batch.step(t(state), t(target)).cpu().numpy()[0]
         self.last_control = u0.astype(np.float64)
         self.loss = self._batch.J.cpu().numpy().copy()
         self.views["w_opt"][:] = self._batch.w.cpu().numpy()[0]
@@ -326,8 +357,23 @@ class RLMPC:
         self.views["model_params"][:] = self._batch.pvec.cpu().numpy()[0]
         return self.last_control.copy(), self.loss
 
+    def _episode_end(self):
+        """rlmpc2.py:900-926: count the episode, checkpoint (latest always, best on a new best return), ask the caller for a reset."""
+        self.episode_count += 1
+        os.makedirs(self.checkpoint_dir, exist_ok=True)
+        meta = {"episode": self.episode_count, "return": self.episode_return, "episode number": self.episode_count}
+        if self.episode_return > self.best_return:
+            self.best_return = self.episode_return
+            self._ppo.save(os.path.join(self.checkpoint_dir, "best_agent.pth"), **meta)
+        self._ppo.save(os.path.join(self.checkpoint_dir, "latest_agent.pth"), **meta)
+        self.events["reset"].set()
+        self.episode_return = 0.0
+
     def close(self):
         self.events["terminate"].set()
+        if getattr(self, "_ppo", None) is not None:
+            self._ppo.close()
+            self._ppo = self._trainer = None
         if getattr(self, "_batch", None) is not None:
             self._batch.engine.close()
             self._batch.policy.close()

@@ -9,6 +9,8 @@ Tolerances (FP32 arithmetic on both sides, different summation orders):
                                              summation-order noise into a fraction of one step)
   GAE / reward / normalisation               1e-5 relative
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -297,3 +299,41 @@ def test_fused_tile_kernel_matches_unfused_chain(built, M, monkeypatch):
     for k in grads[0]:
         ref = grads[1][k]
         assert np.abs(grads[0][k] - ref).max() <= 1e-7 + 2e-5 * np.abs(ref).max(), k
+
+
+def test_rlmpc_facade_training_mode(built, tmp_path):
+    """RLMPC(model, data, {"train": True, ...}) as run.py builds it: sampled actions, rollout of `rollout_len` transitions (one per 8
+    control steps), PPO update, checkpoints in the reference's format when an episode ends, reset request to the caller."""
+    import torch
+    model = dart_b200.GravityModel(-9.81, 0.002); data = dart_b200.StateHolder()
+    b = data.body("cube2"); b.xmat = np.eye(3).reshape(-1); b.xpos[:] = [0.01, -0.02, 0.43]
+    ckdir = str(tmp_path / "ckpt")
+    params = {"Ts": 0.002, "nx": 8, "nu": 2, "N": 20, "Q": [200.0, 2.0, 200.0, 2.0, 0, 0, 0, 0], "Qt": [200.0, 2.0, 200.0, 2.0, 0, 0, 0, 0],
+              "R": [0.1, 0.1, 1.0, 1.0], "u_bounds": (-0.4, 0.4), "body_name": "cube2", "g": 9.81, "max_param_abs": 2.0,
+              "max_delta_abs": 0.02, "train": True, "seed": 0, "checkpoint_dir": ckdir, "rollout_len": 3, "epochs": 2,
+              "mini_batch_size": 2, "max_episode_steps": 30, "w_pos": 40.0}
+    with dart_b200.RLMPC(model, data, params) as ctl:
+        assert ctl.training and ctl._trainer is not None
+        p0 = ctl._ppo.state_dict()
+        tgt = np.array([0.05, 0, 0.05, 0, 0, 0, 0, 0])
+        k0 = ctl.views["model_params"].copy()
+        for step in range(30):
+            u, loss = ctl.solve(tgt)
+            assert u.shape == (2,) and np.all(np.abs(u) <= 0.4 + 1e-12)
+            if step == 0:
+                assert not np.array_equal(ctl.views["model_params"], k0)       # the sampled action moved the parameters
+        assert ctl._trainer.updates == 2 * 2                        # one rollout of 3 transitions -> 2 epochs x 2 minibatches (2 + 1)
+        assert ctl.events["reset"].is_set() and ctl.episode_count == 1   # max_episode_steps reached at the 30th step
+        p1 = ctl._ppo.state_dict()
+        assert any(np.abs(p1[k] - p0[k]).max() > 0 for k in p0)
+    for name in ("best_agent.pth", "latest_agent.pth"):
+        ck = torch.load(os.path.join(ckdir, name), map_location="cpu", weights_only=True)
+        pol = oppo.Policy()
+        pol.load_state_dict(ck["model"])
+        assert ck["episode"] == 1 and all(np.array_equal(ck["model"][k].numpy(), p1[k]) for k in p1)
+    # evaluation run picks the trained actor up from the checkpoint directory, as the reference does (rlmpc2.py:567-573)
+    params_eval = dict(params, train=False)
+    with dart_b200.RLMPC(model, data, params_eval) as ev:
+        assert not ev.training
+        W = ev._batch.policy.weights[0][0]
+        assert np.array_equal(W, p1["mean_net.0.weight"])
