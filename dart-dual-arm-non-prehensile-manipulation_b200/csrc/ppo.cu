@@ -735,6 +735,7 @@ struct ReduceArgs {
     float* grad;             // [NP]
     double* normpart;        // [gridDim.x]
     float* stats;            // [4] policy loss, value loss, entropy, (grad norm: written by the Adam kernel)
+    long long* step_inc;     // optimiser step counter on the device, advanced here when an Adam launch follows (else nullptr)
 };
 __global__ void __launch_bounds__(256) ppo_grad_reduce_kernel(const ReduceArgs a) {
     __shared__ double sh[256];
@@ -755,6 +756,7 @@ __global__ void __launch_bounds__(256) ppo_grad_reduce_kernel(const ReduceArgs a
     if (j < NP) a.grad[j] = g;
     const double ss = block_sum(j < NP ? (double)g * (double)g : 0.0, sh);
     if (threadIdx.x == 0) a.normpart[blockIdx.x] = ss;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.step_inc) *a.step_inc += 1;
     if (blockIdx.x == 0 && threadIdx.x == 0 && a.stats) {
         double pl = 0.0, vl = 0.0, ent = 0.0;
         for (int b = 0; b < a.loss_blocks; ++b) { pl += a.loss_part[(size_t)b * LOSS_W]; vl += a.loss_part[(size_t)b * LOSS_W + 1]; }
@@ -771,7 +773,9 @@ struct AdamArgs {
     const double* normpart;
     const float* grad;
     float *param, *m, *v;
-    float max_norm, wd, beta1, beta2, eps, step_size, bc2_sqrt;
+    float max_norm, wd, beta1, beta2, eps;
+    double lr, beta1d, beta2d;
+    const long long* step;   // device-resident step count (already advanced for this step): keeps the launch replayable from a CUDA graph
     float* stats;
 };
 __global__ void __launch_bounds__(256) ppo_adam_kernel(const AdamArgs a) {
@@ -780,6 +784,13 @@ __global__ void __launch_bounds__(256) ppo_adam_kernel(const AdamArgs a) {
     for (int i = threadIdx.x; i < a.nparts; i += 256) s += a.normpart[i];
     const float gnorm = (float)sqrt(block_sum(s, sh));
     const float coef = fminf(a.max_norm / (gnorm + 1e-6f), 1.f);
+    __shared__ float s_step_size, s_bc2_sqrt;
+    if (threadIdx.x == 0) {               // torch computes these in Python floats (double) and applies them in FP32
+        const double st = (double)*a.step;
+        s_step_size = (float)(a.lr / (1.0 - pow(a.beta1d, st)));
+        s_bc2_sqrt = (float)sqrt(1.0 - pow(a.beta2d, st));
+    }
+    __syncthreads();
     if (blockIdx.x == 0 && threadIdx.x == 0 && a.stats) a.stats[3] = gnorm;
     const int j = blockIdx.x * 256 + threadIdx.x;
     if (j >= NP) return;
@@ -789,8 +800,8 @@ __global__ void __launch_bounds__(256) ppo_adam_kernel(const AdamArgs a) {
     const float v = fmaf(1.f - a.beta2, g * g, a.v[j] * a.beta2);
     a.m[j] = m;
     a.v[j] = v;
-    const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
-    a.param[j] = p - a.step_size * (m / denom);
+    const float denom = sqrtf(v) / s_bc2_sqrt + a.eps;
+    a.param[j] = p - s_step_size * (m / denom);
 }
 
 }  // namespace
@@ -804,7 +815,8 @@ struct dart_ppo {
     float *mb_obs, *mb_act, *mb_logp, *mb_adv, *mb_ret;
     float *part, *part_small;            // [MAX_SPLITS, NPB], [MAX_SPLITS_SMALL, NPS]
     double *loss_part, *normpart;
-    int64_t step, launches;
+    long long* step_dev;                 // optimiser step count, on the device
+    int64_t launches;
 };
 
 namespace {
@@ -932,7 +944,7 @@ int backward_unfused(dart_ppo* h, int M, const float* act, const float* old_logp
 
 void free_all(dart_ppo* h) {
     void* p[] = {h->param, h->grad, h->m, h->v, h->h1, h->h2, h->dz1, h->dz2, h->mean, h->value, h->dmean, h->dvalue,
-                 h->mb_obs, h->mb_act, h->mb_logp, h->mb_adv, h->mb_ret, h->part, h->part_small, h->loss_part, h->normpart};
+                 h->mb_obs, h->mb_act, h->mb_logp, h->mb_adv, h->mb_ret, h->part, h->part_small, h->loss_part, h->normpart, h->step_dev};
     for (void* q : p) if (q) cudaFree(q);
 }
 
@@ -995,7 +1007,7 @@ extern "C" int dart_ppo_create(dart_ppo_handle* out, int device, int32_t obs_dim
         {(void**)&h->mb_ret, cap * sizeof(float)}, {(void**)&h->part, (size_t)MAX_SPLITS * NPB * sizeof(float)},
         {(void**)&h->part_small, (size_t)(h->loss_blocks_cap > MAX_SPLITS_SMALL ? h->loss_blocks_cap : MAX_SPLITS_SMALL) * NPS_LD * sizeof(float)},
         {(void**)&h->loss_part, (size_t)h->loss_blocks_cap * LOSS_W * sizeof(double)},
-        {(void**)&h->normpart, (size_t)((NP + 255) / 256) * sizeof(double)}};
+        {(void**)&h->normpart, (size_t)((NP + 255) / 256) * sizeof(double)}, {(void**)&h->step_dev, sizeof(long long)}};
     int rc = DART_OK;
     for (auto& a : al) {
         if (cudaMalloc(a.p, a.bytes) != cudaSuccess) { *a.p = nullptr; rc = DART_ERR_ALLOC; break; }
@@ -1019,7 +1031,9 @@ extern "C" int dart_ppo_get_state(dart_ppo_handle h, float* params_host, float* 
         (m_host && cudaMemcpy(m_host, h->m, n, cudaMemcpyDeviceToHost) != cudaSuccess) ||
         (v_host && cudaMemcpy(v_host, h->v, n, cudaMemcpyDeviceToHost) != cudaSuccess))
         return DART_ERR_CUDA;
-    if (step) *step = h->step;
+    long long st = 0;
+    if (cudaMemcpy(&st, h->step_dev, sizeof(st), cudaMemcpyDeviceToHost) != cudaSuccess) return DART_ERR_CUDA;
+    if (step) *step = (int64_t)st;
     return DART_OK;
 }
 
@@ -1033,8 +1047,8 @@ extern "C" int dart_ppo_set_state(dart_ppo_handle h, const float* params_host, c
         (m_host && cudaMemcpy(h->m, m_host, n, cudaMemcpyHostToDevice) != cudaSuccess) ||
         (v_host && cudaMemcpy(h->v, v_host, n, cudaMemcpyHostToDevice) != cudaSuccess))
         return DART_ERR_CUDA;
-    h->step = step;
-    return DART_OK;
+    const long long st = (long long)step;
+    return cudaMemcpy(h->step_dev, &st, sizeof(st), cudaMemcpyHostToDevice) == cudaSuccess ? DART_OK : DART_ERR_CUDA;
 }
 
 extern "C" int dart_ppo_get_grad(dart_ppo_handle h, float* grad_host) {
@@ -1151,17 +1165,16 @@ extern "C" int dart_ppo_update(dart_ppo_handle h, int32_t M, const int64_t* idx,
     ra.part_small = h->part_small; ra.loss_part = h->loss_part;
     ra.log_std = P + OFF_LS; ra.ls_min = la.ls_min; ra.ls_max = la.ls_max; ra.ent_coef = (float)c.ent_coef;
     ra.vf_coef = la.vf_coef; ra.grad = h->grad; ra.normpart = h->normpart; ra.stats = stats;
+    ra.step_inc = apply ? h->step_dev : nullptr;
     ppo_grad_reduce_kernel<<<nred, 256, 0, st>>>(ra);
     h->launches += 1;
     if (cudaGetLastError() != cudaSuccess) return DART_ERR_CUDA;
     if (!apply) return DART_OK;
 
-    h->step += 1;
-    const double bc1 = 1.0 - pow(c.beta1, (double)h->step), bc2 = 1.0 - pow(c.beta2, (double)h->step);
     AdamArgs aa;
     aa.nparts = nred; aa.normpart = h->normpart; aa.grad = h->grad; aa.param = h->param; aa.m = h->m; aa.v = h->v;
     aa.max_norm = (float)c.max_grad_norm; aa.wd = (float)c.weight_decay; aa.beta1 = (float)c.beta1; aa.beta2 = (float)c.beta2;
-    aa.eps = (float)c.adam_eps; aa.step_size = (float)(c.lr / bc1); aa.bc2_sqrt = (float)sqrt(bc2); aa.stats = stats;
+    aa.eps = (float)c.adam_eps; aa.lr = c.lr; aa.beta1d = c.beta1; aa.beta2d = c.beta2; aa.step = h->step_dev; aa.stats = stats;
     ppo_adam_kernel<<<nred, 256, 0, st>>>(aa);
     h->launches += 1;
     return cudaGetLastError() == cudaSuccess ? DART_OK : DART_ERR_CUDA;

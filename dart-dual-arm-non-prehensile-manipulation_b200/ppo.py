@@ -129,6 +129,7 @@ class PPOTrainer:
         check(self._lib.dart_ppo_create(C.byref(self._h), self.device, OBS_DIM, HIDDEN, ACT_DIM, self.capacity,
                                         C.c_void_p(flat.ctypes.data), C.byref(cfg)), "dart_ppo_create")
         self.stats = self.torch.zeros(4, dtype=self.torch.float32, device=self.dev)
+        self._graphs, self._gae_buf, self.graph_replays = {}, None, 0
 
     # ---- plumbing ----
     def _stream(self):
@@ -175,17 +176,6 @@ class PPOTrainer:
                                         C.c_void_p(done.data_ptr()), self._stream()), "dart_ppo_reward")
         return rew, done
 
-    def gae(self, rewards, values, dones, last_value):
-        """[T,B] f32 rollouts -> (advantages, returns), both [T,B], un-normalised."""
-        torch, f32 = self.torch, self.torch.float32
-        T, B = rewards.shape
-        adv, ret = torch.empty_like(rewards), torch.empty_like(rewards)
-        check(self._lib.dart_ppo_gae(B, T, self._chk(rewards, f32, (T, B), "rewards"), self._chk(values, f32, (T, B), "values"),
-                                     self._chk(dones, f32, (T, B), "dones"), self._chk(last_value, f32, (B,), "last_value"),
-                                     self.gamma, self.gae_lambda, C.c_void_p(adv.data_ptr()), C.c_void_p(ret.data_ptr()),
-                                     self._stream()), "dart_ppo_gae")
-        return adv, ret
-
     def normalize_(self, x, ddof):
         if x.dtype != self.torch.float32 or not x.is_cuda or not x.is_contiguous():
             raise ValueError("normalize_: need a contiguous float32 CUDA tensor")
@@ -206,24 +196,76 @@ class PPOTrainer:
               "dart_ppo_update")
         return self.stats
 
-    def train_rollout(self, obs, act, logp, rewards, values, dones, last_value, generator=None):
+    def gae(self, rewards, values, dones, last_value, out=None):
+        """[T,B] f32 rollouts -> (advantages, returns), both [T,B], un-normalised (``out`` = (adv, ret) buffers to reuse)."""
+        torch, f32 = self.torch, self.torch.float32
+        T, B = rewards.shape
+        adv, ret = out if out is not None else (torch.empty_like(rewards), torch.empty_like(rewards))
+        check(self._lib.dart_ppo_gae(B, T, self._chk(rewards, f32, (T, B), "rewards"), self._chk(values, f32, (T, B), "values"),
+                                     self._chk(dones, f32, (T, B), "dones"), self._chk(last_value, f32, (B,), "last_value"),
+                                     self.gamma, self.gae_lambda, self._chk(adv, f32, (T, B), "adv"), self._chk(ret, f32, (T, B), "ret"),
+                                     self._stream()), "dart_ppo_gae")
+        return adv, ret
+
+    def _graph_for(self, flat, mb):
+        """CUDA graph of one minibatch step over the (pointer-stable) pooled rollout ``flat`` with the row indices read from a
+        static buffer.  The optimiser step count lives on the device, so the captured launches are replayable."""
+        torch = self.torch
+        key = (mb,) + tuple(t.data_ptr() for t in flat)
+        hit = self._graphs.get(key)
+        if hit is not None:
+            return hit
+        idx_buf = torch.zeros((mb,), dtype=torch.int64, device=self.dev)
+        p, m, v, step = self._get()                         # capture must not change the learner: save, warm up + capture, restore
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            self.update_minibatch(*flat, idx=idx_buf)
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.update_minibatch(*flat, idx=idx_buf)
+        torch.cuda.synchronize(self.dev)
+        cp = lambda a: C.c_void_p(a.ctypes.data)
+        check(self._lib.dart_ppo_set_state(self._h, cp(p), cp(m), cp(v), step), "dart_ppo_set_state")
+        if len(self._graphs) >= 4:
+            self._graphs.clear()
+        self._graphs[key] = (g, idx_buf)
+        return g, idx_buf
+
+    def train_rollout(self, obs, act, logp, rewards, values, dones, last_value, generator=None, graph=False):
         """The reference's update block (rlmpc2.py:777-818) on a pooled rollout: obs [T,B,520], act [T,B,34], the rest [T,B],
         last_value [B].  GAE per instance, returns normalised with the population std, advantages with the sample std,
-        then ``epochs`` passes over random minibatches.  Returns the number of optimiser steps taken."""
+        then ``epochs`` passes over random minibatches.  ``graph=True`` replays each full minibatch step from a CUDA graph
+        (one index copy + one graph launch instead of six kernel launches; same arithmetic, bitwise) -- what pays at the
+        reference's minibatch of 64, where the step is launch-bound.  Returns the number of optimiser steps taken."""
         torch = self.torch
         T, B = rewards.shape
-        adv, ret = self.gae(rewards, values, dones, last_value)
+        if graph:                                           # pointer-stable advantage / return buffers
+            if self._gae_buf is None or tuple(self._gae_buf[0].shape) != (T, B):
+                self._gae_buf = (torch.empty_like(rewards), torch.empty_like(rewards))
+            adv, ret = self.gae(rewards, values, dones, last_value, out=self._gae_buf)
+        else:
+            adv, ret = self.gae(rewards, values, dones, last_value)
         self.normalize_(ret, 0)
         self.normalize_(adv, 1)
         S = T * B
-        obs_f, act_f = obs.reshape(S, OBS_DIM), act.reshape(S, ACT_DIM)
-        logp_f, adv_f, ret_f = logp.reshape(S), adv.reshape(S), ret.reshape(S)
+        flat = (obs.reshape(S, OBS_DIM), act.reshape(S, ACT_DIM), logp.reshape(S), adv.reshape(S), ret.reshape(S))
         mb = min(self.mini_batch_size, self.capacity)
+        g = idx_buf = None
+        if graph and S >= mb:
+            g, idx_buf = self._graph_for(flat, mb)
         steps = 0
         for _ in range(self.epochs):
             perm = torch.randperm(S, device=self.dev, generator=generator)
             for start in range(0, S, mb):
-                self.update_minibatch(obs_f, act_f, logp_f, adv_f, ret_f, idx=perm[start:start + mb])
+                idx = perm[start:start + mb]
+                if g is not None and idx.shape[0] == mb:
+                    idx_buf.copy_(idx)
+                    g.replay()
+                    self.graph_replays += 1
+                else:
+                    self.update_minibatch(*flat, idx=idx)
                 steps += 1
         return steps
 
@@ -295,13 +337,13 @@ class LMPCTrainer:
     [rollout_len, B] buffer goes through ``PPOTrainer.train_rollout``.  The caller owns the plant (MuJoCo in the reference;
     ``lmpc.lmpc_plant_step`` is the surrogate) and resets the instances ``step`` reports as done."""
 
-    def __init__(self, batch, trainer, rollout_len=32, record_every=8, generator=None):
+    def __init__(self, batch, trainer, rollout_len=32, record_every=8, generator=None, graph=False):
         torch = trainer.torch
         self.batch, self.ppo = batch, trainer
         self.B, self.dev = batch.B, trainer.dev
         if trainer.capacity < self.B:
             raise ValueError("PPOTrainer capacity must cover the number of instances")
-        self.T, self.every, self.gen = int(rollout_len), int(record_every), generator
+        self.T, self.every, self.gen, self.graph = int(rollout_len), int(record_every), generator, bool(graph)
         f32, B, T = torch.float32, self.B, self.T
         self.buf_obs = torch.zeros((T, B, OBS_DIM), dtype=f32, device=self.dev)
         self.buf_act = torch.zeros((T, B, ACT_DIM), dtype=f32, device=self.dev)
@@ -337,6 +379,6 @@ class LMPCTrainer:
             if self.k == self.T:
                 self.mean_reward.append(float(self.buf_rew.mean()))
                 self.updates += self.ppo.train_rollout(self.buf_obs, self.buf_act, self.buf_logp, self.buf_rew, self.buf_val,
-                                                       self.buf_done, val.clone(), generator=self.gen)
+                                                       self.buf_done, val.clone(), generator=self.gen, graph=self.graph)
                 self.k = 0
         return u0, rew, done

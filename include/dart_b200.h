@@ -302,7 +302,8 @@ int dart_ppo_normalize(int64_t n, float* x, int32_t ddof, void* stream);
 /* One minibatch step (rlmpc2.py:797-817): forward of both networks, clipped-surrogate + vf_coef * MSE - ent_coef * entropy,
  * backward, clip_grad_norm_, Adam.  idx [M] int64 (nullable) gathers the minibatch rows from obs [*,520] (16-byte
  * aligned), act [*,34], old_logp, adv, ret [*].  apply = 0 computes the gradient only.  stats [4] (nullable, device) =
- * policy loss, value loss, entropy, gradient norm before clipping.  Results are bitwise repeatable. */
+ * policy loss, value loss, entropy, gradient norm before clipping.  Results are bitwise repeatable.  The optimiser step
+ * count lives on the device and no argument changes from step to step, so the launches may be captured in a CUDA graph. */
 int dart_ppo_update(dart_ppo_handle h, int32_t M, const int64_t* idx, const float* obs, const float* act,
                     const float* old_logp, const float* adv, const float* ret, int32_t apply, float* stats, void* stream);
 

@@ -72,3 +72,33 @@ for _ in range(7):
     a.record(); tr.act(obs, eps); b.record(); torch.cuda.synchronize()
     ts.append(a.elapsed_time(b))
 print(json.dumps(dict(kernel="dart_ppo_act", B=B, ms=round(float(np.median(ts)), 4))), flush=True)
+
+# the reference's update block at its own sizes (rollout_len 2048, mini_batch_size 64, epochs 16 -> 512 optimiser steps): eager launches
+# against CUDA-graph replay of the minibatch step, and torch on the host cores
+T = 2048
+g = torch.Generator(device="cuda").manual_seed(0)
+obs = torch.randn(T, 1, 520, device=dev, generator=g); eps = torch.randn(T, 1, 34, device=dev, generator=g)
+rew = torch.randn(T, 1, device=dev, generator=g); done = torch.zeros(T, 1, device=dev)
+res = {}
+for mode in ("eager", "graph"):
+    tr = dart_b200.PPOTrainer(capacity=2048, epochs=16, mini_batch_size=64)
+    act, logp, val, _ = tr.act(obs.reshape(T, 520), eps.reshape(T, 34))
+    act, logp, val = act.view(T, 1, 34), logp.view(T, 1), val.view(T, 1)
+    last = val[-1].clone()
+    tr.train_rollout(obs, act, logp, rew, val, done, last, generator=g, graph=(mode == "graph"))     # warm-up (+ capture)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    steps = tr.train_rollout(obs, act, logp, rew, val, done, last, generator=g, graph=(mode == "graph"))
+    torch.cuda.synchronize(); res[mode] = (time.perf_counter() - t0) * 1e3
+    tr.close()
+pol = oppo.make_policy(3); opt = oppo.make_optimizer(pol)
+o, a_, lp, ad, rt = obs.reshape(T, 520).cpu(), act.reshape(T, 34).cpu(), logp.reshape(T).cpu(), torch.randn(T), torch.randn(T)
+t0 = time.perf_counter()
+for e in range(2):
+    perm = torch.randperm(T)
+    for s in range(0, T, 64):
+        i = perm[s:s + 64]
+        oppo.minibatch_step(pol, opt, o[i], a_[i], lp[i], ad[i], rt[i])
+cpu_ms = (time.perf_counter() - t0) * 1e3 * 8           # 2 of the 16 epochs timed
+print(json.dumps(dict(path="reference-sized update block: 2048 transitions, 16 epochs x 32 minibatches of 64 = 512 optimiser steps", steps=steps,
+                      eager_ms=round(res["eager"], 2), graph_ms=round(res["graph"], 2), torch_cpu_ms=round(cpu_ms, 1),
+                      ms_per_step_graph=round(res["graph"] / steps, 4))), flush=True)

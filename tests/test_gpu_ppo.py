@@ -337,3 +337,34 @@ def test_rlmpc_facade_training_mode(built, tmp_path):
         assert not ev.training
         W = ev._batch.policy.weights[0][0]
         assert np.array_equal(W, p1["mean_net.0.weight"])
+
+
+def test_graph_replay_is_bitwise_equal_to_eager(built):
+    """train_rollout(graph=True): the minibatch step replayed from a CUDA graph (device-resident Adam step count, indices from
+    a static buffer) gives the same parameters, moments and step count as the eager launches, bit for bit; capture itself
+    leaves the learner untouched."""
+    import torch
+    T, B = 8, 40                                             # 320 transitions, minibatch 64 -> 5 full steps per epoch
+    g0 = torch.Generator(device="cuda").manual_seed(1)
+    obs = torch.randn(T, B, 520, device="cuda", generator=g0)
+    eps = torch.randn(T, B, 34, device="cuda", generator=g0)
+    rew = torch.randn(T, B, device="cuda", generator=g0)
+    done = (torch.rand(T, B, device="cuda", generator=g0) < 0.05).float()
+    outs = []
+    for graph in (False, True, True):
+        tr = dart_b200.PPOTrainer(capacity=64, epochs=3, mini_batch_size=64)
+        a, lp, v, _ = zip(*[tr.act(obs[t], eps[t]) for t in range(T)])
+        act, logp, val = torch.stack(a), torch.stack(lp), torch.stack(v)
+        last = val[-1].clone()
+        steps = 0
+        for rollout in range(2):                            # the second rollout reuses the captured graph
+            gen = torch.Generator(device="cuda").manual_seed(5 + rollout)
+            steps += tr.train_rollout(obs, act, logp, rew, val, done, last, generator=gen, graph=graph)
+        assert steps == 2 * 3 * 5
+        assert tr.graph_replays == (steps if graph else 0)
+        p, m, vv, st = tr._get()
+        assert st == steps
+        outs.append((p, m, vv))
+        tr.close()
+    for k in range(3):
+        assert np.array_equal(outs[0][k], outs[1][k]) and np.array_equal(outs[1][k], outs[2][k])
