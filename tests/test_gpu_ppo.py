@@ -368,3 +368,31 @@ def test_graph_replay_is_bitwise_equal_to_eager(built):
         tr.close()
     for k in range(3):
         assert np.array_equal(outs[0][k], outs[1][k]) and np.array_equal(outs[1][k], outs[2][k])
+
+
+def test_reference_trained_policy_golden(built):
+    """The policy the reference itself trained (tests/golden/ppo_reference_checkpoint.npz = best_agent.pth['model'], generated by
+    tests/golden/make_ppo_golden.py) through the device path: rollout-time outputs, loss terms and the minibatch gradient against
+    the committed torch results."""
+    import torch
+    from tests.helpers import ROOT
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ppo_reference_checkpoint.npz"))
+    sd = dart_b200.unpack_params(g["params"])
+    M = g["mean"].shape[0]
+    gen = torch.Generator().manual_seed(2024)
+    obs = torch.randn(M, 520, generator=gen); eps = torch.randn(M, 34, generator=gen)
+    tr = dart_b200.PPOTrainer(capacity=M, state_dict=sd)
+    a, lp, v, mu = tr.act(obs.cuda(), eps.cuda())
+    for name, got in (("mean", mu), ("value", v), ("logp", lp), ("action", a)):
+        ref = g[name]
+        assert np.abs(got.cpu().numpy() - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max()), name
+    t = lambda k: torch.from_numpy(g[k]).cuda()
+    stats = tr.update_minibatch(obs.cuda(), t("action"), t("old_logp"), t("adv"), t("ret"), apply=False).cpu().numpy()
+    assert np.abs(stats[:3] - g["stats"][:3]).max() <= 1e-4 * max(1.0, np.abs(g["stats"][:3]).max())
+    grad = tr.gradient()
+    for k in grad:
+        gf = grad[k].reshape(-1)
+        n_ref = float(g["gnorm/" + k])
+        assert abs(np.linalg.norm(gf.astype(np.float64)) - n_ref) <= 1e-4 * n_ref + 1e-9, k
+        assert np.abs(gf[g["gidx/" + k]] - g["gval/" + k]).max() <= 1e-6 + 2e-4 * np.abs(grad[k]).max(), k
+    tr.close()

@@ -120,3 +120,24 @@ def test_reference_checkpoint_loads_into_oracle_and_packs():
     pg = ck["optimizer"]["param_groups"][0]
     assert pg["weight_decay"] == 1e-5 and tuple(pg["betas"]) == (0.9, 0.999) and pg["eps"] == 1e-8
     assert len(ck["optimizer"]["state"]) == 13                       # every Policy parameter was being trained
+
+
+def test_oracle_reproduces_golden_outputs_on_reference_trained_weights():
+    """tests/golden/ppo_reference_checkpoint.npz holds the policy the REFERENCE trained (best_agent.pth) and torch outputs on seeded
+    inputs; the restated Policy / loss must reproduce them on any machine (same torch arithmetic, FP32 round-off only)."""
+    import importlib.util
+    from tests.helpers import ROOT
+    spec = importlib.util.spec_from_file_location("make_ppo_golden", os.path.join(ROOT, "tests", "golden", "make_ppo_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ppo_reference_checkpoint.npz"))
+    out = mod.compute(g["params"])
+    for k in ("mean", "value", "logp", "action"):
+        assert np.abs(out[k] - g[k]).max() <= 2e-5 * max(1.0, np.abs(g[k]).max()), k
+    assert np.abs(out["stats"] - g["stats"]).max() <= 1e-4 * max(1.0, np.abs(g["stats"]).max())
+    for k in [k for k in g.files if k.startswith("gnorm/")]:
+        assert abs(float(out[k]) - float(g[k])) <= 1e-4 * float(g[k]) + 1e-9, k
+    if os.path.exists(REF_CKPT):                                     # the fixture's weights are the checkpoint's, bit for bit
+        import torch
+        ck = torch.load(REF_CKPT, map_location="cpu", weights_only=False)
+        assert np.array_equal(ppo.pack_params(ck["model"]), g["params"])
