@@ -51,6 +51,7 @@ constexpr int MAX_SPLITS_SMALL = 256;              // layers 2-3: chunks of >= 6
 constexpr int NPB = OFF_W2A;                       // layer-1 block of the flat vector (W1 | b1)
 constexpr int NPS = NPW - OFF_W2A;                 // layers 2-3 block
 constexpr int NPS_LD = (NPS + 3) / 4 * 4;          // row stride of its partial buffer (16-byte aligned rows)
+constexpr int FWD_KCHUNK = 80, FWD_SPLITS = 7;     // layer-1 forward of small minibatches: 520 = 6 x 80 + 40
 constexpr int BIG_MIN_ROWS = 512;                  // minibatches from here on use the 128x128 kernel for the layer-1 GEMMs
 constexpr double HALF_LOG_2PI = 0.91893853320467274178;
 
@@ -453,12 +454,13 @@ constexpr int MS = 64, LDH = 132, LDW = 68, LDO = 36;
 constexpr int SM_H1 = 0, SM_H2 = SM_H1 + MS * LDH, SM_D2 = SM_H2 + MS * LDH, SM_W2 = SM_D2 + MS * LDH,
               SM_W2T = SM_W2 + H2W * LDW, SM_W3 = SM_W2T + HID * LDH, SM_OUT = SM_W3 + 36 * LDW, SM_B = SM_OUT + MS * LDO,
               SM_FLOATS = SM_B + H2W + 36 + 3 * 36;
-constexpr int MID_SMEM = SM_FLOATS * 4 + 2 * LOSS_W * 8;
+constexpr int MID_SMEM = SM_FLOATS * 4 + (GT / 32) * LOSS_W * 8;
 // offsets inside a part_small row (flat layout relative to NPB)
 constexpr int RS_W2A = OFF_W2A - NPB, RS_B2A = OFF_B2A - NPB, RS_W2C = OFF_W2C - NPB, RS_B2C = OFF_B2C - NPB,
               RS_W3A = OFF_W3A - NPB, RS_B3A = OFF_B3A - NPB, RS_W3C = OFF_W3C - NPB, RS_B3C = OFF_B3C - NPB;
 struct MidArgs {
     int M, backward;
+    int h1_splits;           // > 0: h1 points to `h1_splits` K-split partial pre-activations [split][M][128]; bias + tanh applied here
     const float *h1, *P, *act, *old_logp, *adv, *ret;
     float ls_min, ls_max, clip_eps, vf_coef;
     float *mean, *value, *dz1, *part_small;
@@ -470,7 +472,7 @@ __global__ void __launch_bounds__(GT, 1) ppo_mid_kernel(const MidArgs a) {
     float* sH1 = sm + SM_H1; float* sH2 = sm + SM_H2; float* sD2 = sm + SM_D2; float* sW2 = sm + SM_W2;
     float* sW2T = sm + SM_W2T; float* sW3 = sm + SM_W3; float* sOut = sm + SM_OUT; float* sB2 = sm + SM_B;
     float* sB3 = sB2 + H2W; float* s_sd = sB3 + 36; float* s_ls = s_sd + 36; float* s_in = s_ls + 36;
-    double* sLoss = reinterpret_cast<double*>(sm + SM_FLOATS);            // [2][LOSS_W]
+    double* sLoss = reinterpret_cast<double*>(sm + SM_FLOATS);            // [8 warps][LOSS_W]
     const int t = threadIdx.x, ty = t / 16, tx = t % 16;
     const int s0 = blockIdx.x * MS;
     const float* P = a.P;
@@ -478,7 +480,17 @@ __global__ void __launch_bounds__(GT, 1) ppo_mid_kernel(const MidArgs a) {
     for (int e = t; e < MS * (H2W / 4); e += GT) {
         const int s = e / (H2W / 4), c4 = (e % (H2W / 4)) * 4;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (s0 + s < a.M) v = *reinterpret_cast<const float4*>(a.h1 + (size_t)(s0 + s) * H2W + c4);
+        if (s0 + s < a.M) {
+            v = *reinterpret_cast<const float4*>(a.h1 + (size_t)(s0 + s) * H2W + c4);
+            if (a.h1_splits > 0) {            // small minibatches: the layer-1 forward was split over K (fixed summation order)
+                for (int sp = 1; sp < a.h1_splits; ++sp) {
+                    const float4 q = *reinterpret_cast<const float4*>(a.h1 + ((size_t)sp * a.M + s0 + s) * H2W + c4);
+                    v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+                }
+                const float4 b = *reinterpret_cast<const float4*>(P + OFF_B1 + c4);
+                v.x = tanhf(v.x + b.x); v.y = tanhf(v.y + b.y); v.z = tanhf(v.z + b.z); v.w = tanhf(v.w + b.w);
+            }
+        }
         *reinterpret_cast<float4*>(&sH1[s * LDH + c4]) = v;
     }
     for (int e = t; e < H2W * HID; e += GT) {                              // e = c*64 + k over [W2A; W2C]
@@ -555,52 +567,76 @@ __global__ void __launch_bounds__(GT, 1) ppo_mid_kernel(const MidArgs a) {
     }
     if (!a.backward) return;
     __syncthreads();
-    // ---- P3: per-sample loss terms and d(loss)/d(mean, value) (threads 0-63, one sample each); sOut becomes dOut ----
-    if (t < MS) {
-        const int m = s0 + t;
+    // ---- P3: per-sample loss terms and d(loss)/d(mean, value); four lanes per sample, lane q owns the action dimensions
+    //      q, q+4, ...; sOut becomes dOut.  (One thread per sample left six of the eight warps waiting at the barrier below for
+    //      29 % of the kernel's stall samples.) ----
+    {
+        const int s = t / 4, q = t % 4, m = s0 + s;
         const bool on = m < a.M;
-        double pl = 0.0, vl = 0.0, g = 0.0;
-        float z[ACT];
-        if (on) {
-            double lp = 0.0;
+        float zq[9];
+        double lp = 0.0;
 #pragma unroll
-            for (int j = 0; j < ACT; ++j) {
-                const float d = a.act[(size_t)m * ACT + j] - sOut[t * LDO + j];
-                z[j] = d / s_sd[j];
-                lp += -0.5 * (double)z[j] * (double)z[j] - (double)s_ls[j] - HALF_LOG_2PI;
+        for (int i = 0; i < 9; ++i) {
+            const int j = q + 4 * i;
+            float zz = 0.f;
+            if (on && j < ACT) {
+                const float d = a.act[(size_t)m * ACT + j] - sOut[s * LDO + j];
+                zz = d / s_sd[j];
+                lp += -0.5 * (double)zz * (double)zz - (double)s_ls[j] - HALF_LOG_2PI;
             }
+            zq[i] = zz;
+        }
+        lp += __shfl_xor_sync(0xffffffffu, lp, 1);
+        lp += __shfl_xor_sync(0xffffffffu, lp, 2);
+        double pl = 0.0, vl = 0.0, g = 0.0, dvs = 0.0;
+        if (on) {
             const double A = (double)a.adv[m];
             const double ratio = exp((double)(float)lp - (double)a.old_logp[m]);
             const double lo = 1.0 - (double)a.clip_eps, hi = 1.0 + (double)a.clip_eps;
             const double s1 = ratio * A, s2 = fmin(fmax(ratio, lo), hi) * A;
             pl = -fmin(s1, s2);
             g = (s1 <= s2) ? -A * ratio / (double)a.M : 0.0;
-            const double dv = (double)sOut[t * LDO + ACT] - (double)a.ret[m];
+            const double dv = (double)sOut[s * LDO + ACT] - (double)a.ret[m];
             vl = dv * dv;
+            dvs = (double)a.vf_coef * 2.0 * dv / (double)a.M;
+        }
+        __syncwarp();                                   // every lane of the sample has read mean / value before they are overwritten
+        double part[9];
 #pragma unroll
-            for (int j = 0; j < ACT; ++j) sOut[t * LDO + j] = (float)(g * (double)z[j] / (double)s_sd[j]);
-            sOut[t * LDO + ACT] = (float)((double)a.vf_coef * 2.0 * dv / (double)a.M);
-        } else {
+        for (int i = 0; i < 9; ++i) {
+            const int j = q + 4 * i;
+            part[i] = 0.0;
+            if (j < ACT) {
+                sOut[s * LDO + j] = (float)(g * (double)zq[i] / (double)s_sd[j]);
+                part[i] = g * ((double)zq[i] * (double)zq[i] - 1.0) * (double)s_in[j];
+            } else if (j == ACT) sOut[s * LDO + j] = (float)dvs;
+        }
+        if (q != 0) { pl = 0.0; vl = 0.0; }
+        // sums over the 8 samples of the warp (lanes with equal q), then the 8 warp sums in a fixed order
 #pragma unroll
-            for (int j = 0; j <= ACT; ++j) sOut[t * LDO + j] = 0.f;
+        for (int o = 4; o < 32; o <<= 1) {
+            pl += __shfl_xor_sync(0xffffffffu, pl, o);
+            vl += __shfl_xor_sync(0xffffffffu, vl, o);
 #pragma unroll
-            for (int j = 0; j < ACT; ++j) z[j] = 0.f;
+            for (int i = 0; i < 9; ++i) part[i] += __shfl_xor_sync(0xffffffffu, part[i], o);
         }
         const int lane = t & 31, warp = t >> 5;
-#pragma unroll 1
-        for (int q = 0; q < LOSS_W; ++q) {
-            double v;
-            if (q == 0) v = pl;
-            else if (q == 1) v = vl;
-            else if (q == 2) v = 0.0;
-            else { const double zj = (double)z[q - 3]; v = on ? g * (zj * zj - 1.0) * (double)s_in[q - 3] : 0.0; }
+        if (lane < 4) {
+            if (lane == 0) { sLoss[warp * LOSS_W + 0] = pl; sLoss[warp * LOSS_W + 1] = vl; sLoss[warp * LOSS_W + 2] = 0.0; }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-            if (lane == 0) sLoss[warp * LOSS_W + q] = v;
+            for (int i = 0; i < 9; ++i) {
+                const int j = q + 4 * i;
+                if (j < ACT) sLoss[warp * LOSS_W + 3 + j] = part[i];
+            }
         }
     }
     __syncthreads();
-    if (t < LOSS_W) a.loss_part[(size_t)blockIdx.x * LOSS_W + t] = sLoss[t] + sLoss[LOSS_W + t];
+    if (t < LOSS_W) {
+        double r = 0.0;
+#pragma unroll
+        for (int w = 0; w < GT / 32; ++w) r += sLoss[w * LOSS_W + t];
+        a.loss_part[(size_t)blockIdx.x * LOSS_W + t] = r;
+    }
     // ---- P4: dz2[s][c] = (sum_j dOut[s][j] W3[j][c]) (1 - h2^2) ----
     {
         float acA[4][4];
@@ -811,6 +847,7 @@ struct dart_ppo {
     dart_ppo_cfg cfg;
     float *param, *grad, *m, *v;         // [NP]
     float *h1, *h2, *dz1, *dz2;          // [capacity, 128]
+    float* h1part;                       // [FWD_SPLITS, min(capacity, BIG_MIN_ROWS), 128]
     float *mean, *value, *dmean, *dvalue;
     float *mb_obs, *mb_act, *mb_logp, *mb_adv, *mb_ret;
     float *part, *part_small;            // [MAX_SPLITS, NPB], [MAX_SPLITS_SMALL, NPS]
@@ -851,13 +888,21 @@ int forward(dart_ppo* h, int M, const float* obs, cudaStream_t st, bool with_tai
     memset(&g, 0, sizeof(g));
     g.count = 1; g.splits = 1; g.kchunk = OBS; g.split_stride = 0;
     g.p[0] = fwd_prob(obs, OBS, P + OFF_W1, P + OFF_B1, h->h1, H2W, M, H2W, OBS, 1);
-    int rc = M >= BIG_MIN_ROWS ? launch_big(h, g.p[0], 1, OBS, 0, st) : launch_group(h, g, M, H2W, st);
+    int rc;
+    if (M >= BIG_MIN_ROWS) rc = launch_big(h, g.p[0], 1, OBS, 0, st);
+    else if (h->fused) {                  // few rows: split K over FWD_SPLITS CTAs per tile; bias + tanh move into the tile kernel
+        g.splits = FWD_SPLITS; g.kchunk = FWD_KCHUNK; g.split_stride = (long)M * H2W;
+        g.p[0].mode = 0; g.p[0].C = h->h1part;
+        rc = launch_group(h, g, M, H2W, st);
+        g.splits = 1; g.kchunk = OBS; g.split_stride = 0;
+    } else rc = launch_group(h, g, M, H2W, st);
     if (rc != DART_OK) return rc;
     if (h->fused) {
         if (!with_tail) return DART_OK;
         MidArgs ma;
         memset(&ma, 0, sizeof(ma));
         ma.M = M; ma.backward = 0; ma.h1 = h->h1; ma.P = P; ma.mean = h->mean; ma.value = h->value;
+        if (M < BIG_MIN_ROWS) { ma.h1 = h->h1part; ma.h1_splits = FWD_SPLITS; }
         ma.ls_min = (float)h->cfg.log_std_min; ma.ls_max = (float)h->cfg.log_std_max;
         ppo_mid_kernel<<<(M + MS - 1) / MS, GT, MID_SMEM, st>>>(ma);
         h->launches += 1;
@@ -944,7 +989,7 @@ int backward_unfused(dart_ppo* h, int M, const float* act, const float* old_logp
 
 void free_all(dart_ppo* h) {
     void* p[] = {h->param, h->grad, h->m, h->v, h->h1, h->h2, h->dz1, h->dz2, h->mean, h->value, h->dmean, h->dvalue,
-                 h->mb_obs, h->mb_act, h->mb_logp, h->mb_adv, h->mb_ret, h->part, h->part_small, h->loss_part, h->normpart, h->step_dev};
+                 h->mb_obs, h->mb_act, h->mb_logp, h->mb_adv, h->mb_ret, h->part, h->part_small, h->loss_part, h->normpart, h->step_dev, h->h1part};
     for (void* q : p) if (q) cudaFree(q);
 }
 
@@ -1000,6 +1045,7 @@ extern "C" int dart_ppo_create(dart_ppo_handle* out, int device, int32_t obs_dim
         {(void**)&h->m, NP * sizeof(float)}, {(void**)&h->v, NP * sizeof(float)},
         {(void**)&h->h1, cap * H2W * sizeof(float)}, {(void**)&h->h2, cap * H2W * sizeof(float)},
         {(void**)&h->dz1, cap * H2W * sizeof(float)}, {(void**)&h->dz2, cap * H2W * sizeof(float)},
+        {(void**)&h->h1part, (size_t)FWD_SPLITS * (cap < BIG_MIN_ROWS ? cap : BIG_MIN_ROWS) * H2W * sizeof(float)},
         {(void**)&h->mean, cap * ACT * sizeof(float)}, {(void**)&h->value, cap * sizeof(float)},
         {(void**)&h->dmean, cap * ACT * sizeof(float)}, {(void**)&h->dvalue, cap * sizeof(float)},
         {(void**)&h->mb_obs, cap * OBS * sizeof(float)}, {(void**)&h->mb_act, cap * ACT * sizeof(float)},
@@ -1137,7 +1183,9 @@ extern "C" int dart_ppo_update(dart_ppo_handle h, int32_t M, const int64_t* idx,
         const int tiles = (M + MS - 1) / MS;
         MidArgs ma;
         memset(&ma, 0, sizeof(ma));
-        ma.M = M; ma.backward = 1; ma.h1 = h->h1; ma.P = P; ma.act = act; ma.old_logp = old_logp; ma.adv = adv; ma.ret = ret;
+        ma.h1 = h->h1;
+        if (M < BIG_MIN_ROWS) { ma.h1 = h->h1part; ma.h1_splits = FWD_SPLITS; }
+        ma.M = M; ma.backward = 1; ma.P = P; ma.act = act; ma.old_logp = old_logp; ma.adv = adv; ma.ret = ret;
         ma.ls_min = ls_min; ma.ls_max = ls_max; ma.clip_eps = (float)c.clip_eps; ma.vf_coef = (float)c.vf_coef;
         ma.mean = h->mean; ma.value = h->value; ma.dz1 = h->dz1; ma.part_small = h->part_small; ma.loss_part = h->loss_part;
         ppo_mid_kernel<<<tiles, GT, MID_SMEM, st>>>(ma);

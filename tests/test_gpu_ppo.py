@@ -295,10 +295,10 @@ def test_fused_tile_kernel_matches_unfused_chain(built, M, monkeypatch):
         stats.append(tr.update_minibatch(*d, apply=False).cpu().numpy().copy())
         grads.append(tr.gradient())
         tr.close()
-    assert np.abs(stats[0][:3] - stats[1][:3]).max() <= 1e-6 * max(1.0, np.abs(stats[1][:3]).max())
+    assert np.abs(stats[0][:3] - stats[1][:3]).max() <= 1e-5 * max(1.0, np.abs(stats[1][:3]).max())
     for k in grads[0]:
         ref = grads[1][k]
-        assert np.abs(grads[0][k] - ref).max() <= 1e-7 + 2e-5 * np.abs(ref).max(), k
+        assert np.abs(grads[0][k] - ref).max() <= 1e-7 + 1e-4 * np.abs(ref).max(), k      # incl. the split-K layer-1 forward of the fused path
 
 
 def test_rlmpc_facade_training_mode(built, tmp_path):
