@@ -52,6 +52,7 @@ constexpr int NPB = OFF_W2A;                       // layer-1 block of the flat 
 constexpr int NPS = NPW - OFF_W2A;                 // layers 2-3 block
 constexpr int NPS_LD = (NPS + 3) / 4 * 4;          // row stride of its partial buffer (16-byte aligned rows)
 constexpr int FWD_KCHUNK = 80, FWD_SPLITS = 7;     // layer-1 forward of small minibatches: 520 = 6 x 80 + 40
+constexpr int BIG_FWD_SPLITS = 2, BIG_FWD_KCHUNK = 264;   // layer-1 forward of large minibatches: two K halves (multiple of 8)
 constexpr int BIG_MIN_ROWS = 512;                  // minibatches from here on use the 128x128 kernel for the layer-1 GEMMs
 constexpr double HALF_LOG_2PI = 0.91893853320467274178;
 
@@ -773,24 +774,40 @@ struct ReduceArgs {
     float* stats;            // [4] policy loss, value loss, entropy, (grad norm: written by the Adam kernel)
     long long* step_inc;     // optimiser step counter on the device, advanced here when an Adam launch follows (else nullptr)
 };
+// 64 parameters per block, four row groups per parameter (thread = (parameter, row group)): each thread sums every fourth partial
+// row, the four group sums are combined in a fixed order.  (One thread per parameter walked up to 256 rows in one dependent chain.)
+constexpr int RED_P = 64, RED_G = 4;
 __global__ void __launch_bounds__(256) ppo_grad_reduce_kernel(const ReduceArgs a) {
     __shared__ double sh[256];
-    const int j = blockIdx.x * 256 + threadIdx.x;
-    float g = 0.f;
+    __shared__ double sg[RED_G][RED_P];
+    const int tx = threadIdx.x % RED_P, rg = threadIdx.x / RED_P;
+    const int j = blockIdx.x * RED_P + tx;
+    double acc = 0.0;
     if (j < NPB) {
-        for (int s = 0; s < a.splits; ++s) g += a.part[(size_t)s * NPB + j];
+        float f = 0.f;
+        for (int s = rg; s < a.splits; s += RED_G) f += a.part[(size_t)s * NPB + j];
+        acc = (double)f;
     } else if (j < NPW) {
-        for (int s = 0; s < a.splits_small; ++s) g += a.part_small[(size_t)s * NPS_LD + (j - NPB)];
+        float f = 0.f;
+        for (int s = rg; s < a.splits_small; s += RED_G) f += a.part_small[(size_t)s * NPS_LD + (j - NPB)];
+        acc = (double)f;
     } else if (j < NP) {
-        const int jj = j - NPW;
-        double d = 0.0;
-        for (int b = 0; b < a.loss_blocks; ++b) d += a.loss_part[(size_t)b * LOSS_W + 3 + jj];
-        const float raw = a.log_std[jj];
-        if (raw >= a.ls_min && raw <= a.ls_max) d -= (double)a.ent_coef;     // d(-ent_coef * entropy)/dlog_std
-        g = (float)d;
+        for (int b = rg; b < a.loss_blocks; b += RED_G) acc += a.loss_part[(size_t)b * LOSS_W + 3 + (j - NPW)];
     }
-    if (j < NP) a.grad[j] = g;
-    const double ss = block_sum(j < NP ? (double)g * (double)g : 0.0, sh);
+    sg[rg][tx] = acc;
+    __syncthreads();
+    float g = 0.f;
+    if (rg == 0 && j < NP) {
+        if (j < NPW) g = ((float)sg[0][tx] + (float)sg[1][tx]) + ((float)sg[2][tx] + (float)sg[3][tx]);
+        else {
+            double d = (sg[0][tx] + sg[1][tx]) + (sg[2][tx] + sg[3][tx]);
+            const float raw = a.log_std[j - NPW];
+            if (raw >= a.ls_min && raw <= a.ls_max) d -= (double)a.ent_coef;     // d(-ent_coef * entropy)/dlog_std
+            g = (float)d;
+        }
+        a.grad[j] = g;
+    }
+    const double ss = block_sum((double)g * (double)g, sh);
     if (threadIdx.x == 0) a.normpart[blockIdx.x] = ss;
     if (blockIdx.x == 0 && threadIdx.x == 0 && a.step_inc) *a.step_inc += 1;
     if (blockIdx.x == 0 && threadIdx.x == 0 && a.stats) {
@@ -847,7 +864,7 @@ struct dart_ppo {
     dart_ppo_cfg cfg;
     float *param, *grad, *m, *v;         // [NP]
     float *h1, *h2, *dz1, *dz2;          // [capacity, 128]
-    float* h1part;                       // [FWD_SPLITS, min(capacity, BIG_MIN_ROWS), 128]
+    float* h1part;                       // K-split layer-1 pre-activations: [FWD_SPLITS, rows < BIG_MIN_ROWS, 128] or [BIG_FWD_SPLITS, capacity, 128]
     float *mean, *value, *dmean, *dvalue;
     float *mb_obs, *mb_act, *mb_logp, *mb_adv, *mb_ret;
     float *part, *part_small;            // [MAX_SPLITS, NPB], [MAX_SPLITS_SMALL, NPS]
@@ -889,7 +906,10 @@ int forward(dart_ppo* h, int M, const float* obs, cudaStream_t st, bool with_tai
     g.count = 1; g.splits = 1; g.kchunk = OBS; g.split_stride = 0;
     g.p[0] = fwd_prob(obs, OBS, P + OFF_W1, P + OFF_B1, h->h1, H2W, M, H2W, OBS, 1);
     int rc;
-    if (M >= BIG_MIN_ROWS) rc = launch_big(h, g.p[0], 1, OBS, 0, st);
+    if (M >= BIG_MIN_ROWS && h->fused) {  // two K halves: 2 x (M/128) CTAs fill two slots per SM (one half alone leaves 128 CTAs on 148 SMs)
+        g.p[0].mode = 0; g.p[0].C = h->h1part;
+        rc = launch_big(h, g.p[0], BIG_FWD_SPLITS, BIG_FWD_KCHUNK, (long)M * H2W, st);
+    } else if (M >= BIG_MIN_ROWS) rc = launch_big(h, g.p[0], 1, OBS, 0, st);
     else if (h->fused) {                  // few rows: split K over FWD_SPLITS CTAs per tile; bias + tanh move into the tile kernel
         g.splits = FWD_SPLITS; g.kchunk = FWD_KCHUNK; g.split_stride = (long)M * H2W;
         g.p[0].mode = 0; g.p[0].C = h->h1part;
@@ -902,7 +922,7 @@ int forward(dart_ppo* h, int M, const float* obs, cudaStream_t st, bool with_tai
         MidArgs ma;
         memset(&ma, 0, sizeof(ma));
         ma.M = M; ma.backward = 0; ma.h1 = h->h1; ma.P = P; ma.mean = h->mean; ma.value = h->value;
-        if (M < BIG_MIN_ROWS) { ma.h1 = h->h1part; ma.h1_splits = FWD_SPLITS; }
+        ma.h1 = h->h1part; ma.h1_splits = M < BIG_MIN_ROWS ? FWD_SPLITS : BIG_FWD_SPLITS;
         ma.ls_min = (float)h->cfg.log_std_min; ma.ls_max = (float)h->cfg.log_std_max;
         ppo_mid_kernel<<<(M + MS - 1) / MS, GT, MID_SMEM, st>>>(ma);
         h->launches += 1;
@@ -1045,7 +1065,7 @@ extern "C" int dart_ppo_create(dart_ppo_handle* out, int device, int32_t obs_dim
         {(void**)&h->m, NP * sizeof(float)}, {(void**)&h->v, NP * sizeof(float)},
         {(void**)&h->h1, cap * H2W * sizeof(float)}, {(void**)&h->h2, cap * H2W * sizeof(float)},
         {(void**)&h->dz1, cap * H2W * sizeof(float)}, {(void**)&h->dz2, cap * H2W * sizeof(float)},
-        {(void**)&h->h1part, (size_t)FWD_SPLITS * (cap < BIG_MIN_ROWS ? cap : BIG_MIN_ROWS) * H2W * sizeof(float)},
+        {(void**)&h->h1part, (cap < BIG_MIN_ROWS ? (size_t)FWD_SPLITS * cap : (size_t)(BIG_FWD_SPLITS * cap > (size_t)FWD_SPLITS * BIG_MIN_ROWS ? BIG_FWD_SPLITS * cap : (size_t)FWD_SPLITS * BIG_MIN_ROWS)) * H2W * sizeof(float)},
         {(void**)&h->mean, cap * ACT * sizeof(float)}, {(void**)&h->value, cap * sizeof(float)},
         {(void**)&h->dmean, cap * ACT * sizeof(float)}, {(void**)&h->dvalue, cap * sizeof(float)},
         {(void**)&h->mb_obs, cap * OBS * sizeof(float)}, {(void**)&h->mb_act, cap * ACT * sizeof(float)},
@@ -1053,7 +1073,7 @@ extern "C" int dart_ppo_create(dart_ppo_handle* out, int device, int32_t obs_dim
         {(void**)&h->mb_ret, cap * sizeof(float)}, {(void**)&h->part, (size_t)MAX_SPLITS * NPB * sizeof(float)},
         {(void**)&h->part_small, (size_t)(h->loss_blocks_cap > MAX_SPLITS_SMALL ? h->loss_blocks_cap : MAX_SPLITS_SMALL) * NPS_LD * sizeof(float)},
         {(void**)&h->loss_part, (size_t)h->loss_blocks_cap * LOSS_W * sizeof(double)},
-        {(void**)&h->normpart, (size_t)((NP + 255) / 256) * sizeof(double)}, {(void**)&h->step_dev, sizeof(long long)}};
+        {(void**)&h->normpart, (size_t)((NP + RED_P - 1) / RED_P) * sizeof(double)}, {(void**)&h->step_dev, sizeof(long long)}};
     int rc = DART_OK;
     for (auto& a : al) {
         if (cudaMalloc(a.p, a.bytes) != cudaSuccess) { *a.p = nullptr; rc = DART_ERR_ALLOC; break; }
@@ -1184,7 +1204,7 @@ extern "C" int dart_ppo_update(dart_ppo_handle h, int32_t M, const int64_t* idx,
         MidArgs ma;
         memset(&ma, 0, sizeof(ma));
         ma.h1 = h->h1;
-        if (M < BIG_MIN_ROWS) { ma.h1 = h->h1part; ma.h1_splits = FWD_SPLITS; }
+        ma.h1 = h->h1part; ma.h1_splits = M < BIG_MIN_ROWS ? FWD_SPLITS : BIG_FWD_SPLITS;
         ma.M = M; ma.backward = 1; ma.P = P; ma.act = act; ma.old_logp = old_logp; ma.adv = adv; ma.ret = ret;
         ma.ls_min = ls_min; ma.ls_max = ls_max; ma.clip_eps = (float)c.clip_eps; ma.vf_coef = (float)c.vf_coef;
         ma.mean = h->mean; ma.value = h->value; ma.dz1 = h->dz1; ma.part_small = h->part_small; ma.loss_part = h->loss_part;
@@ -1207,20 +1227,20 @@ extern "C" int dart_ppo_update(dart_ppo_handle h, int32_t M, const int64_t* idx,
     LossArgs la;            // (only the clamp bounds are read below)
     la.ls_min = ls_min; la.ls_max = ls_max; la.vf_coef = (float)c.vf_coef;
 
-    const int nred = (NP + 255) / 256;
+    const int nred = (NP + 255) / 256, nred_r = (NP + RED_P - 1) / RED_P;
     ReduceArgs ra;
     ra.splits = splits; ra.splits_small = splits_small; ra.loss_blocks = loss_blocks; ra.M = M; ra.part = h->part;
     ra.part_small = h->part_small; ra.loss_part = h->loss_part;
     ra.log_std = P + OFF_LS; ra.ls_min = la.ls_min; ra.ls_max = la.ls_max; ra.ent_coef = (float)c.ent_coef;
     ra.vf_coef = la.vf_coef; ra.grad = h->grad; ra.normpart = h->normpart; ra.stats = stats;
     ra.step_inc = apply ? h->step_dev : nullptr;
-    ppo_grad_reduce_kernel<<<nred, 256, 0, st>>>(ra);
+    ppo_grad_reduce_kernel<<<nred_r, 256, 0, st>>>(ra);
     h->launches += 1;
     if (cudaGetLastError() != cudaSuccess) return DART_ERR_CUDA;
     if (!apply) return DART_OK;
 
     AdamArgs aa;
-    aa.nparts = nred; aa.normpart = h->normpart; aa.grad = h->grad; aa.param = h->param; aa.m = h->m; aa.v = h->v;
+    aa.nparts = nred_r; aa.normpart = h->normpart; aa.grad = h->grad; aa.param = h->param; aa.m = h->m; aa.v = h->v;
     aa.max_norm = (float)c.max_grad_norm; aa.wd = (float)c.weight_decay; aa.beta1 = (float)c.beta1; aa.beta2 = (float)c.beta2;
     aa.eps = (float)c.adam_eps; aa.lr = c.lr; aa.beta1d = c.beta1; aa.beta2d = c.beta2; aa.step = h->step_dev; aa.stats = stats;
     ppo_adam_kernel<<<nred, 256, 0, st>>>(aa);
