@@ -101,6 +101,9 @@ def lib():
         L.dart_ppo_gae.argtypes = [C.c_int32, C.c_int32] + [vp] * 4 + [C.c_double, C.c_double, vp, vp, vp]
         L.dart_ppo_normalize.argtypes = [C.c_int64, vp, C.c_int32, vp]
         L.dart_ppo_update.argtypes = [vp, C.c_int32] + [vp] * 6 + [C.c_int32, vp, vp]
+        if hasattr(L, "dart_ppo_apply_grad"):
+            L.dart_ppo_export_grad.argtypes = [vp, vp, vp]
+            L.dart_ppo_apply_grad.argtypes = [vp, vp, C.c_double, vp, vp]
     _lib = L
     return L
 

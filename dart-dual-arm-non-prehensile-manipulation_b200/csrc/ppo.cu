@@ -857,6 +857,19 @@ __global__ void __launch_bounds__(256) ppo_adam_kernel(const AdamArgs a) {
     a.param[j] = p - s_step_size * (m / denom);
 }
 
+
+// ---- data-parallel training: the all-reduced gradient comes back from the host side's collective ----
+__global__ void __launch_bounds__(256) ppo_grad_import_kernel(const float* __restrict__ src, float scale, float* __restrict__ grad,
+                                                              double* __restrict__ normpart, long long* step_inc) {
+    __shared__ double sh[256];
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    float g = 0.f;
+    if (j < NP) { g = src[j] * scale; grad[j] = g; }
+    const double ss = block_sum((double)g * (double)g, sh);
+    if (threadIdx.x == 0) normpart[blockIdx.x] = ss;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && step_inc) *step_inc += 1;
+}
+
 }  // namespace
 
 struct dart_ppo {
@@ -1241,6 +1254,29 @@ extern "C" int dart_ppo_update(dart_ppo_handle h, int32_t M, const int64_t* idx,
 
     AdamArgs aa;
     aa.nparts = nred_r; aa.normpart = h->normpart; aa.grad = h->grad; aa.param = h->param; aa.m = h->m; aa.v = h->v;
+    aa.max_norm = (float)c.max_grad_norm; aa.wd = (float)c.weight_decay; aa.beta1 = (float)c.beta1; aa.beta2 = (float)c.beta2;
+    aa.eps = (float)c.adam_eps; aa.lr = c.lr; aa.beta1d = c.beta1; aa.beta2d = c.beta2; aa.step = h->step_dev; aa.stats = stats;
+    ppo_adam_kernel<<<nred, 256, 0, st>>>(aa);
+    h->launches += 1;
+    return cudaGetLastError() == cudaSuccess ? DART_OK : DART_ERR_CUDA;
+}
+
+extern "C" int dart_ppo_export_grad(dart_ppo_handle h, float* dst, void* stream) {
+    if (!h || !dst) return DART_ERR_ARG;
+    return cudaMemcpyAsync(dst, h->grad, NP * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream) == cudaSuccess
+               ? DART_OK : DART_ERR_CUDA;
+}
+
+extern "C" int dart_ppo_apply_grad(dart_ppo_handle h, const float* src, double scale, float* stats, void* stream) {
+    if (!h || !src) return DART_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const dart_ppo_cfg& c = h->cfg;
+    const int nred = (NP + 255) / 256;
+    ppo_grad_import_kernel<<<nred, 256, 0, st>>>(src, (float)scale, h->grad, h->normpart, h->step_dev);
+    h->launches += 1;
+    if (cudaGetLastError() != cudaSuccess) return DART_ERR_CUDA;
+    AdamArgs aa;
+    aa.nparts = nred; aa.normpart = h->normpart; aa.grad = h->grad; aa.param = h->param; aa.m = h->m; aa.v = h->v;
     aa.max_norm = (float)c.max_grad_norm; aa.wd = (float)c.weight_decay; aa.beta1 = (float)c.beta1; aa.beta2 = (float)c.beta2;
     aa.eps = (float)c.adam_eps; aa.lr = c.lr; aa.beta1d = c.beta1; aa.beta2d = c.beta2; aa.step = h->step_dev; aa.stats = stats;
     ppo_adam_kernel<<<nred, 256, 0, st>>>(aa);

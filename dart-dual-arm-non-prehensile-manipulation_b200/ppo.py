@@ -129,7 +129,7 @@ class PPOTrainer:
         check(self._lib.dart_ppo_create(C.byref(self._h), self.device, OBS_DIM, HIDDEN, ACT_DIM, self.capacity,
                                         C.c_void_p(flat.ctypes.data), C.byref(cfg)), "dart_ppo_create")
         self.stats = self.torch.zeros(4, dtype=self.torch.float32, device=self.dev)
-        self._graphs, self._gae_buf, self.graph_replays = {}, None, 0
+        self._graphs, self._gae_buf, self.graph_replays, self._gbuf = {}, None, 0, None
 
     # ---- plumbing ----
     def _stream(self):
@@ -206,6 +206,23 @@ class PPOTrainer:
                                      self.gamma, self.gae_lambda, self._chk(adv, f32, (T, B), "adv"), self._chk(ret, f32, (T, B), "ret"),
                                      self._stream()), "dart_ppo_gae")
         return adv, ret
+
+    def update_minibatch_distributed(self, obs, act, old_logp, adv, ret, idx=None, group=None):
+        """Data-parallel optimiser step: every rank computes the gradient of its own minibatch, ONE all-reduce (NCCL) sums the
+        77 317-entry gradients, every rank applies the mean with the usual clip + Adam -- the replicas stay bitwise identical.
+        With equal local minibatch sizes this is the step on the concatenated minibatch."""
+        import torch.distributed as dist
+        torch = self.torch
+        self.update_minibatch(obs, act, old_logp, adv, ret, idx=idx, apply=False)
+        if self._gbuf is None:
+            self._gbuf = torch.empty((NPARAMS,), dtype=torch.float32, device=self.dev)
+        check(self._lib.dart_ppo_export_grad(self._h, C.c_void_p(self._gbuf.data_ptr()), self._stream()), "dart_ppo_export_grad")
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if world > 1:
+            dist.all_reduce(self._gbuf, group=group)
+        check(self._lib.dart_ppo_apply_grad(self._h, C.c_void_p(self._gbuf.data_ptr()), 1.0 / world,
+                                            C.c_void_p(self.stats.data_ptr()), self._stream()), "dart_ppo_apply_grad")
+        return self.stats
 
     def _graph_for(self, flat, mb):
         """CUDA graph of one minibatch step over the (pointer-stable) pooled rollout ``flat`` with the row indices read from a

@@ -307,6 +307,13 @@ int dart_ppo_normalize(int64_t n, float* x, int32_t ddof, void* stream);
 int dart_ppo_update(dart_ppo_handle h, int32_t M, const int64_t* idx, const float* obs, const float* act,
                     const float* old_logp, const float* adv, const float* ret, int32_t apply, float* stats, void* stream);
 
+/* Data-parallel training (one process per GPU, shared policy): after dart_ppo_update(..., apply = 0) each rank exports its
+ * minibatch gradient [dart_ppo_nparams()] to a device buffer the host side all-reduces (NCCL over NVLink: the one exchange step of
+ * this path, 309 kB per step), then applies scale * sum (scale = 1 / world size) with the usual global-norm clip + Adam.  Every
+ * rank applies the same bits, so the replicas stay identical without a parameter broadcast. */
+int dart_ppo_export_grad(dart_ppo_handle h, float* dst_dev, void* stream);
+int dart_ppo_apply_grad(dart_ppo_handle h, const float* src_dev, double scale, float* stats, void* stream);
+
 /* Measured FP64 FMA-pipe peak of the device in TFLOP/s (DFMA microbenchmark, CUDA-event timed): the roofline
  * denominator bench.py reports the solver kernels against. */
 int dart_measure_fp64_tflops(int device, double* tflops);

@@ -396,3 +396,17 @@ def test_reference_trained_policy_golden(built):
         assert abs(np.linalg.norm(gf.astype(np.float64)) - n_ref) <= 1e-4 * n_ref + 1e-9, k
         assert np.abs(gf[g["gidx/" + k]] - g["gval/" + k]).max() <= 1e-6 + 2e-4 * np.abs(grad[k]).max(), k
     tr.close()
+
+
+def test_data_parallel_step_two_gpus(built):
+    """One process per GPU, gradients all-reduced over NCCL (tests/dist_ppo_check.py): replicas bitwise identical, the step equals the
+    single-GPU step on the concatenated minibatch."""
+    import subprocess
+    import sys
+    import torch
+    from tests.helpers import ROOT
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29617", os.path.join(ROOT, "tests", "dist_ppo_check.py")], capture_output=True, text=True, timeout=300)
+    assert "DIST_PPO_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
