@@ -410,3 +410,19 @@ def test_data_parallel_step_two_gpus(built):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", "29617", os.path.join(ROOT, "tests", "dist_ppo_check.py")], capture_output=True, text=True, timeout=300)
     assert "DIST_PPO_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_training_example_runs(built, tmp_path):
+    """examples/lmpc_train_surrogate.py end to end (small): rollouts complete, a checkpoint in the reference's format is written."""
+    import subprocess
+    import sys
+    import torch
+    from tests.helpers import ROOT
+    ck = str(tmp_path / "agent.pth")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "examples", "lmpc_train_surrogate.py"), "--instances", "64", "--rollouts", "2",
+                        "--rollout-len", "4", "--mini-batch-size", "128", "--epochs", "2", "--checkpoint", ck],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    assert "rollout   2" in r.stdout and "checkpoint written" in r.stdout
+    sd = torch.load(ck, map_location="cpu", weights_only=True)["model"]
+    oppo.Policy().load_state_dict(sd)
