@@ -26,6 +26,11 @@ differentiation of the literal model code), and the optimum is cross-checked
 with scipy's SLSQP on a condensed single-shooting form (``oracle.crosscheck``).
 Golden vectors under ``tests/golden`` are produced by ``tests/golden/make_golden.py``
 from this oracle.
+
+``oracle.ppo`` (the PPO training block of rlmpc2.py) is different: it is restated with torch, the reference's own
+library, and pinned to an artefact of the reference -- the policy it trained and checkpointed
+(``tests/golden/ppo_reference_checkpoint.npz``, written by ``tests/golden/make_ppo_golden.py``).  It is imported on demand
+(it pulls in torch), not with the package.
 """
 
 from . import models, problems, ipm, rls, policy, crosscheck, closed_loop  # noqa: F401
