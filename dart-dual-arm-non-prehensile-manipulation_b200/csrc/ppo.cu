@@ -66,6 +66,7 @@ struct GemmProb {
     const float* bias;
     const float* H; int ldh;
     float* rowsum;                        // split mode: partial sums over k of A(m,k) (the bias gradient), or nullptr
+    const int64_t* gidx; int gmode;       // minibatch gather without a copy: 1 = A's row m -> gidx[m] (ta = 0), 2 = B's k -> gidx[k] (tb = 0)
 };
 struct GemmGroup {
     GemmProb p[2];
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(GT) gemm_kernel(const GemmGroup g) {
             if (P.ta) { k = e / BM; m = e % BM; } else { m = e / BK; k = e % BK; }
             const int gm = m0 + m, gk = k0 + k;
             float v = 0.f;
-            if (gm < P.M && gk < k_end) v = P.ta ? P.A[(size_t)gk * P.lda + gm] : P.A[(size_t)gm * P.lda + gk];
+            if (gm < P.M && gk < k_end) v = P.ta ? P.A[(size_t)gk * P.lda + gm] : P.A[(size_t)(P.gmode == 1 ? P.gidx[gm] : gm) * P.lda + gk];
             As[k][m] = v;
         }
 #pragma unroll
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(GT) gemm_kernel(const GemmGroup g) {
             if (P.tb) { n = e / BK; k = e % BK; } else { k = e / BN; n = e % BN; }
             const int gn = n0 + n, gk = k0 + k;
             float v = 0.f;
-            if (gn < P.N && gk < k_end) v = P.tb ? P.B[(size_t)gn * P.ldb + gk] : P.B[(size_t)gk * P.ldb + gn];
+            if (gn < P.N && gk < k_end) v = P.tb ? P.B[(size_t)gn * P.ldb + gk] : P.B[(size_t)(P.gmode == 2 ? P.gidx[gk] : gk) * P.ldb + gn];
             Bs[k][n] = v;
         }
         __syncthreads();
@@ -154,7 +155,8 @@ __global__ void __launch_bounds__(GT) gemm_kernel(const GemmGroup g) {
 // as gemm_kernel; requires 16-byte aligned operands with leading dimensions that are multiples of 4.
 constexpr int TM = 128, TN = 128, TK = 8, TP = 4;
 __device__ __forceinline__ void load_tile(const float* __restrict__ X, int ld, bool trans_rows_contig, int r0, int R, int k0,
-                                          int k_end, int t, float (&v)[4], int& r, int& k) {
+                                          int k_end, int t, float (&v)[4], int& r, int& k, const int64_t* gidx = nullptr) {
+    // gidx: gather on the sample index (the row r when k is contiguous, the column k when r is contiguous)
     // trans_rows_contig: X(r,k) = X[k*ld + r] (r contiguous) else X[r*ld + k] (k contiguous); returns 4 elements:
     // rows r..r+3 at column k (contiguous r) or row r at columns k..k+3 (contiguous k)
     if (trans_rows_contig) { k = t / 32; r = (t % 32) * 4; } else { r = t / 2; k = (t % 2) * 4; }
@@ -162,13 +164,13 @@ __device__ __forceinline__ void load_tile(const float* __restrict__ X, int ld, b
     v[0] = v[1] = v[2] = v[3] = 0.f;
     if (trans_rows_contig) {
         if (gk < k_end) {
-            const float* src = X + (size_t)gk * ld + gr;
+            const float* src = X + (size_t)(gidx ? gidx[gk] : gk) * ld + gr;
             if (gr + 3 < R) { const float4 q = *reinterpret_cast<const float4*>(src); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
             else { for (int i = 0; i < 4; ++i) if (gr + i < R) v[i] = src[i]; }
         }
     } else {
         if (gr < R) {
-            const float* src = X + (size_t)gr * ld + gk;
+            const float* src = X + (size_t)(gidx ? gidx[gr] : gr) * ld + gk;
             if (gk + 3 < k_end) { const float4 q = *reinterpret_cast<const float4*>(src); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
             else { for (int i = 0; i < 4; ++i) if (gk + i < k_end) v[i] = src[i]; }
         }
@@ -195,12 +197,14 @@ __global__ void __launch_bounds__(GT, 2) gemm128_kernel(const GemmProb P, const 
     float rs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     const bool want_rs = P.rowsum != nullptr && blockIdx.x == 0 && tx == 0;
     const bool a_rc = P.ta != 0, b_rc = P.tb == 0;      // "rows contiguous": A(m,k) with m contiguous / B(k,n) with n contiguous
+    const int64_t* ga = P.gmode == 1 ? P.gidx : nullptr;
+    const int64_t* gb = P.gmode == 2 ? P.gidx : nullptr;
     float va[4], vb[4];
     int ar, ak, br, bk;
     int buf = 0;
     if (k_begin < k_end) {
-        load_tile(P.A, P.lda, a_rc, m0, P.M, k_begin, k_end, t, va, ar, ak);
-        load_tile(P.B, P.ldb, b_rc, n0, P.N, k_begin, k_end, t, vb, br, bk);
+        load_tile(P.A, P.lda, a_rc, m0, P.M, k_begin, k_end, t, va, ar, ak, ga);
+        load_tile(P.B, P.ldb, b_rc, n0, P.N, k_begin, k_end, t, vb, br, bk, gb);
         store_tile(As[0], a_rc, ar, ak, va);
         store_tile(Bs[0], b_rc, br, bk, vb);
     }
@@ -208,8 +212,8 @@ __global__ void __launch_bounds__(GT, 2) gemm128_kernel(const GemmProb P, const 
     for (int k0 = k_begin; k0 < k_end; k0 += TK) {
         const bool more = k0 + TK < k_end;
         if (more) {
-            load_tile(P.A, P.lda, a_rc, m0, P.M, k0 + TK, k_end, t, va, ar, ak);
-            load_tile(P.B, P.ldb, b_rc, n0, P.N, k0 + TK, k_end, t, vb, br, bk);
+            load_tile(P.A, P.lda, a_rc, m0, P.M, k0 + TK, k_end, t, va, ar, ak, ga);
+            load_tile(P.B, P.ldb, b_rc, n0, P.N, k0 + TK, k_end, t, vb, br, bk, gb);
         }
 #pragma unroll
         for (int k = 0; k < TK; ++k) {
@@ -463,6 +467,7 @@ struct MidArgs {
     int M, backward;
     int h1_splits;           // > 0: h1 points to `h1_splits` K-split partial pre-activations [split][M][128]; bias + tanh applied here
     const float *h1, *P, *act, *old_logp, *adv, *ret;
+    const int64_t* idx;      // minibatch rows of act / old_logp / adv / ret (nullptr = rows 0..M-1)
     float ls_min, ls_max, clip_eps, vf_coef;
     float *mean, *value, *dz1, *part_small;
     double* loss_part;
@@ -574,6 +579,7 @@ __global__ void __launch_bounds__(GT, 1) ppo_mid_kernel(const MidArgs a) {
     {
         const int s = t / 4, q = t % 4, m = s0 + s;
         const bool on = m < a.M;
+        const size_t mr = on ? (a.idx ? (size_t)a.idx[m] : (size_t)m) : 0;      // row of the pooled rollout
         float zq[9];
         double lp = 0.0;
 #pragma unroll
@@ -581,7 +587,7 @@ __global__ void __launch_bounds__(GT, 1) ppo_mid_kernel(const MidArgs a) {
             const int j = q + 4 * i;
             float zz = 0.f;
             if (on && j < ACT) {
-                const float d = a.act[(size_t)m * ACT + j] - sOut[s * LDO + j];
+                const float d = a.act[mr * ACT + j] - sOut[s * LDO + j];
                 zz = d / s_sd[j];
                 lp += -0.5 * (double)zz * (double)zz - (double)s_ls[j] - HALF_LOG_2PI;
             }
@@ -591,13 +597,13 @@ __global__ void __launch_bounds__(GT, 1) ppo_mid_kernel(const MidArgs a) {
         lp += __shfl_xor_sync(0xffffffffu, lp, 2);
         double pl = 0.0, vl = 0.0, g = 0.0, dvs = 0.0;
         if (on) {
-            const double A = (double)a.adv[m];
-            const double ratio = exp((double)(float)lp - (double)a.old_logp[m]);
+            const double A = (double)a.adv[mr];
+            const double ratio = exp((double)(float)lp - (double)a.old_logp[mr]);
             const double lo = 1.0 - (double)a.clip_eps, hi = 1.0 + (double)a.clip_eps;
             const double s1 = ratio * A, s2 = fmin(fmax(ratio, lo), hi) * A;
             pl = -fmin(s1, s2);
             g = (s1 <= s2) ? -A * ratio / (double)a.M : 0.0;
-            const double dv = (double)sOut[s * LDO + ACT] - (double)a.ret[m];
+            const double dv = (double)sOut[s * LDO + ACT] - (double)a.ret[mr];
             vl = dv * dv;
             dvs = (double)a.vf_coef * 2.0 * dv / (double)a.M;
         }
@@ -912,12 +918,13 @@ GemmProb fwd_prob(const float* X, int ldx, const float* W, const float* b, float
 }
 
 // Both networks' forward pass for M rows of `obs`: h1, h2 [M,128] (actor columns 0-63, critic 64-127), mean [M,34], value [M].
-int forward(dart_ppo* h, int M, const float* obs, cudaStream_t st, bool with_tail = true) {
+int forward(dart_ppo* h, int M, const float* obs, cudaStream_t st, bool with_tail = true, const int64_t* gidx = nullptr) {
     const float* P = h->param;
     GemmGroup g;
     memset(&g, 0, sizeof(g));
     g.count = 1; g.splits = 1; g.kchunk = OBS; g.split_stride = 0;
     g.p[0] = fwd_prob(obs, OBS, P + OFF_W1, P + OFF_B1, h->h1, H2W, M, H2W, OBS, 1);
+    if (gidx) { g.p[0].gidx = gidx; g.p[0].gmode = 1; }      // rows of the pooled rollout, gathered by the loaders
     int rc;
     if (M >= BIG_MIN_ROWS && h->fused) {  // two K halves: 2 x (M/128) CTAs fill two slots per SM (one half alone leaves 128 CTAs on 148 SMs)
         g.p[0].mode = 0; g.p[0].C = h->h1part;
@@ -1191,13 +1198,15 @@ extern "C" int dart_ppo_update(dart_ppo_handle h, int32_t M, const int64_t* idx,
     if ((reinterpret_cast<uintptr_t>(obs) & 15) != 0) return DART_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const dart_ppo_cfg& c = h->cfg;
-    if (idx) {
+    const int64_t* gidx = nullptr;
+    if (idx && h->fused) gidx = idx;                  // the fused path gathers inside its loaders: no minibatch copy
+    else if (idx) {
         GatherArgs ga{M, idx, obs, act, old_logp, adv, ret, h->mb_obs, h->mb_act, h->mb_logp, h->mb_adv, h->mb_ret};
         ppo_gather_kernel<<<M, 128, 0, st>>>(ga);
         h->launches += 1;
         obs = h->mb_obs; act = h->mb_act; old_logp = h->mb_logp; adv = h->mb_adv; ret = h->mb_ret;
     }
-    int rc = forward(h, M, obs, st, /*with_tail=*/!h->fused);
+    int rc = forward(h, M, obs, st, /*with_tail=*/!h->fused, gidx);
     if (rc != DART_OK) return rc;
     const float* P = h->param;
     int loss_blocks, splits, kchunk, splits_small;
@@ -1218,7 +1227,7 @@ extern "C" int dart_ppo_update(dart_ppo_handle h, int32_t M, const int64_t* idx,
         memset(&ma, 0, sizeof(ma));
         ma.h1 = h->h1;
         ma.h1 = h->h1part; ma.h1_splits = M < BIG_MIN_ROWS ? FWD_SPLITS : BIG_FWD_SPLITS;
-        ma.M = M; ma.backward = 1; ma.P = P; ma.act = act; ma.old_logp = old_logp; ma.adv = adv; ma.ret = ret;
+        ma.M = M; ma.backward = 1; ma.P = P; ma.idx = gidx; ma.act = act; ma.old_logp = old_logp; ma.adv = adv; ma.ret = ret;
         ma.ls_min = ls_min; ma.ls_max = ls_max; ma.clip_eps = (float)c.clip_eps; ma.vf_coef = (float)c.vf_coef;
         ma.mean = h->mean; ma.value = h->value; ma.dz1 = h->dz1; ma.part_small = h->part_small; ma.loss_part = h->loss_part;
         ppo_mid_kernel<<<tiles, GT, MID_SMEM, st>>>(ma);
@@ -1234,6 +1243,7 @@ extern "C" int dart_ppo_update(dart_ppo_handle h, int32_t M, const int64_t* idx,
         memset(&gw, 0, sizeof(gw));
         gw.count = 1; gw.splits = splits; gw.kchunk = kchunk; gw.split_stride = NPB;
         gw.p[0] = wgrad_prob(h->dz1, H2W, obs, OBS, h->part, OFF_W1, M, H2W, OBS);
+        if (gidx) { gw.p[0].gidx = gidx; gw.p[0].gmode = 2; }
         rc = M >= BIG_MIN_ROWS ? launch_big(h, gw.p[0], splits, kchunk, NPB, st) : launch_group(h, gw, H2W, OBS, st);
         if (rc != DART_OK) return rc;
     }

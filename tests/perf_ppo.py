@@ -41,6 +41,16 @@ for M in SIZES:
         tr.update_minibatch(*d)
     b.record(); torch.cuda.synchronize()
     ms_b2b = a.elapsed_time(b) / 20
+    # the same step on a minibatch drawn by a permutation from a pooled rollout of 2 M rows (what train_rollout issues)
+    pool = [torch.cat([t, t]) for t in d]
+    idx = torch.randperm(2 * M, device=dev)[:M]
+    tr.update_minibatch(*pool, idx=idx)
+    torch.cuda.synchronize(); a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(20):
+        tr.update_minibatch(*pool, idx=idx)
+    b.record(); torch.cuda.synchronize()
+    ms_idx = a.elapsed_time(b) / 20
     # the reference's path: torch autograd + Adam on the host cores
     cpu_ms = float("nan")
     if not NOCPU:
@@ -51,7 +61,7 @@ for M in SIZES:
         for _ in range(n_cpu):
             oppo.minibatch_step(pol, opt, obs, act, old, adv, ret)
         cpu_ms = (time.perf_counter() - t0) / n_cpu * 1e3
-    print(json.dumps(dict(kernel="dart_ppo_update", M=M, ms_flushed=round(ms, 4), ms_back_to_back=round(ms_b2b, 4), launches_per_step=launches,
+    print(json.dumps(dict(kernel="dart_ppo_update", M=M, ms_flushed=round(ms, 4), ms_back_to_back=round(ms_b2b, 4), ms_permuted_minibatch=round(ms_idx, 4), launches_per_step=launches,
                           samples_per_s=M / ms_b2b * 1e3, fp32_tflops=FLOP_PER_SAMPLE * M / ms_b2b * 1e-9,
                           hbm_GBps=M * (2 * 2080 + 148) / ms_b2b * 1e-6, torch_cpu_ms=round(cpu_ms, 3), torch_cpu_threads=torch.get_num_threads(),
                           speedup_vs_torch_cpu=cpu_ms / ms_b2b)), flush=True)
