@@ -177,15 +177,18 @@ static int launch_n(const KArgs& a, int block_threads, cudaStream_t st, LaunchIn
         if (bt < unit) bt = unit;
     }
     if (bt > M::MAX_THREADS) bt = M::MAX_THREADS;
-    if (bt % 32 != 0 || bt < unit) return DART_ERR_ARG;
+    // block size: whole warps AND whole instances (the axes of an instance are combined through the shared-memory slots
+    // of ONE block, solve_block: slot + ax * ws_stride), i.e. a multiple of lcm(32, G * NAXIS)
+    int step = 32;
+    while (step % unit != 0) step += 32;
+    if (bt % step != 0 || bt < unit) return DART_ERR_ARG;
     int tpb = bt / G;
     size_t smem = (size_t)tpb * ws_stride * sizeof(double);
-    while (smem > (size_t)max_smem && bt > 32) { bt -= 32; tpb = bt / G; smem = (size_t)tpb * ws_stride * sizeof(double); }
-    if (smem > (size_t)max_smem) return DART_ERR_UNSUPPORTED;
+    while (smem > (size_t)max_smem && bt > step) { bt -= step; tpb = bt / G; smem = (size_t)tpb * ws_stride * sizeof(double); }
+    if (smem > (size_t)max_smem || bt < unit || tpb % M::NAXIS != 0) return DART_ERR_UNSUPPORTED;
     const long probs = (long)a.B * M::NAXIS;
     const int grid = (int)((probs + tpb - 1) / tpb);
     if (ep) {
-        if (tpb % M::NAXIS != 0) return DART_ERR_ARG;   // the axes of an instance must share a block
         auto kern = nmpc_episode_kernel<M, G, NC>;
         static size_t smem_set_ep[kMaxDev] = {0};
         if (smem > smem_set_ep[dev]) {

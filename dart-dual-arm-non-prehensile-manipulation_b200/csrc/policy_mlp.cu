@@ -63,8 +63,11 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// bounded wait: a protocol bug must trap, never hang the GPU
+// Production wait: try_wait suspends the thread in hardware up to a time limit, so the loop carries no extra
+// instructions (round 1 kept a clock64() watchdog here: 34 % of the kernel's warp instructions were that guard).
+// -DDART_MBAR_WATCHDOG restores the bounded wait (a protocol bug then traps instead of hanging) for bring-up.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#ifdef DART_MBAR_WATCHDOG
     const long long t0 = clock64();
     uint32_t done = 0;
     while (true) {
@@ -73,6 +76,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (done) break;
         if (clock64() - t0 > 4000000000LL) __trap();
     }
+#else
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+                 ::"r"(bar), "r"(parity) : "memory");
+#endif
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"

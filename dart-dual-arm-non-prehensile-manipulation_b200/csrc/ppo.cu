@@ -1150,6 +1150,7 @@ extern "C" int dart_ppo_act(dart_ppo_handle h, int32_t B, const float* obs, cons
                             float* value, float* mean, void* stream) {
     if (!h || B < 0 || B > h->capacity || !obs || !action || !logp || !value) return DART_ERR_ARG;
     if (B == 0) return DART_OK;
+    { int cur = -1; if (cudaGetDevice(&cur) != cudaSuccess || cur != h->device) return DART_ERR_ARG; }   // launch from the handle's device
     cudaStream_t st = (cudaStream_t)stream;
     int rc = forward(h, B, obs, st);
     if (rc != DART_OK) return rc;
@@ -1196,6 +1197,7 @@ extern "C" int dart_ppo_update(dart_ppo_handle h, int32_t M, const int64_t* idx,
                                void* stream) {
     if (!h || M < 1 || M > h->capacity || !obs || !act || !old_logp || !adv || !ret) return DART_ERR_ARG;
     if ((reinterpret_cast<uintptr_t>(obs) & 15) != 0) return DART_ERR_ARG;
+    { int cur = -1; if (cudaGetDevice(&cur) != cudaSuccess || cur != h->device) return DART_ERR_ARG; }   // launch from the handle's device
     cudaStream_t st = (cudaStream_t)stream;
     const dart_ppo_cfg& c = h->cfg;
     const int64_t* gidx = nullptr;
@@ -1279,6 +1281,7 @@ extern "C" int dart_ppo_export_grad(dart_ppo_handle h, float* dst, void* stream)
 
 extern "C" int dart_ppo_apply_grad(dart_ppo_handle h, const float* src, double scale, float* stats, void* stream) {
     if (!h || !src) return DART_ERR_ARG;
+    { int cur = -1; if (cudaGetDevice(&cur) != cudaSuccess || cur != h->device) return DART_ERR_ARG; }   // launch from the handle's device
     cudaStream_t st = (cudaStream_t)stream;
     const dart_ppo_cfg& c = h->cfg;
     const int nred = (NP + 255) / 256;

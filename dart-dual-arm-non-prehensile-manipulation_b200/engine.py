@@ -111,6 +111,8 @@ class NMPCEngine:
             status = torch.empty((B,), dtype=i32, device=dev)
         if iters is None:
             iters = torch.empty((B,), dtype=i32, device=dev)
+        if torch.cuda.current_device() != self.device:      # dart_solve rejects a launch from another device
+            torch.cuda.set_device(self.device)
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         check(self._lib.dart_solve(self._h, B, ptr(x0, (B, self.nx), f64, "x0"), ptr(ref, (B, self.nref), f64, "ref"),
                                    ptr(aux, (B, self.naux), f64, "aux"), ptr(warm_w, (B, self.nw), f64, "warm_w"),

@@ -29,31 +29,38 @@ def _torch():
 
 
 def init_policy_weights(seed=3, obs_dim=OBS_DIM, act_dim=ACT_DIM, hidden=HIDDEN, layers=2):
-    """Random actor weights exactly as ``Policy._init_weights`` draws them (orthogonal, gain sqrt(2), zero bias)."""
+    """Random actor weights exactly as the reference draws them: ``Policy(obs_dim, act_dim, {})`` under
+    ``torch.manual_seed(seed)`` (rlmpc2.py:33-69) builds the actor stack, then the critic stack (each ``nn.Linear`` consumes the
+    generator for its default init), then ``_init_weights`` re-draws every Linear orthogonally (gain sqrt(2), zero bias)
+    in module order.  The same sequence of draws is made here, so the actor equals the reference's bit for bit
+    (``tests/test_ref_pin.py``, ``tests/golden/ref_policy.npz``); only the actor is returned."""
     import torch
     torch.manual_seed(seed)
-    dims = [obs_dim] + [hidden] * layers + [act_dim]
-    out = []
-    for i in range(len(dims) - 1):
-        lin = torch.nn.Linear(dims[i], dims[i + 1])
+    dims = [obs_dim] + [hidden] * layers
+    actor = [torch.nn.Linear(dims[i], dims[i + 1]) for i in range(layers)] + [torch.nn.Linear(hidden, act_dim)]
+    critic = [torch.nn.Linear(dims[i], dims[i + 1]) for i in range(layers)] + [torch.nn.Linear(hidden, 1)]
+    for lin in actor + critic:
         torch.nn.init.orthogonal_(lin.weight, gain=float(np.sqrt(2)))
         torch.nn.init.constant_(lin.bias, 0.0)
-        out.append((lin.weight.detach().numpy().copy(), lin.bias.detach().numpy().copy()))
-    return out
+    return [(lin.weight.detach().numpy().copy(), lin.bias.detach().numpy().copy()) for lin in actor]
 
 
-def load_checkpoint_weights(path, trust_pickle=False):
-    """Actor weights from a reference checkpoint (``torch.save({"model": state_dict, ...})``, rlmpc2.py:917-922).
+def load_checkpoint(path, trust_pickle=False):
+    """A reference checkpoint (``torch.save({"model": state_dict, "optimizer": ..., ...})``, rlmpc2.py:917-922) as a dict.
     The files contain numpy scalars, so a safe ``weights_only`` load may fail; ``trust_pickle=True`` opts into
     the reference's own ``weights_only=False`` load (only for files you trust)."""
     import torch
     try:
-        ck = torch.load(path, map_location="cpu", weights_only=True)
+        return torch.load(path, map_location="cpu", weights_only=True)
     except Exception:
         if not trust_pickle:
             raise
-        ck = torch.load(path, map_location="cpu", weights_only=False)
-    sd = ck["model"]
+        return torch.load(path, map_location="cpu", weights_only=False)
+
+
+def load_checkpoint_weights(path, trust_pickle=False):
+    """Actor weights [(W, b)] x 3 from a reference checkpoint."""
+    sd = load_checkpoint(path, trust_pickle)["model"]
     return [(sd[f"mean_net.{i}.weight"].float().numpy().copy(), sd[f"mean_net.{i}.bias"].float().numpy().copy())
             for i in (0, 2, 4)]
 
@@ -115,7 +122,7 @@ class LMPCBatch:
 
     def __init__(self, B, pvec0, weights=None, seed=3, device=0, max_param_abs=2.0, max_delta_abs=0.02, min_k=1e-2,
                  k_ceiling_margin=None, shm_smooth_alpha=0.5, update_every=8, warm_start=True, plan_fallback=False,
-                 warm_mu=1e-4, dual_warm=False, **cfg_kw):
+                 warm_mu=1e-4, dual_warm=False, obs_k0=None, live_params_in_obs=False, eval_std=None, generator=None, **cfg_kw):
         torch = _torch()
         self.torch = torch
         self.B = int(B)
@@ -129,6 +136,18 @@ class LMPCBatch:
         f64, f32 = torch.float64, torch.float32
         self.aux = torch.zeros((B, 36), dtype=f64, device=self.dev)               # [u_prev(2), pvec(34)]
         self.aux[:, 2:] = torch.from_numpy(np.ascontiguousarray(pvec0, dtype=np.float64)).to(self.dev)
+        # ``current_k`` of the observation (rlmpc2.py:649) is the RL worker's LOCAL copy: initialised at :618-623 and
+        # refreshed only after a PPO rollout update (:896) -- not the live shared-memory parameters, which change every
+        # 8th step.  Under the Welford normaliser that slice is therefore exactly 0 between updates, and a reference-
+        # trained checkpoint expects that.  ``live_params_in_obs=True`` feeds the live parameters instead.
+        self.live_params_in_obs = bool(live_params_in_obs)
+        k_obs = pvec0 if obs_k0 is None else obs_k0
+        self.obs_k = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(k_obs, (B, ACT_DIM)), dtype=np.float64)).to(self.dev).contiguous()
+        # evaluation action: the policy mean (deterministic; what the reference applies after each update, :877-896).  The
+        # reference's worker applies a *sample* N(mean, std) on every step even in evaluation (:678); eval_std=0.1
+        # (exp(log_std) of its checkpoints) with a torch generator reproduces that behaviour.
+        self.eval_std = None if eval_std is None else float(eval_std)
+        self.generator = generator
         self.u_prev = torch.zeros((B, 2), dtype=f64, device=self.dev)              # views['control'] of the reference
         self.obs = [torch.zeros((B, OBS_DIM), dtype=f32, device=self.dev) for _ in range(2)]
         self.mean = torch.zeros((B, BASE_DIM), dtype=f64, device=self.dev)
@@ -158,6 +177,7 @@ class LMPCBatch:
             self.plan_pos = torch.zeros((B,), dtype=torch.int64, device=self.dev)
             self._rows = torch.arange(B, device=self.dev)
             self.n_fallback = torch.zeros((), dtype=torch.int64, device=self.dev)     # solves replaced by a plan shift
+            self.have_plan = torch.zeros((B,), dtype=torch.bool, device=self.dev)
 
     def _shifted(self, w):
         """Previous plan advanced by one stage: x_k <- x_{k+1}, u_k <- u_{k+1}, last stage repeated."""
@@ -170,25 +190,53 @@ class LMPCBatch:
     def pvec(self):
         return self.aux[:, 2:]
 
+    def obs_norm_state(self):
+        """Welford state of the observation normaliser (rlmpc2.py:552-555): dict(mean [B,52], M2 [B,52], count)."""
+        return {"mean": self.mean.cpu().numpy(), "M2": self.M2.cpu().numpy(), "count": int(self.count)}
+
+    def set_obs_norm_state(self, st):
+        torch = self.torch
+        mean = np.broadcast_to(np.asarray(st["mean"], dtype=np.float64), (self.B, BASE_DIM))
+        M2 = np.broadcast_to(np.asarray(st["M2"], dtype=np.float64), (self.B, BASE_DIM))
+        self.mean.copy_(torch.from_numpy(np.ascontiguousarray(mean)))
+        self.M2.copy_(torch.from_numpy(np.ascontiguousarray(M2)))
+        self.count = int(st["count"])
+
+    def refresh_obs_params(self):
+        """``current_k = views["model_params"].copy()`` after a PPO rollout update (rlmpc2.py:896)."""
+        self.obs_k.copy_(self.aux[:, 2:])
+
     @property
     def control(self):
         return self.u_prev
 
-    def step(self, state, target):
-        """state, target: CUDA tensors [B,8].  Returns the device tensor of first tilt commands [B,2]."""
+    def step(self, state, target, fresh=None):
+        """state, target: CUDA tensors [B,8].  Returns the device tensor of first tilt commands [B,2].
+
+        ``fresh`` (bool CUDA tensor [B], needs ``plan_fallback``): the reference's asynchronous mailbox in deterministic
+        form -- where False, this call behaves as ``RLMPC.solve`` does when the solver process has published nothing new
+        (rlmpc2.py:1013-1018): the command is the next entry of the last plan (held once the plan is used up, or
+        ``last_control`` when there is no plan yet) and the plan stays the warm start."""
         torch, L = self.torch, _lib.lib()
         p = lambda t: C.c_void_p(t.data_ptr())
         stream = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
         self.count += 1
         obs_in, obs_out = self.obs
-        check(L.dart_policy_obs_push(self.B, self.count, p(state), p(target), p(self.u_prev), C.c_void_p(self.aux.data_ptr() + 16),
-                                     36, p(self.mean), p(self.M2), p(obs_in), p(obs_out), stream), "dart_policy_obs_push")
+        if self.live_params_in_obs:
+            k_ptr, k_stride = C.c_void_p(self.aux.data_ptr() + 16), 36
+        else:
+            k_ptr, k_stride = p(self.obs_k), ACT_DIM
+        check(L.dart_policy_obs_push(self.B, self.count, p(state), p(target), p(self.u_prev), k_ptr,
+                                     k_stride, p(self.mean), p(self.M2), p(obs_in), p(obs_out), stream), "dart_policy_obs_push")
         self.obs = [obs_out, obs_in]
         if self.action_source is None:
             self.policy.forward(obs_out, self.action)          # evaluation: the policy mean (tcgen05 kernel)
+            if self.eval_std:
+                self.action.add_(torch.randn(self.action.shape, dtype=self.action.dtype, device=self.dev, generator=self.generator),
+                                 alpha=self.eval_std)
         else:
             self.action_source(obs_out, self.action)           # training: sampled by the PPO learner (ppo.LMPCTrainer)
-        if self.timestep % self.update_every == 0:
+        if self.update_every > 0 and self.timestep % self.update_every == 0:
             check(L.dart_policy_param_update(self.B, p(self.action), C.c_void_p(self.aux.data_ptr() + 16), 36, self.k_max,
                                              self.max_delta, self.min_k, self.margin, self.alpha, stream),
                   "dart_policy_param_update")
@@ -199,16 +247,22 @@ class LMPCBatch:
             self.engine.set_mu_init(self.warm_mu)
         self.engine.solve_device(state, target, aux=self.aux, warm_w=warm,
                                  w_out=self.w_next, u0_out=self.u0, J_out=self.J, status=self.status, iters=self.iters)
+        if fresh is not None and not self.plan_fallback:
+            raise ValueError("step(fresh=...) needs LMPCBatch(plan_fallback=True)")
         if self.plan_fallback:
             ok = (self.status == _lib.STATUS_CONVERGED) | (self.status == _lib.STATUS_ACCEPTABLE)
-            if self.timestep == 0:
-                ok = torch.ones_like(ok)                  # nothing to fall back on yet: the reference holds u = 0 / the last iterate
+            # no plan to fall back on yet: take the solver's iterate whatever its status (the reference never checks it)
+            ok = ok | ~self.have_plan
+            if fresh is not None:
+                ok = ok & fresh
             N = self.cfg.N
             U_new = self.w_next[:, self._nxw:].view(self.B, N, 2)
             self.n_fallback += (~ok).sum()
             self.plan_U = torch.where(ok[:, None, None], U_new, self.plan_U)
             self.plan_pos = torch.where(ok, torch.zeros_like(self.plan_pos), torch.clamp(self.plan_pos + 1, max=N - 1))
-            self.u0.copy_(self.plan_U[self._rows, self.plan_pos])
+            held = ~ok & ~self.have_plan                   # reference: "else: hold last_control"
+            self.u0.copy_(torch.where(held[:, None], self.u_prev, self.plan_U[self._rows, self.plan_pos]))
+            self.have_plan = self.have_plan | ok
             self.w_next = torch.where(ok[:, None], self.w_next, self.w)
         self.w, self.w_next = self.w_next, self.w
         self.u_prev.copy_(self.u0)
@@ -274,17 +328,29 @@ class RLMPC:
         k0 = np.clip(np.full(self.params_len, base) + jitter, min_k, k_max - margin)
         self.last_control = np.array([0.0, 0.0])
         self.events = {k: _Event() for k in ("state_ready", "ctrl_ready", "data_ready", "terminate", "reset")}
-        weights = None
+        weights = obs_norm = None
         ck = os.path.join(self.checkpoint_dir, "best_agent.pth")
         if not params.get("train", True) and os.path.exists(ck):
-            weights = load_checkpoint_weights(ck, trust_pickle=params.get("trust_checkpoint_pickle", False))
-        self._batch = LMPCBatch(1, k0[None, :], weights=weights, seed=params.get("policy_seed", 3), device=device,
+            ckd = load_checkpoint(ck, trust_pickle=params.get("trust_checkpoint_pickle", False))
+            sd = ckd["model"]
+            weights = [(sd[f"mean_net.{i}.weight"].float().numpy().copy(), sd[f"mean_net.{i}.bias"].float().numpy().copy())
+                       for i in (0, 2, 4)]
+            obs_norm = ckd.get("obs_norm")          # only this package's checkpoints carry it (see PPOTrainer.save)
+        # the worker's start-up write (:623): smoothed against the mailbox's initial content (:143, uniform(0, k_max/2)), soft-clipped
+        alpha = params.get("shm_smooth_alpha", 0.5)
+        prev = rng.uniform(0, k_max / 2, size=self.params_len)
+        lo_k, hi_k = min_k, k_max - margin
+        center, scale = (hi_k + lo_k) / 2, (hi_k - lo_k) / 2 - 1e-3
+        k_shm = center + scale * np.tanh((alpha * k0 + (1 - alpha) * prev - center) / scale)
+        self._batch = LMPCBatch(1, k_shm[None, :], obs_k0=k0[None, :], weights=weights, seed=params.get("policy_seed", 3), device=device,
                                 max_param_abs=k_max, max_delta_abs=params.get("max_delta_abs", 0.1), min_k=min_k,
                                 k_ceiling_margin=margin, shm_smooth_alpha=params.get("shm_smooth_alpha", 0.5),
                                 Ts=params["Ts"], N=N, Q=params["Q"], Qt=params["Qt"], R=params["R"],
                                 u_bounds=params["u_bounds"], plan_fallback=True,
                                 warm_start=params.get("warm_start", True), **dict(params.get("solver_options", {})))
-        self.views["model_params"][:] = k0
+        self.views["model_params"][:] = k_shm
+        if obs_norm is not None and params.get("restore_obs_norm", True):
+            self._batch.set_obs_norm_state({"mean": np.asarray(obs_norm["mean"]), "M2": np.asarray(obs_norm["M2"]), "count": obs_norm["count"]})
         self.loss = np.zeros(1)
         # Training mode (rlmpc2.py:563-578, train=True is the packet default): the RL worker's PPO learner runs on the device and
         # the action applied to the model parameters is its sample, not the mean.  With train=False and no checkpoint the
@@ -309,7 +375,7 @@ class RLMPC:
                                                    max_episode_steps=int(pk("max_episode_steps", 10000))))
             gen = torch.Generator(device=self._batch.dev)
             gen.manual_seed(int(pk("seed", 0) or 0))
-            self._trainer = LMPCTrainer(self._batch, self._ppo, rollout_len=int(pk("rollout_len", 2048)), record_every=8, generator=gen)
+            self._trainer = LMPCTrainer(self._batch, self._ppo, rollout_len=int(pk("rollout_len", 2048)), generator=gen)
 
     def rebind(self, model, data):
         self.setup(model, data, self.params)
@@ -361,7 +427,8 @@ class RLMPC:
         """rlmpc2.py:900-926: count the episode, checkpoint (latest always, best on a new best return), ask the caller for a reset."""
         self.episode_count += 1
         os.makedirs(self.checkpoint_dir, exist_ok=True)
-        meta = {"episode": self.episode_count, "return": self.episode_return, "episode number": self.episode_count}
+        meta = {"episode": self.episode_count, "return": self.episode_return, "episode number": self.episode_count,
+                "obs_norm": self._batch.obs_norm_state()}
         if self.episode_return > self.best_return:
             self.best_return = self.episode_return
             self._ppo.save(os.path.join(self.checkpoint_dir, "best_agent.pth"), **meta)

@@ -133,6 +133,9 @@ class PPOTrainer:
 
     # ---- plumbing ----
     def _stream(self):
+        # dart_ppo_* launch on the CURRENT device and reject a mismatch with the handle's: make the handle's device current
+        if self.torch.cuda.current_device() != self.device:
+            self.torch.cuda.set_device(self.device)
         return C.c_void_p(self.torch.cuda.current_stream(self.dev).cuda_stream)
 
     def _chk(self, t, dtype, shape, name):
@@ -314,24 +317,91 @@ class PPOTrainer:
         sd = self.state_dict()
         return [(sd[f"mean_net.{i}.weight"], sd[f"mean_net.{i}.bias"]) for i in (0, 2, 4)]
 
-    def save(self, path, **extra):
-        """Checkpoint in the reference's format (rlmpc2.py:917-922): ``{"model": state_dict, "optimizer": ..., **extra}``;
-        ``"model"`` loads straight into the reference's ``Policy``.  The optimiser entry holds the flat Adam moments."""
+    def optimizer_state_dict(self):
+        """The Adam state in the layout of ``torch.optim.Adam(policy.parameters(), ...).state_dict()`` -- what the reference
+        stores under ``"optimizer"`` (rlmpc2.py:917-922) and what its ``optimizer.load_state_dict`` reads.  Parameter
+        indices follow ``Policy.parameters()``: the module's own ``log_std`` first, then ``mean_net``, then ``value_net``
+        (= ``STATE_KEYS``)."""
         import torch
-        p, m, v, step = self._get()
-        torch.save({"model": {k: torch.from_numpy(a) for k, a in unpack_params(p).items()},
-                    "optimizer": {"exp_avg": torch.from_numpy(m), "exp_avg_sq": torch.from_numpy(v), "step": step}, **extra}, path)
+        _, m, v, step = self._get()
+        em, ev = unpack_params(m), unpack_params(v)
+        state = {}
+        if step > 0:
+            for i, k in enumerate(STATE_KEYS):
+                state[i] = {"step": torch.tensor(float(step)), "exp_avg": torch.from_numpy(em[k].copy()),
+                            "exp_avg_sq": torch.from_numpy(ev[k].copy())}
+        group = {"lr": float(self.cfg.lr), "betas": (float(self.cfg.beta1), float(self.cfg.beta2)), "eps": float(self.cfg.adam_eps),
+                 "weight_decay": float(self.cfg.weight_decay), "amsgrad": False, "maximize": False, "foreach": None,
+                 "capturable": False, "differentiable": False, "fused": None, "decoupled_weight_decay": False,
+                 "params": list(range(len(STATE_KEYS)))}
+        return {"state": state, "param_groups": [group]}
 
-    def load(self, path):
+    def load_optimizer_state_dict(self, opt):
+        """Accepts torch's ``Adam.state_dict()`` layout (the reference's checkpoints) or this package's round-1 flat layout
+        ``{exp_avg, exp_avg_sq, step}``.  Returns True when moments were restored."""
+        import warnings
+        if not opt:
+            return False
+        if "state" in opt and "param_groups" in opt:
+            st = opt["state"]
+            if not st:
+                return False
+            if sorted(st.keys()) != list(range(len(STATE_KEYS))):
+                warnings.warn("PPOTrainer.load: optimizer state does not cover the 13 Policy parameters; Adam moments dropped")
+                return False
+            p = self._get()[0]
+            shapes = unpack_params(p)
+            g = lambda t: np.asarray(t.detach().cpu().numpy() if hasattr(t, "detach") else t, dtype=np.float32)
+            em = {k: g(st[i]["exp_avg"]) for i, k in enumerate(STATE_KEYS)}
+            ev = {k: g(st[i]["exp_avg_sq"]) for i, k in enumerate(STATE_KEYS)}
+            for k in STATE_KEYS:
+                if em[k].shape != shapes[k].shape:
+                    warnings.warn(f"PPOTrainer.load: optimizer state {k} has shape {em[k].shape}, expected {shapes[k].shape}; Adam moments dropped")
+                    return False
+            steps = {int(float(st[i]["step"])) for i in st}
+            if len(steps) != 1:
+                warnings.warn("PPOTrainer.load: per-parameter Adam step counts differ; using the maximum")
+            m, v = pack_params(em), pack_params(ev)
+            check(self._lib.dart_ppo_set_state(self._h, None, C.c_void_p(m.ctypes.data), C.c_void_p(v.ctypes.data), max(steps)),
+                  "dart_ppo_set_state")
+            return True
+        if "exp_avg" in opt and "exp_avg_sq" in opt:
+            m = np.ascontiguousarray(np.asarray(opt["exp_avg"], dtype=np.float32))
+            v = np.ascontiguousarray(np.asarray(opt["exp_avg_sq"], dtype=np.float32))
+            check(self._lib.dart_ppo_set_state(self._h, None, C.c_void_p(m.ctypes.data), C.c_void_p(v.ctypes.data), int(opt.get("step", 0))),
+                  "dart_ppo_set_state")
+            return True
+        warnings.warn("PPOTrainer.load: unrecognised optimizer entry; Adam moments dropped")
+        return False
+
+    def save(self, path, obs_norm=None, **extra):
+        """Checkpoint in the reference's format (rlmpc2.py:917-922): ``{"model": Policy.state_dict(), "optimizer":
+        Adam.state_dict(), **extra}`` -- both entries load straight into the reference's ``Policy`` / ``optim.Adam``.
+        ``obs_norm`` = dict(mean, M2, count) additionally persists the Welford observation normaliser (rlmpc2.py:552-555),
+        which the reference loses on restart (its evaluation run re-estimates it from scratch); readers that do not know the
+        key ignore it."""
         import torch
-        ck = torch.load(path, map_location="cpu", weights_only=True)
+        p = self._get()[0]
+        ck = {"model": {k: torch.from_numpy(a) for k, a in unpack_params(p).items()}, "optimizer": self.optimizer_state_dict(), **extra}
+        if obs_norm is not None:
+            ck["obs_norm"] = {"mean": torch.as_tensor(np.asarray(obs_norm["mean"], dtype=np.float64)),
+                              "M2": torch.as_tensor(np.asarray(obs_norm["M2"], dtype=np.float64)), "count": int(obs_norm["count"])}
+        torch.save(ck, path)
+
+    def load(self, path, trust_pickle=False):
+        """Reads this package's and the reference's checkpoints.  The reference's files hold numpy scalars (``"return"``), which
+        a safe ``weights_only`` load rejects; ``trust_pickle=True`` opts into the reference's own ``weights_only=False``
+        load (only for files you trust).  Returns the remaining entries (episode, return, obs_norm, ...)."""
+        import torch
+        try:
+            ck = torch.load(path, map_location="cpu", weights_only=True)
+        except Exception:
+            if not trust_pickle:
+                raise
+            ck = torch.load(path, map_location="cpu", weights_only=False)
         p = pack_params(ck["model"])
-        opt = ck.get("optimizer") or {}
-        m = opt["exp_avg"].numpy().astype(np.float32) if "exp_avg" in opt else None
-        v = opt["exp_avg_sq"].numpy().astype(np.float32) if "exp_avg_sq" in opt else None
-        keep = [np.ascontiguousarray(a) if a is not None else None for a in (p, m, v)]
-        check(self._lib.dart_ppo_set_state(self._h, *[C.c_void_p(a.ctypes.data) if a is not None else None for a in keep],
-                                           int(opt.get("step", 0))), "dart_ppo_set_state")
+        check(self._lib.dart_ppo_set_state(self._h, C.c_void_p(p.ctypes.data), None, None, 0), "dart_ppo_set_state")
+        self.load_optimizer_state_dict(ck.get("optimizer"))
         return {k: ck[k] for k in ck if k not in ("model", "optimizer")}
 
     def close(self):
@@ -354,12 +424,20 @@ class LMPCTrainer:
     [rollout_len, B] buffer goes through ``PPOTrainer.train_rollout``.  The caller owns the plant (MuJoCo in the reference;
     ``lmpc.lmpc_plant_step`` is the surrogate) and resets the instances ``step`` reports as done."""
 
-    def __init__(self, batch, trainer, rollout_len=32, record_every=8, generator=None, graph=False):
+    def __init__(self, batch, trainer, rollout_len=32, record_every=None, generator=None, graph=False, sync_reward_cfg=True):
         torch = trainer.torch
         self.batch, self.ppo = batch, trainer
         self.B, self.dev = batch.B, trainer.dev
         if trainer.capacity < self.B:
             raise ValueError("PPOTrainer capacity must cover the number of instances")
+        # a transition is recorded on exactly the steps whose action is applied to the model parameters (rlmpc2.py:742:
+        # both happen under the same ``timestep % 8 == 0``); two independent knobs would train on actions that never acted
+        if record_every is None:
+            record_every = batch.update_every
+        if int(record_every) != int(batch.update_every):
+            raise ValueError(f"record_every ({record_every}) must equal LMPCBatch.update_every ({batch.update_every})")
+        if sync_reward_cfg:                  # the change penalty is on the delta actually applied: max_delta of the batch
+            trainer.reward_cfg.max_delta = float(batch.max_delta)
         self.T, self.every, self.gen, self.graph = int(rollout_len), int(record_every), generator, bool(graph)
         f32, B, T = torch.float32, self.B, self.T
         self.buf_obs = torch.zeros((T, B, OBS_DIM), dtype=f32, device=self.dev)
@@ -398,4 +476,5 @@ class LMPCTrainer:
                 self.updates += self.ppo.train_rollout(self.buf_obs, self.buf_act, self.buf_logp, self.buf_rew, self.buf_val,
                                                        self.buf_done, val.clone(), generator=self.gen, graph=self.graph)
                 self.k = 0
+                self.batch.refresh_obs_params()          # current_k = views["model_params"].copy()  (rlmpc2.py:896)
         return u0, rew, done

@@ -65,6 +65,18 @@ def rmpc_config3(B=4096, seed=2):
     return dict(x0=x0, target=target, mu_plant=mu_plant, c_plant=c_plant)
 
 
+def rmpc_plant_step(x, u, mu_p, c_p, Ts=0.002, gz=-9.81):
+    """Surrogate plant of SURVEY 8(d) config 3: v' = gz sin u - mu g tanh(v/.01) - c v, four explicit Euler sub-steps."""
+    x = np.array(x, dtype=np.float64, copy=True)
+    for _ in range(4):
+        h = Ts / 4
+        ax = gz * np.sin(u[:, 0]) - mu_p * 9.81 * np.tanh(x[:, 1] / 0.01) - c_p * x[:, 1]
+        ay = gz * np.sin(u[:, 1]) - mu_p * 9.81 * np.tanh(x[:, 3] / 0.01) - c_p * x[:, 3]
+        x[:, 0] += h * x[:, 1]; x[:, 2] += h * x[:, 3]
+        x[:, 1] += h * ax; x[:, 3] += h * ay
+    return x
+
+
 def lmpc_config4(B=16384, seed=3):
     """BASELINE config 4 initial conditions: state, target, initial 34-parameter vectors."""
     rng = np.random.default_rng(seed)

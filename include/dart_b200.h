@@ -73,7 +73,7 @@ typedef struct {
     int32_t max_iter;    /* [PMPC 3000->capped 200, RMPC 200, LMPC 200]     */
     double mu_init;      /* [0.1]   initial barrier parameter               */
     int32_t lanes;       /* [auto]  lanes of a warp cooperating on one sub-problem: 2, 4, 8, 16 or 32 */
-    int32_t block_threads; /* [auto] threads per block (multiple of 32)     */
+    int32_t block_threads; /* [auto] threads per block: a multiple of lcm(32, lanes * axes), axes = 2 for PMPC and LMPC (the two axis problems of an instance share a block), 1 for RMPC; other values -> DART_ERR_ARG */
     /* IPOPT's acceptable-level termination (rlmpc2.py:486-488 sets tol 1e-4, acceptable_tol 1e-3, acceptable_iter 5,
      * max_iter 50 for LMPC; PMPC/RMPC leave IPOPT's 1e-6 / 15, which never triggers before tol on this path).
      * [0 / 0 = off: every solve runs to tol] */

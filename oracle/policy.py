@@ -19,17 +19,18 @@ def mlp_forward(obs, weights, dtype=np.float32):
 
 
 def orthogonal_policy_weights(obs_dim=520, act_dim=34, hidden=64, layers=2, seed=3):
-    """Random-init actor weights as ``Policy._init_weights`` draws them (torch, CPU). Returns list of (W,b) float32."""
+    """Random-init actor weights of ``Policy(obs_dim, act_dim, {})`` under ``torch.manual_seed(seed)`` (rlmpc2.py:33-69):
+    actor stack, critic stack (default inits consume the generator), then orthogonal re-draws in module order.
+    Returns the actor as a list of (W, b) float32; equals the reference's construction bit for bit (tests/test_ref_pin.py)."""
     import torch
     torch.manual_seed(seed)
-    dims = [obs_dim] + [hidden] * layers + [act_dim]
-    out = []
-    for i in range(len(dims) - 1):
-        lin = torch.nn.Linear(dims[i], dims[i + 1])
+    dims = [obs_dim] + [hidden] * layers
+    actor = [torch.nn.Linear(dims[i], dims[i + 1]) for i in range(layers)] + [torch.nn.Linear(hidden, act_dim)]
+    critic = [torch.nn.Linear(dims[i], dims[i + 1]) for i in range(layers)] + [torch.nn.Linear(hidden, 1)]
+    for lin in actor + critic:
         torch.nn.init.orthogonal_(lin.weight, gain=float(np.sqrt(2)))
         torch.nn.init.constant_(lin.bias, 0.0)
-        out.append((lin.weight.detach().numpy().copy(), lin.bias.detach().numpy().copy()))
-    return out
+    return [(lin.weight.detach().numpy().copy(), lin.bias.detach().numpy().copy()) for lin in actor]
 
 
 class ObsNormalizer:

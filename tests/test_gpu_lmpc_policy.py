@@ -98,7 +98,7 @@ def test_lmpc_batch_step_matches_oracle_pipeline(built):
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     for step in range(3):
         u_gpu = ctl.step(t(state), t(c["target"])).cpu().numpy()
-        obs = norm.push(state, c["target"], control, k)
+        obs = norm.push(state, c["target"], control, c["pvec"])      # current_k of the observation is the stale start-up copy (rlmpc2.py:649)
         a = policy.mlp_forward(obs, weights)
         if step % 8 == 0:
             k = policy.write_params(policy.param_update(k, a, 2.0, 0.02, 1e-2), k, 2.0, 1e-2, 0.1, 0.5)
@@ -149,7 +149,7 @@ def test_lmpc_pipeline_end_to_end_within_the_tilt_bar(built):
     worst_u = worst_k = 0.0
     for step in range(T):
         u_gpu = ctl.step(t(x_gpu), t(c["target"])).cpu().numpy()
-        obs = norm.push(x_ora, c["target"], control, k)
+        obs = norm.push(x_ora, c["target"], control, c["pvec"])
         a = policy.mlp_forward(obs, weights)
         if step % 8 == 0:
             k = policy.write_params(policy.param_update(k, a, 2.0, 0.02, 1e-2), k, 2.0, 1e-2, 0.1, 0.5)
