@@ -9,7 +9,7 @@ from ._lib import (DART_LMPC, DART_PMPC, DART_RMPC, STATUS_CONVERGED, STATUS_INF
 from .config import cfg_from_yaml, lmpc_cfg, load_config, pmpc_cfg, rmpc_cfg   # noqa: F401
 from .engine import NMPCEngine, measure_fp64_tflops, tilt_to_quat_device        # noqa: F401
 from .pmpc import PMPC, GravityModel, StateHolder, mpc_worker   # noqa: F401
-from .rmpc import RLS, AdaptiveNPMPCSmooth, RMPCBatch, rls_update_device   # noqa: F401
+from .rmpc import RLS, AdaptiveNPMPCSmooth, RMPCBatch, rls_update_device, rmpc_plant_step_device   # noqa: F401
 from .lmpc import RLMPC, LMPCBatch, PolicyMLP, lmpc_plant_step, init_policy_weights, load_checkpoint_weights, load_checkpoint   # noqa: F401
 from .parallel import ShardedSolver, shard_bounds   # noqa: F401
 from .episodes import PMPCEpisodes   # noqa: F401

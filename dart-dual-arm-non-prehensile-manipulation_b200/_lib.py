@@ -82,6 +82,8 @@ def lib():
         L.dart_arm_qp_solve.argtypes = [C.c_int32] + [vp] * 10 + [C.c_double, C.c_int32, vp]
         L.dart_arm_qp_launch_count.restype = C.c_int64
         L.dart_arm_qp_build.argtypes = [C.c_int32] + [vp] * 7 + [C.c_double] + [vp] * 17 + [vp]
+    if hasattr(L, "dart_rmpc_plant_step"):
+        L.dart_rmpc_plant_step.argtypes = [C.c_int32, C.c_double, C.c_double, vp, vp, vp, vp, vp, vp]
     if hasattr(L, "dart_lmpc_plant_step"):
         L.dart_lmpc_plant_step.argtypes = [C.c_int32, C.c_double, vp, vp, vp, vp, vp]
     if hasattr(L, "dart_ppo_create"):

@@ -18,7 +18,35 @@ __global__ void __launch_bounds__(128) pmpc_plant_step_kernel(const PlantArgs a)
     dart::plant_step_one(a, b);
 }
 
+// Surrogate plant of BASELINE config 3: v' = gz sin(u) - mu |g| tanh(v / 0.01) - c v per axis, four explicit
+// Euler sub-steps of Ts / 4 (positions first, with the old velocity) -- workloads.rmpc_plant_step on the host.
+__global__ void __launch_bounds__(128) rmpc_plant_step_kernel(int B, double Ts, double gz, const double* __restrict__ mu,
+                                                              const double* __restrict__ cdamp, const double* __restrict__ u,
+                                                              const double* __restrict__ x_in, double* __restrict__ x_out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double px = x_in[b * 4 + 0], vx = x_in[b * 4 + 1], py = x_in[b * 4 + 2], vy = x_in[b * 4 + 3];
+    const double sx = gz * sin(u[b * 2 + 0]), sy = gz * sin(u[b * 2 + 1]);
+    const double m = mu[b] * 9.81, c = cdamp[b], h = Ts / 4;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const double ax = sx - m * tanh(vx / 0.01) - c * vx;
+        const double ay = sy - m * tanh(vy / 0.01) - c * vy;
+        px += h * vx; py += h * vy;
+        vx += h * ax; vy += h * ay;
+    }
+    x_out[b * 4 + 0] = px; x_out[b * 4 + 1] = vx; x_out[b * 4 + 2] = py; x_out[b * 4 + 3] = vy;
+}
+
 }  // namespace
+
+extern "C" int dart_rmpc_plant_step(int32_t B, double Ts, double gz, const double* mu, const double* c, const double* u,
+                                    const double* state, double* state_out, void* stream) {
+    if (B < 0 || !mu || !c || !u || !state || !state_out || !(Ts > 0.0)) return DART_ERR_ARG;
+    if (B == 0) return DART_OK;
+    rmpc_plant_step_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(B, Ts, gz, mu, c, u, state, state_out);
+    return cudaGetLastError() == cudaSuccess ? DART_OK : DART_ERR_CUDA;
+}
 
 extern "C" int dart_pmpc_plant_step(int32_t B, double Ts, double g, const double* mu, const double* coulomb, const double* u,
                                     const double* target, double* state, int32_t* nsteps, double tol, double* conv_time,

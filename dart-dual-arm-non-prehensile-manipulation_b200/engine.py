@@ -38,6 +38,7 @@ class NMPCEngine:
         self.naux = self._lib.dart_naux(self._h)
         self.nw = self._lib.dart_nw(self._h)
         self.N = cfg.N
+        self._nvtx_name = "dart_solve/" + {0: "pmpc", 1: "rmpc", 2: "lmpc"}.get(int(cfg.method), "nmpc")
 
     def set_mu_init(self, mu_init):
         """Initial barrier parameter of the following solves (0 = default 0.1); see dart_set_mu_init."""
@@ -114,6 +115,13 @@ class NMPCEngine:
         if torch.cuda.current_device() != self.device:      # dart_solve rejects a launch from another device
             torch.cuda.set_device(self.device)
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        torch.cuda.nvtx.range_push(self._nvtx_name)          # NVTX range around the solve launch (tracing)
+        try:
+            return self._solve_device(B, ptr, x0, ref, aux, warm_w, w_out, u0_out, J_out, status, iters, stream, f64, i32)
+        finally:
+            torch.cuda.nvtx.range_pop()
+
+    def _solve_device(self, B, ptr, x0, ref, aux, warm_w, w_out, u0_out, J_out, status, iters, stream, f64, i32):
         check(self._lib.dart_solve(self._h, B, ptr(x0, (B, self.nx), f64, "x0"), ptr(ref, (B, self.nref), f64, "ref"),
                                    ptr(aux, (B, self.naux), f64, "aux"), ptr(warm_w, (B, self.nw), f64, "warm_w"),
                                    ptr(w_out, (B, self.nw), f64, "w_out"), ptr(u0_out, (B, 2), f64, "u0_out"),

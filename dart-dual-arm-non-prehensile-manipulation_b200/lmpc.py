@@ -142,7 +142,7 @@ class LMPCBatch:
         # trained checkpoint expects that.  ``live_params_in_obs=True`` feeds the live parameters instead.
         self.live_params_in_obs = bool(live_params_in_obs)
         k_obs = pvec0 if obs_k0 is None else obs_k0
-        self.obs_k = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(k_obs, (B, ACT_DIM)), dtype=np.float64)).to(self.dev).contiguous()
+        self.obs_k = torch.from_numpy(np.array(np.broadcast_to(k_obs, (B, ACT_DIM)), dtype=np.float64)).to(self.dev).contiguous()
         # evaluation action: the policy mean (deterministic; what the reference applies after each update, :877-896).  The
         # reference's worker applies a *sample* N(mean, std) on every step even in evaluation (:678); eval_std=0.1
         # (exp(log_std) of its checkpoints) with a torch generator reproduces that behaviour.
@@ -222,6 +222,7 @@ class LMPCBatch:
         stream = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
         self.count += 1
         obs_in, obs_out = self.obs
+        torch.cuda.nvtx.range_push("lmpc_policy")          # obs push + policy forward + parameter update
         if self.live_params_in_obs:
             k_ptr, k_stride = C.c_void_p(self.aux.data_ptr() + 16), 36
         else:
@@ -240,6 +241,7 @@ class LMPCBatch:
             check(L.dart_policy_param_update(self.B, p(self.action), C.c_void_p(self.aux.data_ptr() + 16), 36, self.k_max,
                                              self.max_delta, self.min_k, self.margin, self.alpha, stream),
                   "dart_policy_param_update")
+        torch.cuda.nvtx.range_pop()
         warm = None
         if self.warm_start:
             warm = self._shifted(self.w) if (self.warm_start == "shift" and self.timestep > 0) else self.w

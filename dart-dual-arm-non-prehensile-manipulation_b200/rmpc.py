@@ -35,6 +35,22 @@ def rls_update_device(theta, P, phi, y, lam):
     check(_lib.lib().dart_rls_update(B, E, p(theta), p(P), p(phi), p(y), float(lam), stream), "dart_rls_update")
 
 
+def rmpc_plant_step_device(x, u, mu, c, Ts=0.002, gz=-9.81, out=None):
+    """Surrogate plant of BASELINE config 3 on the device (``dart_rmpc_plant_step``; host twin: workloads.rmpc_plant_step).
+    x [B,4], u [B,2], mu [B], c [B] float64 CUDA tensors -> next state [B,4]."""
+    torch = _torch()
+    B = x.shape[0]
+    for t, shp in ((x, (B, 4)), (u, (B, 2)), (mu, (B,)), (c, (B,))):
+        if tuple(t.shape) != shp or t.dtype != torch.float64 or not t.is_cuda or not t.is_contiguous():
+            raise ValueError(f"rmpc_plant_step_device: need contiguous float64 CUDA tensor of shape {shp}")
+    if out is None:
+        out = torch.empty_like(x)
+    stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    check(_lib.lib().dart_rmpc_plant_step(B, float(Ts), float(gz), p(mu), p(c), p(u), p(x), p(out), stream), "dart_rmpc_plant_step")
+    return out
+
+
 class RLS:
     """Scalar-output recursive least squares with forgetting; state lives on the GPU.
 
@@ -174,10 +190,12 @@ class RMPCBatch:
         p = lambda t: C.c_void_p(t.data_ptr())
         stream = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
         c = self.cfg
+        torch.cuda.nvtx.range_push("rmpc_prologue")
         check(_lib.lib().dart_rmpc_prologue(self.B, self.N, c.Ts, c.v_eps, self.lam, self.dr_max, self.alpha_rg,
                                             self.step_fraction, p(xk), p(self.prev_state), p(self.target), p(self.u_prev),
                                             p(self.r_v), p(self.theta), p(self.P), p(self.ref), p(self.aux), stream),
               "dart_rmpc_prologue")
+        torch.cuda.nvtx.range_pop()
         if self.steps == 1 and self.warm_mu:
             self.engine.set_mu_init(self.warm_mu)
         self.engine.solve_device(xk, self.ref, aux=self.aux, warm_w=self.w if self.warm_start else None,

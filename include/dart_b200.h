@@ -238,6 +238,12 @@ int dart_pmpc_episode(dart_handle h, int32_t B, int32_t T, double* state, const 
                       double* effort, double* err, double* u0, double* J, int32_t* status, int32_t* iters,
                       uint64_t* counters, void* stream);
 
+/* RMPC surrogate plant (no reference counterpart -- the reference steps MuJoCo, rob_ctrl.py:365):
+ * v' = gz sin(u) - mu |g| tanh(v / 0.01) - c v per axis, four explicit Euler sub-steps of Ts / 4.  mu, c [B]; u [B,2];
+ * state [B,4] -> state_out [B,4] (may alias state). */
+int dart_rmpc_plant_step(int32_t B, double Ts, double gz, const double* mu, const double* c, const double* u,
+                         const double* state, double* state_out, void* stream);
+
 /* LMPC surrogate plant: one RK4 step (tilt u [B,2] held over Ts) of the 8-state model of
  * rlmpc2.py:260-436 with per-instance TRUE parameters: true_aux [B,36] has the layout of the LMPC solver's aux rows
  * ([u_prev(2), pvec(34)]; the first two columns are ignored).  state [B,8] -> state_out [B,8] (may alias).  With

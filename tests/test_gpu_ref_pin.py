@@ -23,10 +23,13 @@ load = lambda n: np.load(os.path.join(G, n), allow_pickle=False)
 tape = lambda n: Tape.load(os.path.join(G, "tapes", n))
 
 
-def reference_kkt_at(tp, w, p, lbx, ubx, lbg=None, ubg=None, act_tol=1e-6):
+def reference_kkt_at(tp, w, p, lbx, ubx, lbg=None, ubg=None, act_tol=1e-3):
     """Feasibility and stationarity of the REFERENCE NLP at w.  Multipliers: least squares over [lam_g on equality rows and
-    active inequality rows; bound multipliers of active variable bounds]; returns (violation, |f|, relative residual,
-    worst multiplier sign violation)."""
+    near-active inequality rows; bound multipliers of near-active variable bounds]; returns (violation, f, relative
+    stationarity residual, worst of {multiplier sign violation, complementarity |z * slack|} relative to the multiplier
+    scale).  ``act_tol`` is wide on purpose: an interior-point solution leaves a weakly active bound at slack ~ mu / z
+    (1e-9 / 1e-5 = 1e-4), so its multiplier must be allowed in the fit; a bound that is not really active then gets a
+    multiplier ~ 0 and the complementarity term checks exactly that."""
     ev = tp.eval(x=w, p=p)
     g, f = ev["g"], float(ev["f"][0])
     m = len(g)
@@ -54,6 +57,11 @@ def reference_kkt_at(tp, w, p, lbx, ubx, lbg=None, ubg=None, act_tol=1e-6):
         sign = max(sign, (lam[act_lo]).max() / scale)
     for j, b in enumerate(bnd):                      # z = z_U - z_L: >= 0 at an upper bound, <= 0 at a lower bound
         sign = max(sign, (-z[j] if at_hi[b] else z[j]) / scale)
+        sign = max(sign, abs(z[j]) * (ubx[b] - w[b] if at_hi[b] else w[b] - lbx[b]) / scale)
+    if act_hi.any():
+        sign = max(sign, (np.abs(lam[act_hi]) * (ubg - g)[act_hi]).max() / scale)
+    if act_lo.any():
+        sign = max(sign, (np.abs(lam[act_lo]) * (g - lbg)[act_lo]).max() / scale)
     return viol, f, res, sign
 
 
