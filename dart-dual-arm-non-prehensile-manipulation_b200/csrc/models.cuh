@@ -81,7 +81,7 @@ struct PmpcAxis {
     // structure the serial sweep may rely on: the position does not enter the dynamics, so column 0 of the RK4
     // sensitivity A is exactly e_0
     DART_HD static constexpr int a_kind(int a, int b) { return b == 0 ? (a == 0 ? 2 : 1) : 0; }
-    static constexpr int MAX_THREADS = 256, MIN_BLOCKS = 1, BT_LARGE = 64;   // BT_LARGE: block size when the GPU is filled (measured)
+    static constexpr int MAX_THREADS = 256, MIN_BLOCKS = 1, BT_LARGE = 32;   // BT_LARGE: block size when the GPU is filled (measured: 32 < 64 < 128)
     static constexpr int NXF = 6;   // states per stage in the reference's decision vector
     static constexpr int NDEF = 15; // the reference's horizon (compile-time instantiation)
     struct Prm { double Qp, Qv, R, mu, g, Ts, ulo, uhi, rp, rv; };
@@ -333,7 +333,7 @@ struct LmpcAxis {
 // Solve sub-problem (inst, axis) with the lanes of `tile`; `base` is this tile's workspace.
 // Returns per-problem J/status/iters/kkt; writes X/U of this sub-problem into w_out (reference layout).
 template <class M, class T, int NC = 0>
-DART_HD void solve_one(const T& tile, const KArgs& a, int inst, int axis, bool active, const BlockCtx& bc, double* base,
+DART_HD void solve_one(const T& tile, const KArgs& a, int inst, int axis, bool active, bool write, const BlockCtx& bc, double* base,
                        double& J, int32_t& status, int32_t& iters, double& kkt) {
     constexpr int n = M::NX, m = M::NU, np = M::NP;
     const int N = (NC > 0) ? NC : a.N;
@@ -376,11 +376,16 @@ DART_HD void solve_one(const T& tile, const KArgs& a, int inst, int axis, bool a
         const bool dualwarm = a.dual != nullptr && a.warm != nullptr && dual_block()[0] == 1.0;
         if (a.dual != nullptr && !dualwarm) mu0 = dmax(mu0, 1e-4);     // no usable dual state: never below the primal-warm value
         s.init_rows(mu0);
-        if (dualwarm) s.load_duals(dual_block(), mu0);
+        if (T::kLockstep) {
+            // lockstep tiles: the sibling tile of the warp may have a usable dual block when this one has not
+            if (a.dual != nullptr && a.warm != nullptr) s.load_duals(dual_block(), mu0, dualwarm);
+        } else if (dualwarm) {
+            s.load_duals(dual_block(), mu0);
+        }
     }
     s.run(active, mu0, J, status, iters, kkt);
-    if (active && a.dual != nullptr) s.store_duals(dual_block(), status == ST_CONVERGED || status == ST_ACCEPTABLE);
-    if (!active) return;
+    if (write && a.dual != nullptr) s.store_duals(dual_block(), status == ST_CONVERGED || status == ST_ACCEPTABLE);
+    if (!write) return;
     if (M::infeasible0(prm, x0) && status != ST_NUMERIC) status = ST_INFEASIBLE;
     // a solve that ran into NaN/Inf hands back its starting point, not the broken iterate: a closed loop that feeds
     // plans and commands back in must not be poisoned by one failed solve (selected at the output, so that the cold

@@ -8,30 +8,40 @@
 
 namespace dart {
 
-template <int G>
+// LOCK = true: the tiles of a warp run in LOCKSTEP (same instruction stream, see the scan path of Solver::run), so every
+// collective names the full warp with a compile-time mask and compiles to a bare SHFL / one WARPSYNC; the shuffle width
+// still confines data to the tile.  LOCK = false: each tile names only its own lanes.  That mask is a lane-dependent
+// value, so the compiler wraps every __shfl_sync / __syncwarp in a MATCH.ANY loop over the distinct masks of the warp
+// (one pass per tile) and puts a WARPSYNC in front of every shuffle -- measured on the PMPC kernel: 49 such loops, and
+// the collectives, not the arithmetic, set the time of the shuffle-heavy phases.
+template <int G, bool LOCK = false>
 struct DevTile {
     static constexpr int kLanes = G;
-    unsigned mask;
+    static constexpr bool kLockstep = LOCK || G == 32;
+    unsigned mask_;
     int ln;
     __device__ __forceinline__ DevTile() {
         const int l = threadIdx.x & 31;
         ln = l & (G - 1);
-        mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (l - ln));
+        mask_ = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (l - ln));
     }
+    __device__ __forceinline__ unsigned m() const { return kLockstep ? 0xffffffffu : mask_; }
+    __device__ __forceinline__ unsigned warp_ballot(bool p) const { return __ballot_sync(0xffffffffu, p); }
+    __device__ __forceinline__ bool group_all(bool p) const { return __all_sync(m(), p) != 0; }
     __device__ __forceinline__ int lane() const { return ln; }
     __device__ __forceinline__ int size() const { return G; }
-    __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+    __device__ __forceinline__ void sync() const { __syncwarp(m()); }
     __device__ __forceinline__ void block_sync() const { __syncthreads(); }
     __device__ __forceinline__ bool block_any(bool p) const { return __syncthreads_or(p ? 1 : 0) != 0; }
-    __device__ __forceinline__ double shfl(double v, int src) const { return __shfl_sync(mask, v, src, G); }
+    __device__ __forceinline__ double shfl(double v, int src) const { return __shfl_sync(m(), v, src, G); }
     __device__ __forceinline__ double sum(double v) const {
 #pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o, G);
+        for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(m(), v, o, G);
         return v;
     }
     __device__ __forceinline__ double max(double v) const {
 #pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(mask, v, o, G));
+        for (int o = G / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(m(), v, o, G));
         return v;
     }
     // max of values that are >= 0 (|.|, or maxima seeded with 0): for those the IEEE-754 order is the unsigned integer
@@ -40,23 +50,30 @@ struct DevTile {
     __device__ __forceinline__ double max_nonneg(double v) const {
         if (G != 32) return max(v);
         const unsigned hi = (unsigned)__double2hiint(v) & 0x7fffffffu, lo = (unsigned)__double2loint(v);
-        const unsigned mh = __reduce_max_sync(mask, hi);
-        const unsigned ml = __reduce_max_sync(mask, hi == mh ? lo : 0u);
+        const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+        const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
         return __hiloint2double((int)mh, (int)ml);
     }
     // min of positive values (products z * slack of interior iterates), same integer-order argument
     __device__ __forceinline__ double min_pos(double v) const {
         if (G != 32) return min(v);
         const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
-        const unsigned mh = __reduce_min_sync(mask, hi);
-        const unsigned ml = __reduce_min_sync(mask, hi == mh ? lo : 0xffffffffu);
+        const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+        const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
         return __hiloint2double((int)mh, (int)ml);
     }
     __device__ __forceinline__ double min(double v) const {
 #pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(mask, v, o, G));
+        for (int o = G / 2; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(m(), v, o, G));
         return v;
     }
+};
+
+// lockstep tiles: the scan path of Solver::run (2-state / 1-input axis problems, one lane per stage + the terminal cost)
+template <class M, int G, int NC>
+struct TileFor {
+    static constexpr bool lock = M::SERIAL_RICCATI && M::NX == 2 && M::NU == 1 && NC > 0 && G < 32 && (G == NC + 1 || 2 * G == NC + 1);
+    using type = DevTile<G, lock>;
 };
 
 // M::MIN_BLOCKS: occupancy hint (blocks of M::MAX_THREADS per SM) that caps registers where shared memory leaves room.
@@ -64,7 +81,8 @@ struct DevTile {
 template <class M, int G, int NC>
 __device__ __forceinline__ void solve_block(const KArgs& a, const int ws_stride, double* smem) {
     constexpr int NAX = M::NAXIS;
-    const DevTile<G> tile;
+    using TileT = typename TileFor<M, G, NC>::type;
+    const TileT tile;
     const int tpb = blockDim.x / G;
     const int tib = threadIdx.x / G;
     const long prob = (long)blockIdx.x * tpb + tib;
@@ -74,7 +92,13 @@ __device__ __forceinline__ void solve_block(const KArgs& a, const int ws_stride,
     double J = 0.0, kkt = 0.0;
     int32_t status = ST_CONVERGED, iters = 0;
     const BlockCtx bc{smem, ws_stride, tpb, (int)threadIdx.x};
-    solve_one<M, DevTile<G>, NC>(tile, a, inst, axis, active, bc, slot + kSlot, J, status, iters, kkt);
+    if (TileT::kLockstep && G < 32) {
+        // lockstep tiles execute one instruction stream per warp: a tile past the end of the batch solves the last
+        // instance again (same data, same trajectory) and writes nothing
+        solve_one<M, TileT, NC>(tile, a, active ? inst : a.B - 1, axis, true, active, bc, slot + kSlot, J, status, iters, kkt);
+    } else {
+        solve_one<M, TileT, NC>(tile, a, inst, axis, active, active, bc, slot + kSlot, J, status, iters, kkt);
+    }
     if (NAX == 1) {
         if (active && tile.lane() == 0) {
             a.J[inst] = J;

@@ -87,6 +87,10 @@ struct HostTile {
     DART_HD void sync() const {}
     DART_HD void block_sync() const {}
     DART_HD bool block_any(bool p) const { return p; }
+    DART_HD bool warp_any(bool p) const { return p; }
+    static constexpr bool kLockstep = false;
+    DART_HD unsigned warp_ballot(bool p) const { return p ? 1u : 0u; }
+    DART_HD bool group_all(bool p) const { return p; }
     DART_HD double shfl(double v, int) const { return v; }
     DART_HD double sum(double v) const { return v; }
     DART_HD double max(double v) const { return v; }
@@ -102,6 +106,82 @@ struct SerialTile {
     DART_HD int size() const { return 1; }
     DART_HD void sync() const {}
 };
+
+// ------------------------------------------------------------------------------------------------------
+// Parallel-in-time LQ sweeps for 2-state / 1-input stage problems (the PMPC axis problem).
+//
+// The Riccati recursion is a fold of "conditional value functions" under an associative combination rule (Sarkka &
+// Garcia-Fernandez, "Temporal parallelization of dynamic programming and linear quadratic control", 2021), so the
+// value functions of ALL stages follow from a suffix scan: log2(N+1) combination levels instead of N dependent stages.
+// An element describes an interval i -> j of the horizon,
+//     V_{i->j}(x_i, x_j) = max_lam [ 1/2 x_i' J x_i + q' x_i - 1/2 lam' C lam - lam' (x_j - A x_i - b) ],
+// one stage k -> k+1 with diagonal-free coupling (H_xu = 0) is  A = A_k, b = d_k - B g_u / H_uu, C = B B' / H_uu,
+// J = H_xx, q = g_x, and the terminal cost is the element A = 0, b = 0, C = 0, J = P_N, q = p_N.  The combination of
+// stage k with everything after it has J = P_k, q = p_k (the value function of the serial recursion).
+namespace scan2 {
+struct El {
+    double a00, a01, a10, a11, b0, b1, c00, c01, c11, q0, q1, j00, j01, j11;
+};
+// O = L (+) R: L covers the earlier interval, R the later one.
+DART_HD void combine(const El& L, const El& R, El& O) {
+    const double t00 = 1.0 + L.c00 * R.j00 + L.c01 * R.j01, t01 = L.c00 * R.j01 + L.c01 * R.j11;
+    const double t10 = L.c01 * R.j00 + L.c11 * R.j01, t11 = 1.0 + L.c01 * R.j01 + L.c11 * R.j11;
+    const double id = 1.0 / (t00 * t11 - t01 * t10);               // det(I + C_L J_R) >= 1 for positive semidefinite C, J
+    const double m00 = t11 * id, m01 = -t01 * id, m10 = -t10 * id, m11 = t00 * id;
+    const double am00 = R.a00 * m00 + R.a01 * m10, am01 = R.a00 * m01 + R.a01 * m11;
+    const double am10 = R.a10 * m00 + R.a11 * m10, am11 = R.a10 * m01 + R.a11 * m11;
+    const double v0 = L.b0 - (L.c00 * R.q0 + L.c01 * R.q1), v1 = L.b1 - (L.c01 * R.q0 + L.c11 * R.q1);
+    const double x00 = am00 * L.c00 + am01 * L.c01, x01 = am00 * L.c01 + am01 * L.c11;
+    const double x10 = am10 * L.c00 + am11 * L.c01, x11 = am10 * L.c01 + am11 * L.c11;
+    const double r0 = R.q0 + R.j00 * L.b0 + R.j01 * L.b1, r1 = R.q1 + R.j01 * L.b0 + R.j11 * L.b1;
+    const double s0 = m00 * r0 + m10 * r1, s1 = m01 * r0 + m11 * r1;
+    const double y00 = m00 * R.j00 + m10 * R.j01, y01 = m00 * R.j01 + m10 * R.j11;
+    const double y10 = m01 * R.j00 + m11 * R.j01, y11 = m01 * R.j01 + m11 * R.j11;
+    const double z00 = L.a00 * y00 + L.a10 * y10, z01 = L.a00 * y01 + L.a10 * y11;
+    const double z10 = L.a01 * y00 + L.a11 * y10, z11 = L.a01 * y01 + L.a11 * y11;
+    El o;
+    o.a00 = am00 * L.a00 + am01 * L.a10; o.a01 = am00 * L.a01 + am01 * L.a11;
+    o.a10 = am10 * L.a00 + am11 * L.a10; o.a11 = am10 * L.a01 + am11 * L.a11;
+    o.b0 = am00 * v0 + am01 * v1 + R.b0; o.b1 = am10 * v0 + am11 * v1 + R.b1;
+    o.c00 = x00 * R.a00 + x01 * R.a01 + R.c00;
+    o.c01 = 0.5 * ((x00 * R.a10 + x01 * R.a11) + (x10 * R.a00 + x11 * R.a01)) + R.c01;
+    o.c11 = x10 * R.a10 + x11 * R.a11 + R.c11;
+    o.q0 = L.a00 * s0 + L.a10 * s1 + L.q0; o.q1 = L.a01 * s0 + L.a11 * s1 + L.q1;
+    o.j00 = z00 * L.a00 + z01 * L.a10 + L.j00;
+    o.j01 = 0.5 * ((z00 * L.a01 + z01 * L.a11) + (z10 * L.a00 + z11 * L.a10)) + L.j01;
+    o.j11 = z10 * L.a01 + z11 * L.a11 + L.j11;
+    O = o;
+}
+// J and q of L (+) R only (the value function of L's first stage; what the last combination of a scan needs)
+DART_HD void combine_jq(const El& L, const El& R, double& j00, double& j01, double& j11, double& q0, double& q1) {
+    const double t00 = 1.0 + L.c00 * R.j00 + L.c01 * R.j01, t01 = L.c00 * R.j01 + L.c01 * R.j11;
+    const double t10 = L.c01 * R.j00 + L.c11 * R.j01, t11 = 1.0 + L.c01 * R.j01 + L.c11 * R.j11;
+    const double id = 1.0 / (t00 * t11 - t01 * t10);
+    const double m00 = t11 * id, m01 = -t01 * id, m10 = -t10 * id, m11 = t00 * id;
+    const double r0 = R.q0 + R.j00 * L.b0 + R.j01 * L.b1, r1 = R.q1 + R.j01 * L.b0 + R.j11 * L.b1;
+    const double s0 = m00 * r0 + m10 * r1, s1 = m01 * r0 + m11 * r1;
+    const double y00 = m00 * R.j00 + m10 * R.j01, y01 = m00 * R.j01 + m10 * R.j11;
+    const double y10 = m01 * R.j00 + m11 * R.j01, y11 = m01 * R.j01 + m11 * R.j11;
+    const double z00 = L.a00 * y00 + L.a10 * y10, z01 = L.a00 * y01 + L.a10 * y11;
+    const double z10 = L.a01 * y00 + L.a11 * y10, z11 = L.a01 * y01 + L.a11 * y11;
+    q0 = L.a00 * s0 + L.a10 * s1 + L.q0; q1 = L.a01 * s0 + L.a11 * s1 + L.q1;
+    j00 = z00 * L.a00 + z01 * L.a10 + L.j00;
+    j01 = 0.5 * ((z00 * L.a01 + z01 * L.a11) + (z10 * L.a00 + z11 * L.a10)) + L.j01;
+    j11 = z10 * L.a01 + z11 * L.a11 + L.j11;
+}
+// affine maps x -> M x + v of the closed loop: O = later (after) earlier
+struct Af {
+    double m00, m01, m10, m11, v0, v1;
+};
+DART_HD void compose(const Af& later, const Af& earlier, Af& O) {
+    Af o;
+    o.m00 = later.m00 * earlier.m00 + later.m01 * earlier.m10; o.m01 = later.m00 * earlier.m01 + later.m01 * earlier.m11;
+    o.m10 = later.m10 * earlier.m00 + later.m11 * earlier.m10; o.m11 = later.m10 * earlier.m01 + later.m11 * earlier.m11;
+    o.v0 = later.m00 * earlier.v0 + later.m01 * earlier.v1 + later.v0;
+    o.v1 = later.m10 * earlier.v0 + later.m11 * earlier.v1 + later.v1;
+    O = o;
+}
+}  // namespace scan2
 
 template <class M>
 struct Workspace {
@@ -824,9 +904,214 @@ struct Solver {
         }
     }
 
+    // ---- both sweeps of the Newton step as SCANS across the tile (2-state / 1-input problems, one lane per stage plus one
+    // for the terminal cost: lanes == N + 1).  Backward: suffix scan of the conditional value functions (scan2::combine,
+    // log2(N+1) = 4 levels instead of N = 15 dependent Riccati stages) gives P_k, p_k of every stage at once; the gains
+    // are then stage-parallel; forward: prefix scan of the closed-loop affine maps.  Everything stays in registers and
+    // shuffles; no other tile is involved, so tiles of a block run and finish independently (no block barriers).
+    // Pivot regularisation: the serial sweep shifts the pivot H_uu + B'P B when it is not positive; here the shift is
+    // decided on H_uu alone (it must be inverted before P is known).  B'P B >= 0, so the pivot is then positive too;
+    // the two rules differ only when H_uu <= 0 < H_uu + B'P B, and only in that iteration's step, not in the fixed point.
+    template <class TL>
+    DART_HD void sweeps_scan(const TL& tl) {
+        using scan2::El;
+        using scan2::Af;
+        constexpr int G = TL::kLanes;
+        const int lane = tl.lane();
+        const bool stage = lane < N;
+        const int k = stage ? lane : N - 1;                 // the terminal lane reads stage N-1 (values unused)
+        const double a00 = Aat(k, 0, 0), a01 = Aat(k, 0, 1), a10 = Aat(k, 1, 0), a11 = Aat(k, 1, 1);
+        const double B0 = w.Bm[k * sB + 0], B1 = w.Bm[k * sB + 1];
+        const double d0 = w.D[k * n + 0], d1 = w.D[k * n + 1];
+        const double gu = w.GR[k * sG + 2];
+        double huu = w.HS[k * sH + 2];
+        if (!(huu > 0.0)) {
+            double shift = 1e-4;
+            while (!(huu + shift > 0.0) && shift < 1e30) shift *= 8.0;
+            huu += shift;
+        }
+        const double ih = 1.0 / huu;
+        El e;
+        if (stage) {
+            e.a00 = a00; e.a01 = a01; e.a10 = a10; e.a11 = a11;
+            const double t = ih * gu;
+            e.b0 = d0 - B0 * t; e.b1 = d1 - B1 * t;
+            e.c00 = B0 * B0 * ih; e.c01 = B0 * B1 * ih; e.c11 = B1 * B1 * ih;
+            e.q0 = w.GR[k * sG + 0]; e.q1 = w.GR[k * sG + 1];
+            e.j00 = w.HS[k * sH + 0]; e.j01 = 0.0; e.j11 = w.HS[k * sH + 1];
+        } else {
+            e.a00 = e.a01 = e.a10 = e.a11 = e.b0 = e.b1 = e.c00 = e.c01 = e.c11 = 0.0;
+            e.j00 = w.PP[N * nps + 0]; e.j01 = w.PP[N * nps + 1]; e.j11 = w.PP[N * nps + 2];
+            e.q0 = w.PV[N * n + 0]; e.q1 = w.PV[N * n + 1];
+        }
+        DART_UNROLL for (int off = 1; off < G; off <<= 1) {
+            const int src = (lane + off) & (G - 1);
+            El r;
+            r.a00 = tl.shfl(e.a00, src); r.a01 = tl.shfl(e.a01, src); r.a10 = tl.shfl(e.a10, src); r.a11 = tl.shfl(e.a11, src);
+            r.b0 = tl.shfl(e.b0, src); r.b1 = tl.shfl(e.b1, src);
+            r.c00 = tl.shfl(e.c00, src); r.c01 = tl.shfl(e.c01, src); r.c11 = tl.shfl(e.c11, src);
+            r.q0 = tl.shfl(e.q0, src); r.q1 = tl.shfl(e.q1, src);
+            r.j00 = tl.shfl(e.j00, src); r.j01 = tl.shfl(e.j01, src); r.j11 = tl.shfl(e.j11, src);
+            if (lane + off <= N) {
+                if (2 * off >= G) scan2::combine_jq(e, r, e.j00, e.j01, e.j11, e.q0, e.q1);   // last level: only P, p are still needed
+                else scan2::combine(e, r, e);
+            }
+        }
+        // value function of the next stage: lane k needs P_{k+1}, p_{k+1}
+        const int nxt = (lane + 1) & (G - 1);
+        const double P00 = tl.shfl(e.j00, nxt), P01 = tl.shfl(e.j01, nxt), P11 = tl.shfl(e.j11, nxt);
+        const double pv0 = tl.shfl(e.q0, nxt), pv1 = tl.shfl(e.q1, nxt);
+        const double PB0 = P00 * B0 + P01 * B1, PB1 = P01 * B0 + P11 * B1;
+        const double ihh = 1.0 / (huu + B0 * PB0 + B1 * PB1);
+        const double Pd0 = P00 * d0 + P01 * d1 + pv0, Pd1 = P01 * d0 + P11 * d1 + pv1;
+        const double K0 = -ihh * (PB0 * a00 + PB1 * a10), K1 = -ihh * (PB0 * a01 + PB1 * a11);
+        const double kff = -ihh * (gu + B0 * Pd0 + B1 * Pd1);
+        Af f;
+        if (stage) {
+            f.m00 = a00 + B0 * K0; f.m01 = a01 + B0 * K1; f.m10 = a10 + B1 * K0; f.m11 = a11 + B1 * K1;
+            f.v0 = B0 * kff + d0; f.v1 = B1 * kff + d1;
+        } else {
+            f.m00 = 1.0; f.m01 = 0.0; f.m10 = 0.0; f.m11 = 1.0; f.v0 = 0.0; f.v1 = 0.0;
+        }
+        DART_UNROLL for (int off = 1; off < G; off <<= 1) {
+            const int src = (lane - off) & (G - 1);
+            Af r;
+            r.m00 = tl.shfl(f.m00, src); r.m01 = tl.shfl(f.m01, src); r.m10 = tl.shfl(f.m10, src); r.m11 = tl.shfl(f.m11, src);
+            r.v0 = tl.shfl(f.v0, src); r.v1 = tl.shfl(f.v1, src);
+            if (lane >= off) scan2::compose(f, r, f);
+        }
+        // dx_{k+1} = f.v of lane k; dx_k comes from lane k-1 (dx_0 = 0)
+        const int prv = (lane - 1) & (G - 1);
+        double x0 = tl.shfl(f.v0, prv), x1 = tl.shfl(f.v1, prv);
+        if (lane == 0) { x0 = 0.0; x1 = 0.0; w.DX[0] = 0.0; w.DX[1] = 0.0; }
+        if (stage) {
+            w.DU[k] = K0 * x0 + K1 * x1 + kff;
+            w.DX[(k + 1) * n + 0] = f.v0; w.DX[(k + 1) * n + 1] = f.v1;
+            if (k + 1 < N) {                                 // P_N, p_N are already in place (prep)
+                w.PP[(k + 1) * nps + 0] = P00; w.PP[(k + 1) * nps + 1] = P01; w.PP[(k + 1) * nps + 2] = P11;
+                w.PV[(k + 1) * n + 0] = pv0; w.PV[(k + 1) * n + 1] = pv1;
+            }
+        }
+        tl.sync();
+    }
+
+    // ---- the same sweeps with TWO consecutive elements per lane (lanes == (N + 1) / 2; four problems per warp): the lane
+    // combines its two elements, the lane totals are scanned (log2(lanes) = 3 levels), and one reduced combination gives
+    // the value function between the lane's two stages -- 5 combinations per lane for 4 problems per warp instead of
+    // 4 for 2, i.e. 37 % fewer FP64 instructions per problem; the FP64 pipe's issue rate is what bounds this phase.
+    struct StageLQ { double a00, a01, a10, a11, B0, B1, d0, d1, gu, huu, ih; };
+    DART_HD void load_stage(int k, StageLQ& q) const {
+        q.a00 = Aat(k, 0, 0); q.a01 = Aat(k, 0, 1); q.a10 = Aat(k, 1, 0); q.a11 = Aat(k, 1, 1);
+        q.B0 = w.Bm[k * sB + 0]; q.B1 = w.Bm[k * sB + 1];
+        q.d0 = w.D[k * n + 0]; q.d1 = w.D[k * n + 1];
+        q.gu = w.GR[k * sG + 2];
+        double huu = w.HS[k * sH + 2];
+        if (!(huu > 0.0)) {
+            double shift = 1e-4;
+            while (!(huu + shift > 0.0) && shift < 1e30) shift *= 8.0;
+            huu += shift;
+        }
+        q.huu = huu;
+        q.ih = 1.0 / huu;
+    }
+    DART_HD void stage_element(int k, const StageLQ& q, scan2::El& e) const {
+        e.a00 = q.a00; e.a01 = q.a01; e.a10 = q.a10; e.a11 = q.a11;
+        const double t = q.ih * q.gu;
+        e.b0 = q.d0 - q.B0 * t; e.b1 = q.d1 - q.B1 * t;
+        e.c00 = q.B0 * q.B0 * q.ih; e.c01 = q.B0 * q.B1 * q.ih; e.c11 = q.B1 * q.B1 * q.ih;
+        e.q0 = w.GR[k * sG + 0]; e.q1 = w.GR[k * sG + 1];
+        e.j00 = w.HS[k * sH + 0]; e.j01 = 0.0; e.j11 = w.HS[k * sH + 1];
+    }
+    DART_HD void terminal_element(scan2::El& e) const {
+        e.a00 = e.a01 = e.a10 = e.a11 = e.b0 = e.b1 = e.c00 = e.c01 = e.c11 = 0.0;
+        e.j00 = w.PP[N * nps + 0]; e.j01 = w.PP[N * nps + 1]; e.j11 = w.PP[N * nps + 2];
+        e.q0 = w.PV[N * n + 0]; e.q1 = w.PV[N * n + 1];
+    }
+    // gains of one stage from the next stage's value function; also the closed-loop map
+    DART_HD static void stage_gains(const StageLQ& q, double P00, double P01, double P11, double pv0, double pv1, double& K0,
+                                    double& K1, double& kff, scan2::Af& f) {
+        const double PB0 = P00 * q.B0 + P01 * q.B1, PB1 = P01 * q.B0 + P11 * q.B1;
+        const double ihh = 1.0 / (q.huu + q.B0 * PB0 + q.B1 * PB1);
+        const double Pd0 = P00 * q.d0 + P01 * q.d1 + pv0, Pd1 = P01 * q.d0 + P11 * q.d1 + pv1;
+        K0 = -ihh * (PB0 * q.a00 + PB1 * q.a10); K1 = -ihh * (PB0 * q.a01 + PB1 * q.a11);
+        kff = -ihh * (q.gu + q.B0 * Pd0 + q.B1 * Pd1);
+        f.m00 = q.a00 + q.B0 * K0; f.m01 = q.a01 + q.B0 * K1; f.m10 = q.a10 + q.B1 * K0; f.m11 = q.a11 + q.B1 * K1;
+        f.v0 = q.B0 * kff + q.d0; f.v1 = q.B1 * kff + q.d1;
+    }
+    template <class TL>
+    DART_HD static void shfl_el(const TL& tl, const scan2::El& e, int src, scan2::El& r) {
+        r.a00 = tl.shfl(e.a00, src); r.a01 = tl.shfl(e.a01, src); r.a10 = tl.shfl(e.a10, src); r.a11 = tl.shfl(e.a11, src);
+        r.b0 = tl.shfl(e.b0, src); r.b1 = tl.shfl(e.b1, src);
+        r.c00 = tl.shfl(e.c00, src); r.c01 = tl.shfl(e.c01, src); r.c11 = tl.shfl(e.c11, src);
+        r.q0 = tl.shfl(e.q0, src); r.q1 = tl.shfl(e.q1, src);
+        r.j00 = tl.shfl(e.j00, src); r.j01 = tl.shfl(e.j01, src); r.j11 = tl.shfl(e.j11, src);
+    }
+    template <class TL>
+    DART_HD void sweeps_scan2(const TL& tl) {
+        using scan2::El;
+        using scan2::Af;
+        constexpr int G = TL::kLanes;
+        const int lane = tl.lane();
+        const int kA = 2 * lane, kB = 2 * lane + 1;          // kA < N always; kB == N on the last lane (terminal element)
+        const bool hasB = kB < N;
+        StageLQ sa, sb;
+        load_stage(kA, sa);
+        load_stage(hasB ? kB : N - 1, sb);
+        El eA, eB;
+        stage_element(kA, sa, eA);
+        if (hasB) stage_element(kB, sb, eB); else terminal_element(eB);
+        El t;
+        scan2::combine(eA, eB, t);
+        DART_UNROLL for (int off = 1; off < G; off <<= 1) {
+            El r;
+            shfl_el(tl, t, (lane + off) & (G - 1), r);
+            if (lane + off < G) {
+                if (2 * off >= G) scan2::combine_jq(t, r, t.j00, t.j01, t.j11, t.q0, t.q1);   // last level: only P, p are still needed
+                else scan2::combine(t, r, t);
+            }
+        }
+        // t = value function element of stage kA .. end; the next lane's t is that of stage kB + 1 .. end
+        El nx;
+        shfl_el(tl, t, (lane + 1) & (G - 1), nx);
+        // value function after stage kA (= at kB): eB (+) nx, or the terminal element itself on the last lane
+        double Pa00 = eB.j00, Pa01 = eB.j01, Pa11 = eB.j11, pa0 = eB.q0, pa1 = eB.q1;
+        if (hasB) scan2::combine_jq(eB, nx, Pa00, Pa01, Pa11, pa0, pa1);
+        double KA0, KA1, kfA, KB0 = 0.0, KB1 = 0.0, kfB = 0.0;
+        Af fA, fB;
+        stage_gains(sa, Pa00, Pa01, Pa11, pa0, pa1, KA0, KA1, kfA, fA);
+        if (hasB) stage_gains(sb, nx.j00, nx.j01, nx.j11, nx.q0, nx.q1, KB0, KB1, kfB, fB);
+        else { fB.m00 = 1.0; fB.m01 = 0.0; fB.m10 = 0.0; fB.m11 = 1.0; fB.v0 = 0.0; fB.v1 = 0.0; }
+        Af F;
+        scan2::compose(fB, fA, F);
+        DART_UNROLL for (int off = 1; off < G; off <<= 1) {
+            const int src = (lane - off) & (G - 1);
+            Af r;
+            r.m00 = tl.shfl(F.m00, src); r.m01 = tl.shfl(F.m01, src); r.m10 = tl.shfl(F.m10, src); r.m11 = tl.shfl(F.m11, src);
+            r.v0 = tl.shfl(F.v0, src); r.v1 = tl.shfl(F.v1, src);
+            if (lane >= off) scan2::compose(F, r, F);
+        }
+        const int prv = (lane - 1) & (G - 1);
+        double xa0 = tl.shfl(F.v0, prv), xa1 = tl.shfl(F.v1, prv);          // dx at stage kA
+        if (lane == 0) { xa0 = 0.0; xa1 = 0.0; w.DX[0] = 0.0; w.DX[1] = 0.0; }
+        const double xb0 = fA.m00 * xa0 + fA.m01 * xa1 + fA.v0, xb1 = fA.m10 * xa0 + fA.m11 * xa1 + fA.v1;   // dx at kB
+        w.DU[kA] = KA0 * xa0 + KA1 * xa1 + kfA;
+        w.DX[kB * n + 0] = xb0; w.DX[kB * n + 1] = xb1;
+        if (hasB) {
+            w.PP[kB * nps + 0] = Pa00; w.PP[kB * nps + 1] = Pa01; w.PP[kB * nps + 2] = Pa11;
+            w.PV[kB * n + 0] = pa0; w.PV[kB * n + 1] = pa1;
+            w.DU[kB] = KB0 * xb0 + KB1 * xb1 + kfB;
+            w.DX[(kB + 1) * n + 0] = F.v0; w.DX[(kB + 1) * n + 1] = F.v1;
+            if (kB + 1 < N) {
+                w.PP[(kB + 1) * nps + 0] = nx.j00; w.PP[(kB + 1) * nps + 1] = nx.j01; w.PP[(kB + 1) * nps + 2] = nx.j11;
+                w.PV[(kB + 1) * n + 0] = nx.q0; w.PV[(kB + 1) * n + 1] = nx.q1;
+            }
+        }
+        tl.sync();
+    }
+
     // ---- slack steps, step-length limits, directional derivative, then the dual step z += ad dz (stage-parallel).
     // dz is recomputed in the second pass instead of being stored; the new equality multipliers are formed in move_dual.
-    DART_HD void post(double mu, double& ap, double& ad, double& dphi) {
+    DART_HD void post(double mu, double& ap, double& ad, double& dphi, bool ghost = false) {
         const double tau = dmax(o.tau_min, 1.0 - mu);
         double ap_ = 1.0, ad_ = 1.0, dp = 0.0, rp_ = 0.0, rd_ = 0.0;
         for (int k = tile.lane(); k < N; k += tile.size()) {
@@ -862,9 +1147,11 @@ struct Solver {
         rd_ = tile.max_nonneg(rd_);
         ap_ = (rp_ > tau) ? tau / rp_ : 1.0;
         ad_ = (rd_ > tau) ? tau / rd_ : 1.0;
+        if (ghost) { ap_ = 0.0; ad_ = 0.0; }      // a finished tile in lockstep with its sibling: nothing moves
         ap = ap_;
         ad = ad_;
         dphi = tile.sum(dp);
+        if (ad_ != 0.0)
         for (int k = tile.lane(); k < N; k += tile.size()) {
             DART_UNROLL for (int r = 0; r < nr; ++r) {
                 if (masked(k, r)) continue;
@@ -879,6 +1166,7 @@ struct Solver {
     }
 
     DART_HD void move_primal(double da) {
+        if (da != 0.0)                      // a zero step (a tile kept in lockstep by the line search of its warp) moves nothing
         for (int k = tile.lane(); k < N; k += tile.size()) {
             DART_UNROLL for (int i = 0; i < n; ++i) w.X[(k + 1) * n + i] += da * w.DX[(k + 1) * n + i];
             DART_UNROLL for (int j = 0; j < m; ++j) w.U[k * m + j] += da * w.DU[k * m + j];
@@ -889,6 +1177,7 @@ struct Solver {
 
     DART_HD void move_dual(double alpha, double mu) {
         const double ks = 1e10, iks = 1e-10;     // safeguard interval [mu/(ks s), ks mu/s]; a product, not a division
+        if (alpha != 0.0)                        // zero step: a finished / stopping tile kept in lockstep -- its multipliers stay
         for (int k = tile.lane(); k < N; k += tile.size()) {
             DART_UNROLL for (int a = 0; a < n; ++a) {      // new multiplier of stage k+1: P_{k+1} dx_{k+1} + p_{k+1}
                 double ln = w.PV[(k + 1) * n + a];
@@ -935,12 +1224,14 @@ struct Solver {
     // The previous optimum's slacks sit within ~1e-9 of their active bounds; they are pushed 1e-6 of the row's range
     // into the interior, and the bound multipliers are kept from falling below IPOPT's safeguard for the new mu.
     DART_HD static int dual_doubles(int N_) { return 1 + N_ * n + 3 * N_ * nr; }
-    DART_HD void load_duals(const double* blk, double mu) {
+    // `enabled` = false: take part in the tile syncs only (lockstep tiles: the sibling tile of the warp may be loading)
+    DART_HD void load_duals(const double* blk, double mu, bool enabled = true) {
         const double* lam = blk + 1;
         const double* sp = lam + N * n;
         const double* zlp = sp + N * nr;
         const double* zup = zlp + N * nr;
         const double ks = 1e10;
+        if (enabled)
         for (int k = tile.lane(); k < N; k += tile.size()) {
             DART_UNROLL for (int r = 0; r < nr; ++r) {
                 if (masked(k, r)) continue;
@@ -957,6 +1248,7 @@ struct Solver {
         }
         tile.sync();
         if (M::NAUG > 0) {
+            if (enabled)
             for (int k = tile.lane(); k < N; k += tile.size())
                 DART_UNROLL for (int j = 0; j < m; ++j) w.X[(k + 1) * n + np + j] = w.U[k * m + j];
             tile.sync();
@@ -1007,6 +1299,10 @@ struct Solver {
         double E0 = 0.0, is_d = 1.0, is_c = 1.0;
         bool done = !active;
         double* myslot = bc.base + (size_t)(bc.tid / tile.size()) * bc.stride;
+        // scan sweeps: 2-state / 1-input problems on a tile with exactly one lane per stage plus the terminal element
+        // (the tile type says whether the tiles of a warp run in lockstep: nmpc_kernel.cuh TileFor)
+        constexpr bool kScan = M::SERIAL_RICCATI && n == 2 && m == 1 && NC > 0 && T::kLockstep &&
+                               (T::kLanes == NC + 1 || 2 * T::kLanes == NC + 1);
 #ifdef DART_PHASE_CLOCK
         long long ckA = 0, ckB = 0, ckC = 0, ckBb = 0, ckC1 = 0, ckC2 = 0, ckA1 = 0, ckW1 = 0, ckW2 = 0, ck0 = DART_CLOCK();
 #define DART_CK(acc) { long long t_ = DART_CLOCK(); acc += t_ - ck0; ck0 = t_; }
@@ -1040,12 +1336,27 @@ struct Solver {
                         else break;
                     }
                     DART_CK(ckA1)
-                    prep(mu);
-                    if (!M::SERIAL_RICCATI) backward(tile);
                     need_sweep = true;
+                    if constexpr (!kScan) {
+                        prep(mu);
+                        if (!M::SERIAL_RICCATI) backward(tile);
+                    }
                 }
             }
-            if (M::SERIAL_RICCATI) {
+            bool ghost = false;
+            if constexpr (kScan) {
+                // One lane per stage: the tile sweeps by scans, independent of the rest of the block.  The two tiles of a
+                // WARP (the axes of one instance) run the whole iteration in LOCKSTEP so that every collective is a
+                // full-warp instruction with a constant mask: a tile that has finished while its sibling has not keeps
+                // executing the same instructions as a "ghost" -- zero step lengths, so its primal point, objective and
+                // status stay exactly what they were when it finished.
+                DART_CK(ckA)
+                if (tile.warp_ballot(need_sweep) == 0u) break;
+                ghost = !need_sweep;
+                prep(mu);
+                if constexpr (T::kLanes == NC + 1) sweeps_scan(tile); else sweeps_scan2(tile);
+                DART_CK(ckB)
+            } else if (M::SERIAL_RICCATI) {
                 if (tile.lane() == 0) myslot[0] = need_sweep ? 1.0 : 0.0;
                 DART_CK(ckA)
                 const bool any_ = tile.block_any(need_sweep);   // barrier + vote: phase-A writes are visible past this point
@@ -1079,7 +1390,7 @@ struct Solver {
             }
             // ---------------- phase C
             double ap, ad, dphi;
-            post(mu, ap, ad, dphi);
+            post(mu, ap, ad, dphi, ghost);
             DART_CK(ckC1)
             const double phi0 = f - mu * L, th0 = th;
             const double th_max = 1e4 * dmax(1.0, th0);
@@ -1099,17 +1410,30 @@ struct Solver {
                 bool suff = (th <= (1.0 - o.gamma_theta) * th0) || (phit <= phi0 - o.gamma_phi * th0);
                 bool ok = ((switching && th0 <= o.theta_small) ? armijo : suff) && (th <= th_max) && (phit == phit) &&
                           (fabs(phit) < 1e300);
-                if (ok || bt + 1 >= o.max_backtrack) break;
-                alpha *= 0.5;
+                const bool stop_ls = ok || bt + 1 >= o.max_backtrack || ghost;
+                if constexpr (kScan) {
+                    // the tiles of a warp leave the line search together (a tile that is done re-evaluates its accepted
+                    // point with a zero step: same values), so the collectives inside stay warp-converged
+                    if (tile.group_all(stop_ls)) break;
+                    if (!stop_ls) alpha *= 0.5;
+                } else {
+                    if (stop_ls) break;
+                    alpha *= 0.5;
+                }
             }
 #ifdef DART_TRACE
             printf("it %d mu %.3e E0 %.3e dinf %.3e pinf %.3e zsmax %.3e ap %.4f ad %.4f alpha %.5f dphi %.3e th0 %.3e f %.10g\n", it, mu, E0, dinf * is_d, pinf, zs_max * is_c, ap, ad, alpha, dphi, th0, f);
 #endif
             DART_CK(ckC2)
-            ++it;
+            if (!ghost) ++it;
             // the step vanished three times in a row: no restoration phase here -- stop and say so
-            tiny = (alpha <= 1e-6) ? tiny + 1 : 0;
-            if (tiny >= 3) { st = (pinf > 1e-4) ? ST_INFEASIBLE : ST_MAXITER; done = true; continue; }
+            tiny = ghost ? 0 : ((alpha <= 1e-6) ? tiny + 1 : 0);
+            if (tiny >= 3) {
+                st = (pinf > 1e-4) ? ST_INFEASIBLE : ST_MAXITER;
+                done = true;
+                if constexpr (!kScan) continue;
+                alpha = 0.0;                          // scan path: stay in lockstep with the other tile of the warp (its collectives below)
+            }
             move_dual(alpha, mu);
             eval2(dinf, zs_min, zs_max, lam_sum, z_sum);
             DART_CK(ckC)

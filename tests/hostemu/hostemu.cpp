@@ -20,8 +20,8 @@ static void run_all(const KArgs& a) {
             double J = 0, kkt = 0;
             int32_t s = 0, it = 0;
             // same dispatch as the device launcher: compile-time horizon when it is the reference's
-            if (a.N == M::NDEF) solve_one<M, HostTile, M::NDEF>(tile, a, inst, ax, true, bc, ws.data() + kSlot, J, s, it, kkt);
-            else solve_one<M, HostTile, 0>(tile, a, inst, ax, true, bc, ws.data() + kSlot, J, s, it, kkt);
+            if (a.N == M::NDEF) solve_one<M, HostTile, M::NDEF>(tile, a, inst, ax, true, true, bc, ws.data() + kSlot, J, s, it, kkt);
+            else solve_one<M, HostTile, 0>(tile, a, inst, ax, true, true, bc, ws.data() + kSlot, J, s, it, kkt);
             Js += J;
             st = s > st ? s : st;
             itx = it > itx ? it : itx;
