@@ -69,6 +69,7 @@ def lib():
     L.dart_policy_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int32, C.c_int32, C.c_int32] + [vp] * 6
     L.dart_policy_destroy.argtypes = [vp]
     L.dart_policy_forward.argtypes = [vp, C.c_int32, vp, vp, vp]
+    L.dart_policy_set_precision.argtypes = [vp, C.c_int32]
     L.dart_policy_launch_count.argtypes = [vp]
     L.dart_policy_launch_count.restype = C.c_int64
     L.dart_policy_obs_push.argtypes = [C.c_int32, C.c_int32, vp, vp, vp, vp, C.c_int32, vp, vp, vp, vp, vp]

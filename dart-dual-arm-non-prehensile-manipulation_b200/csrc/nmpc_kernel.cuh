@@ -72,7 +72,8 @@ struct DevTile {
 // lockstep tiles: the scan path of Solver::run (2-state / 1-input axis problems, one lane per stage + the terminal cost)
 template <class M, int G, int NC>
 struct TileFor {
-    static constexpr bool lock = M::SERIAL_RICCATI && M::NX == 2 && M::NU == 1 && NC > 0 && G < 32 && (G == NC + 1 || 2 * G == NC + 1);
+    static constexpr bool scan = M::SERIAL_RICCATI && M::NX == 2 && M::NU == 1 && NC > 0 && (G == NC + 1 || 2 * G == NC + 1);
+    static constexpr bool lock = G < 32 && (scan || !M::SERIAL_RICCATI);
     using type = DevTile<G, lock>;
 };
 

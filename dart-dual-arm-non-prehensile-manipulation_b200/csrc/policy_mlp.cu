@@ -17,6 +17,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string.h>
+#include <stdlib.h>
+#include <stdio.h>
 #include <new>
 
 #include "../../include/dart_b200.h"
@@ -282,6 +284,316 @@ policy_mlp_kernel(const __grid_constant__ CUtensorMap tm_obs, const __grid_const
     }
 }
 
+// ======================================================================================= FP32-fidelity forward
+// policy_mlp3_kernel: the production forward.  The reference's Policy runs in FP32 (torch never enables TF32), and a
+// single TF32 pass (policy_mlp_kernel above) is three decimal digits short of that, so:
+//   layer 1 (K = 520, 84 % of the flops and ALL of the HBM traffic) stays on tcgen05 but as a 3xTF32 product,
+//       A W = A_hi W_hi + A_hi W_lo + A_lo W_hi      (hi = top 19 bits, lo = fp32(x - hi); dropped term ~ 2^-22),
+//     W_hi / W_lo are split once on the host; A arrives by TMA as fp32 and four "split" warps rewrite each landed chunk
+//     in place as A_hi and write A_lo beside it (generic -> async proxy fence), then one thread issues the 12 MMAs of the
+//     chunk; fp32 accumulation in TMEM.  The kernel is HBM-bound, so the tripled tensor work is free.
+//   layers 2 and 3 (64x64 and 64x34 per row) run in plain FP32 FMAs on the CUDA cores, thread per row, weights
+//     broadcast from shared memory -- the reference's arithmetic up to summation order, and no hi/lo operand copies of
+//     W2, W3 and of the activations in shared memory.
+// One persistent CTA per SM, warp-specialised: warp 0 TMA producer (3-stage ring: A 16 KB + A_lo 16 KB + W1 hi/lo 16 KB
+// per stage), warp 1 MMA issuer, warps 2-5 split, warps 6-9 epilogue.  The layer-1 accumulator is double-buffered in
+// TMEM, so the stream of tile t+1 runs under the epilogue (layers 2, 3, store) of tile t.
+namespace v3 {
+constexpr int S = 3;
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;                  // A, A_lo, W1_hi, W1_lo chunk
+constexpr int OFF_RING = 0;
+constexpr int OFF_W2T = OFF_RING + S * STAGE_BYTES;                     // W2 transposed [k][j], 64 x 64 fp32
+constexpr int W3LD = 40;                                                // W3 transposed [k][j], 64 x 40 fp32 (34 padded)
+constexpr int OFF_W3T = OFF_W2T + HID * HID * 4;
+constexpr int OFF_BIAS = OFF_W3T + HID * W3LD * 4;                      // b1[64] b2[64] b3[36]
+constexpr int OFF_HS = OFF_BIAS + (HID + HID + W3LD) * 4;               // activations [k][row] fp32 (thread-private columns)
+constexpr int OFF_OUT = OFF_HS + HID * MT * 4;                          // [128, 34] result tile for coalesced stores
+constexpr int OFF_BAR = OFF_OUT + MT * ACT * 4;
+constexpr int NBAR = 3 * S + 4;                                         // full[S] split[S] empty[S] accf[2] acce[2]
+constexpr int BYTES = OFF_BAR + 8 * NBAR + 16 + 1024;                   // + tmem slot + alignment slack
+constexpr int NEPI = 256;                                               // epilogue threads (warps 6..13)
+constexpr int NTHR = 64 + 128 + NEPI;
+constexpr uint32_t TCOLS = 256;                                         // two 128-column layer-1 accumulators ([.. W_hi | .. W_lo] partial sums)
+#ifndef DART_MLP3_REWRITE_HI
+#define DART_MLP3_REWRITE_HI 0      // 1: the split warps also rewrite A in place with its top 19 bits (if tcgen05 rounded instead of truncating)
+#endif
+static_assert(BYTES <= 232448, "shared memory budget of one CTA per SM");
+}  // namespace v3
+
+__device__ __forceinline__ unsigned long long pack2(float x, float y) {
+    unsigned long long v;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(x), "f"(y));
+    return v;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& x, float& y) { asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v)); }
+// two FP32 FMAs in one instruction (FFMA2, sm_100): acc += a * b, element-wise on register pairs
+__device__ __forceinline__ void ffma2(unsigned long long& acc, unsigned long long a, unsigned long long b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+// tanh(x) = 1 - 2 / (1 + e^(2x)) with the SFU exponential and reciprocal (each ~1e-7 relative): absolute error <= 3e-7,
+// the same size as the rounding of an FP32 tanh; |x| large saturates cleanly (e^(2x) -> 0 or inf)
+__device__ __forceinline__ float tanh_fast(float x) {
+    const float e = exp2f(x * 2.885390081777927f);            // e^(2x); exp2f compiles to MUFU.EX2 (+ denormal scaling)
+    return 1.0f - __fdividef(2.0f, 1.0f + e);
+}
+
+struct Mlp3Args {
+    int B, ntiles;
+    const float *W2, *b1, *b2, *W3, *b3;        // global fp32 (row-major [out][in]); staged transposed in shared memory
+    float* mean;
+};
+
+__global__ void __launch_bounds__(v3::NTHR, 1)
+policy_mlp3_kernel(const __grid_constant__ CUtensorMap tm_obs, const __grid_constant__ CUtensorMap tm_w1h,
+                   const __grid_constant__ CUtensorMap tm_w1l, const Mlp3Args a) {
+    using namespace v3;
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment (SWIZZLE_128B atoms) by an OFFSET into the __shared__ array: a pointer rebuilt from an integer
+    // would lose its address space and every access below would compile to a generic LD/ST instead of LDS/STS
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar0 = sbase + OFF_BAR;
+    auto FULL = [&](int s) { return bar0 + 8 * s; };
+    auto SPLIT = [&](int s) { return bar0 + 8 * (S + s); };
+    auto EMPTY = [&](int s) { return bar0 + 8 * (2 * S + s); };
+    auto ACCF = [&](int b) { return bar0 + 8 * (3 * S + b); };
+    auto ACCE = [&](int b) { return bar0 + 8 * (3 * S + 2 + b); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 8 * NBAR);
+    auto stageA = [&](int s) { return (uint32_t)(OFF_RING + s * STAGE_BYTES); };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) { mbar_init(FULL(s), 1); mbar_init(SPLIT(s), 128); mbar_init(EMPTY(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(ACCF(b), 1); mbar_init(ACCE(b), v3::NEPI); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TCOLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+                for (int kb = 0; kb < NKB; ++kb, ++it) {
+                    const int s = it % S;
+                    const uint32_t ph = (it / S) & 1;
+                    mbar_wait(EMPTY(s), ph ^ 1);
+                    mbar_expect_tx(FULL(s), A_BYTES + 2 * B_BYTES);
+                    tma_load_2d(sbase + stageA(s), &tm_obs, kb * BK, tile * MT, FULL(s));
+                    tma_load_2d(sbase + stageA(s) + 2 * A_BYTES, &tm_w1h, kb * BK, 0, FULL(s));
+                    tma_load_2d(sbase + stageA(s) + 2 * A_BYTES + B_BYTES, &tm_w1l, kb * BK, 0, FULL(s));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            constexpr uint32_t ID64 = idesc_tf32(MT, HID), ID128 = idesc_tf32(MT, 2 * HID);
+            uint32_t it = 0;
+            int lt = 0;
+            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++lt) {
+                const int b = lt & 1;
+                mbar_wait(ACCE(b), (((uint32_t)lt >> 1) & 1) ^ 1);            // the epilogue has drained this accumulator
+                fence_after();
+                const uint32_t acc = tmem + (uint32_t)(b * 2 * HID);
+                for (int kb = 0; kb < NKB; ++kb, ++it) {
+                    const int s = it % S;
+                    const uint32_t ph = (it / S) & 1;
+                    mbar_wait(SPLIT(s), ph);
+                    fence_after();
+                    const uint64_t dah = sdesc(sbase + stageA(s)), dal = sdesc(sbase + stageA(s) + A_BYTES);
+                    const uint64_t dbw = sdesc(sbase + stageA(s) + 2 * A_BYTES);      // [W1_hi chunk ; W1_lo chunk]: 128 rows
+#pragma unroll
+                    for (int k = 0; k < BK / 8; ++k) {
+                        // columns 0..63 += A_hi W_hi, columns 64..127 += A_hi W_lo: A_hi is read from shared memory once
+                        umma_tf32(acc, dah + 2 * k, dbw + 2 * k, ID128, (kb | k) != 0);
+                        umma_tf32(acc, dal + 2 * k, dbw + 2 * k, ID64, 1);            // columns 0..63 += A_lo W_hi
+                    }
+                    umma_commit(EMPTY(s));
+                }
+                umma_commit(ACCF(b));
+            }
+        }
+    } else if (warp < 6) {
+        // ===== split warps: landed fp32 chunk -> A_hi (in place) + A_lo =====
+        const int t = threadIdx.x - 64;                                  // 0..127
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+            for (int kb = 0; kb < NKB; ++kb, ++it) {
+                const int s = it % S;
+                const uint32_t ph = (it / S) & 1;
+                mbar_wait(FULL(s), ph);
+                uint4* A = reinterpret_cast<uint4*>(smem + stageA(s));
+                float4* L = reinterpret_cast<float4*>(smem + stageA(s) + A_BYTES);
+#pragma unroll
+                for (int i = 0; i < A_BYTES / 16 / 128; ++i) {
+                    const int u = t + 128 * i;
+                    uint4 v = A[u];
+                    uint4 h;
+                    h.x = v.x & 0xffffe000u; h.y = v.y & 0xffffe000u; h.z = v.z & 0xffffe000u; h.w = v.w & 0xffffe000u;
+                    float4 l;
+                    l.x = __uint_as_float(v.x) - __uint_as_float(h.x); l.y = __uint_as_float(v.y) - __uint_as_float(h.y);
+                    l.z = __uint_as_float(v.z) - __uint_as_float(h.z); l.w = __uint_as_float(v.w) - __uint_as_float(h.w);
+#if DART_MLP3_REWRITE_HI
+                    A[u] = h;
+#endif
+                    L[u] = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(SPLIT(s));
+            }
+        }
+    } else {
+        // ===== epilogue warps 6..13 (TMEM lane quarter = warp % 4; two warps per quarter and per SM sub-partition, so that
+        // one hides the other's shared-memory latency): layer-1 epilogue, then layers 2 and 3 in FP32 =====
+        // Layers 2/3 are register-tiled like a small SGEMM (a thread per row would pull every weight through the
+        // 128 B/clk shared-memory pipe for every row: 2 MB per tile): layer 2 as 8 rows x 4 columns per thread, layer 3
+        // as 4 rows x 5 columns, operands from shared memory ([k][row] activations, [k][j] weights), FMAs issued as
+        // packed FFMA2 (fma.rn.f32x2: same FP32 rate, half the issue slots).
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int grp = (warp - 6) >> 2;                                  // which 32 accumulator columns this warp converts
+        const int et = (warp - 6) * 32 + lane;                            // 0..255
+        float* W2t = reinterpret_cast<float*>(smem + OFF_W2T);
+        float* W3t = reinterpret_cast<float*>(smem + OFF_W3T);
+        float* bias = reinterpret_cast<float*>(smem + OFF_BIAS);
+        float* hs = reinterpret_cast<float*>(smem + OFF_HS);
+        float* outs = reinterpret_cast<float*>(smem + OFF_OUT);
+        for (int i = et; i < HID * HID; i += NEPI) W2t[(i & 63) * HID + (i >> 6)] = __ldg(a.W2 + i);          // i = j*64 + k
+        for (int i = et; i < HID * W3LD; i += NEPI) {
+            const int k = i / W3LD, j = i % W3LD;
+            W3t[i] = j < ACT ? __ldg(a.W3 + j * HID + k) : 0.0f;
+        }
+        for (int i = et; i < HID; i += NEPI) { bias[i] = __ldg(a.b1 + i); bias[HID + i] = __ldg(a.b2 + i); }
+        for (int i = et; i < W3LD; i += NEPI) bias[2 * HID + i] = i < ACT ? __ldg(a.b3 + i) : 0.0f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
+        const int r2 = (et >> 4) * 8, c2 = (et & 15) * 4;                 // layer-2 tile: rows r2..r2+7, columns c2..c2+3
+        const int r3 = (et >> 3) * 4, c3 = (et & 7) * 5;                  // layer-3 tile: rows r3..r3+3, columns c3..c3+4
+        int lt = 0;
+#ifdef DART_MLP3_CLOCK
+        long long ck[6] = {0, 0, 0, 0, 0, 0}, c0_ = clock64();
+#define MLP3_CK(i) { long long t_ = clock64(); ck[i] += t_ - c0_; c0_ = t_; }
+#else
+#define MLP3_CK(i)
+#endif
+        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++lt) {
+            const int b = lt & 1;
+            mbar_wait(ACCF(b), ((uint32_t)lt >> 1) & 1);
+            fence_after();
+            MLP3_CK(0)
+            // layer-1 accumulator row (hi-product + lo-product halves) -> + b1 -> tanh -> hs[k][row]
+#pragma unroll
+            for (int cc = 0; cc < 32; cc += 16) {
+                const int c0 = grp * 32 + cc;
+                uint32_t r[16], rl[16];
+                tmem_ld16(tl + (uint32_t)(b * 2 * HID) + c0, r);
+                tmem_ld16(tl + (uint32_t)(b * 2 * HID) + HID + c0, rl);
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    hs[(c0 + j) * MT + row] = tanh_fast((__uint_as_float(r[j]) + __uint_as_float(rl[j])) + bias[c0 + j]);
+            }
+            fence_before();
+            mbar_arrive(ACCE(b));                                         // the accumulator may be overwritten (tile lt + 2)
+            asm volatile("bar.sync 1, 256;" ::: "memory");               // h1 complete
+            MLP3_CK(1)
+            {
+                unsigned long long acc[8][2];                             // [row][column pair]
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const unsigned long long bv = pack2(bias[HID + c2 + 2 * c], bias[HID + c2 + 2 * c + 1]);
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) acc[r][c] = bv;
+                }
+#pragma unroll 8
+                for (int k = 0; k < HID; ++k) {
+                    const float4 ha = *reinterpret_cast<const float4*>(hs + k * MT + r2), hb = *reinterpret_cast<const float4*>(hs + k * MT + r2 + 4);
+                    const ulonglong2 wa = *reinterpret_cast<const ulonglong2*>(W2t + k * HID + c2);
+                    const float hv[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        const unsigned long long hh = pack2(hv[r], hv[r]);
+                        ffma2(acc[r][0], hh, wa.x); ffma2(acc[r][1], hh, wa.y);
+                    }
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");           // every thread has read h1: overwrite it with h2
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    float lo[8], hi[8];
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) { unpack2(acc[r][c], lo[r], hi[r]); lo[r] = tanh_fast(lo[r]); hi[r] = tanh_fast(hi[r]); }
+                    float* d0 = hs + (c2 + 2 * c) * MT + r2;
+                    *reinterpret_cast<float4*>(d0) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                    *reinterpret_cast<float4*>(d0 + 4) = make_float4(lo[4], lo[5], lo[6], lo[7]);
+                    *reinterpret_cast<float4*>(d0 + MT) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<float4*>(d0 + MT + 4) = make_float4(hi[4], hi[5], hi[6], hi[7]);
+                }
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");               // h2 complete
+            MLP3_CK(2)
+            {
+                unsigned long long acc[2][5];                             // [row pair][column]
+#pragma unroll
+                for (int c = 0; c < 5; ++c) {
+                    const float bb = bias[2 * HID + c3 + c];
+                    acc[0][c] = pack2(bb, bb); acc[1][c] = acc[0][c];
+                }
+#pragma unroll 8
+                for (int k = 0; k < HID; ++k) {
+                    const ulonglong2 hp = *reinterpret_cast<const ulonglong2*>(hs + k * MT + r3);      // rows (r3, r3+1), (r3+2, r3+3)
+                    const float* wp = W3t + k * W3LD + c3;
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) {
+                        const unsigned long long ww = pack2(wp[c], wp[c]);
+                        ffma2(acc[0][c], hp.x, ww); ffma2(acc[1][c], hp.y, ww);
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 5; ++c) {
+                    const int j = c3 + c;
+                    if (j < ACT) {
+                        float v0, v1, v2, v3;
+                        unpack2(acc[0][c], v0, v1);
+                        unpack2(acc[1][c], v2, v3);
+                        outs[(r3 + 0) * ACT + j] = v0; outs[(r3 + 1) * ACT + j] = v1;
+                        outs[(r3 + 2) * ACT + j] = v2; outs[(r3 + 3) * ACT + j] = v3;
+                    }
+                }
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            MLP3_CK(3)
+            {
+                const long row0 = (long)tile * MT;
+                const int valid = (a.B - row0 < MT) ? (int)(a.B - row0) : MT;
+                const int nflt = valid * ACT;
+                float* g = a.mean + row0 * ACT;                   // 16-byte aligned: MT * ACT * 4 is a multiple of 16
+                const int nv = nflt >> 2;
+                for (int i = et; i < nv; i += NEPI) reinterpret_cast<float4*>(g)[i] = reinterpret_cast<const float4*>(outs)[i];
+                for (int i = (nv << 2) + et; i < nflt; i += NEPI) g[i] = outs[i];
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");        // the next tile's epilogue reuses hs / outs
+            MLP3_CK(4)
+        }
+#ifdef DART_MLP3_CLOCK
+        if (blockIdx.x == 0 && et == 0 && lt > 0)
+            printf("mlp3 epilogue cycles/tile over %d tiles: wait %lld  l1-epi %lld  layer2 %lld  layer3 %lld  store %lld\n", lt, ck[0] / lt, ck[1] / lt, ck[2] / lt, ck[3] / lt, ck[4] / lt);
+#endif
+    }
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(v3::TCOLS) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------------ obs build
 struct ObsArgs {
     int B, count;     // count = number of pushes including this one (shared by all instances)
@@ -382,7 +694,9 @@ int make_map(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, ui
 struct dart_policy {
     int device, sms;
     float *W1, *b1, *W2, *b2, *W3, *b3;
-    CUtensorMap tm_w1, tm_w2, tm_w3;
+    float *W1h, *W1l;                         // 3xTF32 split of W1 (top 19 bits / remainder)
+    CUtensorMap tm_w1, tm_w2, tm_w3, tm_w1h, tm_w1l;
+    int legacy;                               // DART_POLICY_TF32: the single-pass TF32 kernel (dart_policy_set_precision)
     int64_t launches;
 };
 
@@ -413,12 +727,36 @@ extern "C" int dart_policy_create(dart_policy_handle* out, int device, int32_t o
             cudaMemcpy(*dst[i], src[i], n[i] * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess)
             rc = DART_ERR_CUDA;
     }
+    if (rc == DART_OK) {
+        // W1 = W1_hi + W1_lo: hi keeps the top 19 bits (an exact TF32 value), lo = fp32(W1 - hi), itself cut to TF32
+        float* hi = new (std::nothrow) float[n[0]];
+        float* lo = new (std::nothrow) float[n[0]];
+        if (!hi || !lo) rc = DART_ERR_ALLOC;
+        for (size_t i = 0; rc == DART_OK && i < n[0]; ++i) {
+            uint32_t u;
+            memcpy(&u, &W1[i], 4);
+            u &= 0xffffe000u;
+            memcpy(&hi[i], &u, 4);
+            float l = W1[i] - hi[i];
+            memcpy(&u, &l, 4);
+            u &= 0xffffe000u;
+            memcpy(&lo[i], &u, 4);
+        }
+        if (rc == DART_OK && (cudaMalloc(&h->W1h, n[0] * 4) != cudaSuccess || cudaMalloc(&h->W1l, n[0] * 4) != cudaSuccess)) rc = DART_ERR_ALLOC;
+        if (rc == DART_OK && (cudaMemcpy(h->W1h, hi, n[0] * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+                              cudaMemcpy(h->W1l, lo, n[0] * 4, cudaMemcpyHostToDevice) != cudaSuccess)) rc = DART_ERR_CUDA;
+        delete[] hi;
+        delete[] lo;
+    }
     if (rc == DART_OK && (make_map(&h->tm_w1, h->W1, HID, OBS, HID) || make_map(&h->tm_w2, h->W2, HID, HID, HID) ||
-                          make_map(&h->tm_w3, h->W3, N3, HID, N3)))
+                          make_map(&h->tm_w3, h->W3, N3, HID, N3) || make_map(&h->tm_w1h, h->W1h, HID, OBS, HID) ||
+                          make_map(&h->tm_w1l, h->W1l, HID, OBS, HID)))
         rc = DART_ERR_CUDA;
+    h->legacy = 0;
     if (rc != DART_OK) { dart_policy_destroy(h); return rc; }
     if (cudaFuncSetAttribute(policy_mlp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<2>::BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(policy_mlp_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<4>::BYTES) != cudaSuccess) {
+        cudaFuncSetAttribute(policy_mlp_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<4>::BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(policy_mlp3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v3::BYTES) != cudaSuccess) {
         dart_policy_destroy(h);
         return DART_ERR_CUDA;
     }
@@ -429,8 +767,8 @@ extern "C" int dart_policy_create(dart_policy_handle* out, int device, int32_t o
 extern "C" int dart_policy_destroy(dart_policy_handle h) {
     if (!h) return DART_ERR_ARG;
     cudaSetDevice(h->device);
-    float* p[6] = {h->W1, h->b1, h->W2, h->b2, h->W3, h->b3};
-    for (int i = 0; i < 6; ++i) if (p[i]) cudaFree(p[i]);
+    float* p[8] = {h->W1, h->b1, h->W2, h->b2, h->W3, h->b3, h->W1h, h->W1l};
+    for (int i = 0; i < 8; ++i) if (p[i]) cudaFree(p[i]);
     delete h;
     return DART_OK;
 }
@@ -443,6 +781,15 @@ extern "C" int dart_policy_forward(dart_policy_handle h, int32_t B, const float*
     CUtensorMap tm_obs;
     int rc = make_map(&tm_obs, obs, (uint64_t)B, OBS, MT);
     if (rc != DART_OK) return rc;
+    if (!h->legacy) {
+        Mlp3Args a3;
+        a3.B = B; a3.ntiles = (B + MT - 1) / MT; a3.W2 = h->W2; a3.b1 = h->b1; a3.b2 = h->b2; a3.W3 = h->W3; a3.b3 = h->b3;
+        a3.mean = act_mean;
+        const int grid = a3.ntiles < h->sms ? a3.ntiles : h->sms;           // one persistent CTA per SM
+        policy_mlp3_kernel<<<grid, v3::NTHR, v3::BYTES, (cudaStream_t)stream>>>(tm_obs, h->tm_w1h, h->tm_w1l, a3);
+        h->launches += 1;
+        return cudaGetLastError() == cudaSuccess ? DART_OK : DART_ERR_CUDA;
+    }
     MlpArgs a;
     a.B = B; a.ntiles = (B + MT - 1) / MT; a.b1 = h->b1; a.b2 = h->b2; a.b3 = h->b3; a.mean = act_mean;
     if (a.ntiles <= h->sms) {
@@ -456,6 +803,12 @@ extern "C" int dart_policy_forward(dart_policy_handle h, int32_t B, const float*
 }
 
 extern "C" int64_t dart_policy_launch_count(dart_policy_handle h) { return h ? h->launches : -1; }
+
+extern "C" int dart_policy_set_precision(dart_policy_handle h, int32_t precision) {
+    if (!h || (precision != DART_POLICY_FP32 && precision != DART_POLICY_TF32)) return DART_ERR_ARG;
+    h->legacy = precision == DART_POLICY_TF32 ? 1 : 0;
+    return DART_OK;
+}
 
 extern "C" int dart_policy_obs_push(int32_t B, int32_t count, const double* state, const double* target, const double* control,
                                     const double* cur_k, int32_t ld_k, double* mean, double* M2, const float* obs_in,

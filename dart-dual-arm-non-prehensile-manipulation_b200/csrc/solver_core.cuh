@@ -1303,6 +1303,9 @@ struct Solver {
         // (the tile type says whether the tiles of a warp run in lockstep: nmpc_kernel.cuh TileFor)
         constexpr bool kScan = M::SERIAL_RICCATI && n == 2 && m == 1 && NC > 0 && T::kLockstep &&
                                (T::kLanes == NC + 1 || 2 * T::kLanes == NC + 1);
+        // sub-warp tiles whose warp runs ONE instruction stream (collectives with a constant full-warp mask)
+        constexpr bool kLock = T::kLockstep && T::kLanes < 32;
+        static_assert(!kLock || kScan || !M::SERIAL_RICCATI, "lockstep tiles need the scan sweeps or the tiled Riccati sweep");
 #ifdef DART_PHASE_CLOCK
         long long ckA = 0, ckB = 0, ckC = 0, ckBb = 0, ckC1 = 0, ckC2 = 0, ckA1 = 0, ckW1 = 0, ckW2 = 0, ck0 = DART_CLOCK();
 #define DART_CK(acc) { long long t_ = DART_CLOCK(); acc += t_ - ck0; ck0 = t_; }
@@ -1337,24 +1340,31 @@ struct Solver {
                     }
                     DART_CK(ckA1)
                     need_sweep = true;
-                    if constexpr (!kScan) {
+                    if constexpr (!kLock) {
                         prep(mu);
                         if (!M::SERIAL_RICCATI) backward(tile);
                     }
                 }
             }
             bool ghost = false;
-            if constexpr (kScan) {
-                // One lane per stage: the tile sweeps by scans, independent of the rest of the block.  The two tiles of a
-                // WARP (the axes of one instance) run the whole iteration in LOCKSTEP so that every collective is a
-                // full-warp instruction with a constant mask: a tile that has finished while its sibling has not keeps
-                // executing the same instructions as a "ghost" -- zero step lengths, so its primal point, objective and
-                // status stay exactly what they were when it finished.
+            if constexpr (kLock) {
+                // Lockstep tiles: the tiles of a WARP run the whole iteration as one instruction stream, so that every
+                // collective is a full-warp instruction with a constant mask.  A tile that has finished while a sibling
+                // has not keeps executing the same instructions as a "ghost" -- zero step lengths, so its primal point,
+                // objective and status stay exactly what they were when it finished.  No block barriers: warps are
+                // independent.  (PMPC axis problems sweep by scans, the larger models by the tiled Riccati sweep.)
                 DART_CK(ckA)
                 if (tile.warp_ballot(need_sweep) == 0u) break;
                 ghost = !need_sweep;
                 prep(mu);
-                if constexpr (T::kLanes == NC + 1) sweeps_scan(tile); else sweeps_scan2(tile);
+                if constexpr (kScan) {
+                    if constexpr (T::kLanes == NC + 1) sweeps_scan(tile); else sweeps_scan2(tile);
+                } else {
+                    backward(tile);
+                    if (T::kLanes >= n) forward_tile(tile);
+                    else if (tile.lane() == 0) forward();
+                    tile.sync();
+                }
                 DART_CK(ckB)
             } else if (M::SERIAL_RICCATI) {
                 if (tile.lane() == 0) myslot[0] = need_sweep ? 1.0 : 0.0;
@@ -1411,7 +1421,7 @@ struct Solver {
                 bool ok = ((switching && th0 <= o.theta_small) ? armijo : suff) && (th <= th_max) && (phit == phit) &&
                           (fabs(phit) < 1e300);
                 const bool stop_ls = ok || bt + 1 >= o.max_backtrack || ghost;
-                if constexpr (kScan) {
+                if constexpr (kLock) {
                     // the tiles of a warp leave the line search together (a tile that is done re-evaluates its accepted
                     // point with a zero step: same values), so the collectives inside stay warp-converged
                     if (tile.group_all(stop_ls)) break;
@@ -1431,8 +1441,8 @@ struct Solver {
             if (tiny >= 3) {
                 st = (pinf > 1e-4) ? ST_INFEASIBLE : ST_MAXITER;
                 done = true;
-                if constexpr (!kScan) continue;
-                alpha = 0.0;                          // scan path: stay in lockstep with the other tile of the warp (its collectives below)
+                if constexpr (!kLock) continue;
+                alpha = 0.0;                          // lockstep tiles: stay with the other tiles of the warp (their collectives below)
             }
             move_dual(alpha, mu);
             eval2(dinf, zs_min, zs_max, lam_sum, z_sum);

@@ -112,14 +112,15 @@ class NMPCEngine:
             status = torch.empty((B,), dtype=i32, device=dev)
         if iters is None:
             iters = torch.empty((B,), dtype=i32, device=dev)
-        if torch.cuda.current_device() != self.device:      # dart_solve rejects a launch from another device
-            torch.cuda.set_device(self.device)
-        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        torch.cuda.nvtx.range_push(self._nvtx_name)          # NVTX range around the solve launch (tracing)
-        try:
-            return self._solve_device(B, ptr, x0, ref, aux, warm_w, w_out, u0_out, J_out, status, iters, stream, f64, i32)
-        finally:
-            torch.cuda.nvtx.range_pop()
+        # dart_solve launches on the CURRENT device and rejects a mismatch with the handle's (DART_ERR_ARG): run under the
+        # handle's device and restore the caller's afterwards
+        with torch.cuda.device(self.device):
+            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            torch.cuda.nvtx.range_push(self._nvtx_name)          # NVTX range around the solve launch (tracing)
+            try:
+                return self._solve_device(B, ptr, x0, ref, aux, warm_w, w_out, u0_out, J_out, status, iters, stream, f64, i32)
+            finally:
+                torch.cuda.nvtx.range_pop()
 
     def _solve_device(self, B, ptr, x0, ref, aux, warm_w, w_out, u0_out, J_out, status, iters, stream, f64, i32):
         check(self._lib.dart_solve(self._h, B, ptr(x0, (B, self.nx), f64, "x0"), ptr(ref, (B, self.nref), f64, "ref"),

@@ -68,7 +68,9 @@ def load_checkpoint_weights(path, trust_pickle=False):
 class PolicyMLP:
     """``Policy.mean_net`` forward on the tcgen05 kernel: obs [B,520] f32 CUDA tensor -> mean [B,34] f32."""
 
-    def __init__(self, weights=None, seed=3, device=0):
+    def __init__(self, weights=None, seed=3, device=0, precision="fp32"):
+        """precision: "fp32" (default; within 2e-5 of the reference's FP32 torch forward: 3xTF32 tensor-core layer 1, FP32
+        layers 2-3) or "tf32" (single-pass TF32 tensor cores: faster streaming, |error| <= 8e-3)."""
         self._lib = _lib.lib()
         self.device = int(device)
         self.weights = init_policy_weights(seed) if weights is None else weights
@@ -80,6 +82,10 @@ class PolicyMLP:
         self._h = C.c_void_p()
         check(self._lib.dart_policy_create(C.byref(self._h), self.device, OBS_DIM, HIDDEN, ACT_DIM,
                                            *[C.c_void_p(a.ctypes.data) for a in flat]), "dart_policy_create")
+        if precision not in ("fp32", "tf32"):
+            raise ValueError("precision: 'fp32' or 'tf32'")
+        self.precision = precision
+        check(self._lib.dart_policy_set_precision(self._h, 1 if precision == "tf32" else 0), "dart_policy_set_precision")
 
     def forward(self, obs, out=None):
         torch = _torch()

@@ -176,7 +176,12 @@ int dart_policy_create(dart_policy_handle* out, int device, int32_t obs_dim, int
 int dart_policy_destroy(dart_policy_handle h);
 
 /* Policy.mean_net forward: obs [B,520] f32 (device, 16-byte aligned) -> act_mean [B,34] f32 (device).
- * TMA-fed tcgen05 (TF32 inputs, FP32 accumulate) with all three layers fused on chip. */
+ * One fused launch.  Default arithmetic DART_POLICY_FP32 matches the reference's FP32 torch forward to <= 2e-5
+ * (layer 1: TMA-fed tcgen05 as a 3xTF32 product A_hi W_hi + A_hi W_lo + A_lo W_hi, FP32 accumulate; layers 2, 3: FP32
+ * FMAs).  DART_POLICY_TF32 is the single-pass TF32 tensor-core kernel: 1.6x the streaming rate, |error| <= 8e-3. */
+#define DART_POLICY_FP32 0
+#define DART_POLICY_TF32 1
+int dart_policy_set_precision(dart_policy_handle h, int32_t precision);
 int dart_policy_forward(dart_policy_handle h, int32_t B, const float* obs, float* act_mean, void* stream);
 int64_t dart_policy_launch_count(dart_policy_handle h);
 

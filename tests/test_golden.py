@@ -68,4 +68,4 @@ def test_gpu_rls_and_mlp_vs_golden(built):
     g = load("policy_mlp.npz")
     pol = dart_b200.PolicyMLP([(g[f"W{i}"], g[f"b{i}"]) for i in range(3)], device=0)
     out = pol.forward(torch.from_numpy(g["obs"]).to(dev)).cpu().numpy()
-    assert np.abs(out - g["mean"]).max() <= 8e-3      # TF32 inputs, see tests/test_gpu_lmpc_policy.py
+    assert np.abs(out - g["mean"]).max() <= 2e-5      # FP32-fidelity forward, see tests/test_gpu_lmpc_policy.py

@@ -258,8 +258,16 @@ def test_two_devices_in_one_process(built):
         torch.cuda.synchronize(d)
         assert np.array_equal(o["u0"].cpu().numpy(), outs[-1]["u0"])
         if dev == 1:
+            # the C ABI refuses a launch from another current device; the Python wrapper runs under the handle's device
+            import ctypes as C
             torch.cuda.set_device(0)
-            with pytest.raises(dart_b200.DartError):
-                eng.solve_device(t(c["state"]), t(c["target"]), aux=t(aux))
+            x, r, a_ = t(c["state"]), t(c["target"]), t(aux)
+            u0 = torch.empty((x.shape[0], 2), dtype=torch.float64, device=d); J = torch.empty((x.shape[0],), dtype=torch.float64, device=d)
+            p_ = lambda z: C.c_void_p(z.data_ptr())
+            rc = dart_b200._lib.lib().dart_solve(eng._h, x.shape[0], p_(x), p_(r), p_(a_), None, None, p_(u0), p_(J), None, None, None)
+            assert rc == -1
+            o2 = eng.solve_device(x, r, aux=a_)
+            torch.cuda.synchronize(d)
+            assert torch.cuda.current_device() == 0 and np.array_equal(o2["u0"].cpu().numpy(), outs[-1]["u0"])
     torch.cuda.set_device(0)
     assert np.array_equal(outs[0]["u0"], outs[1]["u0"]) and np.array_equal(outs[0]["J"], outs[1]["J"])

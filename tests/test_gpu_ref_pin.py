@@ -170,7 +170,7 @@ def _mean_net(d, prefix):
     return [(d[f"{prefix}mean_net__{i}__weight"], d[f"{prefix}mean_net__{i}__bias"]) for i in (0, 2, 4)]
 
 
-TOL_MLP_REF = 8e-3          # tightened to FP32 level once the 3xTF32 split is in (see test_gpu_lmpc_policy.TOL_MLP)
+TOL_MLP_REF = 2e-5          # FP32-fidelity forward (see test_gpu_lmpc_policy.TOL_MLP)
 
 
 def test_policy_kernel_matches_reference_policy_class(built):
