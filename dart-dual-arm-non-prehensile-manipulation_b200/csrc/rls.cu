@@ -81,8 +81,8 @@ __global__ void __launch_bounds__(128) rls_update_kernel(int nest, int E, double
 struct PrologueArgs {
     int B, N;
     double Ts, v_eps, lam, dr_max, alpha_rg, step_fraction;
-    const double *xk, *prev_state, *target, *u_prev;
-    double *r_v, *theta, *P, *ref, *aux;
+    const double *xk, *target, *u_prev;
+    double *prev_state, *r_v, *theta, *P, *ref, *aux;
 };
 
 __global__ void __launch_bounds__(128) rmpc_prologue_kernel(const PrologueArgs a) {
@@ -96,6 +96,12 @@ __global__ void __launch_bounds__(128) rmpc_prologue_kernel(const PrologueArgs a
     ph[0] = ps[0]; ph[1] = ps[1]; ph[2] = ps[2]; ph[3] = ps[3];
     ph[4] = tanh(ps[1] / a.v_eps); ph[5] = tanh(ps[3] / a.v_eps); ph[6] = 1.0;
     const double ymeas = (xs[1 + 2 * est] - ps[1 + 2 * est]) / a.Ts;
+    // prev_state <- xk for the next step (rob_ctrl.py:365 `prev_state = xk.copy()`): each of the instance's two threads
+    // writes its own axis once BOTH have read the old values (they are neighbours in one warp)
+    const double nx0 = xs[2 * est], nx1 = xs[2 * est + 1];
+    __syncwarp();
+    a.prev_state[(size_t)b * 4 + 2 * est] = nx0;
+    a.prev_state[(size_t)b * 4 + 2 * est + 1] = nx1;
     double th[P7], Pm[P7 * P7];
 #pragma unroll
     for (int i = 0; i < P7; ++i) th[i] = a.theta[(size_t)e * P7 + i];
@@ -137,13 +143,13 @@ extern "C" int dart_rls_update(int32_t B, int32_t E, double* theta, double* P, c
 }
 
 extern "C" int dart_rmpc_prologue(int32_t B, int32_t N, double Ts, double v_eps, double lam, double dr_max, double alpha_rg,
-                                  double step_fraction, const double* xk, const double* prev_state, const double* target,
+                                  double step_fraction, const double* xk, double* prev_state, const double* target,
                                   const double* u_prev, double* r_v, double* theta, double* P, double* ref, double* aux,
                                   void* stream) {
     if (B < 0 || N < 1 || !xk || !prev_state || !target || !u_prev || !r_v || !theta || !P || !ref || !aux) return DART_ERR_ARG;
     if (!(Ts > 0.0) || !(v_eps > 0.0) || !(lam > 0.0)) return DART_ERR_ARG;
     if (B == 0) return DART_OK;
-    PrologueArgs a{B, N, Ts, v_eps, lam, dr_max, alpha_rg, step_fraction, xk, prev_state, target, u_prev, r_v, theta, P, ref, aux};
+    PrologueArgs a{B, N, Ts, v_eps, lam, dr_max, alpha_rg, step_fraction, xk, target, u_prev, prev_state, r_v, theta, P, ref, aux};
     rmpc_prologue_kernel<<<(2 * B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
     return cudaGetLastError() == cudaSuccess ? DART_OK : DART_ERR_CUDA;
 }

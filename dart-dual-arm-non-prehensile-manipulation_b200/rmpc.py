@@ -159,14 +159,14 @@ class RMPCBatch:
         self.target = t(target)
         self.prev_state = t(x_init)
         self.r_v = torch.zeros((B, 4), dtype=f64, device=self.dev)
-        self.u_prev = torch.zeros((B, 2), dtype=f64, device=self.dev)
         self.theta = torch.zeros((B, 2, 7), dtype=f64, device=self.dev)
         self.P = (torch.eye(7, dtype=f64, device=self.dev) * float(rls_P0)).repeat(B, 2, 1, 1).contiguous()
         self.ref = torch.empty((B, (self.N + 1) * 4), dtype=f64, device=self.dev)
         self.aux = torch.empty((B, 16), dtype=f64, device=self.dev)
         self.w = torch.zeros((B, self.engine.nw), dtype=f64, device=self.dev)      # reference: w0 = zeros at first call
         self.w_next = torch.empty_like(self.w)
-        self.u0 = torch.empty((B, 2), dtype=f64, device=self.dev)
+        self.u0 = torch.zeros((B, 2), dtype=f64, device=self.dev)          # also u_prev of the next step (rob_ctrl.py: u_prev = 0 at start)
+        self.u_prev = self.u0
         self.J = torch.empty((B,), dtype=f64, device=self.dev)
         self.status = torch.empty((B,), dtype=torch.int32, device=self.dev)
         self.iters = torch.empty((B,), dtype=torch.int32, device=self.dev)
@@ -202,6 +202,5 @@ class RMPCBatch:
                                  w_out=self.w_next, u0_out=self.u0, J_out=self.J, status=self.status, iters=self.iters)
         self.steps += 1
         self.w, self.w_next = self.w_next, self.w
-        self.prev_state.copy_(xk)
-        self.u_prev.copy_(self.u0)
+        # no eager glue: the prologue kernel has set prev_state <- xk, and the next prologue reads u_prev from u0
         return self.u0

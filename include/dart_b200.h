@@ -157,10 +157,12 @@ int dart_rls_update(int32_t B, int32_t E, double* theta, double* P, const double
 /* One RMPC closed-loop step's pre-solve glue (rob_ctrl.py:335-351) fused into one launch: finite-difference
  * acceleration, regressor of prev_state, the x and y RLS updates, reference governor, build_ref_traj, and the
  * solver's aux rows.  Device pointers:
- *   xk, prev_state, target [B,4]   u_prev [B,2]   r_v [B,4] in/out   theta [B,2,7] in/out   P [B,2,7,7] in/out
+ *   xk, target [B,4]   prev_state [B,4] in/out (set to xk for the next step, rob_ctrl.py:365; xk != prev_state)
+ *   u_prev [B,2] (the last command: may be the u0 buffer of the previous dart_solve)   r_v [B,4] in/out
+ *   theta [B,2,7] in/out   P [B,2,7,7] in/out
  *   ref [B,(N+1)*4] out (Rref_flat)   aux [B,16] out ([u_prev, theta_hat] as dart_solve expects for RMPC) */
 int dart_rmpc_prologue(int32_t B, int32_t N, double Ts, double v_eps, double lam, double dr_max, double alpha_rg,
-                       double step_fraction, const double* xk, const double* prev_state, const double* target,
+                       double step_fraction, const double* xk, double* prev_state, const double* target,
                        const double* u_prev, double* r_v, double* theta, double* P, double* ref, double* aux,
                        void* stream);
 

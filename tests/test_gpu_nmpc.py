@@ -230,6 +230,32 @@ def test_mpc_worker_queue_protocol(built):
         assert abs(loss[0] - ref["J"][i]) <= helpers.TOL_J * abs(ref["J"][i])
 
 
+def test_mpc_worker_in_a_spawned_process(built):
+    """The reference's launcher contract (PMPC/main_parallel.py:46,138-145, mpc_3d.py:161): the worker runs in a process
+    started with the ``spawn`` method and talks through ``mp.Queue`` -- so the arguments and the reply tuple must pickle
+    and the CUDA context is created in the child."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    sq, cq = ctx.Queue(), ctx.Queue()
+    model, data = dart_b200.GravityModel(-9.81, 0.002), dart_b200.StateHolder()
+    params = {"Ts": 0.002, "nx": 6, "nu": 2, "N": 15, "Qp": 600, "Qv": 5, "R": 0.1, "u_bounds": (-0.6, 0.6), "mu": 0.1}
+    proc = ctx.Process(target=dart_b200.mpc_worker, args=((model, data), "cube", params, sq, cq), daemon=True)
+    proc.start()
+    c, aux, p = helpers.pmpc_case(1)
+    cube = [i for i in range(p.B) if c["Qp"][i] == 600 and c["mu"][i] == 0.1][:3]
+    for i in cube:
+        sq.put((c["state"][i], c["target"][i]))
+    ref = ipm.solve(p)
+    for i in cube:
+        u_cmd, loss, solve_time = cq.get(timeout=180)          # the first reply pays the child's imports and CUDA start-up
+        assert isinstance(u_cmd, np.ndarray) and u_cmd.shape == (2,) and loss.shape == (1,) and solve_time > 0
+        assert np.abs(u_cmd - ref["U"][i, 0]).max() <= helpers.TOL_U0
+        assert abs(loss[0] - ref["J"][i]) <= helpers.TOL_J * abs(ref["J"][i])
+    sq.put("STOP")
+    proc.join(timeout=60)
+    assert proc.exitcode == 0
+
+
 def test_pmpc_class_is_a_dropin(built):
     model, data = dart_b200.GravityModel(-9.81, 0.002), dart_b200.StateHolder()
     ctl = dart_b200.PMPC(model, data, Ts=0.002, nx=6, nu=2, N=15, Qp=400, Qv=2, R=0.2, u_bounds=(-0.6, 0.6), mu=0.1)
