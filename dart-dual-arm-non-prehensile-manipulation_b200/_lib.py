@@ -75,7 +75,7 @@ def lib():
     L.dart_policy_obs_push.argtypes = [C.c_int32, C.c_int32, vp, vp, vp, vp, C.c_int32, vp, vp, vp, vp, vp]
     L.dart_policy_param_update.argtypes = [C.c_int32, vp, vp, C.c_int32] + [C.c_double] * 5 + [vp]
     if hasattr(L, "dart_pmpc_plant_step"):
-        L.dart_pmpc_plant_step.argtypes = [C.c_int32, C.c_double, C.c_double] + [vp] * 6 + [C.c_double] + [vp] * 3 + [vp]
+        L.dart_pmpc_plant_step.argtypes = [C.c_int32, C.c_double, C.c_double] + [vp] * 6 + [C.c_double] + [vp] * 6 + [vp]
     L.dart_measure_fp64_tflops.argtypes = [C.c_int, dp]
     if hasattr(L, "dart_pmpc_episode"):
         L.dart_pmpc_episode.argtypes = [vp, C.c_int32, C.c_int32] + [vp] * 5 + [C.c_double] + [vp] * 9 + [vp]
@@ -87,6 +87,7 @@ def lib():
         L.dart_rmpc_plant_step.argtypes = [C.c_int32, C.c_double, C.c_double, vp, vp, vp, vp, vp, vp]
     if hasattr(L, "dart_lmpc_plant_step"):
         L.dart_lmpc_plant_step.argtypes = [C.c_int32, C.c_double, vp, vp, vp, vp, vp]
+        L.dart_lmpc_post_step.argtypes = [C.c_int32, C.c_int32] + [vp] * 11 + [vp]
     if hasattr(L, "dart_ppo_create"):
         L.dart_ppo_default_cfg.argtypes = [vp]
         L.dart_ppo_default_reward_cfg.argtypes = [vp]

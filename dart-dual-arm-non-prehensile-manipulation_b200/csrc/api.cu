@@ -22,6 +22,10 @@ struct dart_solver {
     int32_t rows_cap;
     double* dual;      // dart_set_dual_state
     int32_t dual_cap;
+    // hand-over area of the two-axis models (KArgs::axis_part / axis_sync), grown on demand
+    double* axis_part;
+    int32_t* axis_sync;
+    int32_t axis_cap;
 };
 
 extern "C" int dart_default_cfg(int32_t method, dart_cfg* c) {
@@ -78,6 +82,7 @@ extern "C" int dart_create(dart_handle* out, const dart_cfg* cfg, int device) {
     h->launches = 0;
     memset(&h->last, 0, sizeof(h->last));
     h->pin = nullptr; h->pin_bytes = 0; h->dev = nullptr; h->dev_bytes = 0; h->rows = nullptr; h->rows_cap = 0; h->dual = nullptr; h->dual_cap = 0;
+    h->axis_part = nullptr; h->axis_sync = nullptr; h->axis_cap = 0;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return DART_ERR_CUDA; }
     *out = h;
     return DART_OK;
@@ -88,6 +93,8 @@ extern "C" int dart_destroy(dart_handle h) {
     cudaSetDevice(h->device);
     if (h->pin) cudaFreeHost(h->pin);
     if (h->dev) cudaFree(h->dev);
+    if (h->axis_part) cudaFree(h->axis_part);
+    if (h->axis_sync) cudaFree(h->axis_sync);
     cudaStreamDestroy(h->stream);
     delete h;
     return DART_OK;
@@ -133,11 +140,26 @@ extern "C" int dart_solve(dart_handle h, int32_t B, const double* x0, const doub
     if (h->dual && B > h->dual_cap) return DART_ERR_ARG;       // the registered dual-state buffer is too small
     int cur = -1;
     if (cudaGetDevice(&cur) != cudaSuccess || cur != h->device) return DART_ERR_ARG;   // launch from the handle's device
+    cudaStream_t st = (cudaStream_t)stream;
+    if (h->cfg.method == DART_LMPC && B > h->axis_cap) {
+        // first solve of this size: (re)allocate the axes' hand-over area.  The counters are zero between launches
+        // (the kernel re-arms them).  Allocation synchronises the device: size the handle with one warm-up solve
+        // before capturing solves into a CUDA graph.
+        if (cudaDeviceSynchronize() != cudaSuccess) return DART_ERR_CUDA;
+        if (h->axis_part) cudaFree(h->axis_part);
+        if (h->axis_sync) cudaFree(h->axis_sync);
+        h->axis_part = nullptr; h->axis_sync = nullptr; h->axis_cap = 0;
+        const size_t cap = (size_t)B + (size_t)B / 4 + 64;
+        if (cudaMalloc(&h->axis_part, cap * LmpcAxis::NAXIS * 4 * sizeof(double)) != cudaSuccess) return DART_ERR_ALLOC;
+        if (cudaMalloc(&h->axis_sync, cap * sizeof(int32_t)) != cudaSuccess) { cudaFree(h->axis_part); h->axis_part = nullptr; return DART_ERR_ALLOC; }
+        if (cudaMemset(h->axis_sync, 0, cap * sizeof(int32_t)) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) return DART_ERR_CUDA;
+        h->axis_cap = (int32_t)cap;
+    }
     KArgs a;
     a.B = B; a.N = h->cfg.N; a.o = h->opts; a.cfg = h->cfg;
     a.x0 = x0; a.ref = ref; a.aux = aux; a.warm = warm_w;
     a.w_out = w_out; a.u0 = u0_out; a.J = J_out; a.status = status; a.iters = iters; a.rows = h->rows; a.dual = h->dual;
-    cudaStream_t st = (cudaStream_t)stream;
+    a.axis_part = h->axis_part; a.axis_sync = h->axis_sync;
     int rc = launch_solve(a, h->cfg.lanes, h->cfg.block_threads, st, &h->last);
     if (rc != DART_OK) return rc;
     h->launches += 1;
@@ -224,7 +246,7 @@ extern "C" int dart_pmpc_episode(dart_handle h, int32_t B, int32_t T, double* st
     KArgs a;
     a.B = B; a.N = h->cfg.N; a.o = h->opts; a.cfg = h->cfg;
     a.x0 = state; a.ref = target; a.aux = aux; a.warm = nullptr;
-    a.w_out = nullptr; a.u0 = u0; a.J = J; a.status = status; a.iters = iters; a.rows = nullptr; a.dual = nullptr;
+    a.w_out = nullptr; a.u0 = u0; a.J = J; a.status = status; a.iters = iters; a.rows = nullptr; a.dual = nullptr; a.axis_part = nullptr; a.axis_sync = nullptr;
     PlantArgs pl{B, h->cfg.Ts, h->cfg.g, tol, mu_plant, coulomb, u0, target, state, conv_time, effort, err, nsteps};
     int rc = launch_episode_pmpc(a, T, pl, (unsigned long long*)counters, h->cfg.lanes, (cudaStream_t)stream, &h->last);
     if (rc != DART_OK) return rc;

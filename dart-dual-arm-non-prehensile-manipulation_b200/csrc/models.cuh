@@ -28,6 +28,10 @@ struct KArgs {
     int32_t *status, *iters;
     double* rows;      // optional packed result rows [B,4] = [u0x, u0y, J, status] for the multi-GPU gather
     double* dual;      // optional dual-state blocks [B, NAXIS * dual_doubles(N)] (read when warm is given, always written)
+    // optional hand-over area for models whose axes are solved by different warps: per-axis [J, status, iters, kkt]
+    // records [B, NAXIS, 4] and an arrival counter per instance (zero between launches); see solve_block
+    double* axis_part;
+    int32_t* axis_sync;
 };
 
 // Generic RK4 step with forward sensitivities.  Md::deriv(prm, x, u, f, fx, fu) gives xdot and its
@@ -223,7 +227,13 @@ struct LmpcAxis {
     // one instance (two axis tiles) per block; 168 registers -> 6 blocks = 12 warps per SM (shared memory allows 14).
     // Measured at 16 384 instances: bounds (64,5) 7.06 ms, (128,3) 7.58 ms (same register count, worse schedule),
     // (64,4) / (128,2) with 255 registers and 8 warps 7.30 ms, (64,7) with 128 registers 8.2 ms
-    static constexpr int MAX_THREADS = 64, MIN_BLOCKS = 5, BT_LARGE = 64;
+#ifndef DART_LMPC_MAXT
+#define DART_LMPC_MAXT 64
+#endif
+#ifndef DART_LMPC_MINB
+#define DART_LMPC_MINB 5
+#endif
+    static constexpr int MAX_THREADS = DART_LMPC_MAXT, MIN_BLOCKS = DART_LMPC_MINB, BT_LARGE = 64;
     static constexpr int NXF = 8;
     static constexpr int NDEF = 20;
     struct Prm {

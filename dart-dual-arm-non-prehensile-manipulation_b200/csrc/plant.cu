@@ -12,9 +12,24 @@
 namespace {
 using dart::PlantArgs;
 
-__global__ void __launch_bounds__(128) pmpc_plant_step_kernel(const PlantArgs a) {
+// status / iters / counters (all or none): the solve statistics of the step that produced `u` are accumulated here as
+// the persistent episode kernel does (counters[0] += iterations, counters[1] += solves that did not end converged), so the
+// stepwise closed loop needs no reduction launches of its own
+__global__ void __launch_bounds__(128) pmpc_plant_step_kernel(const PlantArgs a, const int32_t* __restrict__ status,
+                                                              const int32_t* __restrict__ iters, unsigned long long* counters) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= a.B) return;
+    const bool in = b < a.B;
+    if (counters != nullptr) {
+        unsigned long long it = in ? (unsigned long long)iters[b] : 0ull;
+        unsigned nc = (in && status[b] != 0 /* ST_CONVERGED */) ? 1u : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { it += __shfl_xor_sync(0xffffffffu, it, o); nc += __shfl_xor_sync(0xffffffffu, nc, o); }
+        if ((threadIdx.x & 31) == 0) {
+            if (it) atomicAdd(&counters[0], it);
+            if (nc) atomicAdd(&counters[1], (unsigned long long)nc);
+        }
+    }
+    if (!in) return;
     dart::plant_step_one(a, b);
 }
 
@@ -50,10 +65,12 @@ extern "C" int dart_rmpc_plant_step(int32_t B, double Ts, double gz, const doubl
 
 extern "C" int dart_pmpc_plant_step(int32_t B, double Ts, double g, const double* mu, const double* coulomb, const double* u,
                                     const double* target, double* state, int32_t* nsteps, double tol, double* conv_time,
-                                    double* effort, double* err, void* stream) {
+                                    double* effort, double* err, const int32_t* status, const int32_t* iters,
+                                    uint64_t* counters, void* stream) {
     if (B < 0 || !mu || !u || !target || !state || !nsteps || !conv_time || !effort || !err || !(Ts > 0.0)) return DART_ERR_ARG;
+    if (counters && (!status || !iters)) return DART_ERR_ARG;
     if (B == 0) return DART_OK;
     PlantArgs a{B, Ts, g, tol, mu, coulomb, u, target, state, conv_time, effort, err, nsteps};
-    pmpc_plant_step_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
+    pmpc_plant_step_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a, status, iters, (unsigned long long*)counters);
     return cudaGetLastError() == cudaSuccess ? DART_OK : DART_ERR_CUDA;
 }

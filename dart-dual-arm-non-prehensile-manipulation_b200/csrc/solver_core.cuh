@@ -47,6 +47,9 @@
 #endif
 #endif
 
+#ifndef DART_TREE_SUMS
+#define DART_TREE_SUMS 1
+#endif
 #ifndef DART_SWEEP_UNROLL
 #define DART_SWEEP_UNROLL 3
 #endif
@@ -68,6 +71,30 @@ struct SolverOpts {
 
 DART_HD double dmax(double a, double b) { return a > b ? a : b; }
 DART_HD double dmin(double a, double b) { return a < b ? a : b; }
+
+// two consecutive doubles at a 16-byte aligned address: one 128-bit shared-memory access on the device
+struct alignas(16) D2 { double x, y; };
+DART_HD D2 ld2(const double* p) {
+#ifdef __CUDA_ARCH__
+    return *reinterpret_cast<const D2*>(p);
+#else
+    D2 r; r.x = p[0]; r.y = p[1]; return r;
+#endif
+}
+DART_HD void st2(double* p, double x, double y) {
+#ifdef __CUDA_ARCH__
+    D2 v; v.x = x; v.y = y;
+    *reinterpret_cast<D2*>(p) = v;
+#else
+    p[0] = x; p[1] = y;
+#endif
+}
+// load c consecutive doubles (c compile-time) from an aligned address with 128-bit accesses (+ one 64-bit tail)
+template <int C>
+DART_HD void ldv(const double* p, double* out) {
+    DART_UNROLL for (int i = 0; i + 1 < C; i += 2) { const D2 v = ld2(p + i); out[i] = v.x; out[i + 1] = v.y; }
+    if (C & 1) out[C - 1] = p[C - 1];
+}
 
 // Per-tile result / hand-shake slot (doubles) at the head of each problem's workspace stride.
 constexpr int kSlot = 4;
@@ -203,47 +230,63 @@ struct Workspace {
         return true;
     }
     static_assert(rows_fit(), "a two-variable constraint row couples variables outside the stored Hessian pattern");
-    // per-stage strides (in doubles) of the arrays that lanes index by stage: odd, so that lanes working on
-    // consecutive stages hit distinct shared-memory banks (16 banks of 8 bytes)
-    static constexpr int sA = npa | 1, sB = npb | 1, sH = NH | 1, sG = ny | 1, sK = (m * n) | 1;
+    // kVec (the models whose Riccati sweep runs across the tile): the arrays the sweeps gather from are laid out so that
+    // what one lane reads per stage is CONTIGUOUS and 16-byte aligned -- A and B column-major (a lane of the backward sweep
+    // multiplies one column of [A B d]), even strides, every array at an even offset -- so a column is two 128-bit loads
+    // at immediate offsets from one per-lane pointer instead of four 64-bit gathers with computed addresses.
+    static constexpr bool kVec = !M::SERIAL_RICCATI;
+    DART_HD static constexpr int ev(int x) { return (x + 1) & ~1; }
+    // even stride >= x that is an ODD multiple of 16 bytes: lanes working on consecutive stages then cover the banks
+    // with 128-bit accesses (and are at worst 2-way conflicted with 64-bit ones)
+    DART_HD static constexpr int pad2(int x) { return (ev(x) % 4 == 2) ? ev(x) : ev(x) + 2; }
+    // per-stage strides (in doubles) of the arrays that lanes index by stage.  Scalar-access arrays: odd, so that lanes
+    // working on consecutive stages hit distinct shared-memory banks (16 banks of 8 bytes)
+    static constexpr int sA = kVec ? pad2(npa) : (npa | 1), sB = kVec ? pad2(npb) : (npb | 1), sD = kVec ? pad2(n) : n;
+    static constexpr int sH = NH | 1, sG = ny | 1, sK = kVec ? ev(m * n) : ((m * n) | 1);
     static constexpr int sM = ny | 1;
-    // stage scratch MM of the tiled Riccati sweep: W = P [A B d] over the nq = np + m variables with computed
-    // curvature (+ gradient column), then the packed upper triangle of the stage matrix (+ gradient column)
-    static constexpr int nq = np + m, nW = n * (nq + 1), nMq = nq * (nq + 1) / 2 + nq;
-    static constexpr int nscr = M::SERIAL_RICCATI ? sM * (ny + 1) : nW + nMq;
+    // index of dF_a/dx_b, dF_a/du_j inside a stage block (column-major for kVec)
+    DART_HD static constexpr int aidx(int a, int b) { return kVec ? b * np + a : a * np + b; }
+    DART_HD static constexpr int bidx(int a, int j) { return kVec ? j * np + a : a * m + j; }
+    // stage scratch MM of the tiled Riccati sweep: the full P_{k+1} (row stride rP), W = P [A B d] column-major over the
+    // nq = np + m variables with computed curvature + the d column (column stride rP), then the packed upper triangle
+    // of the stage matrix (+ gradient column)
+    static constexpr int nq = np + m, rP = ev(n), nPF = n * rP, nW = (nq + 1) * rP, nMq = nq * (nq + 1) / 2 + nq;
+    static constexpr int nscr = M::SERIAL_RICCATI ? sM * (ny + 1) : nPF + nW + ev(nMq);
     double *X, *U, *A, *Bm, *D, *LAM, *PP, *PV, *K, *KFF, *DX, *DU, *BL;
     double *S, *ZL, *ZU, *ISL, *ISU, *RC, *DS, *MM, *TANU, *HS, *GR, *ZR, *REF;
 
+    // every array starts at an even offset (16-byte aligned when the workspace is)
     DART_HD static int doubles(int N) {
-        return (N + 1) * n + N * m + N * sA + N * sB + N * n + N * n + (N + 1) * nps + (N + 1) * n + N * sK + N * m +
-               (N + 1) * n + N * m + N * m + 7 * N * nr + nscr + N * m + N * sH + N * sG + 1 + M::ref_doubles(N);
+        return ev((N + 1) * n) + ev(N * m) + ev(N * sA) + ev(N * sB) + ev(N * sD) + ev(N * n) + ev((N + 1) * nps) + ev((N + 1) * n) +
+               ev(N * sK) + ev(N * m) + ev((N + 1) * n) + ev(N * m) + ev(N * m) + 7 * ev(N * nr) + ev(nscr) + ev(N * m) +
+               ev(N * sH) + ev(N * sG) + 2 + ev(M::ref_doubles(N));
     }
     DART_HD void bind(double* p, int N) {
-        X = p;   p += (N + 1) * n;
-        U = p;   p += N * m;
-        A = p;   p += N * sA;
-        Bm = p;  p += N * sB;
-        D = p;   p += N * n;
-        LAM = p; p += N * n;
-        PP = p;  p += (N + 1) * nps;
-        PV = p;  p += (N + 1) * n;
-        K = p;   p += N * sK;
-        KFF = p; p += N * m;
-        DX = p;  p += (N + 1) * n;
-        DU = p;  p += N * m;
-        BL = p;  p += N * m;
-        S = p;   p += N * nr;
-        ZL = p;  p += N * nr;
-        ZU = p;  p += N * nr;
-        ISL = p; p += N * nr;
-        ISU = p; p += N * nr;
-        RC = p;  p += N * nr;
-        DS = p;  p += N * nr;
-        MM = p;  p += nscr;
-        TANU = p; p += N * m;
-        HS = p;  p += N * sH;
-        GR = p;  p += N * sG;
-        ZR = p;  p += 1;          // a stored 0.0: gather target for structural zeros
+        X = p;   p += ev((N + 1) * n);
+        U = p;   p += ev(N * m);
+        A = p;   p += ev(N * sA);
+        Bm = p;  p += ev(N * sB);
+        D = p;   p += ev(N * sD);
+        LAM = p; p += ev(N * n);
+        PP = p;  p += ev((N + 1) * nps);
+        PV = p;  p += ev((N + 1) * n);
+        K = p;   p += ev(N * sK);
+        KFF = p; p += ev(N * m);
+        DX = p;  p += ev((N + 1) * n);
+        DU = p;  p += ev(N * m);
+        BL = p;  p += ev(N * m);
+        S = p;   p += ev(N * nr);
+        ZL = p;  p += ev(N * nr);
+        ZU = p;  p += ev(N * nr);
+        ISL = p; p += ev(N * nr);
+        ISU = p; p += ev(N * nr);
+        RC = p;  p += ev(N * nr);
+        DS = p;  p += ev(N * nr);
+        MM = p;  p += ev(nscr);
+        TANU = p; p += ev(N * m);
+        HS = p;  p += ev(N * sH);
+        GR = p;  p += ev(N * sG);
+        ZR = p;  p += 2;          // a stored 0.0: gather target for structural zeros
         REF = p;
     }
 };
@@ -267,14 +310,15 @@ struct Solver {
         : tile(t), prm(p), o(oo), N(NC > 0 ? NC : NN), w(ww), bc(b) {}
 
     static constexpr int npa = W::npa, npb = W::npb, nps = W::nps;
-    static constexpr int sA = W::sA, sB = W::sB, sH = W::sH, sG = W::sG, sK = W::sK, sM = W::sM;
+    static constexpr int sA = W::sA, sB = W::sB, sD = W::sD, sH = W::sH, sG = W::sG, sK = W::sK, sM = W::sM;
+    static constexpr bool kVec = W::kVec;
     // packed upper-triangular index of a symmetric d x d matrix
     DART_HD static constexpr int sidx(int i, int j, int d) {
         return i <= j ? i * d - i * (i - 1) / 2 + (j - i) : j * d - j * (j - 1) / 2 + (i - j);
     }
     // full stage Jacobians from the stored physical blocks (carried-input rows: A = 0, B = identity)
-    DART_HD double Aat(int k, int a, int b) const { return (a < np && b < np) ? w.A[k * sA + a * np + b] : 0.0; }
-    DART_HD double Bat(int k, int a, int j) const { return (a < np) ? w.Bm[k * sB + a * m + j] : ((a - np) == j ? 1.0 : 0.0); }
+    DART_HD double Aat(int k, int a, int b) const { return (a < np && b < np) ? w.A[k * sA + W::aidx(a, b)] : 0.0; }
+    DART_HD double Bat(int k, int a, int j) const { return (a < np) ? w.Bm[k * sB + W::bidx(a, j)] : ((a - np) == j ? 1.0 : 0.0); }
     DART_HD double Pat(int k, int a, int b) const { return w.PP[k * nps + sidx(a, b, n)]; }
     DART_HD double Hat(int k, int i, int c) const { return W::hslot(i, c) < 0 ? 0.0 : w.HS[k * sH + (W::hslot(i, c) < 0 ? 0 : W::hslot(i, c))]; }
     // gather descriptor of H[i][c] (structural zeros read the stored 0.0)
@@ -329,12 +373,20 @@ struct Solver {
             double tanu[m];
             M::dyn(prm, x, u, F, Aloc, Bloc, tanu);
             DART_UNROLL for (int j = 0; j < m; ++j) w.TANU[k * m + j] = tanu[j];
-            DART_UNROLL for (int i = 0; i < npa; ++i) w.A[k * sA + i] = Aloc[i];
-            DART_UNROLL for (int i = 0; i < npb; ++i) w.Bm[k * sB + i] = Bloc[i];
+            if (kVec) {
+                // column-major stage blocks, written as 128-bit pairs (np is even for these models)
+                DART_UNROLL for (int b = 0; b < np; ++b)
+                    DART_UNROLL for (int a = 0; a + 1 < np; a += 2) st2(&w.A[k * sA + b * np + a], Aloc[a * np + b], Aloc[(a + 1) * np + b]);
+                DART_UNROLL for (int j = 0; j < m; ++j)
+                    DART_UNROLL for (int a = 0; a + 1 < np; a += 2) st2(&w.Bm[k * sB + j * np + a], Bloc[a * m + j], Bloc[(a + 1) * m + j]);
+            } else {
+                DART_UNROLL for (int i = 0; i < npa; ++i) w.A[k * sA + i] = Aloc[i];
+                DART_UNROLL for (int i = 0; i < npb; ++i) w.Bm[k * sB + i] = Bloc[i];
+            }
             DART_UNROLL for (int a = np; a < n; ++a) F[a] = u[a - np];
             DART_UNROLL for (int a = 0; a < n; ++a) {
                 double d = F[a] - w.X[(k + 1) * n + a];
-                w.D[k * n + a] = d;
+                w.D[k * sD + a] = d;
                 th_ += fabs(d);
                 pi_ = dmax(pi_, fabs(d));
             }
@@ -396,12 +448,12 @@ struct Solver {
             DART_UNROLL for (int i = 0; i < n; ++i) {
                 double acc = 0.0;
                 DART_UNROLL for (int a = 0; a < np; ++a)
-                    if (i < np) acc += w.A[k * sA + a * np + i] * lam[a];
+                    if (i < np) acc += w.A[k * sA + W::aidx(a, i)] * lam[a];
                 g[i] += acc - (k >= 1 ? w.LAM[(k - 1) * n + i] : 0.0);
             }
             DART_UNROLL for (int j = 0; j < m; ++j) {
                 double acc = 0.0;
-                DART_UNROLL for (int a = 0; a < np; ++a) acc += w.Bm[k * sB + a * m + j] * lam[a];
+                DART_UNROLL for (int a = 0; a < np; ++a) acc += w.Bm[k * sB + W::bidx(a, j)] * lam[a];
                 if (M::NAUG > 0) acc += lam[np + j];
                 w.BL[k * m + j] = acc;
                 g[n + j] += acc;
@@ -540,9 +592,12 @@ struct Solver {
     //   2. M = [H g] + [A B]^T W  (upper triangle + g)     nq(nq+1)/2 + nq elements
     //   3. pivot inverse, gains K, P_k = Mxx + Mxu K       n(n+1)/2 + n elements
     // with nq = np + m: rows/columns of carried-input states are structural (A = 0, B = I), so their entries of M are
-    // those of [H g] and are read from there.  What a lane reads depends only on its element, not on the stage: the
-    // gather offsets (relative to w.X; the workspace is one allocation) are decoded once, before the stage loop, so the
-    // loop itself is branch-free loads, a short FMA chain and one store per round.
+    // those of [H g] and are read from there.  What a lane reads depends only on its element, not on the stage, and it
+    // is contiguous: round 1 multiplies one ROW of the full P_{k+1} (kept in a scratch block next to the packed history)
+    // with one COLUMN of [A B d] (stored column-major), round 2 one column of [A B] with one column of W (written
+    // column-major by round 1).  So a lane holds one pointer per operand -- decoded once, before the stage loop, stepped
+    // by the stage stride -- and the loop body is 128-bit loads at immediate offsets, a short FMA chain and one store per
+    // round (measured before this layout: 357 instructions per stage of which 58 were FP64 arithmetic and 93 IMADs).
     struct Gat {
         int off, ks;                                    // element of stage k: w.X[off + k * ks]
     };
@@ -555,47 +610,53 @@ struct Solver {
     template <class TL>
     DART_HD void backward(const TL& tl) {
         constexpr int G = TL::kLanes;
-        constexpr int nq = W::nq, ncw = nq + 1, ntri = nq * (nq + 1) / 2;
-        constexpr int nW = W::nW, nM = W::nMq, nPt = n * (n + 1) / 2, nP = nPt + n;
+        constexpr int nq = W::nq, ncw = nq + 1, ntri = nq * (nq + 1) / 2, rP = W::rP;
+        constexpr int nW = n * ncw, nM = W::nMq, nPt = n * (n + 1) / 2, nP = nPt + n;
         constexpr int PW = (nW + G - 1) / G, PM = (nM + G - 1) / G, PQ = (nP + G - 1) / G;
         constexpr int NZ = (M::NAUG > 0) ? M::NAUG : 1;
+        static_assert(np % 2 == 0, "the vectorised sweep reads columns of [A B d] as 128-bit pairs");
         const int lane = tl.lane();
         double* const base = w.X;
-        double* const WW = w.MM;
-        double* const MQ = w.MM + nW;
+        double* const PF = w.MM;                        // full P_{k+1}, row stride rP
+        double* const WW = w.MM + W::nPF;               // W column-major, column stride rP
+        double* const MQ = WW + W::nW;
         const int oA = offs(w.A), oB = offs(w.Bm), oD = offs(w.D), oG = offs(w.GR), oMQ = offs(MQ);
         const int oPP = offs(w.PP), oPV = offs(w.PV), oK = offs(w.K), oKF = offs(w.KFF);
 
-        // terminal value function
+        // terminal value function: packed history entry, full scratch copy, p_N
         for (int c = lane; c <= n; c += G) {
             if (c < n) {
-                DART_UNROLL for (int i = 0; i < n; ++i)
-                    if (i <= c) w.PP[N * nps + sidx(i, c, n)] = (i == c) ? 2.0 * M::wT(prm, c) : 0.0;
+                DART_UNROLL for (int i = 0; i < n; ++i) {
+                    const double v = (i == c) ? 2.0 * M::wT(prm, c) : 0.0;
+                    if (i <= c) w.PP[N * nps + sidx(i, c, n)] = v;
+                    PF[i * rP + c] = v;
+                }
             } else {
                 DART_UNROLL for (int i = 0; i < n; ++i)
                     w.PV[N * n + i] = 2.0 * M::wT(prm, i) * (w.X[N * n + i] - M::rT(prm, w.REF, N, i));
             }
         }
 
-        // ---- round 1 gathers: element (a, cw), cw < np: state column, cw < nq: input column, cw == nq: d/p column
-        struct DW { int pP[n]; int tOff, tRs, tKs, pv; double ez[NZ]; bool isg, act; };
+        // ---- round 1: element (a, cw); cw < np: state column, cw < nq: input column, cw == nq: d/p column
+        struct DW { const double* prow; const double* tcol; double* wout; int tKs, pv; double gsel, ez[NZ]; bool act; };
         DW dw[PW];
         DART_UNROLL for (int ps = 0; ps < PW; ++ps) {
             DW& d = dw[ps];
             const int e = lane + ps * G;
             d.act = e < nW;
             const int ee = d.act ? e : 0;
-            const int a = ee / ncw, cw = ee % ncw;
-            DART_UNROLL for (int b = 0; b < n; ++b) d.pP[b] = oPP + nps + sidx(a, b, n);
+            const int cw = ee / n, a = ee % n;
+            d.prow = PF + a * rP;
             d.pv = oPV + n + a;
-            d.isg = cw == nq;
+            d.gsel = (cw == nq) ? 1.0 : 0.0;
             DART_UNROLL for (int z = 0; z < NZ; ++z) d.ez[z] = (M::NAUG > 0 && cw >= np && cw < nq && cw - np == z) ? 1.0 : 0.0;
-            if (cw < np) { d.tOff = oA + cw; d.tRs = np; d.tKs = sA; }
-            else if (cw < nq) { d.tOff = oB + (cw - np); d.tRs = m; d.tKs = sB; }
-            else { d.tOff = oD; d.tRs = 1; d.tKs = n; }
+            if (cw < np) { d.tcol = w.A + (N - 1) * sA + cw * np; d.tKs = sA; }
+            else if (cw < nq) { d.tcol = w.Bm + (N - 1) * sB + (cw - np) * np; d.tKs = sB; }
+            else { d.tcol = w.D + (N - 1) * sD; d.tKs = sD; }
+            d.wout = WW + cw * rP + a;
         }
-        // ---- round 2 gathers: element (iq, cq) of the upper triangle over the nq active variables, or (iq, g)
-        struct DM { int tOff, tRs, tKs, hOff, hKs, cw, augOff; double augOn; bool act; };
+        // ---- round 2: element (iq, cq) of the upper triangle over the nq active variables, or (iq, g)
+        struct DM { const double* tcol; const double* wcol; int tKs, hOff, hKs; double augc[NZ]; bool act; };
         DM dm[PM];
         DART_UNROLL for (int ps = 0; ps < PM; ++ps) {
             DM& d = dm[ps];
@@ -605,17 +666,16 @@ struct Solver {
             int iq, cq;
             if (ee < ntri) tri_decode(ee, nq, iq, cq); else { iq = ee - ntri; cq = nq; }
             const int fi = iq < np ? iq : n + (iq - np);              // index among the ny stage variables
-            d.cw = cq;
-            if (iq < np) { d.tOff = oA + iq; d.tRs = np; d.tKs = sA; }
-            else { d.tOff = oB + (iq - np); d.tRs = m; d.tKs = sB; }
+            if (iq < np) { d.tcol = w.A + (N - 1) * sA + iq * np; d.tKs = sA; }
+            else { d.tcol = w.Bm + (N - 1) * sB + (iq - np) * np; d.tKs = sB; }
+            d.wcol = WW + cq * rP;
             if (cq < nq) { const int fc = cq < np ? cq : n + (cq - np); hgat(fi, fc, d.hOff, d.hKs); }
             else { d.hOff = oG + fi; d.hKs = sG; }
-            const bool aug = M::NAUG > 0 && iq >= np;                 // input row: + W[np + j][.] (B = I on carried inputs)
-            d.augOn = aug ? 1.0 : 0.0;
-            d.augOff = (aug ? (np + (iq - np)) * ncw : 0) + cq;
+            // input row: + W[np + j][.] (B = I on the carried inputs)
+            DART_UNROLL for (int z = 0; z < NZ; ++z) d.augc[z] = (M::NAUG > 0 && iq >= np && iq - np == z) ? 1.0 : 0.0;
         }
-        // ---- round 3 gathers: element (i, c) of the upper triangle of P_k, or p_k[i]
-        struct DQ { Gat mu[m], mic, miu[m], st; int kOff, kJs, kKs; bool storeK, act; };
+        // ---- round 3: element (i, c) of the upper triangle of P_k, or p_k[i]
+        struct DQ { Gat mu[m], mic, miu[m], st; int kOff, kJs, kKs, pf0, pf1; bool storeK, act, isP; };
         DQ dq[PQ];
         DART_UNROLL for (int ps = 0; ps < PQ; ++ps) {
             DQ& d = dq[ps];
@@ -637,6 +697,9 @@ struct Solver {
             else if (i < np && c < np) d.mic = Gat{oMQ + sidx(i, c, nq), 0};
             else hgat(i, c, d.mic.off, d.mic.ks);
             d.st = (c == n) ? Gat{oPV + i, n} : Gat{oPP + sidx(i, c, n), nps};
+            d.isP = d.act && c < n;
+            d.pf0 = (c < n) ? i * rP + c : 0;
+            d.pf1 = (c < n) ? c * rP + i : 0;
             d.storeK = d.act && i == 0;
             if (c == n) { d.kOff = oKF; d.kJs = 1; d.kKs = m; }
             else { d.kOff = oK + c; d.kJs = n; d.kKs = sK; }
@@ -644,39 +707,71 @@ struct Solver {
         tl.sync();
 
         for (int k = N - 1; k >= 0; --k) {
+            // carried-input defects of this stage (the d column of the structural rows), one uniform address
+            double dz[NZ];
+            if (M::NAUG > 0) { DART_UNROLL for (int z = 0; z < M::NAUG; ++z) dz[z] = w.D[k * sD + np + z]; }
             DART_UNROLL for (int ps = 0; ps < PW; ++ps) {
-                const DW& d = dw[ps];
-                double acc = base[d.pv + k * n];
-                acc = d.isg ? acc : 0.0;
-                DART_UNROLL for (int t = 0; t < np; ++t)
-                    acc += base[d.pP[t] + k * nps] * base[d.tOff + t * d.tRs + k * d.tKs];
+                DW& d = dw[ps];
+                double pr[n], tc[np];
+                ldv<n>(d.prow, pr);
+                ldv<np>(d.tcol, tc);
+                d.tcol -= d.tKs;
+                // three short independent chains instead of one of depth np + NAUG + 1 (the sweep is latency-bound)
+                double s0 = pr[0] * tc[0], s1 = pr[np / 2] * tc[np / 2], s2 = d.gsel * base[d.pv + k * n];
+                DART_UNROLL for (int t = 1; t < np / 2; ++t) s0 += pr[t] * tc[t];
+                DART_UNROLL for (int t = np / 2 + 1; t < np; ++t) s1 += pr[t] * tc[t];
                 if (M::NAUG > 0) {
-                    DART_UNROLL for (int z = 0; z < M::NAUG; ++z) {
-                        const double dz = w.D[k * n + np + z];
-                        acc += base[d.pP[np + z] + k * nps] * (d.isg ? dz : d.ez[z]);
-                    }
+                    DART_UNROLL for (int z = 0; z < M::NAUG; ++z) s2 += pr[np + z] * (d.ez[z] + d.gsel * dz[z]);
                 }
-                if (d.act) WW[lane + ps * G] = acc;
+#if DART_TREE_SUMS
+                if (d.act) *d.wout = (s0 + s1) + s2;
+#else
+                {
+                    double acc = d.gsel * base[d.pv + k * n];
+                    DART_UNROLL for (int t = 0; t < np; ++t) acc += pr[t] * tc[t];
+                    if (M::NAUG > 0) { DART_UNROLL for (int z = 0; z < M::NAUG; ++z) acc += pr[np + z] * (d.ez[z] + d.gsel * dz[z]); }
+                    if (d.act) *d.wout = acc;
+                }
+#endif
             }
             tl.sync();
             DART_UNROLL for (int ps = 0; ps < PM; ++ps) {
-                const DM& d = dm[ps];
-                double acc = base[d.hOff + k * d.hKs];
-                DART_UNROLL for (int a = 0; a < np; ++a)
-                    acc += base[d.tOff + a * d.tRs + k * d.tKs] * WW[a * ncw + d.cw];
-                if (M::NAUG > 0) acc += d.augOn * WW[d.augOff];
-                if (d.act) MQ[lane + ps * G] = acc;
+                DM& d = dm[ps];
+                double tc[np], wc[n];
+                ldv<np>(d.tcol, tc);
+                d.tcol -= d.tKs;
+                ldv<n>(d.wcol, wc);
+                double s0 = base[d.hOff + k * d.hKs], s1 = tc[np / 2] * wc[np / 2];
+                DART_UNROLL for (int a = 0; a < np / 2; ++a) s0 += tc[a] * wc[a];
+                DART_UNROLL for (int a = np / 2 + 1; a < np; ++a) s1 += tc[a] * wc[a];
+                if (M::NAUG > 0) { DART_UNROLL for (int z = 0; z < M::NAUG; ++z) s1 += d.augc[z] * wc[np + z]; }
+#if DART_TREE_SUMS
+                if (d.act) MQ[lane + ps * G] = s0 + s1;
+#else
+                {
+                    double acc = base[d.hOff + k * d.hKs];
+                    DART_UNROLL for (int a = 0; a < np; ++a) acc += tc[a] * wc[a];
+                    if (M::NAUG > 0) { DART_UNROLL for (int z = 0; z < M::NAUG; ++z) acc += d.augc[z] * wc[np + z]; }
+                    if (d.act) MQ[lane + ps * G] = acc;
+                }
+#endif
             }
             tl.sync();
             // every lane inverts the same m x m pivot block (+ escalating shift if it is not positive definite)
             double Lc[m * m];
-            double shift = 0.0;
-            for (int tries = 0; tries < 40; ++tries) {
-                DART_UNROLL for (int i = 0; i < m; ++i)
-                    DART_UNROLL for (int j = 0; j < m; ++j)
-                        Lc[i * m + j] = MQ[sidx(np + i, np + j, nq)] + (i == j ? shift : 0.0);
-                if (chol(Lc)) break;
-                shift = (shift == 0.0) ? 1e-4 : shift * 8.0;
+            DART_UNROLL for (int i = 0; i < m; ++i)
+                DART_UNROLL for (int j = 0; j < m; ++j) Lc[i * m + j] = MQ[sidx(np + i, np + j, nq)];
+            if (!chol(Lc)) {
+                // cold path (kept rolled: it is almost never taken and must not bloat the stage loop)
+                double shift = 1e-4;
+                DART_UNROLL_N(1)
+                for (int tries = 0; tries < 40; ++tries) {
+                    DART_UNROLL for (int i = 0; i < m; ++i)
+                        DART_UNROLL for (int j = 0; j < m; ++j)
+                            Lc[i * m + j] = MQ[sidx(np + i, np + j, nq)] + (i == j ? shift : 0.0);
+                    if (chol(Lc)) break;
+                    shift *= 8.0;
+                }
             }
             DART_UNROLL for (int ps = 0; ps < PQ; ++ps) {
                 const DQ& d = dq[ps];
@@ -688,6 +783,7 @@ struct Solver {
                     double v = base[d.mic.off + k * d.mic.ks];
                     DART_UNROLL for (int j = 0; j < m; ++j) v += base[d.miu[j].off + k * d.miu[j].ks] * kt[j];
                     if (d.act) base[d.st.off + k * d.st.ks] = v;
+                    if (d.isP) { PF[d.pf0] = v; PF[d.pf1] = v; }
                 }
             }
             tl.sync();
@@ -713,7 +809,7 @@ struct Solver {
             DART_UNROLL for (int a = 0; a < n; ++a) {
                 DART_UNROLL for (int b = 0; b < n; ++b) T_[a * nc + b] = (tkind(a, b) == 0) ? Aat(k, a, b) : (tkind(a, b) == 2 ? 1.0 : 0.0);
                 DART_UNROLL for (int j = 0; j < m; ++j) T_[a * nc + n + j] = Bat(k, a, j);
-                T_[a * nc + ny] = w.D[k * n + a];
+                T_[a * nc + ny] = w.D[k * sD + a];
             }
             DART_UNROLL for (int i = 0; i < ny; ++i) {
                 DART_UNROLL for (int c = i; c < ny; ++c) H_[i * nc + c] = hzero(i, c) ? 0.0 : Hat(k, i, c);
@@ -823,7 +919,7 @@ struct Solver {
                 DART_UNROLL for (int b = 0; b < n; ++b) A_[a * n + b] = (M::a_kind(a, b) == 0) ? Aat(k, a, b) : 0.0;
                 DART_UNROLL for (int j = 0; j < m; ++j) B_[a * m + j] = Bat(k, a, j);
             }
-            DART_UNROLL for (int i = 0; i < n; ++i) d_[i] = w.D[k * n + i];
+            DART_UNROLL for (int i = 0; i < n; ++i) d_[i] = w.D[k * sD + i];
         };
         load(0, Kc, kc, Ac, Bc, dc);
         DART_UNROLL_N(DART_SWEEP_UNROLL)
@@ -859,7 +955,8 @@ struct Solver {
 
     // ---- forward sweep across the tile (larger models): every lane keeps dx_k in registers and forms du_k; lane a
     // forms row a of dx_{k+1} = A dx + B du + d, and the rows are exchanged by shuffles -- per stage one n-deep and one
-    // m-deep FMA chain plus a shuffle instead of the whole stage in one lane.  Needs at least n lanes.
+    // m-deep FMA chain plus a shuffle instead of the whole stage in one lane.  Needs at least n lanes.  (Measured: forming
+    // the closed-loop row A + B K off the chain instead costs 12 more FMAs per stage and is 3 % slower.)
     template <class TL>
     DART_HD void forward_tile(const TL& tl) {
         const int lane = tl.lane();
@@ -874,11 +971,12 @@ struct Solver {
         // stage data is loaded one stage ahead: it does not depend on dx, only the FMA chain and the shuffle do
         double Kc[m * n], kc[m], Ar[np], Br[m], dc;
         auto load = [&](int k, double* K_, double* k_, double* A_, double* B_, double& d_) {
-            DART_UNROLL for (int i = 0; i < m * n; ++i) K_[i] = w.K[k * sK + i];
+            if (kVec) ldv<m * n>(&w.K[k * sK], K_);
+            else { DART_UNROLL for (int i = 0; i < m * n; ++i) K_[i] = w.K[k * sK + i]; }
             DART_UNROLL for (int j = 0; j < m; ++j) k_[j] = w.KFF[k * m + j];
-            DART_UNROLL for (int i = 0; i < np; ++i) A_[i] = w.A[k * sA + ap * np + i];
-            DART_UNROLL for (int j = 0; j < m; ++j) B_[j] = w.Bm[k * sB + ap * m + j];
-            d_ = w.D[k * n + a];
+            DART_UNROLL for (int i = 0; i < np; ++i) A_[i] = w.A[k * sA + W::aidx(ap, i)];
+            DART_UNROLL for (int j = 0; j < m; ++j) B_[j] = w.Bm[k * sB + W::bidx(ap, j)];
+            d_ = w.D[k * sD + a];
         };
         load(0, Kc, kc, Ar, Br, dc);
         for (int k = 0; k < N; ++k) {
@@ -922,7 +1020,7 @@ struct Solver {
         const int k = stage ? lane : N - 1;                 // the terminal lane reads stage N-1 (values unused)
         const double a00 = Aat(k, 0, 0), a01 = Aat(k, 0, 1), a10 = Aat(k, 1, 0), a11 = Aat(k, 1, 1);
         const double B0 = w.Bm[k * sB + 0], B1 = w.Bm[k * sB + 1];
-        const double d0 = w.D[k * n + 0], d1 = w.D[k * n + 1];
+        const double d0 = w.D[k * sD + 0], d1 = w.D[k * sD + 1];
         const double gu = w.GR[k * sG + 2];
         double huu = w.HS[k * sH + 2];
         if (!(huu > 0.0)) {
@@ -1003,7 +1101,7 @@ struct Solver {
     DART_HD void load_stage(int k, StageLQ& q) const {
         q.a00 = Aat(k, 0, 0); q.a01 = Aat(k, 0, 1); q.a10 = Aat(k, 1, 0); q.a11 = Aat(k, 1, 1);
         q.B0 = w.Bm[k * sB + 0]; q.B1 = w.Bm[k * sB + 1];
-        q.d0 = w.D[k * n + 0]; q.d1 = w.D[k * n + 1];
+        q.d0 = w.D[k * sD + 0]; q.d1 = w.D[k * sD + 1];
         q.gu = w.GR[k * sG + 2];
         double huu = w.HS[k * sH + 2];
         if (!(huu > 0.0)) {

@@ -49,8 +49,8 @@ class PMPCEpisodes:
             self.w = torch.zeros((self.B, self.engine.nw), dtype=f64, device=self.dev)
             self.w_next = torch.empty_like(self.w)
         self._graph = None
-        self.not_converged_solves = torch.zeros((), dtype=torch.int64, device=self.dev)
-        self.iter_sum = torch.zeros((), dtype=torch.int64, device=self.dev)
+        self._counters = torch.zeros(2, dtype=torch.int64, device=self.dev)      # [iterations, solves not converged]
+        self.iter_sum, self.not_converged_solves = self._counters[0], self._counters[1]
 
     def step(self):
         torch = self.torch
@@ -63,13 +63,13 @@ class PMPCEpisodes:
         else:
             self.engine.solve_device(self.state, self.target, aux=self.params, u0_out=self.u0, J_out=self.J,
                                      status=self.status, iters=self.iters)
-        self.not_converged_solves += (self.status != 0).sum()
-        self.iter_sum += self.iters.sum()
+        # the plant kernel also accumulates the solve statistics (no reduction launches of the loop's own)
         p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
         stream = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
         check(_lib.lib().dart_pmpc_plant_step(self.B, self.cfg.Ts, self.cfg.g, p(self.mu_plant), p(self.coulomb), p(self.u0),
                                               p(self.target), p(self.state), p(self.nsteps), self.tol, p(self.conv_time),
-                                              p(self.effort), p(self.err), stream), "dart_pmpc_plant_step")
+                                              p(self.effort), p(self.err), p(self.status), p(self.iters), p(self._counters),
+                                              stream), "dart_pmpc_plant_step")
         self.step_index += 1
 
     def run(self, steps, trace_every=0, graph=False, persistent=False):
@@ -91,8 +91,7 @@ class PMPCEpisodes:
                                                    p(self.mu_plant), p(self.coulomb), self.tol, p(self.nsteps), p(self.conv_time),
                                                    p(self.effort), p(self.err), p(self.u0), p(self.J), p(self.status), p(self.iters),
                                                    p(counters), stream), "dart_pmpc_episode")
-            self.iter_sum += counters[0]
-            self.not_converged_solves += counters[1]
+            self._counters += counters
             self.step_index += int(steps)
         elif graph and not trace_every and steps > 2:
             if self._graph is None:

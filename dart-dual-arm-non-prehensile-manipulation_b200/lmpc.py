@@ -181,7 +181,6 @@ class LMPCBatch:
         if self.plan_fallback:
             self.plan_U = torch.zeros((B, N, 2), dtype=f64, device=self.dev)
             self.plan_pos = torch.zeros((B,), dtype=torch.int64, device=self.dev)
-            self._rows = torch.arange(B, device=self.dev)
             self.n_fallback = torch.zeros((), dtype=torch.int64, device=self.dev)     # solves replaced by a plan shift
             self.have_plan = torch.zeros((B,), dtype=torch.bool, device=self.dev)
 
@@ -257,24 +256,13 @@ class LMPCBatch:
                                  w_out=self.w_next, u0_out=self.u0, J_out=self.J, status=self.status, iters=self.iters)
         if fresh is not None and not self.plan_fallback:
             raise ValueError("step(fresh=...) needs LMPCBatch(plan_fallback=True)")
-        if self.plan_fallback:
-            ok = (self.status == _lib.STATUS_CONVERGED) | (self.status == _lib.STATUS_ACCEPTABLE)
-            # no plan to fall back on yet: take the solver's iterate whatever its status (the reference never checks it)
-            ok = ok | ~self.have_plan
-            if fresh is not None:
-                ok = ok & fresh
-            N = self.cfg.N
-            U_new = self.w_next[:, self._nxw:].view(self.B, N, 2)
-            self.n_fallback += (~ok).sum()
-            self.plan_U = torch.where(ok[:, None, None], U_new, self.plan_U)
-            self.plan_pos = torch.where(ok, torch.zeros_like(self.plan_pos), torch.clamp(self.plan_pos + 1, max=N - 1))
-            held = ~ok & ~self.have_plan                   # reference: "else: hold last_control"
-            self.u0.copy_(torch.where(held[:, None], self.u_prev, self.plan_U[self._rows, self.plan_pos]))
-            self.have_plan = self.have_plan | ok
-            self.w_next = torch.where(ok[:, None], self.w_next, self.w)
+        # one launch: plan fallback (if enabled), u_prev <- u0, aux[:, :2] <- u0
+        pf = self.plan_fallback
+        check(L.dart_lmpc_post_step(self.B, self.cfg.N, p(self.status), (p(fresh) if fresh is not None else None), p(self.w),
+                                    p(self.w_next), p(self.u0), p(self.u_prev), p(self.aux), (p(self.plan_U) if pf else None),
+                                    (p(self.plan_pos) if pf else None), (p(self.have_plan) if pf else None),
+                                    (p(self.n_fallback) if pf else None), stream), "dart_lmpc_post_step")
         self.w, self.w_next = self.w_next, self.w
-        self.u_prev.copy_(self.u0)
-        self.aux[:, :2] = self.u0
         self.timestep += 1
         return self.u0
 

@@ -205,10 +205,13 @@ int dart_policy_param_update(int32_t B, const float* action, double* pvec, int32
  * metrics of PMPC/src/logger.py:155-176 accumulated in place: err [B] = position error of the logged state,
  * conv_time [B] (initialise to -1) = first logged time with err < tol, effort [B] += |u| Ts; nsteps [B] int32
  * (initialise to 0) is the per-instance step counter, kept on the device so that the launch can be replayed from a
- * CUDA graph.  Device pointers. */
+ * CUDA graph.  status, iters [B] and counters [2] (uint64) are optional (all or none): the statistics of the solve that
+ * produced u are added to counters as dart_pmpc_episode does ([0] += iterations, [1] += solves not converged).
+ * Device pointers. */
 int dart_pmpc_plant_step(int32_t B, double Ts, double g, const double* mu, const double* coulomb, const double* u,
                          const double* target, double* state, int32_t* nsteps, double tol, double* conv_time,
-                         double* effort, double* err, void* stream);
+                         double* effort, double* err, const int32_t* status, const int32_t* iters, uint64_t* counters,
+                         void* stream);
 
 /* Low-level arm controller QP: replaces the per-cycle ca.nlpsol('solver','ipopt',...) construction and call of
  * ARMCONTROL.solver_worker, PMPC/src/controller/arm.py:337-457, for B arms at once:
@@ -255,6 +258,16 @@ int dart_rmpc_plant_step(int32_t B, double Ts, double gz, const double* mu, cons
  * rlmpc2.py:260-436 with per-instance TRUE parameters: true_aux [B,36] has the layout of the LMPC solver's aux rows
  * ([u_prev(2), pvec(34)]; the first two columns are ignored).  state [B,8] -> state_out [B,8] (may alias).  With
  * true_aux equal to the controller's aux the result is the controller's own one-step prediction, bit for bit. */
+/* End of one LMPC closed-loop step in ONE launch.  Always: u_prev [B,2] <- u0 and aux[:,0:2] <- u0 (aux [B,36] are the LMPC
+ * solver's rows; rlmpc2.py:1019-1021 `last_control`, views['control']).  With plan_U != NULL also the facade's "no fresh
+ * solution" branch (RLMPC.solve, rlmpc2.py:1013-1018) in deterministic form: an instance whose solve did not end converged /
+ * acceptable (status [B]), or whose fresh [B] flag (uint8, optional) is 0, gets the next entry of its last good plan as u0
+ * (plan_U [B,N,2], plan_pos [B] int64, have_plan [B] uint8; last_control while there is no plan yet), keeps that plan as the
+ * warm start (w_next [B,nw] <- w_prev) and adds 1 to n_fallback (uint64); otherwise the new plan is taken over. */
+int dart_lmpc_post_step(int32_t B, int32_t N, const int32_t* status, const uint8_t* fresh, const double* w_prev,
+                        double* w_next, double* u0, double* u_prev, double* aux, double* plan_U, int64_t* plan_pos,
+                        uint8_t* have_plan, uint64_t* n_fallback, void* stream);
+
 int dart_lmpc_plant_step(int32_t B, double Ts, const double* true_aux, const double* u, const double* state,
                          double* state_out, void* stream);
 
