@@ -25,6 +25,7 @@
 #include <new>
 
 #include "../../include/dart_b200.h"
+#include "ppo_tc.h"
 
 namespace {
 
@@ -880,6 +881,7 @@ __global__ void __launch_bounds__(256) ppo_grad_import_kernel(const float* __res
 
 struct dart_ppo {
     int device, capacity, splits_cap, loss_blocks_cap, fused, sms;
+    int tc;                              // layer-1 GEMMs of large minibatches on tcgen05 (ppo_tc.cu); DART_PPO_SIMT=1 keeps the FP32 SIMT kernels
     dart_ppo_cfg cfg;
     float *param, *grad, *m, *v;         // [NP]
     float *h1, *h2, *dz1, *dz2;          // [capacity, 128]
@@ -926,7 +928,10 @@ int forward(dart_ppo* h, int M, const float* obs, cudaStream_t st, bool with_tai
     g.p[0] = fwd_prob(obs, OBS, P + OFF_W1, P + OFF_B1, h->h1, H2W, M, H2W, OBS, 1);
     if (gidx) { g.p[0].gidx = gidx; g.p[0].gmode = 1; }      // rows of the pooled rollout, gathered by the loaders
     int rc;
-    if (M >= BIG_MIN_ROWS && h->fused) {  // two K halves: 2 x (M/128) CTAs fill two slots per SM (one half alone leaves 128 CTAs on 148 SMs)
+    if (M >= BIG_MIN_ROWS && h->fused && h->tc) {      // tensor cores: 3xTF32, one CTA per 128 rows, pre-activation to h1part
+        rc = dart_ppo_tc::l1_forward(M, obs, gidx, P + OFF_W1, h->h1part, st);
+        h->launches += 1;
+    } else if (M >= BIG_MIN_ROWS && h->fused) {  // two K halves: 2 x (M/128) CTAs fill two slots per SM (one half alone leaves 128 CTAs on 148 SMs)
         g.p[0].mode = 0; g.p[0].C = h->h1part;
         rc = launch_big(h, g.p[0], BIG_FWD_SPLITS, BIG_FWD_KCHUNK, (long)M * H2W, st);
     } else if (M >= BIG_MIN_ROWS) rc = launch_big(h, g.p[0], 1, OBS, 0, st);
@@ -942,7 +947,7 @@ int forward(dart_ppo* h, int M, const float* obs, cudaStream_t st, bool with_tai
         MidArgs ma;
         memset(&ma, 0, sizeof(ma));
         ma.M = M; ma.backward = 0; ma.h1 = h->h1; ma.P = P; ma.mean = h->mean; ma.value = h->value;
-        ma.h1 = h->h1part; ma.h1_splits = M < BIG_MIN_ROWS ? FWD_SPLITS : BIG_FWD_SPLITS;
+        ma.h1 = h->h1part; ma.h1_splits = M < BIG_MIN_ROWS ? FWD_SPLITS : (h->tc ? 1 : BIG_FWD_SPLITS);
         ma.ls_min = (float)h->cfg.log_std_min; ma.ls_max = (float)h->cfg.log_std_max;
         ppo_mid_kernel<<<(M + MS - 1) / MS, GT, MID_SMEM, st>>>(ma);
         h->launches += 1;
@@ -1078,7 +1083,8 @@ extern "C" int dart_ppo_create(dart_ppo_handle* out, int device, int32_t obs_dim
     h->device = device; h->capacity = capacity; h->cfg = *cfg;
     h->loss_blocks_cap = (capacity + MS - 1) / MS;          // the fused path has one loss row per 64-sample tile
     cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, device);
-    h->fused = getenv("DART_PPO_UNFUSED") ? 0 : 1;         // A/B switch: the first, unfused kernel chain
+    h->fused = getenv("DART_PPO_UNFUSED") ? 0 : 1;
+    h->tc = getenv("DART_PPO_SIMT") ? 0 : 1;         // A/B switch: the first, unfused kernel chain
     const size_t cap = (size_t)capacity;
     struct { void** p; size_t bytes; } al[] = {
         {(void**)&h->param, NP * sizeof(float)}, {(void**)&h->grad, NP * sizeof(float)},
@@ -1228,7 +1234,7 @@ extern "C" int dart_ppo_update(dart_ppo_handle h, int32_t M, const int64_t* idx,
         MidArgs ma;
         memset(&ma, 0, sizeof(ma));
         ma.h1 = h->h1;
-        ma.h1 = h->h1part; ma.h1_splits = M < BIG_MIN_ROWS ? FWD_SPLITS : BIG_FWD_SPLITS;
+        ma.h1 = h->h1part; ma.h1_splits = M < BIG_MIN_ROWS ? FWD_SPLITS : (h->tc ? 1 : BIG_FWD_SPLITS);
         ma.M = M; ma.backward = 1; ma.P = P; ma.idx = gidx; ma.act = act; ma.old_logp = old_logp; ma.adv = adv; ma.ret = ret;
         ma.ls_min = ls_min; ma.ls_max = ls_max; ma.clip_eps = (float)c.clip_eps; ma.vf_coef = (float)c.vf_coef;
         ma.mean = h->mean; ma.value = h->value; ma.dz1 = h->dz1; ma.part_small = h->part_small; ma.loss_part = h->loss_part;
@@ -1246,6 +1252,15 @@ extern "C" int dart_ppo_update(dart_ppo_handle h, int32_t M, const int64_t* idx,
         gw.count = 1; gw.splits = splits; gw.kchunk = kchunk; gw.split_stride = NPB;
         gw.p[0] = wgrad_prob(h->dz1, H2W, obs, OBS, h->part, OFF_W1, M, H2W, OBS);
         if (gidx) { gw.p[0].gidx = gidx; gw.p[0].gmode = 2; }
+        if (M >= BIG_MIN_ROWS && h->fused && h->tc) {
+            // tensor cores: four feature slabs x `splits` sample ranges, one CTA per SM in a single wave
+            int per = 0;
+            int want = h->sms / 4;                 // four feature slabs per split
+            if (want > MAX_SPLITS) want = MAX_SPLITS;
+            splits = dart_ppo_tc::l1_wgrad_splits(M, want, &per);
+            rc = dart_ppo_tc::l1_wgrad(M, splits, per, h->dz1, obs, gidx, h->part + OFF_W1, NPB, st);
+            h->launches += 1;
+        } else
         rc = M >= BIG_MIN_ROWS ? launch_big(h, gw.p[0], splits, kchunk, NPB, st) : launch_group(h, gw, H2W, OBS, st);
         if (rc != DART_OK) return rc;
     }

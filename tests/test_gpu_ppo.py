@@ -140,6 +140,34 @@ def test_minibatch_gather_and_repeatability(built):
         assert np.array_equal(outs[0][k], outs[2][k]), k          # device gather == host gather
 
 
+@pytest.mark.parametrize("M", [777, 4096])
+def test_tensor_core_layer1_matches_simt_layer1(built, M, monkeypatch):
+    """The tcgen05 layer-1 GEMMs (3xTF32, csrc/ppo_tc.cu: forward and weight gradient, minibatch gathered by the loaders,
+    ragged last tile / last sample chunk) against the FP32 SIMT kernels they replace (DART_PPO_SIMT=1): same gradient to
+    FP32 summation-order noise, and the tensor-core path is bitwise repeatable."""
+    import torch
+    pol = _perturbed_policy()
+    S = M + 333
+    obs, eps, action, logp, value, mean, old_logp, adv, ret = _rollout(S, 23, pol)
+    idx = torch.randperm(S, generator=torch.Generator().manual_seed(9))[:M].cuda()
+    d = [t.cuda() for t in (obs, action, old_logp, adv, ret)]
+    grads = []
+    for mode in ("tc", "tc", "simt"):
+        if mode == "simt":
+            monkeypatch.setenv("DART_PPO_SIMT", "1")
+        else:
+            monkeypatch.delenv("DART_PPO_SIMT", raising=False)
+        tr = dart_b200.PPOTrainer(capacity=M, state_dict=pol.state_dict())
+        tr.update_minibatch(*d, idx=idx, apply=False)
+        grads.append(tr.gradient())
+        tr.close()
+    for k in grads[0]:
+        assert np.array_equal(grads[0][k], grads[1][k]), k
+        ref = grads[2][k]
+        # the actor's gradient carries ~2e-5 of FP32 noise in either path (std = 0.1 amplifies the forward's rounding ~100x)
+        assert np.abs(grads[0][k] - ref).max() <= 1e-7 + 1e-4 * np.abs(ref).max(), (k, np.abs(grads[0][k] - ref).max(), np.abs(ref).max())
+
+
 def test_gae_reward_normalise(built):
     import torch
     rng = np.random.default_rng(4)
