@@ -44,10 +44,17 @@ DART_HD void rk4_sens(const typename Md::Prm& p, const double* x, const double* 
     // the input is held over the step and enters only through sin/cos: evaluate them once
     double su[m], cu[m];
     DART_UNROLL for (int j = 0; j < m; ++j) { sincos(u[j], &su[j], &cu[j]); tanu[j] = su[j] / cu[j]; }
+    // Md::fx_kind(a, q) / fu_kind(a, j): 0 = general entry, 1 = structurally zero, 2 = exactly one.  The kinematic rows
+    // (position' = velocity) are unit rows: their products drop out at compile time (IEEE arithmetic does not let the
+    // compiler fold 0 * x or 1 * x itself) -- same values, 40-50 % fewer FMAs in the sensitivity propagation.
+    auto fxv = [&](int a, int q) { return Md::fx_kind(a, q) == 0 ? fx[a * np + q] : (Md::fx_kind(a, q) == 2 ? 1.0 : 0.0); };
+    auto fuv = [&](int a, int j) { return Md::fu_kind(a, j) == 0 ? fu[a * m + j] : (Md::fu_kind(a, j) == 2 ? 1.0 : 0.0); };
     // stage 1
     Md::deriv(p, x, su, cu, k, fx, fu);
-    DART_UNROLL for (int i = 0; i < np * np; ++i) { Sx[i] = fx[i]; A[i] = fx[i]; }
-    DART_UNROLL for (int i = 0; i < np * m; ++i) { Su[i] = fu[i]; Bm[i] = fu[i]; }
+    DART_UNROLL for (int a = 0; a < np; ++a) {
+        DART_UNROLL for (int b = 0; b < np; ++b) { Sx[a * np + b] = fxv(a, b); A[a * np + b] = fxv(a, b); }
+        DART_UNROLL for (int j = 0; j < m; ++j) { Su[a * m + j] = fuv(a, j); Bm[a * m + j] = fuv(a, j); }
+    }
     DART_UNROLL for (int i = 0; i < np; ++i) { acc[i] = k[i]; xs[i] = x[i] + 0.5 * h * k[i]; }
     // stages 2..4
     DART_UNROLL for (int st = 2; st <= 4; ++st) {
@@ -57,13 +64,21 @@ DART_HD void rk4_sens(const typename Md::Prm& p, const double* x, const double* 
         double Nx[np * np], Nu[np * m];
         DART_UNROLL for (int a = 0; a < np; ++a) {
             DART_UNROLL for (int b = 0; b < np; ++b) {
-                double v = fx[a * np + b];
-                DART_UNROLL for (int q = 0; q < np; ++q) v += fx[a * np + q] * (c * Sx[q * np + b]);
+                double v = fxv(a, b);
+                DART_UNROLL for (int q = 0; q < np; ++q) {
+                    if (Md::fx_kind(a, q) == 1) continue;
+                    if (Md::fx_kind(a, q) == 2) v += c * Sx[q * np + b];
+                    else v += fx[a * np + q] * (c * Sx[q * np + b]);
+                }
                 Nx[a * np + b] = v;
             }
             DART_UNROLL for (int j = 0; j < m; ++j) {
-                double v = fu[a * m + j];
-                DART_UNROLL for (int q = 0; q < np; ++q) v += fx[a * np + q] * (c * Su[q * m + j]);
+                double v = fuv(a, j);
+                DART_UNROLL for (int q = 0; q < np; ++q) {
+                    if (Md::fx_kind(a, q) == 1) continue;
+                    if (Md::fx_kind(a, q) == 2) v += c * Su[q * m + j];
+                    else v += fx[a * np + q] * (c * Su[q * m + j]);
+                }
                 Nu[a * m + j] = v;
             }
         }
@@ -85,6 +100,9 @@ struct PmpcAxis {
     // structure the serial sweep may rely on: the position does not enter the dynamics, so column 0 of the RK4
     // sensitivity A is exactly e_0
     DART_HD static constexpr int a_kind(int a, int b) { return b == 0 ? (a == 0 ? 2 : 1) : 0; }
+    // structure of the continuous-time Jacobians (deriv below): fx = [[0, 1], [0, -mu]], fu = [0, g cos u]
+    DART_HD static constexpr int fx_kind(int a, int q) { return a == 0 ? (q == 1 ? 2 : 1) : (q == 0 ? 1 : 0); }
+    DART_HD static constexpr int fu_kind(int a, int) { return a == 0 ? 1 : 0; }
     static constexpr int MAX_THREADS = 256, MIN_BLOCKS = 1, BT_LARGE = 32;   // BT_LARGE: block size when the GPU is filled (measured: 32 < 64 < 128)
     static constexpr int NXF = 6;   // states per stage in the reference's decision vector
     static constexpr int NDEF = 15; // the reference's horizon (compile-time instantiation)
@@ -146,6 +164,9 @@ struct Rmpc {
     static constexpr int NX = 6, NU = 2, NR = 6, NP = 4, NAUG = 2, NAXIS = 1;
     static constexpr bool SERIAL_RICCATI = false;
     DART_HD static constexpr int a_kind(int, int) { return 0; }
+    // rows 0 and 2 are the kinematic unit rows (p' = v); rows 1 and 3 are dense; u_j enters the acceleration of axis j only
+    DART_HD static constexpr int fx_kind(int a, int q) { return (a == 0 || a == 2) ? (q == a + 1 ? 2 : 1) : 0; }
+    DART_HD static constexpr int fu_kind(int a, int j) { return ((a == 1 && j == 0) || (a == 3 && j == 1)) ? 0 : 1; }
     static constexpr int MAX_THREADS = 256, MIN_BLOCKS = 1, BT_LARGE = 32;
     static constexpr int NXF = 4;
     static constexpr int NDEF = 20;
@@ -224,6 +245,11 @@ struct LmpcAxis {
     static constexpr int NX = 5, NU = 1, NR = 1, NP = 4, NAUG = 1, NAXIS = 2;
     static constexpr bool SERIAL_RICCATI = false;   // measured: the tiled sweep is 1.3-2x faster than the per-lane one at n = 5
     DART_HD static constexpr int a_kind(int, int) { return 0; }
+    // rows 0 and 2 kinematic; row 1 (translation) does not see the angle, row 3 (rotation) does not see the position
+    DART_HD static constexpr int fx_kind(int a, int q) {
+        return (a == 0 || a == 2) ? (q == a + 1 ? 2 : 1) : (a == 1 ? (q == 2 ? 1 : 0) : (q == 0 ? 1 : 0));
+    }
+    DART_HD static constexpr int fu_kind(int a, int) { return a == 1 ? 0 : 1; }
     // one instance (two axis tiles) per block; 168 registers -> 6 blocks = 12 warps per SM (shared memory allows 14).
     // Measured at 16 384 instances: bounds (64,5) 7.06 ms, (128,3) 7.58 ms (same register count, worse schedule),
     // (64,4) / (128,2) with 255 registers and 8 warps 7.30 ms, (64,7) with 128 registers 8.2 ms
