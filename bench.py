@@ -10,7 +10,8 @@ one pass of the hot path (one batched solve) over that batch.
 * `value`    solves/s with inputs resident in HBM (device-pointer C ABI, CUDA-event timed per step, an L2 flush between
              steps outside the timed events, max over ranks).  N > 1: every rank solves its own seeded batch (weak
              scaling) and ONE NCCL all_gather of the result rows per step runs INSIDE the timed events.
-* `e2e`      the same metric through the public host API (dart_solve_host: pinned staging, H2D, solve, D2H); N > 1:
+* `e2e`      the same metric through the public host API (dart_solve_host: host arrays -> pinned staging -> device over the
+             host link (kernel-side reads of the mapped block below 1 MB, copy engines above) -> solve -> results back); N > 1:
              pinned H2D + dart_solve + all_gather + D2H of the gathered rows.
 * `roofline` FP64 FMA pipe: algorithmic flops (66.9 kflop per PMPC interior-point iteration x the iterations
              actually taken) / solve-kernel time, against the DFMA peak measured in this run.
@@ -574,7 +575,8 @@ def run_ours(args):
         e2e_value = e2e_conv * Ke / e2e_s
         h2d = B * (6 + 6 + 4) * 8
         d2h = B * (2 + 1) * 8 + B * 2 * 4
-        e2e_path = "dart_solve_host (pinned staging, H2D, solve, D2H)"
+        e2e_path = ("dart_solve_host: host arrays -> pinned staging block; this batch is < 1 MB, so the kernel reads its inputs from and writes "
+                    "its results to that block over the host link itself (mapped pinned memory, no copy-engine launches); sync; copy out")
     else:
         pin = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (c["state"], c["target"], aux_h)]
         host_rows = torch.empty((world * B, 4), dtype=torch.float64).pin_memory()

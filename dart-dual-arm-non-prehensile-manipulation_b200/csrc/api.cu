@@ -1,6 +1,7 @@
 // C ABI (include/dart_b200.h) over the sm_100a kernels.  No CPU fallback: every entry point needs a CUDA device.
 #include <cuda_runtime.h>
 #include <string.h>
+#include <stdlib.h>
 #include <new>
 
 #include "launch.h"
@@ -171,6 +172,13 @@ extern "C" int dart_solve(dart_handle h, int32_t B, const double* x0, const doub
     return DART_OK;
 }
 
+// DART_HOST_STAGED=1: always stage through device memory (A/B switch of the zero-copy path of dart_solve_host)
+static bool getenv_staged() {
+    static int v = -1;
+    if (v < 0) v = getenv("DART_HOST_STAGED") ? 1 : 0;
+    return v == 1;
+}
+
 static int ensure(dart_solver* h, size_t bytes) {
     if (bytes <= h->pin_bytes) return DART_OK;
     if (h->pin) cudaFreeHost(h->pin);
@@ -210,7 +218,14 @@ extern "C" int dart_solve_host(dart_handle h, int32_t B, const double* x0, const
     size_t o_aux = 0, o_warm = 0;
     if (aux) { memcpy(pin + o, aux, n_aux * 8); o_aux = o; o += n_aux; }
     if (warm_w) { memcpy(pin + o, warm_w, n_warm * 8); o_warm = o; o += n_warm; }
-    if (cudaMemcpyAsync(dev, pin, in_d * 8, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) return DART_ERR_CUDA;
+    // Small batches (the headline 1152-instance batch moves 147 kB in and 37 kB out): the kernel reads its inputs from and
+    // writes its results to the PINNED staging block directly (mapped host memory under unified addressing) -- each input
+    // row is read exactly once, at the start of its instance's solve, so the transfer is the same bytes over the same link
+    // without two copy-engine launches and their serialisation in front of and behind a 0.08 ms kernel.  Larger batches, and
+    // calls that carry plans (warm_w / w_out, re-read by the kernels), go through device staging with the copy engines.
+    const bool zero_copy = !warm_w && !w_out && (in_d + out_d) * sizeof(double) <= (size_t)(1u << 20) && !getenv_staged();
+    if (zero_copy) dev = pin;
+    else if (cudaMemcpyAsync(dev, pin, in_d * 8, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) return DART_ERR_CUDA;
     double* d_out = dev + in_d;
     double* d_u0 = d_out;
     double* d_J = d_out + (size_t)B * 2;
@@ -221,7 +236,7 @@ extern "C" int dart_solve_host(dart_handle h, int32_t B, const double* x0, const
                     d_w, d_u0, d_J, d_st, d_it, (void*)h->stream);
     if (rc != DART_OK) return rc;
     double* p_out = pin + in_d;
-    if (cudaMemcpyAsync(p_out, d_out, out_d * 8 + out_i * 4, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) return DART_ERR_CUDA;
+    if (!zero_copy && cudaMemcpyAsync(p_out, d_out, out_d * 8 + out_i * 4, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) return DART_ERR_CUDA;
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) return DART_ERR_CUDA;
     memcpy(u0_out, p_out, (size_t)B * 2 * 8);
     memcpy(J_out, p_out + (size_t)B * 2, (size_t)B * 8);

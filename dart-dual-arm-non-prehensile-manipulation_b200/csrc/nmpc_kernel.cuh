@@ -253,6 +253,9 @@ static int launch_n(const KArgs& a, int block_threads, cudaStream_t st, LaunchIn
     while (step % unit != 0) step += 32;
     if (bt % step != 0 || bt < unit) return DART_ERR_ARG;
     int tpb = bt / G;
+#ifdef DART_SMEM_PAD
+    ws_stride += DART_SMEM_PAD / 8;       // occupancy experiment: waste shared memory per problem
+#endif
     size_t smem = (size_t)tpb * ws_stride * sizeof(double);
     while (smem > (size_t)max_smem && bt > step) { bt -= step; tpb = bt / G; smem = (size_t)tpb * ws_stride * sizeof(double); }
     if (smem > (size_t)max_smem || bt < unit || (!handover && tpb % M::NAXIS != 0)) return DART_ERR_UNSUPPORTED;

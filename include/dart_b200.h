@@ -128,8 +128,10 @@ int dart_solve(dart_handle h, int32_t B, const double* x0, const double* ref, co
                const double* warm_w, double* w_out, double* u0_out, double* J_out, int32_t* status,
                int32_t* iters, void* stream);
 
-/* Same call with HOST pointers: stages through pinned buffers, copies inputs to the device, solves,
- * copies results back and synchronises.  This is the call the Python drop-in classes make. */
+/* Same call with HOST pointers: stages through a pinned buffer, moves inputs to the device, solves, moves results back and
+ * synchronises.  This is the call the Python drop-in classes make.  Batches of up to 1 MB without plans (warm_w, w_out NULL)
+ * are read from / written to the pinned block by the kernel itself (mapped host memory: the same bytes over the same link,
+ * no copy-engine launches); larger ones use device staging and cudaMemcpyAsync.  DART_HOST_STAGED=1 forces the latter. */
 int dart_solve_host(dart_handle h, int32_t B, const double* x0, const double* ref, const double* aux,
                     const double* warm_w, double* w_out, double* u0_out, double* J_out,
                     int32_t* status, int32_t* iters);
