@@ -17,6 +17,13 @@
 #include "solver_core.cuh"
 #include "../../include/dart_b200.h"
 
+#ifndef DART_ROLL_RK4
+#define DART_ROLL_RK4 1
+#endif
+#ifndef DART_FOLD_RK4
+#define DART_FOLD_RK4 0
+#endif
+
 namespace dart {
 
 struct KArgs {
@@ -49,17 +56,32 @@ DART_HD void rk4_sens(const typename Md::Prm& p, const double* x, const double* 
     // compiler fold 0 * x or 1 * x itself) -- same values, 40-50 % fewer FMAs in the sensitivity propagation.
     auto fxv = [&](int a, int q) { return Md::fx_kind(a, q) == 0 ? fx[a * np + q] : (Md::fx_kind(a, q) == 2 ? 1.0 : 0.0); };
     auto fuv = [&](int a, int j) { return Md::fu_kind(a, j) == 0 ? fu[a * m + j] : (Md::fu_kind(a, j) == 2 ? 1.0 : 0.0); };
-    // stage 1
-    Md::deriv(p, x, su, cu, k, fx, fu);
-    DART_UNROLL for (int a = 0; a < np; ++a) {
-        DART_UNROLL for (int b = 0; b < np; ++b) { Sx[a * np + b] = fxv(a, b); A[a * np + b] = fxv(a, b); }
-        DART_UNROLL for (int j = 0; j < m; ++j) { Su[a * m + j] = fuv(a, j); Bm[a * m + j] = fuv(a, j); }
+    // DART_ROLL_RK4 (models with np > 2): stages 2-4 stay a rolled LOOP.  The stage body (derivative with its
+    // transcendentals + sensitivity propagation) is the bulk of the solve kernel's code and every eval1 call site carries a
+    // copy of it; the LMPC kernel's largest stall reason was instruction fetch (no_instruction 30 % of the stall samples;
+    // instruction cache 32 kB, kernel 180 kB).  Measured on one box: LMPC 6.50 -> 6.07 ms, RMPC 1.47 -> 1.41 ms; the small
+    // PMPC body is faster unrolled.  DART_FOLD_RK4 also runs stage 1 through the loop (as the general stage with S = 0, c = 0:
+    // the same values bit for bit, another 600 instructions less code) -- no measurable difference in a same-box A/B (LMPC
+    // 6.00 vs 6.02 ms: the extra FMAs on zeros cost what the fetches save), so it is off.
+    constexpr bool kRoll = DART_ROLL_RK4 && Md::NP > 2;
+    constexpr bool kFold = DART_FOLD_RK4 && kRoll;
+    if (kFold) {
+        DART_UNROLL for (int i = 0; i < np * np; ++i) { Sx[i] = 0.0; A[i] = 0.0; }
+        DART_UNROLL for (int i = 0; i < np * m; ++i) { Su[i] = 0.0; Bm[i] = 0.0; }
+        DART_UNROLL for (int i = 0; i < np; ++i) { acc[i] = 0.0; xs[i] = x[i]; }
+    } else {
+        // stage 1
+        Md::deriv(p, x, su, cu, k, fx, fu);
+        DART_UNROLL for (int a = 0; a < np; ++a) {
+            DART_UNROLL for (int b = 0; b < np; ++b) { Sx[a * np + b] = fxv(a, b); A[a * np + b] = fxv(a, b); }
+            DART_UNROLL for (int j = 0; j < m; ++j) { Su[a * m + j] = fuv(a, j); Bm[a * m + j] = fuv(a, j); }
+        }
+        DART_UNROLL for (int i = 0; i < np; ++i) { acc[i] = k[i]; xs[i] = x[i] + 0.5 * h * k[i]; }
     }
-    DART_UNROLL for (int i = 0; i < np; ++i) { acc[i] = k[i]; xs[i] = x[i] + 0.5 * h * k[i]; }
-    // stages 2..4
-    DART_UNROLL for (int st = 2; st <= 4; ++st) {
-        const double c = (st == 4) ? h : 0.5 * h;      // step used to reach this stage's evaluation point
-        const double wgt = (st == 4) ? 1.0 : 2.0;
+    DART_UNROLL_N(kRoll ? 1 : 3)
+    for (int st = kFold ? 1 : 2; st <= 4; ++st) {
+        const double c = (st == 4) ? h : (st == 1 ? 0.0 : 0.5 * h);      // step used to reach this stage's evaluation point
+        const double wgt = (st == 4 || st == 1) ? 1.0 : 2.0;
         Md::deriv(p, xs, su, cu, k, fx, fu);
         double Nx[np * np], Nu[np * m];
         DART_UNROLL for (int a = 0; a < np; ++a) {
@@ -167,7 +189,13 @@ struct Rmpc {
     // rows 0 and 2 are the kinematic unit rows (p' = v); rows 1 and 3 are dense; u_j enters the acceleration of axis j only
     DART_HD static constexpr int fx_kind(int a, int q) { return (a == 0 || a == 2) ? (q == a + 1 ? 2 : 1) : 0; }
     DART_HD static constexpr int fu_kind(int a, int j) { return ((a == 1 && j == 0) || (a == 3 && j == 1)) ? 0 : 1; }
-    static constexpr int MAX_THREADS = 256, MIN_BLOCKS = 1, BT_LARGE = 32;
+#ifndef DART_RMPC_MAXT
+#define DART_RMPC_MAXT 256
+#endif
+#ifndef DART_RMPC_MINB
+#define DART_RMPC_MINB 1
+#endif
+    static constexpr int MAX_THREADS = DART_RMPC_MAXT, MIN_BLOCKS = DART_RMPC_MINB, BT_LARGE = 32;
     static constexpr int NXF = 4;
     static constexpr int NDEF = 20;
     struct Prm { double Qp, Qv, Ru, Rdu, gz, Ts, ulo, uhi, dlo, dhi, vmax, inv_eps; double th[14]; };

@@ -1386,11 +1386,14 @@ struct Solver {
         DART_UNROLL for (int r = 0; r < nr; ++r) nact += M::row_skip0(r) ? N - 1 : N;
         double inv_nd = 0.0, inv_nc = 0.0;
         if (active) {
-            eval1(f, L, th, pinf);
-            eval2(dinf, zs_min, zs_max, lam_sum, z_sum);
             inv_nd = 1.0 / (double)(N * n + 2 * nact);
             inv_nc = 1.0 / (double)(2 * (nact > 0 ? nact : 1));
         }
+        // The starting point is evaluated by the FIRST PASS of the loop below, through the same two call sites of eval1 /
+        // eval2 that the iterations use: every call site is an inlined copy of the RK4 + sensitivity code, the kernels are
+        // 150-190 kB of SASS against a 32 kB instruction cache, and instruction fetch was the LMPC kernel's largest stall
+        // reason (no_instruction 30 % of the stall samples).
+        bool first = true;
         const double mu_min = o.tol / 10.0;
         int it = 0, tiny = 0, nacc = 0;
         int32_t st = ST_MAXITER;
@@ -1411,6 +1414,9 @@ struct Solver {
 #define DART_CK(acc)
 #endif
         for (;;) {
+            bool ghost = false;
+            double ap = 0.0, ad = 0.0, dphi = 0.0;
+            if (!first) {
             // ---------------- phase A
             bool need_sweep = false;
             if (!done) {
@@ -1444,7 +1450,6 @@ struct Solver {
                     }
                 }
             }
-            bool ghost = false;
             if constexpr (kLock) {
                 // Lockstep tiles: the tiles of a WARP run the whole iteration as one instruction stream, so that every
                 // collective is a full-warp instruction with a constant mask.  A tile that has finished while a sibling
@@ -1497,16 +1502,19 @@ struct Solver {
                 DART_CK(ckB)
             }
             // ---------------- phase C
-            double ap, ad, dphi;
             post(mu, ap, ad, dphi, ghost);
             DART_CK(ckC1)
+            }   // !first
             const double phi0 = f - mu * L, th0 = th;
             const double th_max = 1e4 * dmax(1.0, th0);
             double alpha = ap, applied = 0.0;
             for (int bt = 0;; ++bt) {
-                move_primal(alpha - applied);
-                applied = alpha;
-                eval1(f, L, th, pinf);
+                if (!first) {
+                    move_primal(alpha - applied);
+                    applied = alpha;
+                }
+                if (!first || active) eval1(f, L, th, pinf);
+                if (first) break;
                 const double phit = f - mu * L;
                 // alpha |dphi|^s_phi > delta th0^s_theta, compared in the log domain (only needed when th0 is small);
                 // single precision is ample for this heuristic test (and keeps three FP64 logs off the serial path)
@@ -1533,17 +1541,20 @@ struct Solver {
             printf("it %d mu %.3e E0 %.3e dinf %.3e pinf %.3e zsmax %.3e ap %.4f ad %.4f alpha %.5f dphi %.3e th0 %.3e f %.10g\n", it, mu, E0, dinf * is_d, pinf, zs_max * is_c, ap, ad, alpha, dphi, th0, f);
 #endif
             DART_CK(ckC2)
-            if (!ghost) ++it;
-            // the step vanished three times in a row: no restoration phase here -- stop and say so
-            tiny = ghost ? 0 : ((alpha <= 1e-6) ? tiny + 1 : 0);
-            if (tiny >= 3) {
-                st = (pinf > 1e-4) ? ST_INFEASIBLE : ST_MAXITER;
-                done = true;
-                if constexpr (!kLock) continue;
-                alpha = 0.0;                          // lockstep tiles: stay with the other tiles of the warp (their collectives below)
+            if (!first) {
+                if (!ghost) ++it;
+                // the step vanished three times in a row: no restoration phase here -- stop and say so
+                tiny = ghost ? 0 : ((alpha <= 1e-6) ? tiny + 1 : 0);
+                if (tiny >= 3) {
+                    st = (pinf > 1e-4) ? ST_INFEASIBLE : ST_MAXITER;
+                    done = true;
+                    if constexpr (!kLock) continue;
+                    alpha = 0.0;                      // lockstep tiles: stay with the other tiles of the warp (their collectives below)
+                }
+                move_dual(alpha, mu);
             }
-            move_dual(alpha, mu);
-            eval2(dinf, zs_min, zs_max, lam_sum, z_sum);
+            if (!first || active) eval2(dinf, zs_min, zs_max, lam_sum, z_sum);
+            first = false;
             DART_CK(ckC)
         }
 #ifdef DART_PHASE_CLOCK
