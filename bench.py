@@ -495,14 +495,45 @@ def run_ours(args):
     rows = torch.empty((B, 4), dtype=torch.float64, device=dev)          # [u0x, u0y, J, status] result rows
     gathered = torch.empty((world * B, 4), dtype=torch.float64, device=dev) if world > 1 else None
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    peer = None
+    gather_kind = "none"
     if world > 1:
         eng.set_result_rows(rows)        # the solve kernel writes the packed [u0x, u0y, J, status] rows itself
+        gather_kind = "NCCL all_gather_into_tensor of the result rows"
+        if not os.environ.get("DART_BENCH_NCCL_GATHER"):
+            # gather without a collective: the solve kernel stores the rows into every rank's buffer over NVLink (peer memory),
+            # one hand-shake launch per step; checked here against the NCCL gather before it is used
+            try:
+                peer = dart_b200.parallel.PeerRows.create(eng, B, local)
+            except Exception as e:
+                peer = None
+                if rank == 0:
+                    print(f"peer-rows gather unavailable ({e!r}); using NCCL", file=sys.stderr)
+            if peer is not None:
+                eng.solve_device(x0_d, tg_d, aux=aux_d, u0_out=u0, J_out=J, status=st, iters=it)
+                peer.handshake()
+                dist.all_gather_into_tensor(gathered, rows)
+                torch.cuda.synchronize()
+                same = torch.tensor([1 if (torch.equal(peer.gathered, gathered) and int(peer.timed_out.item()) == 0) else 0],
+                                    dtype=torch.int32, device=dev)
+                dist.all_reduce(same, op=dist.ReduceOp.MIN)
+                if int(same.item()) == 0:
+                    peer.close()
+                    peer = None
+                    if rank == 0:
+                        print("peer-rows gather did not reproduce the NCCL gather; using NCCL", file=sys.stderr)
+            if peer is not None:
+                gather_kind = ("peer memory: the solve kernel stores every row into all ranks' gathered buffers over NVLink "
+                               "(CUDA IPC), one flag hand-shake launch per step; verified equal to the NCCL all_gather at start-up")
 
     def step():
         eng.solve_device(x0_d, tg_d, aux=aux_d, u0_out=u0, J_out=J, status=st, iters=it)
         if world > 1:
             torch.cuda.nvtx.range_push("gather")
-            dist.all_gather_into_tensor(gathered, rows)      # synchronous: the launching stream waits for the collective
+            if peer is not None:
+                peer.handshake()                             # the rows are already on their way: wait for every peer's flag
+            else:
+                dist.all_gather_into_tensor(gathered, rows)  # synchronous: the launching stream waits for the collective
             torch.cuda.nvtx.range_pop()
 
     clocks = ClockSampler(local)
@@ -527,7 +558,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    launches = eng.launch_count - l0
+    launches = eng.launch_count - l0 + (K if peer is not None else 0)      # + one hand-shake launch per step
     ms = np.array([a.elapsed_time(b) for a, b in zip(ev0, ev1)])
     total_s = float(ms.sum() * 1e-3)
     conv = int((st == 0).sum().item())
@@ -535,6 +566,7 @@ def run_ours(args):
     # kernel-only time of the solve (for the roofline) when the step also holds the gather
     kern_ms = float(np.mean(ms))
     gather_ms = 0.0
+    nccl_gather_ms = 0.0
     if world > 1:
         k0, k1 = _ev(torch), _ev(torch)
         torch.cuda.synchronize()
@@ -547,9 +579,17 @@ def run_ours(args):
         g0, g1 = _ev(torch), _ev(torch)
         g0.record()
         for _ in range(10):
-            dist.all_gather_into_tensor(gathered, rows)
+            if peer is not None:
+                peer.handshake()
+            else:
+                dist.all_gather_into_tensor(gathered, rows)
         g1.record(); torch.cuda.synchronize()
         gather_ms = g0.elapsed_time(g1) / 10
+        g0.record()
+        for _ in range(10):
+            dist.all_gather_into_tensor(gathered, rows)
+        g1.record(); torch.cuda.synchronize()
+        nccl_gather_ms = g0.elapsed_time(g1) / 10
         eng.set_result_rows(None)
     tt = torch.tensor([total_s], dtype=torch.float64, device=dev)
     cv = torch.tensor([conv], dtype=torch.float64, device=dev)
@@ -586,8 +626,12 @@ def run_ours(args):
             for dst, src in zip((x0_d, tg_d, aux_d), pin):
                 dst.copy_(src, non_blocking=True)
             eng.solve_device(x0_d, tg_d, aux=aux_d, u0_out=u0, J_out=J, status=st, iters=it)
-            dist.all_gather_into_tensor(gathered, rows)
-            host_rows.copy_(gathered, non_blocking=True)
+            if peer is not None:
+                peer.handshake()
+                host_rows.copy_(peer.gathered, non_blocking=True)
+            else:
+                dist.all_gather_into_tensor(gathered, rows)
+                host_rows.copy_(gathered, non_blocking=True)
             torch.cuda.synchronize()
 
         for _ in range(3):
@@ -605,8 +649,13 @@ def run_ours(args):
         e2e_value = e2e_conv * Ke / float(e2.item())
         h2d = B * (6 + 6 + 4) * 8
         d2h = world * B * 4 * 8
-        e2e_path = "pinned H2D of the rank's inputs, dart_solve, NCCL all_gather of result rows, D2H of all ranks' rows"
+        e2e_path = ("pinned H2D of the rank's inputs, dart_solve, gather of the result rows (" +
+                    ("peer-memory stores + hand-shake" if peer is not None else "NCCL all_gather") + "), D2H of all ranks' rows")
         eng.set_result_rows(None)
+        if peer is not None:
+            if int(peer.timed_out.item()) != 0:
+                raise SystemExit("peer hand-shake timed out")
+            peer.close()
 
     # ---- BASELINE config 5 scale sweep (every N; strong scaling)
     sweep = None
@@ -701,12 +750,13 @@ def run_ours(args):
             "config": {"workload": f"PMPC batched (BASELINE config 2): 18 objects x {STATES_PER_OBJECT} states = {B} "
                                    f"instances/step/GPU, cold start, tol 1e-8", "N": 15, "instances_per_gpu": B,
                        "l2": "256 MiB flush write between timed steps", "launch": launch_cfg,
-                       "parallelism": f"instance sharding x{world}" + (", one NCCL all_gather of result rows per step INSIDE the timed events" if world > 1 else "")},
+                       "parallelism": f"instance sharding x{world}" + (", one gather of the result rows per step INSIDE the timed events" if world > 1 else ""),
+                       "gather": gather_kind},
             "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "p50_batch_latency_ms": float(np.median(lat) * 1e3), "path": e2e_path},
             "p50_solve_latency_ms": {"B=1 host API": float(np.median(one) * 1e3),
                                      "per-batch/B": float(np.median(lat) * 1e3 / B)},
-            "gpu_launches": int(launches), "converged": conv, "gather_ms": gather_ms, "clocks": clk, "roofline": roofline,
+            "gpu_launches": int(launches), "converged": conv, "gather_ms": gather_ms, "nccl_gather_ms": nccl_gather_ms, "clocks": clk, "roofline": roofline,
             "cpu_baseline": cpu, "throughput_variant": big, "scale_sweep": sweep, "configs": configs}
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -59,6 +59,14 @@ def lib():
     if hasattr(L, "dart_set_dual_state"):
         L.dart_set_dual_state.argtypes = [vp, vp, C.c_int32]
         L.dart_ndual.argtypes = [vp]
+    if hasattr(L, "dart_set_result_rows_peers"):
+        L.dart_set_result_rows_peers.argtypes = [vp, C.POINTER(vp), C.c_int32, C.c_int64]
+        L.dart_enable_peer_access.argtypes = [C.c_int, C.c_int]
+        L.dart_peer_alloc.argtypes = [C.c_int64, C.POINTER(vp), C.c_char_p]
+        L.dart_peer_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+        L.dart_peer_close.argtypes = [vp]
+        L.dart_peer_free.argtypes = [vp]
+        L.dart_peer_handshake.argtypes = [C.POINTER(vp), C.c_int32, C.c_int32, C.c_int64, vp, vp]
     L.dart_launch_count.argtypes = [vp]
     L.dart_launch_count.restype = C.c_int64
     L.dart_last_launch_config.argtypes = [vp, ip, ip, ip, ip]

@@ -27,6 +27,9 @@ struct dart_solver {
     double* axis_part;
     int32_t* axis_sync;
     int32_t axis_cap;
+    double* peer_rows[DART_MAX_PEERS];     // dart_set_result_rows_peers
+    int32_t n_peers;
+    int64_t peer_off;
 };
 
 extern "C" int dart_default_cfg(int32_t method, dart_cfg* c) {
@@ -84,6 +87,7 @@ extern "C" int dart_create(dart_handle* out, const dart_cfg* cfg, int device) {
     memset(&h->last, 0, sizeof(h->last));
     h->pin = nullptr; h->pin_bytes = 0; h->dev = nullptr; h->dev_bytes = 0; h->rows = nullptr; h->rows_cap = 0; h->dual = nullptr; h->dual_cap = 0;
     h->axis_part = nullptr; h->axis_sync = nullptr; h->axis_cap = 0;
+    h->n_peers = 0; h->peer_off = 0;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return DART_ERR_CUDA; }
     *out = h;
     return DART_OK;
@@ -161,6 +165,8 @@ extern "C" int dart_solve(dart_handle h, int32_t B, const double* x0, const doub
     a.x0 = x0; a.ref = ref; a.aux = aux; a.warm = warm_w;
     a.w_out = w_out; a.u0 = u0_out; a.J = J_out; a.status = status; a.iters = iters; a.rows = h->rows; a.dual = h->dual;
     a.axis_part = h->axis_part; a.axis_sync = h->axis_sync;
+    a.n_peers = h->n_peers; a.peer_off = h->peer_off;
+    for (int p = 0; p < DART_MAX_PEERS; ++p) a.peer_rows[p] = p < h->n_peers ? h->peer_rows[p] : nullptr;
     int rc = launch_solve(a, h->cfg.lanes, h->cfg.block_threads, st, &h->last);
     if (rc != DART_OK) return rc;
     h->launches += 1;
@@ -261,7 +267,7 @@ extern "C" int dart_pmpc_episode(dart_handle h, int32_t B, int32_t T, double* st
     KArgs a;
     a.B = B; a.N = h->cfg.N; a.o = h->opts; a.cfg = h->cfg;
     a.x0 = state; a.ref = target; a.aux = aux; a.warm = nullptr;
-    a.w_out = nullptr; a.u0 = u0; a.J = J; a.status = status; a.iters = iters; a.rows = nullptr; a.dual = nullptr; a.axis_part = nullptr; a.axis_sync = nullptr;
+    a.w_out = nullptr; a.u0 = u0; a.J = J; a.status = status; a.iters = iters; a.rows = nullptr; a.dual = nullptr; a.axis_part = nullptr; a.axis_sync = nullptr; a.n_peers = 0; a.peer_off = 0;
     PlantArgs pl{B, h->cfg.Ts, h->cfg.g, tol, mu_plant, coulomb, u0, target, state, conv_time, effort, err, nsteps};
     int rc = launch_episode_pmpc(a, T, pl, (unsigned long long*)counters, h->cfg.lanes, (cudaStream_t)stream, &h->last);
     if (rc != DART_OK) return rc;
@@ -274,6 +280,63 @@ extern "C" int dart_set_result_rows(dart_handle h, double* rows, int32_t capacit
     h->rows = rows;
     h->rows_cap = rows ? capacity_rows : 0;
     return DART_OK;
+}
+
+extern "C" int dart_set_result_rows_peers(dart_handle h, double* const* peers, int32_t n_peers, int64_t row_offset) {
+    if (!h || n_peers < 0 || n_peers > DART_MAX_PEERS || (n_peers > 0 && !peers) || row_offset < 0) return DART_ERR_ARG;
+    for (int p = 0; p < n_peers; ++p) {
+        if (!peers[p]) return DART_ERR_ARG;
+        h->peer_rows[p] = peers[p];
+    }
+    h->n_peers = n_peers;
+    h->peer_off = row_offset;
+    return DART_OK;
+}
+
+extern "C" int dart_enable_peer_access(int device, int peer) {
+    if (device == peer) return DART_OK;
+    int can = 0;
+    if (cudaDeviceCanAccessPeer(&can, device, peer) != cudaSuccess || !can) { cudaGetLastError(); return DART_ERR_UNSUPPORTED; }
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess) return DART_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return DART_ERR_CUDA;
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+    cudaSetDevice(cur);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return DART_ERR_CUDA; }
+    cudaGetLastError();
+    return DART_OK;
+}
+
+// ---- peer-shared device buffers (CUDA IPC): dedicated cudaMalloc blocks, so the exported handle maps exactly the buffer
+extern "C" int dart_peer_alloc(int64_t bytes, void** ptr, uint8_t* handle64) {
+    if (bytes <= 0 || !ptr || !handle64) return DART_ERR_ARG;
+    void* p = nullptr;
+    if (cudaMalloc(&p, (size_t)bytes) != cudaSuccess) { cudaGetLastError(); return DART_ERR_ALLOC; }
+    if (cudaMemset(p, 0, (size_t)bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) { cudaFree(p); return DART_ERR_CUDA; }
+    cudaIpcMemHandle_t h;
+    static_assert(sizeof(h) == 64, "CUDA IPC handles are 64 bytes");
+    if (cudaIpcGetMemHandle(&h, p) != cudaSuccess) { cudaGetLastError(); cudaFree(p); return DART_ERR_UNSUPPORTED; }
+    memcpy(handle64, &h, 64);
+    *ptr = p;
+    return DART_OK;
+}
+// opened on the CURRENT device with lazy peer access: kernels of this device may then load / store the peer's buffer
+extern "C" int dart_peer_open(const uint8_t* handle64, void** ptr) {
+    if (!handle64 || !ptr) return DART_ERR_ARG;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return DART_ERR_UNSUPPORTED; }
+    *ptr = p;
+    return DART_OK;
+}
+extern "C" int dart_peer_close(void* ptr) {
+    if (!ptr) return DART_ERR_ARG;
+    return cudaIpcCloseMemHandle(ptr) == cudaSuccess ? DART_OK : DART_ERR_CUDA;
+}
+extern "C" int dart_peer_free(void* ptr) {
+    if (!ptr) return DART_ERR_ARG;
+    return cudaFree(ptr) == cudaSuccess ? DART_OK : DART_ERR_CUDA;
 }
 
 extern "C" int64_t dart_launch_count(dart_handle h) { return h ? h->launches : -1; }

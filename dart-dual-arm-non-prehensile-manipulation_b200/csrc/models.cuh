@@ -39,7 +39,25 @@ struct KArgs {
     // records [B, NAXIS, 4] and an arrival counter per instance (zero between launches); see solve_block
     double* axis_part;
     int32_t* axis_sync;
+    // optional peer result rows (multi-GPU gather without a collective): every instance's row [u0x, u0y, J, status] is ALSO
+    // stored at peer_rows[p] + (peer_off + inst) * 4 for p < n_peers -- peer-mapped gathered buffers of the other GPUs (and
+    // this GPU's own), written over NVLink from the solve kernel's epilogue
+    double* peer_rows[DART_MAX_PEERS];
+    int32_t n_peers;
+    int64_t peer_off;
 };
+
+// the packed result row of one instance: local rows buffer and / or every peer's gathered buffer
+DART_HD void store_result_row(const KArgs& a, int inst, double u0x, double u0y, double J, double st) {
+    if (a.rows) {
+        double* r = a.rows + (long)inst * 4;
+        r[0] = u0x; r[1] = u0y; r[2] = J; r[3] = st;
+    }
+    for (int p = 0; p < a.n_peers; ++p) {
+        double* r = a.peer_rows[p] + (a.peer_off + inst) * 4;
+        r[0] = u0x; r[1] = u0y; r[2] = J; r[3] = st;
+    }
+}
 
 // Generic RK4 step with forward sensitivities.  Md::deriv(prm, x, u, f, fx, fu) gives xdot and its
 // Jacobians for the NP physical states.

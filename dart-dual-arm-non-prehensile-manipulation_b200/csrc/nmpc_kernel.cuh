@@ -109,10 +109,7 @@ __device__ __forceinline__ void solve_block(const KArgs& a, const int ws_stride,
             a.J[inst] = J;
             if (a.status) a.status[inst] = status;
             if (a.iters) a.iters[inst] = iters;
-            if (a.rows) {
-                double* r = a.rows + (long)inst * 4;
-                r[0] = a.u0[(long)inst * 2]; r[1] = a.u0[(long)inst * 2 + 1]; r[2] = J; r[3] = (double)status;
-            }
+            store_result_row(a, inst, a.u0[(long)inst * 2], a.u0[(long)inst * 2 + 1], J, (double)status);
         }
         return;
     }
@@ -142,10 +139,8 @@ __device__ __forceinline__ void solve_block(const KArgs& a, const int ws_stride,
                     a.J[inst] = Js;
                     if (a.status) a.status[inst] = st;
                     if (a.iters) a.iters[inst] = itx;
-                    if (a.rows) {
-                        double* r = a.rows + (long)inst * 4;
-                        r[0] = __ldcg(a.u0 + (long)inst * 2); r[1] = __ldcg(a.u0 + (long)inst * 2 + 1); r[2] = Js; r[3] = (double)st;
-                    }
+                    if (a.rows || a.n_peers > 0)
+                        store_result_row(a, inst, __ldcg(a.u0 + (long)inst * 2), __ldcg(a.u0 + (long)inst * 2 + 1), Js, (double)st);
                     a.axis_sync[inst] = 0;
                 }
             }
@@ -173,10 +168,8 @@ __device__ __forceinline__ void solve_block(const KArgs& a, const int ws_stride,
         a.J[inst] = Js;
         if (a.status) a.status[inst] = st;
         if (a.iters) a.iters[inst] = itx;
-        if (a.rows) {       // u0 of every axis was stored before the barrier above
-            double* r = a.rows + (long)inst * 4;
-            r[0] = a.u0[(long)inst * 2]; r[1] = a.u0[(long)inst * 2 + 1]; r[2] = Js; r[3] = (double)st;
-        }
+        // u0 of every axis was stored before the barrier above
+        if (a.rows || a.n_peers > 0) store_result_row(a, inst, a.u0[(long)inst * 2], a.u0[(long)inst * 2 + 1], Js, (double)st);
     }
 }
 

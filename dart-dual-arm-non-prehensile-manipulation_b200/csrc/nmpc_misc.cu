@@ -52,4 +52,39 @@ int launch_tilt_to_quat(int B, const double* u, double* q, cudaStream_t st) {
     return cudaGetLastError() == cudaSuccess ? DART_OK : DART_ERR_CUDA;
 }
 
+// Step hand-shake of the peer-rows gather (dart_peer_handshake): one thread per peer.  The rows of this step were stored by
+// the solve kernel that precedes this launch on the stream, so they are complete; the system-scope fence orders them before
+// the flag for an observer on another GPU.  Then every thread waits for ITS peer's flag in this GPU's own array.
+struct PeerFlags { long long* f[DART_MAX_PEERS]; };
+
+__global__ void peer_handshake_kernel(const PeerFlags pf, int n_peers, int my_rank, long long step, int* timed_out) {
+    const int p = threadIdx.x;
+    if (p >= n_peers) return;
+    __threadfence_system();
+    *reinterpret_cast<volatile long long*>(pf.f[p] + my_rank) = step;
+    __threadfence_system();
+    const volatile long long* mine = pf.f[my_rank] + p;
+    const long long t0 = clock64();
+    while (*mine < step) {
+        __nanosleep(200);
+        if (clock64() - t0 > 4000000000LL) {            // ~2 s at 1.9 GHz: a peer is gone
+            if (timed_out) *timed_out = 1;
+            break;
+        }
+    }
+    __threadfence_system();
+}
+
 }  // namespace dart
+
+extern "C" int dart_peer_handshake(int64_t* const* peer_flags, int32_t n_peers, int32_t my_rank, int64_t step, int32_t* timed_out,
+                                   void* stream) {
+    if (!peer_flags || n_peers < 1 || n_peers > DART_MAX_PEERS || my_rank < 0 || my_rank >= n_peers) return DART_ERR_ARG;
+    dart::PeerFlags pf;
+    for (int p = 0; p < DART_MAX_PEERS; ++p) {
+        pf.f[p] = p < n_peers ? reinterpret_cast<long long*>(peer_flags[p]) : nullptr;
+        if (p < n_peers && !pf.f[p]) return DART_ERR_ARG;
+    }
+    dart::peer_handshake_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pf, n_peers, my_rank, (long long)step, timed_out);
+    return cudaGetLastError() == cudaSuccess ? DART_OK : DART_ERR_CUDA;
+}

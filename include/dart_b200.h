@@ -142,6 +142,29 @@ int dart_solve_host(dart_handle h, int32_t B, const double* x0, const double* re
  * (u_cmd, loss, solve_time) tuples of main_parallel.py's control_queue (:43, :201-205). */
 int dart_set_result_rows(dart_handle h, double* rows, int32_t capacity_rows);
 
+/* Multi-GPU gather WITHOUT a collective (the instances are independent, so the only exchange of the path is this gather;
+ * main_parallel.py:43,201-205 moves the same tuples through mp.Queue): the solve kernel stores every instance's row
+ * [u0x, u0y, J, status] directly into the gathered buffers of up to DART_MAX_PEERS GPUs of the node -- peers[p] are
+ * peer-mapped device pointers (CUDA IPC / peer access; this GPU's own buffer included), row (row_offset + instance) of each.
+ * n_peers = 0 switches it off.  dart_peer_handshake then tells every rank that all rows of a step have landed. */
+#define DART_MAX_PEERS 8
+int dart_set_result_rows_peers(dart_handle h, double* const* peers, int32_t n_peers, int64_t row_offset);
+/* Buffers that other processes of the node can map (CUDA IPC): dart_peer_alloc allocates and zeroes `bytes` on the current
+ * device and exports its 64-byte handle; dart_peer_open maps a peer's handle for the CURRENT device (lazy peer access over
+ * NVLink), dart_peer_close unmaps it, dart_peer_free releases an own buffer (after every peer has closed it). */
+int dart_peer_alloc(int64_t bytes, void** ptr, uint8_t* handle64);
+int dart_peer_open(const uint8_t* handle64, void** ptr);
+int dart_peer_close(void* ptr);
+int dart_peer_free(void* ptr);
+/* Enable direct access from `device` to `peer` memory (cudaDeviceEnablePeerAccess; already enabled is not an error). */
+int dart_enable_peer_access(int device, int peer);
+/* Step hand-shake over peer memory, one launch on `stream`: writes `step` into slot `my_rank` of every peer's flag array
+ * (peer_flags[p], int64 [n_peers], peer-mapped) after a system-scope fence, then waits until all n_peers slots of the own array
+ * (peer_flags[my_rank]) hold a value >= step.  Work enqueued on the stream after it sees every peer's rows of that step.
+ * The wait gives up after about two seconds (a crashed peer must not hang the GPU) and sets *timed_out (device int32). */
+int dart_peer_handshake(int64_t* const* peer_flags, int32_t n_peers, int32_t my_rank, int64_t step, int32_t* timed_out,
+                        void* stream);
+
 /* Number of kernels launched by this handle since creation (for bench.py's gpu_launches). */
 int64_t dart_launch_count(dart_handle h);
 

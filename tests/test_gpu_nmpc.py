@@ -297,3 +297,18 @@ def test_two_devices_in_one_process(built):
             assert torch.cuda.current_device() == 0 and np.array_equal(o2["u0"].cpu().numpy(), outs[-1]["u0"])
     torch.cuda.set_device(0)
     assert np.array_equal(outs[0]["u0"], outs[1]["u0"]) and np.array_equal(outs[0]["J"], outs[1]["J"])
+
+
+def test_peer_rows_gather_two_gpus(built):
+    """Gather without a collective (tests/dist_peer_rows_check.py): the rows the solve kernels store into every rank's buffer
+    over NVLink equal the NCCL all_gather bit for bit after the flag hand-shake, for all three methods, over several steps."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29641", os.path.join(helpers.ROOT, "tests", "dist_peer_rows_check.py")],
+                       capture_output=True, text=True, timeout=300)
+    assert "PEER_ROWS_OK" in r.stdout or "PEER_ROWS_UNAVAILABLE" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
