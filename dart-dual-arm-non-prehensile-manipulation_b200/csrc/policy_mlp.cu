@@ -232,34 +232,38 @@ policy_mlp_kernel(const __grid_constant__ CUtensorMap tm_obs, const __grid_const
 // single TF32 pass (policy_mlp_kernel above) is three decimal digits short of that, so:
 //   layer 1 (K = 520, 84 % of the flops and ALL of the HBM traffic) stays on tcgen05 but as a 3xTF32 product,
 //       A W = A_hi W_hi + A_hi W_lo + A_lo W_hi      (hi = top 19 bits, lo = fp32(x - hi); dropped term ~ 2^-22),
-//     W_hi / W_lo are split once on the host; A arrives by TMA as fp32 and four "split" warps rewrite each landed chunk
-//     in place as A_hi and write A_lo beside it (generic -> async proxy fence), then one thread issues the 12 MMAs of the
-//     chunk; fp32 accumulation in TMEM.  The kernel is HBM-bound, so the tripled tensor work is free.
-//   layers 2 and 3 (64x64 and 64x34 per row) run in plain FP32 FMAs on the CUDA cores, thread per row, weights
-//     broadcast from shared memory -- the reference's arithmetic up to summation order, and no hi/lo operand copies of
+//     W_hi / W_lo are split once on the host; A arrives by TMA as fp32 and serves as A_hi as it is (the tensor core ignores
+//     the low 13 mantissa bits of a TF32 operand), four "split" warps write A_lo = A - top19(A) into a second buffer
+//     (generic -> async proxy fence), then one thread issues the 8 MMAs of the chunk; fp32 accumulation in TMEM.
+//   layers 2 and 3 (64x64 and 64x34 per row) run in plain FP32 FMAs on the CUDA cores, register-tiled, weights and
+//     activations in shared memory -- the reference's arithmetic up to summation order, and no hi/lo operand copies of
 //     W2, W3 and of the activations in shared memory.
-// One persistent CTA per SM, warp-specialised: warp 0 TMA producer (3-stage ring: A 16 KB + A_lo 16 KB + W1 hi/lo 16 KB
-// per stage), warp 1 MMA issuer, warps 2-5 split, warps 6-9 epilogue.  The layer-1 accumulator is double-buffered in
-// TMEM, so the stream of tile t+1 runs under the epilogue (layers 2, 3, store) of tile t.
+// One persistent CTA per SM, warp-specialised: warp 0 TMA producer of the observation chunks (5-stage ring, 16 KB each),
+// warp 14 TMA producer of the [W1_hi ; W1_lo] chunks (3-stage ring, 16 KB each, L2-resident source), warps 2-5 split
+// (A_lo double buffer), warp 1 MMA issuer, warps 6-13 epilogue.  The layer-1 accumulator is double-buffered in TMEM, so the
+// stream of tile t+1 runs under the epilogue (layers 2, 3, store) of tile t.
 namespace v3 {
-constexpr int S = 3;
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;                  // A, A_lo, W1_hi, W1_lo chunk
-constexpr int OFF_RING = 0;
-constexpr int OFF_W2T = OFF_RING + S * STAGE_BYTES;                     // W2 transposed [k][j], 64 x 64 fp32
-constexpr int W3LD = 40;                                                // W3 transposed [k][j], 64 x 40 fp32 (34 padded)
-constexpr int OFF_W3T = OFF_W2T + HID * HID * 4;
-constexpr int OFF_BIAS = OFF_W3T + HID * W3LD * 4;                      // b1[64] b2[64] b3[36]
-constexpr int OFF_HS = OFF_BIAS + (HID + HID + W3LD) * 4;               // activations [k][row] fp32 (thread-private columns)
-constexpr int OFF_OUT = OFF_HS + HID * MT * 4;                          // [128, 34] result tile for coalesced stores
-constexpr int OFF_BAR = OFF_OUT + MT * ACT * 4;
-constexpr int NBAR = 3 * S + 4;                                         // full[S] split[S] empty[S] accf[2] acce[2]
+constexpr int NA = 5;                                                   // A ring: fp32 observation chunks landing from HBM (16 KB each)
+constexpr int NW = 3;                                                   // W ring: [W1_hi chunk ; W1_lo chunk] from L2 (16 KB each)
+constexpr int NL = 2;                                                   // A_lo double buffer (written by the split warps)
+constexpr int OFF_A = 0;
+constexpr int OFF_W = OFF_A + NA * A_BYTES;
+constexpr int OFF_L = OFF_W + NW * 2 * B_BYTES;
+// layers 2-3 operand block, one bulk copy from the blob dart_policy_create prepares: W2 and W3 transposed [k][j], biases
+constexpr int W3LD = 40;                                                // 34 action columns padded to 40
+constexpr int OFF_W2T = OFF_L + NL * A_BYTES;                           // [64 k][64 j] fp32
+constexpr int OFF_W3T = OFF_W2T + HID * HID * 4;                        // [64 k][40 j] fp32
+constexpr int OFF_BIAS = OFF_W3T + HID * W3LD * 4;                      // b1[64] b2[64] b3[40]
+constexpr int BLOB_BYTES = HID * HID * 4 + HID * W3LD * 4 + (HID + HID + W3LD) * 4;
+constexpr int OFF_HS = OFF_BIAS + (HID + HID + W3LD) * 4;               // activations [k][row] fp32; reused as the [128, 34] result tile
+constexpr int OFF_BAR = OFF_HS + HID * MT * 4;
+constexpr int NBAR = 2 * NA + 2 * NW + 2 * NL + 5;                      // fullA emptyA fullW emptyW split lfree accf[2] acce[2] blob
 constexpr int BYTES = OFF_BAR + 8 * NBAR + 16 + 1024;                   // + tmem slot + alignment slack
+static_assert(BLOB_BYTES % 16 == 0 && OFF_W2T % 16 == 0, "bulk copy granularity");
 constexpr int NEPI = 256;                                               // epilogue threads (warps 6..13)
-constexpr int NTHR = 64 + 128 + NEPI;
+constexpr int NTHR = 64 + 128 + NEPI + 32;                              // + warp 14: W producer
 constexpr uint32_t TCOLS = 256;                                         // two 128-column layer-1 accumulators ([.. W_hi | .. W_lo] partial sums)
-#ifndef DART_MLP3_REWRITE_HI
-#define DART_MLP3_REWRITE_HI 0      // 1: the split warps also rewrite A in place with its top 19 bits (if tcgen05 rounded instead of truncating)
-#endif
+static_assert(MT * ACT <= HID * MT, "the result tile fits in the activation buffer");
 static_assert(BYTES <= 232448, "shared memory budget of one CTA per SM");
 }  // namespace v3
 
@@ -282,7 +286,7 @@ __device__ __forceinline__ float tanh_fast(float x) {
 
 struct Mlp3Args {
     int B, ntiles;
-    const float *W2, *b1, *b2, *W3, *b3;        // global fp32 (row-major [out][in]); staged transposed in shared memory
+    const float* blob;                          // [W2 transposed [k][j] | W3 transposed, 40 columns | b1 b2 b3]: v3::BLOB_BYTES, built at create
     float* mean;
 };
 
@@ -291,23 +295,32 @@ policy_mlp3_kernel(const __grid_constant__ CUtensorMap tm_obs, const __grid_cons
                    const __grid_constant__ CUtensorMap tm_w1l, const Mlp3Args a) {
     using namespace v3;
     extern __shared__ uint8_t smem_raw[];
+#ifdef DART_MLP3_CLOCK
+    const long long t_entry = clock64();
+#endif
     // 1024-byte alignment (SWIZZLE_128B atoms) by an OFFSET into the __shared__ array: a pointer rebuilt from an integer
     // would lose its address space and every access below would compile to a generic LD/ST instead of LDS/STS
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar0 = sbase + OFF_BAR;
-    auto FULL = [&](int s) { return bar0 + 8 * s; };
-    auto SPLIT = [&](int s) { return bar0 + 8 * (S + s); };
-    auto EMPTY = [&](int s) { return bar0 + 8 * (2 * S + s); };
-    auto ACCF = [&](int b) { return bar0 + 8 * (3 * S + b); };
-    auto ACCE = [&](int b) { return bar0 + 8 * (3 * S + 2 + b); };
+    auto FULLA = [&](int s) { return bar0 + 8 * s; };
+    auto EMPTYA = [&](int s) { return bar0 + 8 * (NA + s); };
+    auto FULLW = [&](int s) { return bar0 + 8 * (2 * NA + s); };
+    auto EMPTYW = [&](int s) { return bar0 + 8 * (2 * NA + NW + s); };
+    auto SPLIT = [&](int l) { return bar0 + 8 * (2 * NA + 2 * NW + l); };
+    auto LFREE = [&](int l) { return bar0 + 8 * (2 * NA + 2 * NW + NL + l); };
+    auto ACCF = [&](int b) { return bar0 + 8 * (2 * NA + 2 * NW + 2 * NL + b); };
+    auto ACCE = [&](int b) { return bar0 + 8 * (2 * NA + 2 * NW + 2 * NL + 2 + b); };
+    const uint32_t BLOB = bar0 + 8 * (2 * NA + 2 * NW + 2 * NL + 4);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 8 * NBAR);
-    auto stageA = [&](int s) { return (uint32_t)(OFF_RING + s * STAGE_BYTES); };
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < S; ++s) { mbar_init(FULL(s), 1); mbar_init(SPLIT(s), 128); mbar_init(EMPTY(s), 1); }
+        for (int s = 0; s < NA; ++s) { mbar_init(FULLA(s), 1); mbar_init(EMPTYA(s), 1); }
+        for (int s = 0; s < NW; ++s) { mbar_init(FULLW(s), 1); mbar_init(EMPTYW(s), 1); }
+        for (int l = 0; l < NL; ++l) { mbar_init(SPLIT(l), 128); mbar_init(LFREE(l), 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(ACCF(b), 1); mbar_init(ACCE(b), v3::NEPI); }
+        mbar_init(BLOB, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -319,19 +332,37 @@ policy_mlp3_kernel(const __grid_constant__ CUtensorMap tm_obs, const __grid_cons
     fence_after();
     const uint32_t tmem = *tmem_slot;
 
+    // The observation chunks (HBM, ~1 us away) and the weight chunks (L2) ride separate rings with their own producers, and
+    // the A ring is the deep one: a stage is busy from the TMA issue until the MMAs that read it retire, so with S stages in
+    // flight an SM streams S x 16 KB per (memory latency + split + MMA) -- at S = 3, with the weights in the same stage, that
+    // was 18 GB/s per SM (measured: 15 of the kernel's 26 us at 16 384 rows), a third of the SM's share of HBM.
     if (warp == 0) {
-        // ===== TMA producer =====
+        // ===== TMA producer, observation chunks =====
         if (lane == 0) {
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
                 for (int kb = 0; kb < NKB; ++kb, ++it) {
-                    const int s = it % S;
-                    const uint32_t ph = (it / S) & 1;
-                    mbar_wait(EMPTY(s), ph ^ 1);
-                    mbar_expect_tx(FULL(s), A_BYTES + 2 * B_BYTES);
-                    tma_load_2d(sbase + stageA(s), &tm_obs, kb * BK, tile * MT, FULL(s));
-                    tma_load_2d(sbase + stageA(s) + 2 * A_BYTES, &tm_w1h, kb * BK, 0, FULL(s));
-                    tma_load_2d(sbase + stageA(s) + 2 * A_BYTES + B_BYTES, &tm_w1l, kb * BK, 0, FULL(s));
+                    const int s = it % NA;
+                    mbar_wait(EMPTYA(s), ((it / NA) & 1) ^ 1);
+                    mbar_expect_tx(FULLA(s), A_BYTES);
+                    tma_load_2d(sbase + OFF_A + s * A_BYTES, &tm_obs, kb * BK, tile * MT, FULLA(s));
+                }
+            }
+        }
+    } else if (warp == 14) {
+        // ===== TMA producer, W1 hi / lo chunks (and, first, the layers 2-3 operand block) =====
+        if (lane == 0) {
+            mbar_expect_tx(BLOB, BLOB_BYTES);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(sbase + OFF_W2T), "l"(a.blob), "r"(BLOB_BYTES), "r"(BLOB) : "memory");
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+                for (int kb = 0; kb < NKB; ++kb, ++it) {
+                    const int s = it % NW;
+                    mbar_wait(EMPTYW(s), ((it / NW) & 1) ^ 1);
+                    mbar_expect_tx(FULLW(s), 2 * B_BYTES);
+                    tma_load_2d(sbase + OFF_W + s * 2 * B_BYTES, &tm_w1h, kb * BK, 0, FULLW(s));
+                    tma_load_2d(sbase + OFF_W + s * 2 * B_BYTES + B_BYTES, &tm_w1l, kb * BK, 0, FULLW(s));
                 }
             }
         }
@@ -347,50 +378,52 @@ policy_mlp3_kernel(const __grid_constant__ CUtensorMap tm_obs, const __grid_cons
                 fence_after();
                 const uint32_t acc = tmem + (uint32_t)(b * 2 * HID);
                 for (int kb = 0; kb < NKB; ++kb, ++it) {
-                    const int s = it % S;
-                    const uint32_t ph = (it / S) & 1;
-                    mbar_wait(SPLIT(s), ph);
+                    const int sa = it % NA, sw = it % NW, l = it % NL;
+                    mbar_wait(FULLW(sw), (it / NW) & 1);
+                    mbar_wait(FULLA(sa), (it / NA) & 1);
+                    mbar_wait(SPLIT(l), (it / NL) & 1);                       // A_lo written by the split warps
                     fence_after();
-                    const uint64_t dah = sdesc(sbase + stageA(s)), dal = sdesc(sbase + stageA(s) + A_BYTES);
-                    const uint64_t dbw = sdesc(sbase + stageA(s) + 2 * A_BYTES);      // [W1_hi chunk ; W1_lo chunk]: 128 rows
+                    const uint64_t dah = sdesc(sbase + OFF_A + sa * A_BYTES), dal = sdesc(sbase + OFF_L + l * A_BYTES);
+                    const uint64_t dbw = sdesc(sbase + OFF_W + sw * 2 * B_BYTES);     // [W1_hi chunk ; W1_lo chunk]: 128 rows
 #pragma unroll
                     for (int k = 0; k < BK / 8; ++k) {
                         // columns 0..63 += A_hi W_hi, columns 64..127 += A_hi W_lo: A_hi is read from shared memory once
+                        // (A itself: the tensor core ignores the low 13 mantissa bits of a TF32 operand)
                         umma_tf32(acc, dah + 2 * k, dbw + 2 * k, ID128, (kb | k) != 0);
                         umma_tf32(acc, dal + 2 * k, dbw + 2 * k, ID64, 1);            // columns 0..63 += A_lo W_hi
                     }
-                    umma_commit(EMPTY(s));
+                    umma_commit(EMPTYA(sa));
+                    umma_commit(EMPTYW(sw));
+                    umma_commit(LFREE(l));
                 }
                 umma_commit(ACCF(b));
             }
         }
     } else if (warp < 6) {
-        // ===== split warps: landed fp32 chunk -> A_hi (in place) + A_lo =====
+        // ===== split warps: landed fp32 chunk -> A_lo = A - top19(A) =====
         const int t = threadIdx.x - 64;                                  // 0..127
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
             for (int kb = 0; kb < NKB; ++kb, ++it) {
-                const int s = it % S;
-                const uint32_t ph = (it / S) & 1;
-                mbar_wait(FULL(s), ph);
-                uint4* A = reinterpret_cast<uint4*>(smem + stageA(s));
-                float4* L = reinterpret_cast<float4*>(smem + stageA(s) + A_BYTES);
+                const int sa = it % NA, l = it % NL;
+                mbar_wait(LFREE(l), ((it / NL) & 1) ^ 1);
+                mbar_wait(FULLA(sa), (it / NA) & 1);
+                const uint4* A = reinterpret_cast<const uint4*>(smem + OFF_A + sa * A_BYTES);
+                float4* L = reinterpret_cast<float4*>(smem + OFF_L + l * A_BYTES);
+                uint4 v[A_BYTES / 16 / 128];
+#pragma unroll
+                for (int i = 0; i < A_BYTES / 16 / 128; ++i) v[i] = A[t + 128 * i];
 #pragma unroll
                 for (int i = 0; i < A_BYTES / 16 / 128; ++i) {
-                    const int u = t + 128 * i;
-                    uint4 v = A[u];
-                    uint4 h;
-                    h.x = v.x & 0xffffe000u; h.y = v.y & 0xffffe000u; h.z = v.z & 0xffffe000u; h.w = v.w & 0xffffe000u;
-                    float4 l;
-                    l.x = __uint_as_float(v.x) - __uint_as_float(h.x); l.y = __uint_as_float(v.y) - __uint_as_float(h.y);
-                    l.z = __uint_as_float(v.z) - __uint_as_float(h.z); l.w = __uint_as_float(v.w) - __uint_as_float(h.w);
-#if DART_MLP3_REWRITE_HI
-                    A[u] = h;
-#endif
-                    L[u] = l;
+                    float4 lo;
+                    lo.x = __uint_as_float(v[i].x) - __uint_as_float(v[i].x & 0xffffe000u);
+                    lo.y = __uint_as_float(v[i].y) - __uint_as_float(v[i].y & 0xffffe000u);
+                    lo.z = __uint_as_float(v[i].z) - __uint_as_float(v[i].z & 0xffffe000u);
+                    lo.w = __uint_as_float(v[i].w) - __uint_as_float(v[i].w & 0xffffe000u);
+                    L[t + 128 * i] = lo;
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_arrive(SPLIT(s));
+                mbar_arrive(SPLIT(l));
             }
         }
     } else {
@@ -404,25 +437,19 @@ policy_mlp3_kernel(const __grid_constant__ CUtensorMap tm_obs, const __grid_cons
         const int row = q * 32 + lane;
         const int grp = (warp - 6) >> 2;                                  // which 32 accumulator columns this warp converts
         const int et = (warp - 6) * 32 + lane;                            // 0..255
-        float* W2t = reinterpret_cast<float*>(smem + OFF_W2T);
-        float* W3t = reinterpret_cast<float*>(smem + OFF_W3T);
-        float* bias = reinterpret_cast<float*>(smem + OFF_BIAS);
+        const float* W2t = reinterpret_cast<const float*>(smem + OFF_W2T);
+        const float* W3t = reinterpret_cast<const float*>(smem + OFF_W3T);
+        const float* bias = reinterpret_cast<const float*>(smem + OFF_BIAS);
         float* hs = reinterpret_cast<float*>(smem + OFF_HS);
-        float* outs = reinterpret_cast<float*>(smem + OFF_OUT);
-        for (int i = et; i < HID * HID; i += NEPI) W2t[(i & 63) * HID + (i >> 6)] = __ldg(a.W2 + i);          // i = j*64 + k
-        for (int i = et; i < HID * W3LD; i += NEPI) {
-            const int k = i / W3LD, j = i % W3LD;
-            W3t[i] = j < ACT ? __ldg(a.W3 + j * HID + k) : 0.0f;
-        }
-        for (int i = et; i < HID; i += NEPI) { bias[i] = __ldg(a.b1 + i); bias[HID + i] = __ldg(a.b2 + i); }
-        for (int i = et; i < W3LD; i += NEPI) bias[2 * HID + i] = i < ACT ? __ldg(a.b3 + i) : 0.0f;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        float* outs = hs;                                                 // the result tile reuses the activation buffer
+        mbar_wait(BLOB, 0);                                               // W2, W3, biases have landed (one bulk copy, under the stream)
         const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
         const int r2 = (et >> 4) * 8, c2 = (et & 15) * 4;                 // layer-2 tile: rows r2..r2+7, columns c2..c2+3
         const int r3 = (et >> 3) * 4, c3 = (et & 7) * 5;                  // layer-3 tile: rows r3..r3+3, columns c3..c3+4
         int lt = 0;
 #ifdef DART_MLP3_CLOCK
         long long ck[6] = {0, 0, 0, 0, 0, 0}, c0_ = clock64();
+        const long long t_staged = c0_;
 #define MLP3_CK(i) { long long t_ = clock64(); ck[i] += t_ - c0_; c0_ = t_; }
 #else
 #define MLP3_CK(i)
@@ -498,6 +525,7 @@ policy_mlp3_kernel(const __grid_constant__ CUtensorMap tm_obs, const __grid_cons
                         ffma2(acc[0][c], hp.x, ww); ffma2(acc[1][c], hp.y, ww);
                     }
                 }
+                asm volatile("bar.sync 1, 256;" ::: "memory");           // every thread has read h2: overwrite it with the result tile
 #pragma unroll
                 for (int c = 0; c < 5; ++c) {
                     const int j = c3 + c;
@@ -525,6 +553,8 @@ policy_mlp3_kernel(const __grid_constant__ CUtensorMap tm_obs, const __grid_cons
             MLP3_CK(4)
         }
 #ifdef DART_MLP3_CLOCK
+        if (blockIdx.x == 0 && et == 0 && lt > 0)
+            printf("mlp3 entry -> epilogue warps staged %lld cycles, -> end %lld\n", t_staged - t_entry, clock64() - t_entry);
         if (blockIdx.x == 0 && et == 0 && lt > 0)
             printf("mlp3 epilogue cycles/tile over %d tiles: wait %lld  l1-epi %lld  layer2 %lld  layer3 %lld  store %lld\n", lt, ck[0] / lt, ck[1] / lt, ck[2] / lt, ck[3] / lt, ck[4] / lt);
 #endif
@@ -638,6 +668,7 @@ struct dart_policy {
     int device, sms;
     float *W1, *b1, *W2, *b2, *W3, *b3;
     float *W1h, *W1l;                         // 3xTF32 split of W1 (top 19 bits / remainder)
+    float* blob;                              // layers 2-3 operand block of policy_mlp3_kernel (v3::BLOB_BYTES)
     CUtensorMap tm_w1, tm_w2, tm_w3, tm_w1h, tm_w1l;
     int legacy;                               // DART_POLICY_TF32: the single-pass TF32 kernel (dart_policy_set_precision)
     int64_t launches;
@@ -691,6 +722,25 @@ extern "C" int dart_policy_create(dart_policy_handle* out, int device, int32_t o
         delete[] hi;
         delete[] lo;
     }
+    if (rc == DART_OK) {
+        // layers 2-3 operand block: W2, W3 transposed to [k][j] (W3 padded to 40 columns), then b1, b2, b3 (padded)
+        float* blob = new (std::nothrow) float[v3::BLOB_BYTES / 4]();
+        if (!blob) rc = DART_ERR_ALLOC;
+        if (rc == DART_OK) {
+            float* w2t = blob;
+            float* w3t = blob + HID * HID;
+            float* bs = w3t + HID * v3::W3LD;
+            for (int k = 0; k < HID; ++k) {
+                for (int j = 0; j < HID; ++j) w2t[k * HID + j] = W2[j * HID + k];
+                for (int j = 0; j < ACT; ++j) w3t[k * v3::W3LD + j] = W3[j * HID + k];
+            }
+            for (int i = 0; i < HID; ++i) { bs[i] = b1[i]; bs[HID + i] = b2[i]; }
+            for (int i = 0; i < ACT; ++i) bs[2 * HID + i] = b3[i];
+            if (cudaMalloc(&h->blob, v3::BLOB_BYTES) != cudaSuccess) { h->blob = nullptr; rc = DART_ERR_ALLOC; }
+            else if (cudaMemcpy(h->blob, blob, v3::BLOB_BYTES, cudaMemcpyHostToDevice) != cudaSuccess) rc = DART_ERR_CUDA;
+        }
+        delete[] blob;
+    }
     if (rc == DART_OK && (make_map(&h->tm_w1, h->W1, HID, OBS, HID) || make_map(&h->tm_w2, h->W2, HID, HID, HID) ||
                           make_map(&h->tm_w3, h->W3, N3, HID, N3) || make_map(&h->tm_w1h, h->W1h, HID, OBS, HID) ||
                           make_map(&h->tm_w1l, h->W1l, HID, OBS, HID)))
@@ -710,8 +760,8 @@ extern "C" int dart_policy_create(dart_policy_handle* out, int device, int32_t o
 extern "C" int dart_policy_destroy(dart_policy_handle h) {
     if (!h) return DART_ERR_ARG;
     cudaSetDevice(h->device);
-    float* p[8] = {h->W1, h->b1, h->W2, h->b2, h->W3, h->b3, h->W1h, h->W1l};
-    for (int i = 0; i < 8; ++i) if (p[i]) cudaFree(p[i]);
+    float* p[9] = {h->W1, h->b1, h->W2, h->b2, h->W3, h->b3, h->W1h, h->W1l, h->blob};
+    for (int i = 0; i < 9; ++i) if (p[i]) cudaFree(p[i]);
     delete h;
     return DART_OK;
 }
@@ -726,7 +776,7 @@ extern "C" int dart_policy_forward(dart_policy_handle h, int32_t B, const float*
     if (rc != DART_OK) return rc;
     if (!h->legacy) {
         Mlp3Args a3;
-        a3.B = B; a3.ntiles = (B + MT - 1) / MT; a3.W2 = h->W2; a3.b1 = h->b1; a3.b2 = h->b2; a3.W3 = h->W3; a3.b3 = h->b3;
+        a3.B = B; a3.ntiles = (B + MT - 1) / MT; a3.blob = h->blob;
         a3.mean = act_mean;
         const int grid = a3.ntiles < h->sms ? a3.ntiles : h->sms;           // one persistent CTA per SM
         policy_mlp3_kernel<<<grid, v3::NTHR, v3::BYTES, (cudaStream_t)stream>>>(tm_obs, h->tm_w1h, h->tm_w1l, a3);
