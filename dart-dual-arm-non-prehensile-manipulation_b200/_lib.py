@@ -56,6 +56,7 @@ def lib():
         L.dart_set_result_rows.argtypes = [vp, vp, C.c_int32]
     if hasattr(L, "dart_set_mu_init"):
         L.dart_set_mu_init.argtypes = [vp, C.c_double]
+    L.dart_set_barrier_strategy.argtypes = [vp, C.c_int32]
     if hasattr(L, "dart_set_dual_state"):
         L.dart_set_dual_state.argtypes = [vp, vp, C.c_int32]
         L.dart_ndual.argtypes = [vp]

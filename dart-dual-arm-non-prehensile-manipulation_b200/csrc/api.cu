@@ -30,6 +30,7 @@ struct dart_solver {
     double* peer_rows[DART_MAX_PEERS];     // dart_set_result_rows_peers
     int32_t n_peers;
     int64_t peer_off;
+    int32_t barrier;   // dart_set_barrier_strategy: -1 = default of fill_opts
 };
 
 extern "C" int dart_default_cfg(int32_t method, dart_cfg* c) {
@@ -88,6 +89,7 @@ extern "C" int dart_create(dart_handle* out, const dart_cfg* cfg, int device) {
     h->pin = nullptr; h->pin_bytes = 0; h->dev = nullptr; h->dev_bytes = 0; h->rows = nullptr; h->rows_cap = 0; h->dual = nullptr; h->dual_cap = 0;
     h->axis_part = nullptr; h->axis_sync = nullptr; h->axis_cap = 0;
     h->n_peers = 0; h->peer_off = 0;
+    h->barrier = -1;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return DART_ERR_CUDA; }
     *out = h;
     return DART_OK;
@@ -127,6 +129,14 @@ extern "C" int dart_set_mu_init(dart_handle h, double mu_init) {
     if (!h || !(mu_init >= 0.0)) return DART_ERR_ARG;
     h->cfg.mu_init = mu_init;                  // 0 selects the default (0.1)
     fill_opts(h->cfg, h->opts);
+    if (h->barrier >= 0) h->opts.mehrotra = h->barrier;
+    return DART_OK;
+}
+
+extern "C" int dart_set_barrier_strategy(dart_handle h, int32_t strategy) {
+    if (!h || (strategy != DART_BARRIER_MONOTONE && strategy != DART_BARRIER_MEHROTRA)) return DART_ERR_ARG;
+    h->barrier = strategy;
+    h->opts.mehrotra = strategy;
     return DART_OK;
 }
 

@@ -136,6 +136,7 @@ DART_HD void rk4_sens(const typename Md::Prm& p, const double* x, const double* 
 // =============================================================================================== PMPC
 struct PmpcAxis {
     static constexpr int NX = 2, NU = 1, NR = 1, NP = 2, NAUG = 0, NAXIS = 2;
+    static constexpr bool MEHROTRA = true;      // Solver::sweeps_scan_pc (solver_core.cuh)
     static constexpr bool SERIAL_RICCATI = true;
     // structure the serial sweep may rely on: the position does not enter the dynamics, so column 0 of the RK4
     // sensitivity A is exactly e_0
@@ -202,6 +203,7 @@ struct PmpcAxis {
 // =============================================================================================== RMPC
 struct Rmpc {
     static constexpr int NX = 6, NU = 2, NR = 6, NP = 4, NAUG = 2, NAXIS = 1;
+    static constexpr bool MEHROTRA = false;
     static constexpr bool SERIAL_RICCATI = false;
     DART_HD static constexpr int a_kind(int, int) { return 0; }
     // rows 0 and 2 are the kinematic unit rows (p' = v); rows 1 and 3 are dense; u_j enters the acceleration of axis j only
@@ -289,6 +291,7 @@ struct Rmpc {
 // =============================================================================================== LMPC
 struct LmpcAxis {
     static constexpr int NX = 5, NU = 1, NR = 1, NP = 4, NAUG = 1, NAXIS = 2;
+    static constexpr bool MEHROTRA = false;
     static constexpr bool SERIAL_RICCATI = false;   // measured: the tiled sweep is 1.3-2x faster than the per-lane one at n = 5
     DART_HD static constexpr int a_kind(int, int) { return 0; }
     // rows 0 and 2 kinematic; row 1 (translation) does not see the angle, row 3 (rotation) does not see the position

@@ -1,5 +1,6 @@
 // Solver option defaults shared by the C ABI and the host-emulation test harness.
 #pragma once
+#include <stdlib.h>
 #include "solver_core.cuh"
 #include "../../include/dart_b200.h"
 
@@ -14,5 +15,8 @@ inline void fill_opts(const dart_cfg& c, SolverOpts& o) {
     o.max_backtrack = 12;
     o.acc_tol = c.acceptable_tol;
     o.acc_iter = (c.acceptable_iter > 0 && c.acceptable_tol > 0) ? c.acceptable_iter : 0;
+    // barrier strategy (IPOPT's mu_strategy): predictor-corrector where the kernel has it (PMPC axis problems on the scan
+    // path), the monotone schedule elsewhere; DART_BARRIER_MONOTONE=1 or dart_set_barrier_strategy select the monotone one
+    o.mehrotra = getenv("DART_BARRIER_MONOTONE") ? 0 : 1;
 }
 }  // namespace dart

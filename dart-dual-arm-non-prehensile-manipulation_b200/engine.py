@@ -44,6 +44,12 @@ class NMPCEngine:
         """Initial barrier parameter of the following solves (0 = default 0.1); see dart_set_mu_init."""
         check(self._lib.dart_set_mu_init(self._h, float(mu_init)), "dart_set_mu_init")
 
+    def set_barrier_strategy(self, strategy):
+        """'mehrotra' (default: predictor-corrector where the kernel has it, i.e. PMPC at the reference horizon) or
+        'monotone' (IPOPT's default schedule for every method); see dart_set_barrier_strategy."""
+        code = {"monotone": 0, "mehrotra": 1}[strategy]
+        check(self._lib.dart_set_barrier_strategy(self._h, code), "dart_set_barrier_strategy")
+
     @property
     def ndual(self):
         return self._lib.dart_ndual(self._h)

@@ -89,6 +89,16 @@ typedef struct dart_solver* dart_handle;
  * IPOPT's mu_init (arm.py:306 sets it for its warm-started worker). */
 int dart_set_mu_init(dart_handle h, double mu_init);
 
+/* Barrier-parameter strategy of the solves that follow (IPOPT's `mu_strategy`; the reference leaves IPOPT's default,
+ * "monotone", at mpc_3d.py:82 -- the strategy changes the iterate path, not the KKT point a solve converges to).
+ * DART_BARRIER_MEHROTRA (the default): predictor-corrector steps with an adaptive barrier parameter where the kernel
+ * implements them -- the PMPC axis problems at the reference horizon -- and the monotone schedule everywhere else;
+ * DART_BARRIER_MONOTONE: Fiacco-McCormick schedule (mu0 = mu_init, kappa_mu 0.2, theta_mu 1.5) for every method.
+ * The environment variable DART_BARRIER_MONOTONE=1 makes monotone the default of new handles. */
+#define DART_BARRIER_MONOTONE 0
+#define DART_BARRIER_MEHROTRA 1
+int dart_set_barrier_strategy(dart_handle h, int32_t strategy);
+
 /* Dual warm start for closed loops (IPOPT's warm_start_init_point with lam_x0 / lam_g0, which the reference passes
  * for its arm worker at arm.py:420-424 but not for the tray controllers).  `dual` is a DEVICE buffer of
  * [capacity_rows, dart_ndual(h)] doubles that the caller zero-initialises once and then leaves alone: every dart_solve

@@ -44,6 +44,10 @@ class Options:
     kappa_mu: float = 0.2
     theta_mu: float = 1.5
     kappa_eps: float = 10.0
+    # experiments (tools/ipm_variants.py; the CUDA solver runs the monotone method): second-order corrector on the
+    # complementarity products, and Mehrotra's adaptive barrier parameter from an affine-scaling predictor
+    corrector: int = 0
+    mehrotra: int = 0
     tau_min: float = 0.99
     bound_push: float = 1e-2
     eta: float = 1e-4
@@ -225,12 +229,16 @@ def solve(prob: StageProblem, X0=None, U0=None, opts: Options = None, trace=None
         iters[~done] += 1
         # ---- monotone barrier update (Waechter & Biegler eq. 7), possibly several reductions at once
         mu_min = o.tol / 10.0
-        for _ in range(8):
+        for _ in range(0 if o.mehrotra else 8):
             Emu = np.maximum(np.maximum(dual_inf / s_d, prim_inf), compl(mu) / s_c)
             red = (~done) & (Emu <= o.kappa_eps * mu) & (mu > mu_min)
             if not red.any():
                 break
             mu = np.where(red, np.maximum(mu_min, np.minimum(o.kappa_mu * mu, mu ** o.theta_mu)), mu)
+        if o.mehrotra:
+            cnt = 2.0 * nrows_act
+            mu_c = ((zl * sl + zu * su) * msk).sum(axis=(1, 2)) / cnt      # mean complementarity product
+            mu = np.zeros(B)                                               # predictor: affine-scaling direction
         mu3 = mu[:, None, None]
         # ---- condensed Newton system
         Sig = (zl / sl + zu / su) * msk
@@ -285,6 +293,40 @@ def solve(prob: StageProblem, X0=None, U0=None, opts: Options = None, trace=None
         ds = (dy @ C.T + rc) * msk
         dzl = (mu3 / sl - zl - (zl / sl) * ds) * msk
         dzu = (mu3 / su - zu + (zu / su) * ds) * msk
+        if o.mehrotra:
+            # barrier parameter from the predictor: mu = sigma * mean(z s), sigma = (mean after the longest affine step / mean)^3
+            with np.errstate(divide='ignore', invalid='ignore'):
+                a1 = np.where(ds < 0, -sl / ds, np.inf)
+                a2 = np.where(ds > 0, su / ds, np.inf)
+                apa = np.minimum(1.0, np.minimum(np.where(msk > 0, a1, np.inf).min(axis=(1, 2)),
+                                                 np.where(msk > 0, a2, np.inf).min(axis=(1, 2))))
+                b1 = np.where(dzl < 0, -zl / dzl, np.inf)
+                b2 = np.where(dzu < 0, -zu / dzu, np.inf)
+                ada = np.minimum(1.0, np.minimum(np.where(msk > 0, b1, np.inf).min(axis=(1, 2)),
+                                                 np.where(msk > 0, b2, np.inf).min(axis=(1, 2))))
+            pa, da = apa[:, None, None], ada[:, None, None]
+            mu_aff = (((sl + pa * ds) * (zl + da * dzl) + (su - pa * ds) * (zu + da * dzu)) * msk).sum(axis=(1, 2)) / cnt
+            mu = np.maximum(np.clip((mu_aff / mu_c) ** 3, 1e-8, 1.0) * mu_c, o.tol / 10.0)
+            mu3 = mu[:, None, None]
+        if o.corrector or o.mehrotra:
+            # second solve with the same matrix: (s + ds)(z + dz) = mu keeps the product ds dz of the first direction
+            ml = mu3 - ds * dzl
+            mu_ = mu3 + ds * dzu
+            gs2 = gy + ((mu_ / su - ml / sl + Sig * rc) * msk) @ C
+            for k in range(N):
+                rhs[:, iu(k)] = -gs2[:, k, n:]
+                if k >= 1:
+                    rhs[:, ix(k)] = -gs2[:, k, :n]
+            sol = np.linalg.solve(K, rhs[..., None])[..., 0]
+            dv = sol[:, :nv].reshape(B, N, m + n)
+            dU = dv[:, :, :m]
+            dX = np.zeros((B, N + 1, n))
+            dX[:, 1:] = dv[:, :, m:]
+            lam_new = sol[:, nv:].reshape(B, N, n)
+            dy = np.concatenate([dX[:, :N], dU], axis=-1)
+            ds = (dy @ C.T + rc) * msk
+            dzl = (ml / sl - zl - (zl / sl) * ds) * msk
+            dzu = (mu_ / su - zu + (zu / su) * ds) * msk
         # ---- fraction to the boundary
         tau = np.maximum(o.tau_min, 1.0 - mu)[:, None, None]
         with np.errstate(divide='ignore', invalid='ignore'):

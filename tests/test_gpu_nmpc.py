@@ -50,14 +50,43 @@ def test_pmpc_decision_vector_layout_and_z_rows(pmpc_engine):
 
 @pytest.mark.parametrize("lanes", [2, 4, 8, 16])
 def test_pmpc_lane_widths_agree(built, lanes):
+    """Same algorithm (the monotone barrier schedule), different mapping of the horizon to lanes: same iterates up to
+    summation order.  (The 16-lane tiles run predictor-corrector steps by default; that pair is compared below.)"""
     c, aux, p = helpers.pmpc_case(8)
-    base = dart_b200.NMPCEngine(dart_b200.pmpc_cfg(), device=0).solve(c["state"], c["target"], aux=aux)
+    ref = dart_b200.NMPCEngine(dart_b200.pmpc_cfg(), device=0)
+    ref.set_barrier_strategy("monotone")
+    base = ref.solve(c["state"], c["target"], aux=aux)
     eng = dart_b200.NMPCEngine(dart_b200.pmpc_cfg(lanes=lanes), device=0)
+    eng.set_barrier_strategy("monotone")
     out = eng.solve(c["state"], c["target"], aux=aux)
     assert eng.last_launch_config()["lanes"] == lanes
     assert (out["status"] == 0).all()
     assert np.abs(out["u0"] - base["u0"]).max() < 1e-6
     assert (np.abs(out["J"] - base["J"]) / np.abs(base["J"])).max() < 1e-8
+    assert np.array_equal(out["iters"], base["iters"])
+
+
+def test_pmpc_barrier_strategies_reach_the_same_kkt_points(built):
+    """dart_set_barrier_strategy: Mehrotra predictor-corrector steps (default on the 16-lane scan path) against the monotone
+    schedule on the headline batch -- a different iterate path to the same KKT points (both against the oracle's, which
+    runs the monotone method), in fewer iterations."""
+    c, aux, p = helpers.pmpc_case(64)
+    ref = ipm.solve(p)
+    outs = {}
+    for strat in ("monotone", "mehrotra"):
+        eng = dart_b200.NMPCEngine(dart_b200.pmpc_cfg(), device=0)
+        eng.set_barrier_strategy(strat)
+        outs[strat] = eng.solve(c["state"], c["target"], aux=aux)
+        assert eng.last_launch_config()["lanes"] == 16
+        helpers.assert_parity(outs[strat], ref, "pmpc " + strat)
+    mono, pc = outs["monotone"], outs["mehrotra"]
+    assert np.abs(pc["u0"] - mono["u0"]).max() <= helpers.TOL_U0
+    assert (np.abs(pc["J"] - mono["J"]) / np.abs(mono["J"])).max() <= helpers.TOL_J
+    assert pc["iters"].max() < mono["iters"].max() and pc["iters"].mean() < 0.75 * mono["iters"].mean()
+    # the oracle's own predictor-corrector variant (same algorithm, coupled 6-state problem, dense KKT solves)
+    ref_pc = ipm.solve(p, opts=ipm.Options(mehrotra=1))
+    assert (ref_pc["status"] == 0).all()
+    assert abs(float(pc["iters"].mean()) - float(ref_pc["iters"].mean())) < 0.5
 
 
 def test_rmpc_parity(built):
