@@ -13,8 +13,10 @@ one pass of the hot path (one batched solve) over that batch.
 * `e2e`      the same metric through the public host API (dart_solve_host: host arrays -> pinned staging -> device over the
              host link (kernel-side reads of the mapped block below 1 MB, copy engines above) -> solve -> results back); N > 1:
              pinned H2D + dart_solve + all_gather + D2H of the gathered rows.
-* `roofline` FP64 FMA pipe: algorithmic flops (66.9 kflop per PMPC interior-point iteration x the iterations
-             actually taken) / solve-kernel time, against the DFMA peak measured in this run.
+* `roofline` FP64 FMA pipe: algorithmic flops (66.9 kflop per PMPC interior-point iteration + 4.7 kflop for the
+             corrector's second solve, x the iterations actually taken) / solve-kernel time, against the DFMA peak measured
+             in this run.  The predictor-corrector steps cut the iterations (9.0 -> 5.7 on average, 15 -> 10 for the slowest
+             instance), so solves/s rises while this fraction, which credits flops and not solves, does not.
 * `cpu_baseline` the oracle (oracle/ipm.py, a numpy port; NOT CasADi/IPOPT, which cannot be installed here) on a bounded
              sample of the same batch, one core.
 * `scale_sweep` (every N) BASELINE config 5: 2^20 mixed PMPC/RMPC/LMPC instances (1/3 each, re-seeded per shard),
@@ -43,7 +45,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-FLOPS_PER_ITER = {"pmpc": 66.9e3, "rmpc": 55.3e3, "lmpc": 245.7e3}      # N * (F_ric + F_dyn) per IPM iteration
+# N * (F_ric + F_dyn) per IPM iteration.  PMPC runs predictor-corrector iterations: one
+# factorisation and TWO solves, so the dense count gains the vector parts of a second sweep pair, N * [(4 n^2 + 4 n m) +
+# (2 n (n + m) + 2 n m)] = 15 * 312 = 4.7 k at n = 6, m = 2 (the monotone method's figure is 66.9 k).
+FLOPS_PER_ITER = {"pmpc": 66.9e3 + 4.68e3, "rmpc": 55.3e3, "lmpc": 245.7e3}
+if os.environ.get("DART_BARRIER_MONOTONE"):
+    FLOPS_PER_ITER["pmpc"] = 66.9e3
 PMPC_FLOPS_PER_ITER = FLOPS_PER_ITER["pmpc"]
 STATES_PER_OBJECT = 64
 SWEEP_TOTAL = 2 ** 20
@@ -711,6 +718,37 @@ def run_ours(args):
     torch.cuda.synchronize()
     launch_cfg = eng.last_launch_config()
 
+    # ---- the same batch under the monotone barrier schedule (the previous rounds' method): more iterations, each a
+    # little cheaper -- shows that the roofline fraction below fell because flops were removed, not because they got slower
+    mono = None
+    if not os.environ.get("DART_BARRIER_MONOTONE"):
+        try:
+            eng.set_barrier_strategy("monotone")
+            for _ in range(3):
+                eng.solve_device(x0_d, tg_d, aux=aux_d, u0_out=u0, J_out=J, status=st, iters=it)
+            torch.cuda.synchronize()
+            mm = []
+            for _ in range(10):
+                flush.zero_()
+                a_, b_ = _ev(torch), _ev(torch)
+                a_.record()
+                eng.solve_device(x0_d, tg_d, aux=aux_d, u0_out=u0, J_out=J, status=st, iters=it)
+                b_.record()
+                torch.cuda.synchronize()
+                mm.append(a_.elapsed_time(b_))
+            m_ms = float(np.mean(mm))
+            m_it = int(it.sum().item())
+            m_tf = m_it * 66.9e3 / (m_ms * 1e-3) / 1e12
+            mono = {"what": "same batch, dart_set_barrier_strategy(MONOTONE)", "kernel_ms": m_ms, "mean_iters": m_it / B,
+                    "solves_per_s": float((st == 0).sum().item()) / (m_ms * 1e-3), "flops_per_iteration": 66.9e3,
+                    "achieved": m_tf, "frac": m_tf / peak_tf if peak_tf else None}
+        except Exception as e:
+            mono = {"error": repr(e)[:200]}
+        finally:
+            eng.set_barrier_strategy("mehrotra")
+            eng.solve_device(x0_d, tg_d, aux=aux_d, u0_out=u0, J_out=J, status=st, iters=it)
+            torch.cuda.synchronize()
+
     # ---- roofline of the solve kernel (the only kernel of the step at N = 1)
     kern_s = kern_ms * 1e-3
     flops = iters_sum * PMPC_FLOPS_PER_ITER
@@ -721,7 +759,10 @@ def run_ours(args):
                 "peak_source": "measured in this run (dart_measure_fp64_tflops DFMA microbenchmark); MEASURED_PEAKS.json "
                                "has no FP64 entry",
                 "kernel": f"nmpc_solve_kernel<PmpcAxis,{launch_cfg['lanes']},15>", "kernel_ms": kern_ms, "algorithmic_flops_per_launch": flops,
-                "mean_iters": iters_sum / B, "note": "latency-bound: 1152 instances occupy a fraction of the SMs; see "
+                "mean_iters": iters_sum / B, "flops_per_iteration": PMPC_FLOPS_PER_ITER,
+                "barrier_strategy": "monotone" if os.environ.get("DART_BARRIER_MONOTONE") else "mehrotra predictor-corrector",
+                "monotone_variant": mono,
+                "note": "latency-bound: 1152 instances occupy a fraction of the SMs; see "
                                                       "throughput_variant for the filled-GPU figure"}
 
     cpu = None

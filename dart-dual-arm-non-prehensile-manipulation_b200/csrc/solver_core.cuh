@@ -1274,8 +1274,13 @@ struct Solver {
     // gains of one stage from the next stage's value function; also the closed-loop map
     DART_HD static void stage_gains(const StageLQ& q, double P00, double P01, double P11, double pv0, double pv1, double& K0,
                                     double& K1, double& kff, scan2::Af& f) {
+        double ihh;
+        stage_gains(q, P00, P01, P11, pv0, pv1, K0, K1, kff, f, ihh);
+    }
+    DART_HD static void stage_gains(const StageLQ& q, double P00, double P01, double P11, double pv0, double pv1, double& K0,
+                                    double& K1, double& kff, scan2::Af& f, double& ihh) {
         const double PB0 = P00 * q.B0 + P01 * q.B1, PB1 = P01 * q.B0 + P11 * q.B1;
-        const double ihh = 1.0 / (q.huu + q.B0 * PB0 + q.B1 * PB1);
+        ihh = 1.0 / (q.huu + q.B0 * PB0 + q.B1 * PB1);
         const double Pd0 = P00 * q.d0 + P01 * q.d1 + pv0, Pd1 = P01 * q.d0 + P11 * q.d1 + pv1;
         K0 = -ihh * (PB0 * q.a00 + PB1 * q.a10); K1 = -ihh * (PB0 * q.a01 + PB1 * q.a11);
         kff = -ihh * (q.gu + q.B0 * Pd0 + q.B1 * Pd1);
@@ -1351,6 +1356,141 @@ struct Solver {
             }
         }
         tl.sync();
+    }
+
+    // ---- the predictor-corrector step (see sweeps_scan_pc) with two consecutive stages per lane
+    template <class TL>
+    DART_HD static void shfl_af(const TL& tl, const scan2::Af& f, int src, scan2::Af& r) {
+        r.m00 = tl.shfl(f.m00, src); r.m01 = tl.shfl(f.m01, src); r.m10 = tl.shfl(f.m10, src); r.m11 = tl.shfl(f.m11, src);
+        r.v0 = tl.shfl(f.v0, src); r.v1 = tl.shfl(f.v1, src);
+    }
+    struct RowPC { double sl, su, zl, zu, isl, isu, ds, dzl, dzu; };
+    DART_HD void row_affine(int k, double du, double lo, double hi, RowPC& r) const {
+        const double sv = w.S[k * nr];
+        r.zl = w.ZL[k * nr]; r.zu = w.ZU[k * nr]; r.isl = w.ISL[k * nr]; r.isu = w.ISU[k * nr];
+        r.sl = sv - lo; r.su = hi - sv;
+        r.ds = M::row_sa(0) * du + w.RC[k * nr];
+        r.dzl = -r.zl - r.zl * r.isl * r.ds; r.dzu = -r.zu + r.zu * r.isu * r.ds;
+    }
+    template <class TL>
+    DART_HD double sweeps_scan2_pc(const TL& tl, double mu_min) {
+        static_assert(nr == 1 && m == 1 && n == 2, "predictor-corrector step: 2-state / 1-input problems with one bound row");
+        using scan2::El;
+        using scan2::Af;
+        constexpr int G = TL::kLanes;
+        const int lane = tl.lane();
+        const int kA = 2 * lane, kB = 2 * lane + 1;
+        const bool hasB = kB < N;
+        const int kBs = hasB ? kB : N - 1;                   // stage the B slot reads when it is the terminal element (unused values)
+        StageLQ sa, sb;
+        load_stage(kA, sa);
+        load_stage(kBs, sb);
+        El eA, eB;
+        stage_element(kA, sa, eA);
+        if (hasB) stage_element(kB, sb, eB); else terminal_element(eB);
+        El t;
+        scan2::combine(eA, eB, t);
+        DART_UNROLL for (int off = 1; off < G; off <<= 1) {
+            El r;
+            shfl_el(tl, t, (lane + off) & (G - 1), r);
+            if (lane + off < G) {
+                if (2 * off >= G) scan2::combine_jq(t, r, t.j00, t.j01, t.j11, t.q0, t.q1);
+                else scan2::combine(t, r, t);
+            }
+        }
+        const int nxt = (lane + 1) & (G - 1), prv = (lane - 1) & (G - 1);
+        const bool last = lane == G - 1;
+        El nx;
+        shfl_el(tl, t, nxt, nx);
+        double Pa00 = eB.j00, Pa01 = eB.j01, Pa11 = eB.j11, pa0 = eB.q0, pa1 = eB.q1;
+        if (hasB) scan2::combine_jq(eB, nx, Pa00, Pa01, Pa11, pa0, pa1);
+        double KA0, KA1, kfA, ihA, KB0 = 0.0, KB1 = 0.0, kfB = 0.0, ihB = 0.0;
+        Af fA, fB;
+        stage_gains(sa, Pa00, Pa01, Pa11, pa0, pa1, KA0, KA1, kfA, fA, ihA);
+        if (hasB) stage_gains(sb, nx.j00, nx.j01, nx.j11, nx.q0, nx.q1, KB0, KB1, kfB, fB, ihB);
+        else { fB.m00 = 1.0; fB.m01 = 0.0; fB.m10 = 0.0; fB.m11 = 1.0; fB.v0 = 0.0; fB.v1 = 0.0; }
+        Af F;
+        scan2::compose(fB, fA, F);
+        DART_UNROLL for (int off = 1; off < G; off <<= 1) {
+            Af r;
+            shfl_af(tl, F, (lane - off) & (G - 1), r);
+            if (lane >= off) scan2::compose(F, r, F);
+        }
+        double xa0 = tl.shfl(F.v0, prv), xa1 = tl.shfl(F.v1, prv);          // predictor dx at stage kA
+        if (lane == 0) { xa0 = 0.0; xa1 = 0.0; }
+        const double xb0 = fA.m00 * xa0 + fA.m01 * xa1 + fA.v0, xb1 = fA.m10 * xa0 + fA.m11 * xa1 + fA.v1;
+        const double duA = KA0 * xa0 + KA1 * xa1 + kfA, duB = KB0 * xb0 + KB1 * xb1 + kfB;
+        // ---- predictor's slack / multiplier steps, longest steps, complementarity left
+        double lo, hi;
+        M::bounds(prm, 0, lo, hi);
+        RowPC ra, rb;
+        row_affine(kA, duA, lo, hi, ra);
+        row_affine(kBs, duB, lo, hi, rb);
+        double rp = dmax(-ra.ds * ra.isl, ra.ds * ra.isu), rd = dmax(-ra.dzl / ra.zl, -ra.dzu / ra.zu);
+        double comp = ra.zl * ra.sl + ra.zu * ra.su;
+        if (hasB) {
+            rp = dmax(rp, dmax(-rb.ds * rb.isl, rb.ds * rb.isu));
+            rd = dmax(rd, dmax(-rb.dzl / rb.zl, -rb.dzu / rb.zu));
+            comp += rb.zl * rb.sl + rb.zu * rb.su;
+        }
+        rp = tl.max(dmax(rp, 0.0));
+        rd = tl.max(dmax(rd, 0.0));
+        comp = tl.sum(comp);
+        const double apa = (rp > 1.0) ? 1.0 / rp : 1.0, ada = (rd > 1.0) ? 1.0 / rd : 1.0;
+        double caff = (ra.sl + apa * ra.ds) * (ra.zl + ada * ra.dzl) + (ra.su - apa * ra.ds) * (ra.zu + ada * ra.dzu);
+        if (hasB) caff += (rb.sl + apa * rb.ds) * (rb.zl + ada * rb.dzl) + (rb.su - apa * rb.ds) * (rb.zu + ada * rb.dzu);
+        caff = tl.sum(caff);
+        const double ratio = caff / comp;
+        const double sigma = dmin(1.0, dmax(1e-8, ratio * ratio * ratio));
+        const double mu = dmax(mu_min, sigma * comp * (0.5 / (double)N));
+        // ---- corrector
+        const double clA = ra.ds * ra.dzl, cuA = ra.ds * ra.dzu, clB = rb.ds * rb.dzl, cuB = rb.ds * rb.dzu;
+        const double dgA = M::row_sa(0) * ((mu + cuA) * ra.isu - (mu - clA) * ra.isl);
+        const double dgB = hasB ? M::row_sa(0) * ((mu + cuB) * rb.isu - (mu - clB) * rb.isl) : 0.0;
+        // backward: p -> Phi' p + K' dg per stage; the lane's map applies stage kB first, then kA
+        Af bA, bB, bt;
+        bA.m00 = fA.m00; bA.m01 = fA.m10; bA.m10 = fA.m01; bA.m11 = fA.m11; bA.v0 = KA0 * dgA; bA.v1 = KA1 * dgA;
+        bB.m00 = fB.m00; bB.m01 = fB.m10; bB.m10 = fB.m01; bB.m11 = fB.m11; bB.v0 = KB0 * dgB; bB.v1 = KB1 * dgB;
+        scan2::compose(bA, bB, bt);
+        DART_UNROLL for (int off = 1; off < G; off <<= 1) {
+            Af r;
+            shfl_af(tl, bt, (lane + off) & (G - 1), r);
+            if (lane + off < G) scan2::compose(bt, r, bt);
+        }
+        double q0 = tl.shfl(bt.v0, nxt), q1 = tl.shfl(bt.v1, nxt);          // dp at stage kB + 1 (0 past the horizon)
+        if (last) { q0 = 0.0; q1 = 0.0; }
+        const double dpB0 = bB.m00 * q0 + bB.m01 * q1 + bB.v0, dpB1 = bB.m10 * q0 + bB.m11 * q1 + bB.v1;   // dp at stage kB
+        const double dkB = hasB ? -ihB * (dgB + sb.B0 * q0 + sb.B1 * q1) : 0.0;
+        const double dkA = -ihA * (dgA + sa.B0 * dpB0 + sa.B1 * dpB1);
+        // forward: dx -> Phi dx + B dkff per stage
+        Af cA, cB, ct;
+        cA.m00 = fA.m00; cA.m01 = fA.m01; cA.m10 = fA.m10; cA.m11 = fA.m11; cA.v0 = sa.B0 * dkA; cA.v1 = sa.B1 * dkA;
+        cB.m00 = fB.m00; cB.m01 = fB.m01; cB.m10 = fB.m10; cB.m11 = fB.m11; cB.v0 = hasB ? sb.B0 * dkB : 0.0; cB.v1 = hasB ? sb.B1 * dkB : 0.0;
+        scan2::compose(cB, cA, ct);
+        DART_UNROLL for (int off = 1; off < G; off <<= 1) {
+            Af r;
+            shfl_af(tl, ct, (lane - off) & (G - 1), r);
+            if (lane >= off) scan2::compose(ct, r, ct);
+        }
+        double ya0 = tl.shfl(ct.v0, prv), ya1 = tl.shfl(ct.v1, prv);        // correction of dx at stage kA
+        if (lane == 0) { ya0 = 0.0; ya1 = 0.0; w.DX[0] = 0.0; w.DX[1] = 0.0; }
+        const double yb0 = cA.m00 * ya0 + cA.m01 * ya1 + cA.v0, yb1 = cA.m10 * ya0 + cA.m11 * ya1 + cA.v1;
+        w.DU[kA] = duA + KA0 * ya0 + KA1 * ya1 + dkA;
+        w.DX[kB * n + 0] = xb0 + yb0; w.DX[kB * n + 1] = xb1 + yb1;
+        CL()[kA] = clA; CU()[kA] = cuA;
+        if (hasB) {
+            w.PP[kB * nps + 0] = Pa00; w.PP[kB * nps + 1] = Pa01; w.PP[kB * nps + 2] = Pa11;
+            w.PV[kB * n + 0] = pa0 + dpB0; w.PV[kB * n + 1] = pa1 + dpB1;
+            w.DU[kB] = duB + KB0 * yb0 + KB1 * yb1 + dkB;
+            w.DX[(kB + 1) * n + 0] = F.v0 + ct.v0; w.DX[(kB + 1) * n + 1] = F.v1 + ct.v1;
+            CL()[kB] = clB; CU()[kB] = cuB;
+            if (kB + 1 < N) {
+                w.PP[(kB + 1) * nps + 0] = nx.j00; w.PP[(kB + 1) * nps + 1] = nx.j01; w.PP[(kB + 1) * nps + 2] = nx.j11;
+                w.PV[(kB + 1) * n + 0] = nx.q0 + q0; w.PV[(kB + 1) * n + 1] = nx.q1 + q1;
+            }
+        }
+        tl.sync();
+        return mu;
     }
 
     // ---- slack steps, step-length limits, directional derivative, then the dual step z += ad dz (stage-parallel).
@@ -1556,7 +1696,7 @@ struct Solver {
         // sub-warp tiles whose warp runs ONE instruction stream (collectives with a constant full-warp mask)
         constexpr bool kLock = T::kLockstep && T::kLanes < 32;
         // Mehrotra predictor-corrector instead of the monotone barrier schedule: where the step is built by sweeps_scan_pc
-        constexpr bool kPC = kScan && M::MEHROTRA && T::kLanes == NC + 1;
+        constexpr bool kPC = kScan && M::MEHROTRA;
         const bool pc = kPC && o.mehrotra != 0;
         static_assert(!kLock || kScan || !M::SERIAL_RICCATI, "lockstep tiles need the scan sweeps or the tiled Riccati sweep");
 #ifdef DART_PHASE_CLOCK
@@ -1616,7 +1756,8 @@ struct Solver {
                 if constexpr (kPC) {
                     if (pc) {
                         prep(0.0);                                   // affine-scaling right-hand side
-                        const double mu_new = sweeps_scan_pc(tile, mu_min);
+                        double mu_new;
+                        if constexpr (T::kLanes == NC + 1) mu_new = sweeps_scan_pc(tile, mu_min); else mu_new = sweeps_scan2_pc(tile, mu_min);
                         if (!ghost) mu = mu_new;
                         stepped = true;
                     }
