@@ -134,7 +134,7 @@ extern "C" int dart_set_mu_init(dart_handle h, double mu_init) {
 }
 
 extern "C" int dart_set_barrier_strategy(dart_handle h, int32_t strategy) {
-    if (!h || (strategy != DART_BARRIER_MONOTONE && strategy != DART_BARRIER_MEHROTRA)) return DART_ERR_ARG;
+    if (!h || (strategy != DART_BARRIER_MONOTONE && strategy != DART_BARRIER_MEHROTRA && strategy != DART_BARRIER_AUTO)) return DART_ERR_ARG;
     h->barrier = strategy;
     h->opts.mehrotra = strategy;
     return DART_OK;

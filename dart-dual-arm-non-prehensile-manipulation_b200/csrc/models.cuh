@@ -137,6 +137,7 @@ DART_HD void rk4_sens(const typename Md::Prm& p, const double* x, const double* 
 struct PmpcAxis {
     static constexpr int NX = 2, NU = 1, NR = 1, NP = 2, NAUG = 0, NAXIS = 2;
     static constexpr bool MEHROTRA = true;      // Solver::sweeps_scan_pc (solver_core.cuh)
+    static constexpr bool PC_DEFAULT = true;    // DART_BARRIER_AUTO: 9.0 -> 5.7 iterations, 0.082 -> 0.068 ms at the headline batch
     static constexpr bool SERIAL_RICCATI = true;
     // structure the serial sweep may rely on: the position does not enter the dynamics, so column 0 of the RK4
     // sensitivity A is exactly e_0
@@ -203,7 +204,10 @@ struct PmpcAxis {
 // =============================================================================================== RMPC
 struct Rmpc {
     static constexpr int NX = 6, NU = 2, NR = 6, NP = 4, NAUG = 2, NAXIS = 1;
-    static constexpr bool MEHROTRA = false;
+    static constexpr bool MEHROTRA = true;       // Solver::pc_rows + corrector_tile (solver_core.cuh)
+    // DART_BARRIER_AUTO: 12.95 -> 9.43 iterations, but each costs 37 % more (the corrector's two vector sweeps against an
+    // 11.5 k-instruction iteration): 1.45 ms either way at 4096 instances, so the monotone schedule stays the default
+    static constexpr bool PC_DEFAULT = false;
     static constexpr bool SERIAL_RICCATI = false;
     DART_HD static constexpr int a_kind(int, int) { return 0; }
     // rows 0 and 2 are the kinematic unit rows (p' = v); rows 1 and 3 are dense; u_j enters the acceleration of axis j only
@@ -291,7 +295,8 @@ struct Rmpc {
 // =============================================================================================== LMPC
 struct LmpcAxis {
     static constexpr int NX = 5, NU = 1, NR = 1, NP = 4, NAUG = 1, NAXIS = 2;
-    static constexpr bool MEHROTRA = false;
+    static constexpr bool MEHROTRA = true;       // Solver::pc_rows + corrector_tile (solver_core.cuh)
+    static constexpr bool PC_DEFAULT = true;     // DART_BARRIER_AUTO: 10.8 -> 7.2 iterations, each 29 % dearer: 5.99 -> 5.18 ms at 16 384
     static constexpr bool SERIAL_RICCATI = false;   // measured: the tiled sweep is 1.3-2x faster than the per-lane one at n = 5
     DART_HD static constexpr int a_kind(int, int) { return 0; }
     // rows 0 and 2 kinematic; row 1 (translation) does not see the angle, row 3 (rotation) does not see the position

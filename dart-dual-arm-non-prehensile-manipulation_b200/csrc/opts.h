@@ -15,8 +15,9 @@ inline void fill_opts(const dart_cfg& c, SolverOpts& o) {
     o.max_backtrack = 12;
     o.acc_tol = c.acceptable_tol;
     o.acc_iter = (c.acceptable_iter > 0 && c.acceptable_tol > 0) ? c.acceptable_iter : 0;
-    // barrier strategy (IPOPT's mu_strategy): predictor-corrector where the kernel has it (PMPC axis problems on the scan
-    // path), the monotone schedule elsewhere; DART_BARRIER_MONOTONE=1 or dart_set_barrier_strategy select the monotone one
-    o.mehrotra = getenv("DART_BARRIER_MONOTONE") ? 0 : 1;
+    // barrier strategy (IPOPT's mu_strategy), dart_set_barrier_strategy: 2 = DART_BARRIER_AUTO (per method, what measured faster:
+    // Model::PC_DEFAULT), 1 = predictor-corrector wherever the kernel has it, 0 = monotone schedule.  The environment
+    // variables DART_BARRIER_MONOTONE=1 / DART_BARRIER_MEHROTRA=1 change the default of new handles (A/B runs, host tests).
+    o.mehrotra = getenv("DART_BARRIER_MONOTONE") ? 0 : (getenv("DART_BARRIER_MEHROTRA") ? 1 : 2);
 }
 }  // namespace dart

@@ -959,7 +959,9 @@ struct Solver {
     // forms row a of dx_{k+1} = A dx + B du + d, and the rows are exchanged by shuffles -- per stage one n-deep and one
     // m-deep FMA chain plus a shuffle instead of the whole stage in one lane.  Needs at least n lanes.  (Measured: forming
     // the closed-loop row A + B K off the chain instead costs 12 more FMAs per stage and is 3 % slower.)
-    template <class TL>
+    // CORR: the corrector's recursion (corrector_tile) -- feed-forward terms from KFF as rewritten by it, no defects, and
+    // the result is ADDED to the predictor's step in DX / DU.
+    template <class TL, bool CORR = false>
     DART_HD void forward_tile(const TL& tl) {
         const int lane = tl.lane();
         const int a = lane < n ? lane : n - 1;               // lanes >= n shadow the last row (no stores)
@@ -969,7 +971,7 @@ struct Solver {
         DART_UNROLL for (int j = 0; j < m; ++j) sel[j] = (M::NAUG > 0 && a - np == j) ? 1.0 : 0.0;
         double dx[n];
         DART_UNROLL for (int i = 0; i < n; ++i) dx[i] = 0.0;
-        if (lane < n) w.DX[lane] = 0.0;
+        if (!CORR && lane < n) w.DX[lane] = 0.0;
         // stage data is loaded one stage ahead: it does not depend on dx, only the FMA chain and the shuffle do
         double Kc[m * n], kc[m], Ar[np], Br[m], dc;
         auto load = [&](int k, double* K_, double* k_, double* A_, double* B_, double& d_) {
@@ -978,7 +980,7 @@ struct Solver {
             DART_UNROLL for (int j = 0; j < m; ++j) k_[j] = w.KFF[k * m + j];
             DART_UNROLL for (int i = 0; i < np; ++i) A_[i] = w.A[k * sA + W::aidx(ap, i)];
             DART_UNROLL for (int j = 0; j < m; ++j) B_[j] = w.Bm[k * sB + W::bidx(ap, j)];
-            d_ = w.D[k * sD + a];
+            d_ = CORR ? 0.0 : w.D[k * sD + a];
         };
         load(0, Kc, kc, Ar, Br, dc);
         for (int k = 0; k < N; ++k) {
@@ -994,13 +996,184 @@ struct Solver {
             DART_UNROLL for (int i = 0; i < np; ++i) vp += Ar[i] * dx[i];
             DART_UNROLL for (int j = 0; j < m; ++j) { vp += Br[j] * du[j]; va += sel[j] * du[j]; }
             const double v = (M::NAUG > 0 && !phys) ? va : vp;
-            if (lane < n) w.DX[(k + 1) * n + lane] = v;
-            if (lane == 0) { DART_UNROLL for (int j = 0; j < m; ++j) w.DU[k * m + j] = du[j]; }
+            if (CORR) {
+                if (lane < n) w.DX[(k + 1) * n + lane] += v;
+                if (lane == 0) { DART_UNROLL for (int j = 0; j < m; ++j) w.DU[k * m + j] += du[j]; }
+            } else {
+                if (lane < n) w.DX[(k + 1) * n + lane] = v;
+                if (lane == 0) { DART_UNROLL for (int j = 0; j < m; ++j) w.DU[k * m + j] = du[j]; }
+            }
             DART_UNROLL for (int i = 0; i < n; ++i) dx[i] = tl.shfl(v, i);
             DART_UNROLL for (int i = 0; i < m * n; ++i) Kc[i] = Kn[i];
             DART_UNROLL for (int j = 0; j < m; ++j) { kc[j] = kn[j]; Br[j] = Bn[j]; }
             DART_UNROLL for (int i = 0; i < np; ++i) Ar[i] = An[i];
             dc = dn;
+        }
+    }
+
+    // ---- Mehrotra predictor-corrector step for the models whose Riccati sweep runs across the tile (the scan path has its
+    // own: sweeps_scan_pc).  The predictor is the ordinary sweep pair on the affine-scaling right-hand side (prep(0)).
+    // pc_rows(): the predictor's slack / multiplier steps, its longest steps, mu = sigma * mean(z s) with
+    // sigma = (mean after the longest affine step / mean)^3 (oracle/ipm.py, Options.mehrotra), and the CHANGE of the stage
+    // gradients that the corrector's complementarity target (s + ds)(z + dz) = mu - ds_a dz_a makes against the
+    // predictor's; it goes into GR (free after the backward sweep), the predictor's row steps into DS (post() reads them).
+    DART_HD double pc_rows(double mu_min, double inv_pairs) {
+        double rp = 0.0, rd = 0.0, comp = 0.0;
+        for (int k = tile.lane(); k < N; k += tile.size()) {
+            DART_UNROLL for (int r = 0; r < nr; ++r) {
+                if (masked(k, r)) { w.DS[k * nr + r] = 0.0; continue; }
+                const int ia = M::row_ia(r), ib = M::row_ib(r);
+                double dy = M::row_sa(r) * ((ia < n) ? w.DX[k * n + ia] : w.DU[k * m + (ia - n)]);
+                if (ib >= 0) dy += M::row_sb(r) * ((ib < n) ? w.DX[k * n + ib] : w.DU[k * m + (ib - n)]);
+                const double dsa = dy + w.RC[k * nr + r];
+                const double isl = w.ISL[k * nr + r], isu = w.ISU[k * nr + r];
+                double lo, hi;
+                M::bounds(prm, r, lo, hi);
+                const double sv = w.S[k * nr + r];
+                w.DS[k * nr + r] = dsa;
+                rp = dmax(rp, dmax(-dsa * isl, dsa * isu));
+                rd = dmax(rd, dmax(1.0 + isl * dsa, 1.0 - isu * dsa));          // -dz_l / z_l, -dz_u / z_u of the predictor
+                comp += w.ZL[k * nr + r] * (sv - lo) + w.ZU[k * nr + r] * (hi - sv);
+            }
+        }
+        rp = tile.max_nonneg(rp);
+        rd = tile.max_nonneg(rd);
+        comp = tile.sum(comp);
+        const double apa = (rp > 1.0) ? 1.0 / rp : 1.0, ada = (rd > 1.0) ? 1.0 / rd : 1.0;
+        double caff = 0.0;
+        for (int k = tile.lane(); k < N; k += tile.size()) {
+            DART_UNROLL for (int r = 0; r < nr; ++r) {
+                if (masked(k, r)) continue;
+                const double dsa = w.DS[k * nr + r];
+                const double zl = w.ZL[k * nr + r], zu = w.ZU[k * nr + r];
+                double lo, hi;
+                M::bounds(prm, r, lo, hi);
+                const double sv = w.S[k * nr + r];
+                const double dzl = -zl - zl * w.ISL[k * nr + r] * dsa, dzu = -zu + zu * w.ISU[k * nr + r] * dsa;
+                caff += ((sv - lo) + apa * dsa) * (zl + ada * dzl) + ((hi - sv) - apa * dsa) * (zu + ada * dzu);
+            }
+        }
+        caff = tile.sum(caff);
+        const double ratio = caff / comp;
+        const double sigma = dmin(1.0, dmax(1e-8, ratio * ratio * ratio));
+        const double mu = dmax(mu_min, sigma * comp * inv_pairs);
+        for (int k = tile.lane(); k < N; k += tile.size()) {
+            double g[ny];
+            DART_UNROLL for (int i = 0; i < ny; ++i) g[i] = 0.0;
+            DART_UNROLL for (int r = 0; r < nr; ++r) {
+                if (masked(k, r)) continue;
+                const double dsa = w.DS[k * nr + r];
+                const double isl = w.ISL[k * nr + r], isu = w.ISU[k * nr + r];
+                const double zl = w.ZL[k * nr + r], zu = w.ZU[k * nr + r];
+                const double cl = dsa * (-zl - zl * isl * dsa), cu = dsa * (-zu + zu * isu * dsa);
+                const double dg = (mu + cu) * isu - (mu - cl) * isl;
+                g[M::row_ia(r)] += M::row_sa(r) * dg;
+                if (M::row_ib(r) >= 0) g[M::row_ib(r) >= 0 ? M::row_ib(r) : 0] += M::row_sb(r) * dg;
+            }
+            DART_UNROLL for (int i = 0; i < ny; ++i) w.GR[k * sG + i] = g[i];
+        }
+        tile.sync();
+        return mu;
+    }
+
+    // The corrector's solve with the predictor's factorisation.  Only the stage gradients differ (dg, in GR), so with the
+    // gains K_k, the inverse pivots and the stage Jacobians the difference of the two directions is a pair of vector
+    // recursions:   backward   dm_u = dg_u + B' dp_{k+1},  dp_k = dg_x + A' dp_{k+1} + K' dm_u,  dkff_k = -Muu^-1 dm_u
+    //               forward    ddu_k = K ddx_k + dkff_k,   ddx_{k+1} = A ddx_k + B ddu_k          (forward_tile<CORR>)
+    // Lane a forms row a of dp_k (every lane forms the m entries of dm_u), rows are exchanged by shuffles as in the
+    // forward sweep.  p_k (PV) and the step (DX, DU) are updated in place; KFF is overwritten by dkff.
+    // The inverse pivots are not stored (the RMPC workspace has no room: 8 problems per SM): the stage matrix's block
+    // M[u][carried inputs] is the stored diagonal h_j = H[u_j][x_{np+j}] (tilt-rate cost and rate rows; never zero, the rate
+    // rows' barrier terms are in it), and K[:, np+j] = -Muu^-1 e_j h_j, so  -Muu^-1 dm_u = sum_j K[:, np+j] dm_u[j] / h_j.
+    // The loop leaves dm_u in KFF; feedforward() converts it stage-parallel (the divisions run once, not per stage).
+    DART_HD void feedforward() {
+        static_assert(M::NAUG == m, "the inverse pivot is recovered from the gains of the carried-input columns");
+        for (int k = tile.lane(); k < N; k += tile.size()) {
+            double sc[m], out[m];
+            DART_UNROLL for (int j = 0; j < m; ++j) sc[j] = w.KFF[k * m + j] / w.HS[k * sH + W::hslot(np + j, n + j)];
+            DART_UNROLL for (int i = 0; i < m; ++i) {
+                double acc = 0.0;
+                DART_UNROLL for (int j = 0; j < m; ++j) acc += w.K[k * sK + i * n + np + j] * sc[j];
+                out[i] = acc;
+            }
+            DART_UNROLL for (int i = 0; i < m; ++i) w.KFF[k * m + i] = out[i];
+        }
+        tile.sync();
+    }
+    template <class TL>
+    DART_HD void corrector_tile(const TL& tl) {
+        static_assert(kVec && np % 2 == 0, "corrector_tile: tiled-sweep models");
+        const int lane = tl.lane();
+        const int a = lane < n ? lane : n - 1;
+        const bool phys = a < np;
+        const int ac = phys ? a : np - 1;
+        double dp[n];
+        DART_UNROLL for (int i = 0; i < n; ++i) dp[i] = 0.0;
+        for (int k = N - 1; k >= 0; --k) {
+            double Ac[np], Bc[np * m], Kc[m], mug[m];
+            ldv<np>(&w.A[k * sA + ac * np], Ac);                 // column ac of A_k: dF_b / dx_ac
+            ldv<np * m>(&w.Bm[k * sB], Bc);                      // column-major: dF_b / du_j at [j * np + b]
+            DART_UNROLL for (int j = 0; j < m; ++j) Kc[j] = w.K[k * sK + j * n + a];
+            double t = w.GR[k * sG + a];
+            DART_UNROLL for (int j = 0; j < m; ++j) {
+                // two short chains per entry
+                double s0 = w.GR[k * sG + n + j] + dp[np + j];   // carried-input rows: B = identity
+                double s1 = Bc[j * np + np / 2] * dp[np / 2];
+                DART_UNROLL for (int b = 0; b < np / 2; ++b) s0 += Bc[j * np + b] * dp[b];
+                DART_UNROLL for (int b = np / 2 + 1; b < np; ++b) s1 += Bc[j * np + b] * dp[b];
+                mug[j] = s0 + s1;
+            }
+            if (phys) { DART_UNROLL for (int b = 0; b < np; ++b) t += Ac[b] * dp[b]; }
+            double v = t;
+            DART_UNROLL for (int j = 0; j < m; ++j) v += Kc[j] * mug[j];
+            if (lane == 0) { DART_UNROLL for (int j = 0; j < m; ++j) w.KFF[k * m + j] = mug[j]; }
+            if (lane < n && k > 0) w.PV[k * n + lane] += v;
+            DART_UNROLL for (int i = 0; i < n; ++i) dp[i] = tl.shfl(v, i);
+        }
+        tl.sync();
+        feedforward();
+        forward_tile<TL, true>(tl);
+    }
+
+    // the same recursions by one lane in plain loops (tiles narrower than the state, and the host build's 1-lane tile)
+    DART_HD void corrector_serial_backward() {
+        double dp[n];
+        DART_UNROLL for (int i = 0; i < n; ++i) dp[i] = 0.0;
+        for (int k = N - 1; k >= 0; --k) {
+            double mug[m], v[n];
+            for (int j = 0; j < m; ++j) {
+                double acc = w.GR[k * sG + n + j];
+                for (int b = 0; b < n; ++b) acc += Bat(k, b, j) * dp[b];
+                mug[j] = acc;
+            }
+            for (int i = 0; i < n; ++i) {
+                double acc = w.GR[k * sG + i];
+                for (int b = 0; b < n; ++b) acc += Aat(k, b, i) * dp[b];
+                for (int j = 0; j < m; ++j) acc += w.K[k * sK + j * n + i] * mug[j];
+                v[i] = acc;
+            }
+            for (int j = 0; j < m; ++j) w.KFF[k * m + j] = mug[j];
+            for (int i = 0; i < n; ++i) { if (k > 0) w.PV[k * n + i] += v[i]; dp[i] = v[i]; }
+        }
+    }
+    DART_HD void corrector_serial_forward() {
+        double dx[n];
+        DART_UNROLL for (int i = 0; i < n; ++i) dx[i] = 0.0;
+        for (int k = 0; k < N; ++k) {
+            double du[m], nx[n];
+            for (int j = 0; j < m; ++j) {
+                double acc = w.KFF[k * m + j];
+                for (int i = 0; i < n; ++i) acc += w.K[k * sK + j * n + i] * dx[i];
+                du[j] = acc;
+                w.DU[k * m + j] += acc;
+            }
+            for (int b = 0; b < n; ++b) {
+                double acc = 0.0;
+                for (int i = 0; i < n; ++i) acc += Aat(k, b, i) * dx[i];
+                for (int j = 0; j < m; ++j) acc += Bat(k, b, j) * du[j];
+                nx[b] = acc;
+            }
+            for (int b = 0; b < n; ++b) { dx[b] = nx[b]; w.DX[(k + 1) * n + b] += nx[b]; }
         }
     }
 
@@ -1513,7 +1686,20 @@ struct Solver {
                 const double ds = dy + w.RC[k * nr + r];
                 const double isl = w.ISL[k * nr + r], isu = w.ISU[k * nr + r];
                 const double zl = w.ZL[k * nr + r], zu = w.ZU[k * nr + r];
-                const double ml = pc ? mu - CL()[k * nr + r] : mu, mu_u = pc ? mu + CU()[k * nr + r] : mu;
+                double ml = mu, mu_u = mu;
+                if (pc) {
+                    if constexpr (kVec) {
+                        // tiled path (pc_rows): DS holds the predictor's row step; it moves to RC, which is dead until
+                        // the line search's eval1 rewrites it, for the second pass below
+                        const double dsa = w.DS[k * nr + r];
+                        w.RC[k * nr + r] = dsa;
+                        ml = mu - dsa * (-zl - zl * isl * dsa);
+                        mu_u = mu + dsa * (-zu + zu * isu * dsa);
+                    } else {
+                        ml = mu - CL()[k * nr + r];
+                        mu_u = mu + CU()[k * nr + r];
+                    }
+                }
                 const double dzl = ml * isl - zl - zl * isl * ds;
                 const double dzu = mu_u * isu - zu + zu * isu * ds;
                 w.DS[k * nr + r] = ds;
@@ -1544,7 +1730,17 @@ struct Solver {
                 const double ds = w.DS[k * nr + r];
                 const double isl = w.ISL[k * nr + r], isu = w.ISU[k * nr + r];
                 const double zl = w.ZL[k * nr + r], zu = w.ZU[k * nr + r];
-                const double ml = pc ? mu - CL()[k * nr + r] : mu, mu_u = pc ? mu + CU()[k * nr + r] : mu;
+                double ml = mu, mu_u = mu;
+                if (pc) {
+                    if constexpr (kVec) {
+                        const double dsa = w.RC[k * nr + r];
+                        ml = mu - dsa * (-zl - zl * isl * dsa);
+                        mu_u = mu + dsa * (-zu + zu * isu * dsa);
+                    } else {
+                        ml = mu - CL()[k * nr + r];
+                        mu_u = mu + CU()[k * nr + r];
+                    }
+                }
                 w.ZL[k * nr + r] = zl + ad_ * (ml * isl - zl - zl * isl * ds);
                 w.ZU[k * nr + r] = zu + ad_ * (mu_u * isu - zu + zu * isu * ds);
             }
@@ -1696,8 +1892,22 @@ struct Solver {
         // sub-warp tiles whose warp runs ONE instruction stream (collectives with a constant full-warp mask)
         constexpr bool kLock = T::kLockstep && T::kLanes < 32;
         // Mehrotra predictor-corrector instead of the monotone barrier schedule: where the step is built by sweeps_scan_pc
-        constexpr bool kPC = kScan && M::MEHROTRA;
-        const bool pc = kPC && o.mehrotra != 0;
+        // (kPCT: the tiled-sweep models -- ordinary sweeps on the affine-scaling right-hand side, then pc_rows + corrector_*)
+        constexpr bool kPCT = kVec && M::MEHROTRA;
+        constexpr bool kPC = (kScan || kPCT) && M::MEHROTRA;
+        const bool pc = kPC && (o.mehrotra == 1 || (o.mehrotra == 2 && M::PC_DEFAULT));      // 2: DART_BARRIER_AUTO
+        auto corrector = [&]() {
+            if constexpr (kPCT) {
+                if constexpr (T::kLanes >= n) corrector_tile(tile);
+                else {
+                    if (tile.lane() == 0) corrector_serial_backward();
+                    tile.sync();
+                    feedforward();
+                    if (tile.lane() == 0) corrector_serial_forward();
+                }
+                tile.sync();
+            }
+        };
         static_assert(!kLock || kScan || !M::SERIAL_RICCATI, "lockstep tiles need the scan sweeps or the tiled Riccati sweep");
 #ifdef DART_PHASE_CLOCK
         long long ckA = 0, ckB = 0, ckC = 0, ckBb = 0, ckC1 = 0, ckC2 = 0, ckA1 = 0, ckW1 = 0, ckW2 = 0, ck0 = DART_CLOCK();
@@ -1738,7 +1948,7 @@ struct Solver {
                     DART_CK(ckA1)
                     need_sweep = true;
                     if constexpr (!kLock) {
-                        prep(mu);
+                        prep((kPCT && pc) ? 0.0 : mu);
                         if (!M::SERIAL_RICCATI) backward(tile);
                     }
                 }
@@ -1753,7 +1963,7 @@ struct Solver {
                 if (tile.warp_ballot(need_sweep) == 0u) break;
                 ghost = !need_sweep;
                 bool stepped = false;
-                if constexpr (kPC) {
+                if constexpr (kPC && kScan) {
                     if (pc) {
                         prep(0.0);                                   // affine-scaling right-hand side
                         double mu_new;
@@ -1762,7 +1972,7 @@ struct Solver {
                         stepped = true;
                     }
                 }
-                if (!stepped) prep(mu);
+                if (!stepped) prep((kPCT && pc) ? 0.0 : mu);
                 DART_CK(ckW1)
                 if constexpr (kScan) {
                     if (!stepped) { if constexpr (T::kLanes == NC + 1) sweeps_scan(tile); else sweeps_scan2(tile); }
@@ -1771,6 +1981,13 @@ struct Solver {
                     if (T::kLanes >= n) forward_tile(tile);
                     else if (tile.lane() == 0) forward();
                     tile.sync();
+                    if constexpr (kPCT) {
+                        if (pc) {
+                            const double mu_new = pc_rows(mu_min, inv_nc);
+                            if (!ghost) mu = mu_new;
+                            corrector();
+                        }
+                    }
                 }
                 DART_CK(ckB)
             } else if (M::SERIAL_RICCATI) {
@@ -1803,6 +2020,12 @@ struct Solver {
                 if (T::kLanes >= n) forward_tile(tile);
                 else if (tile.lane() == 0) forward();
                 tile.sync();
+                if constexpr (kPCT) {
+                    if (pc) {
+                        mu = pc_rows(mu_min, inv_nc);
+                        corrector();
+                    }
+                }
                 DART_CK(ckB)
             }
             // ---------------- phase C

@@ -45,9 +45,10 @@ class NMPCEngine:
         check(self._lib.dart_set_mu_init(self._h, float(mu_init)), "dart_set_mu_init")
 
     def set_barrier_strategy(self, strategy):
-        """'mehrotra' (default: predictor-corrector where the kernel has it, i.e. PMPC at the reference horizon) or
-        'monotone' (IPOPT's default schedule for every method); see dart_set_barrier_strategy."""
-        code = {"monotone": 0, "mehrotra": 1}[strategy]
+        """'auto' (default: per method, the strategy measured faster -- predictor-corrector for PMPC / LMPC, monotone for
+        RMPC), 'mehrotra' (predictor-corrector wherever the kernel has it) or 'monotone' (IPOPT's default schedule for every
+        method); see dart_set_barrier_strategy."""
+        code = {"monotone": 0, "mehrotra": 1, "auto": 2}[strategy]
         check(self._lib.dart_set_barrier_strategy(self._h, code), "dart_set_barrier_strategy")
 
     @property

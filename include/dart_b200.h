@@ -91,12 +91,16 @@ int dart_set_mu_init(dart_handle h, double mu_init);
 
 /* Barrier-parameter strategy of the solves that follow (IPOPT's `mu_strategy`; the reference leaves IPOPT's default,
  * "monotone", at mpc_3d.py:82 -- the strategy changes the iterate path, not the KKT point a solve converges to).
- * DART_BARRIER_MEHROTRA (the default): predictor-corrector steps with an adaptive barrier parameter where the kernel
- * implements them -- the PMPC axis problems at the reference horizon -- and the monotone schedule everywhere else;
- * DART_BARRIER_MONOTONE: Fiacco-McCormick schedule (mu0 = mu_init, kappa_mu 0.2, theta_mu 1.5) for every method.
- * The environment variable DART_BARRIER_MONOTONE=1 makes monotone the default of new handles. */
+ * DART_BARRIER_MEHROTRA: Mehrotra predictor-corrector steps with an adaptive barrier parameter wherever the kernel
+ * implements them -- PMPC axis problems at the reference horizon (scan sweeps), RMPC and LMPC (tiled sweeps; the corrector
+ * re-uses the Riccati factorisation, two extra vector sweeps) -- and the monotone schedule elsewhere;
+ * DART_BARRIER_MONOTONE: Fiacco-McCormick schedule (mu0 = mu_init, kappa_mu 0.2, theta_mu 1.5) for every method;
+ * DART_BARRIER_AUTO (the default of a new handle): per method, the one measured faster on B200 -- predictor-corrector
+ * for PMPC and LMPC, monotone for RMPC (fewer iterations, but the same time per solve).
+ * The environment variables DART_BARRIER_MONOTONE=1 / DART_BARRIER_MEHROTRA=1 change the default of new handles. */
 #define DART_BARRIER_MONOTONE 0
 #define DART_BARRIER_MEHROTRA 1
+#define DART_BARRIER_AUTO 2
 int dart_set_barrier_strategy(dart_handle h, int32_t strategy);
 
 /* Dual warm start for closed loops (IPOPT's warm_start_init_point with lam_x0 / lam_g0, which the reference passes

@@ -169,6 +169,7 @@ def solve(prob: StageProblem, X0=None, U0=None, opts: Options = None, trace=None
         lam = np.where(v[:, None, None], warm["lam"], lam)
     iters = np.zeros(B, dtype=np.int32)
     tiny = np.zeros(B, dtype=np.int32)
+    ls_evals = np.zeros(B, dtype=np.int64)     # trial points evaluated by the line searches (cost statistics for the tools)
     done = np.zeros(B, dtype=bool)
     nv = N * (m + n)
     ne = N * n
@@ -355,6 +356,7 @@ def solve(prob: StageProblem, X0=None, U0=None, opts: Options = None, trace=None
         alpha = ap.copy()
         accepted = done.copy()
         for _ in range(o.max_backtrack):
+            ls_evals += ~accepted
             a3 = alpha[:, None, None]
             Xt, Ut, st = X + a3 * dX, U + a3 * dU, s + a3 * ds
             phit, tht = barrier_obj(Xt, Ut, st)
@@ -391,4 +393,4 @@ def solve(prob: StageProblem, X0=None, U0=None, opts: Options = None, trace=None
 
     status = np.where(infeasible0 & (status != STATUS_NUMERIC), STATUS_INFEASIBLE, status)
     return dict(X=X, U=U, J=prob.objective(X, U), status=status, iters=iters, lam=lam, zl=zl, zu=zu, s=s,
-                kkt=kkt_final, mu=mu)
+                kkt=kkt_final, mu=mu, ls_evals=ls_evals)

@@ -140,6 +140,65 @@ def test_lmpc_lane_widths_agree(built, lanes):
     assert (np.abs(out["J"] - base["J"]) / np.abs(base["J"])).max() < 1e-8
 
 
+def test_rmpc_predictor_corrector_matches_oracle_variant(built):
+    """dart_set_barrier_strategy(MEHROTRA) on the tiled-sweep path (pc_rows + corrector_tile): RMPC is one undivided NLP
+    on both sides, so the kernel and the oracle's predictor-corrector variant take the same iterates; against the
+    monotone schedule (RMPC's default under DART_BARRIER_AUTO) the KKT points coincide in about a quarter fewer iterations."""
+    d, p = helpers.rmpc_case(256)
+    eng = dart_b200.NMPCEngine(dart_b200.rmpc_cfg(), device=0)
+    mono = eng.solve(d["x0"], d["ref"], aux=d["aux"])
+    eng.set_barrier_strategy("mehrotra")
+    out = eng.solve(d["x0"], d["ref"], aux=d["aux"])
+    ref = ipm.solve(p, opts=ipm.Options(mehrotra=1))
+    du0, dJ = helpers.assert_parity(out, ref, "rmpc predictor-corrector")
+    assert np.abs(out["iters"] - ref["iters"]).max() <= 1
+    assert np.abs(out["u0"] - ref["U"][:, 0]).max() < 1e-8
+    assert np.abs(out["u0"] - mono["u0"]).max() <= helpers.TOL_U0
+    assert (np.abs(out["J"] - mono["J"]) / np.abs(mono["J"])).max() <= helpers.TOL_J
+    assert out["iters"].mean() < 0.8 * mono["iters"].mean()
+    eng.set_barrier_strategy("auto")
+    again = eng.solve(d["x0"], d["ref"], aux=d["aux"])
+    assert np.array_equal(again["iters"], mono["iters"]) and np.array_equal(again["u0"], mono["u0"])
+
+
+@pytest.mark.parametrize("method,lanes", [("rmpc", 8), ("rmpc", 16), ("lmpc", 4), ("lmpc", 8), ("lmpc", 16)])
+def test_predictor_corrector_lane_widths_agree(built, method, lanes):
+    """Sub-warp tiles run the predictor-corrector step in lockstep with the other tiles of their warp (finished tiles as
+    ghosts); 4-lane LMPC tiles (< nx) run the corrector's recursions in one lane."""
+    case, cfg = (helpers.rmpc_case, dart_b200.rmpc_cfg) if method == "rmpc" else (helpers.lmpc_case, dart_b200.lmpc_cfg)
+    d, p = case(64)
+    outs = []
+    for ln in (0, lanes):
+        eng = dart_b200.NMPCEngine(cfg(lanes=ln), device=0)
+        eng.set_barrier_strategy("mehrotra")
+        outs.append(eng.solve(d["x0"], d["ref"], aux=d["aux"]))
+        if ln:
+            assert eng.last_launch_config()["lanes"] == lanes
+    base, out = outs
+    assert (out["status"] == 0).all() and (base["status"] == 0).all()
+    assert np.abs(out["u0"] - base["u0"]).max() < 1e-6
+    assert (np.abs(out["J"] - base["J"]) / np.abs(base["J"])).max() < 1e-8
+    assert np.abs(out["iters"] - base["iters"]).max() <= 1
+
+
+def test_lmpc_barrier_strategies_reach_the_same_kkt_points(built):
+    """LMPC's default (DART_BARRIER_AUTO) is the predictor-corrector step: same KKT points as the monotone schedule and
+    as the oracle (coupled 10-state problem, either variant), in about a third fewer iterations."""
+    d, p = helpers.lmpc_case(256)
+    outs = {}
+    for strat in ("monotone", "mehrotra", "auto"):
+        eng = dart_b200.NMPCEngine(dart_b200.lmpc_cfg(), device=0)
+        eng.set_barrier_strategy(strat)
+        outs[strat] = eng.solve(d["x0"], d["ref"], aux=d["aux"])
+    ref_pc = ipm.solve(p, opts=ipm.Options(mehrotra=1))
+    helpers.assert_parity(outs["mehrotra"], ref_pc, "lmpc predictor-corrector")
+    helpers.assert_parity(outs["monotone"], ipm.solve(p), "lmpc monotone")
+    assert np.array_equal(outs["auto"]["iters"], outs["mehrotra"]["iters"]) and np.array_equal(outs["auto"]["u0"], outs["mehrotra"]["u0"])
+    assert np.abs(outs["mehrotra"]["u0"] - outs["monotone"]["u0"]).max() <= helpers.TOL_U0
+    assert np.abs(outs["mehrotra"]["iters"] - ref_pc["iters"]).max() <= 1
+    assert outs["mehrotra"]["iters"].mean() < 0.75 * outs["monotone"]["iters"].mean()
+
+
 def test_device_pointer_entry_and_quaternion(pmpc_engine):
     import torch
     c, aux, p = helpers.pmpc_case(4)
