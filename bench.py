@@ -45,12 +45,18 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-# N * (F_ric + F_dyn) per IPM iteration.  PMPC runs predictor-corrector iterations: one
-# factorisation and TWO solves, so the dense count gains the vector parts of a second sweep pair, N * [(4 n^2 + 4 n m) +
-# (2 n (n + m) + 2 n m)] = 15 * 312 = 4.7 k at n = 6, m = 2 (the monotone method's figure is 66.9 k).
-FLOPS_PER_ITER = {"pmpc": 66.9e3 + 4.68e3, "rmpc": 55.3e3, "lmpc": 245.7e3}
+# N * (F_ric + F_dyn) per IPM iteration.  PMPC and LMPC run predictor-corrector iterations (DESIGN.md section
+# 2; RMPC stays on the monotone schedule under DART_BARRIER_AUTO): one factorisation and TWO solves, so the dense count gains
+# the vector parts of a second sweep pair, N * [(4 n^2 + 4 n m) + (2 n (n + m) + 2 n m)] = 15 * 312 = 4.7 k at n = 6, m = 2
+# (PMPC; the monotone method's figure is 66.9 k) and 20 * 760 = 15.2 k at n = 10, m = 2 (LMPC; monotone 245.7 k).
+_FLOPS_MONOTONE = {"pmpc": 66.9e3, "rmpc": 55.3e3, "lmpc": 245.7e3}
+_FLOPS_CORRECTOR = {"pmpc": 4.68e3, "rmpc": 20 * 312.0, "lmpc": 15.2e3}
+_PC = {"pmpc": True, "rmpc": False, "lmpc": True}            # Model::PC_DEFAULT (csrc/models.cuh)
 if os.environ.get("DART_BARRIER_MONOTONE"):
-    FLOPS_PER_ITER["pmpc"] = 66.9e3
+    _PC = {k: False for k in _PC}
+elif os.environ.get("DART_BARRIER_MEHROTRA"):
+    _PC = {k: True for k in _PC}
+FLOPS_PER_ITER = {k: _FLOPS_MONOTONE[k] + (_FLOPS_CORRECTOR[k] if _PC[k] else 0.0) for k in _PC}
 PMPC_FLOPS_PER_ITER = FLOPS_PER_ITER["pmpc"]
 STATES_PER_OBJECT = 64
 SWEEP_TOTAL = 2 ** 20

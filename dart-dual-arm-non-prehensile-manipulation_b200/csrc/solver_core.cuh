@@ -50,6 +50,11 @@
 #ifndef DART_TREE_SUMS
 #define DART_TREE_SUMS 1
 #endif
+// vector recursions of the tiled sweeps (forward_tile, corrector_tile): the lanes hand the new vector to each other through
+// the shared-memory copy they store anyway (1) instead of 2 n SHFL per stage (0)
+#ifndef DART_XCHG_SMEM
+#define DART_XCHG_SMEM 1
+#endif
 #ifndef DART_SWEEP_UNROLL
 #define DART_SWEEP_UNROLL 3
 #endif
@@ -959,9 +964,7 @@ struct Solver {
     // forms row a of dx_{k+1} = A dx + B du + d, and the rows are exchanged by shuffles -- per stage one n-deep and one
     // m-deep FMA chain plus a shuffle instead of the whole stage in one lane.  Needs at least n lanes.  (Measured: forming
     // the closed-loop row A + B K off the chain instead costs 12 more FMAs per stage and is 3 % slower.)
-    // CORR: the corrector's recursion (corrector_tile) -- feed-forward terms from KFF as rewritten by it, no defects, and
-    // the result is ADDED to the predictor's step in DX / DU.
-    template <class TL, bool CORR = false>
+    template <class TL>
     DART_HD void forward_tile(const TL& tl) {
         const int lane = tl.lane();
         const int a = lane < n ? lane : n - 1;               // lanes >= n shadow the last row (no stores)
@@ -971,7 +974,7 @@ struct Solver {
         DART_UNROLL for (int j = 0; j < m; ++j) sel[j] = (M::NAUG > 0 && a - np == j) ? 1.0 : 0.0;
         double dx[n];
         DART_UNROLL for (int i = 0; i < n; ++i) dx[i] = 0.0;
-        if (!CORR && lane < n) w.DX[lane] = 0.0;
+        if (lane < n) w.DX[lane] = 0.0;
         // stage data is loaded one stage ahead: it does not depend on dx, only the FMA chain and the shuffle do
         double Kc[m * n], kc[m], Ar[np], Br[m], dc;
         auto load = [&](int k, double* K_, double* k_, double* A_, double* B_, double& d_) {
@@ -980,7 +983,7 @@ struct Solver {
             DART_UNROLL for (int j = 0; j < m; ++j) k_[j] = w.KFF[k * m + j];
             DART_UNROLL for (int i = 0; i < np; ++i) A_[i] = w.A[k * sA + W::aidx(ap, i)];
             DART_UNROLL for (int j = 0; j < m; ++j) B_[j] = w.Bm[k * sB + W::bidx(ap, j)];
-            d_ = CORR ? 0.0 : w.D[k * sD + a];
+            d_ = w.D[k * sD + a];
         };
         load(0, Kc, kc, Ar, Br, dc);
         for (int k = 0; k < N; ++k) {
@@ -996,14 +999,15 @@ struct Solver {
             DART_UNROLL for (int i = 0; i < np; ++i) vp += Ar[i] * dx[i];
             DART_UNROLL for (int j = 0; j < m; ++j) { vp += Br[j] * du[j]; va += sel[j] * du[j]; }
             const double v = (M::NAUG > 0 && !phys) ? va : vp;
-            if (CORR) {
-                if (lane < n) w.DX[(k + 1) * n + lane] += v;
-                if (lane == 0) { DART_UNROLL for (int j = 0; j < m; ++j) w.DU[k * m + j] += du[j]; }
-            } else {
-                if (lane < n) w.DX[(k + 1) * n + lane] = v;
-                if (lane == 0) { DART_UNROLL for (int j = 0; j < m; ++j) w.DU[k * m + j] = du[j]; }
-            }
+            if (lane < n) w.DX[(k + 1) * n + lane] = v;
+            if (lane == 0) { DART_UNROLL for (int j = 0; j < m; ++j) w.DU[k * m + j] = du[j]; }
+#if DART_XCHG_SMEM
+            tl.sync();
+            if (n % 2 == 0) ldv<n>(&w.DX[(k + 1) * n], dx);
+            else { DART_UNROLL for (int i = 0; i < n; ++i) dx[i] = w.DX[(k + 1) * n + i]; }
+#else
             DART_UNROLL for (int i = 0; i < n; ++i) dx[i] = tl.shfl(v, i);
+#endif
             DART_UNROLL for (int i = 0; i < m * n; ++i) Kc[i] = Kn[i];
             DART_UNROLL for (int j = 0; j < m; ++j) { kc[j] = kn[j]; Br[j] = Bn[j]; }
             DART_UNROLL for (int i = 0; i < np; ++i) Ar[i] = An[i];
@@ -1077,26 +1081,27 @@ struct Solver {
     }
 
     // The corrector's solve with the predictor's factorisation.  Only the stage gradients differ (dg, in GR), so with the
-    // gains K_k, the inverse pivots and the stage Jacobians the difference of the two directions is a pair of vector
-    // recursions:   backward   dm_u = dg_u + B' dp_{k+1},  dp_k = dg_x + A' dp_{k+1} + K' dm_u,  dkff_k = -Muu^-1 dm_u
-    //               forward    ddu_k = K ddx_k + dkff_k,   ddx_{k+1} = A ddx_k + B ddu_k          (forward_tile<CORR>)
+    // gains K_k, the inverse pivots and the stage Jacobians the corrected direction costs one backward VECTOR recursion,
+    //       dm_u = dg_u + B' dp_{k+1},   dp_k = dg_x + A' dp_{k+1} + K' dm_u,   dkff_k = -Muu^-1 dm_u,
+    // and then the ordinary forward sweep again with the feed-forward terms kff + dkff (it is linear in them: the result is
+    // the corrected step itself, with plain stores -- no second code path, no read-modify-write on the sweep's chain).
     // Lane a forms row a of dp_k (every lane forms the m entries of dm_u), rows are exchanged by shuffles as in the
-    // forward sweep.  p_k (PV) and the step (DX, DU) are updated in place; KFF is overwritten by dkff.
+    // forward sweep; dp_k and dm_u go to DX / DU, which are free once pc_rows() has used the predictor's step.
     // The inverse pivots are not stored (the RMPC workspace has no room: 8 problems per SM): the stage matrix's block
     // M[u][carried inputs] is the stored diagonal h_j = H[u_j][x_{np+j}] (tilt-rate cost and rate rows; never zero, the rate
     // rows' barrier terms are in it), and K[:, np+j] = -Muu^-1 e_j h_j, so  -Muu^-1 dm_u = sum_j K[:, np+j] dm_u[j] / h_j.
-    // The loop leaves dm_u in KFF; feedforward() converts it stage-parallel (the divisions run once, not per stage).
+    // feedforward() does that and p_k += dp_k stage-parallel (the divisions run once, not once per stage of the recursion).
     DART_HD void feedforward() {
         static_assert(M::NAUG == m, "the inverse pivot is recovered from the gains of the carried-input columns");
         for (int k = tile.lane(); k < N; k += tile.size()) {
-            double sc[m], out[m];
-            DART_UNROLL for (int j = 0; j < m; ++j) sc[j] = w.KFF[k * m + j] / w.HS[k * sH + W::hslot(np + j, n + j)];
+            double sc[m];
+            DART_UNROLL for (int j = 0; j < m; ++j) sc[j] = w.DU[k * m + j] / w.HS[k * sH + W::hslot(np + j, n + j)];
             DART_UNROLL for (int i = 0; i < m; ++i) {
-                double acc = 0.0;
+                double acc = w.KFF[k * m + i];
                 DART_UNROLL for (int j = 0; j < m; ++j) acc += w.K[k * sK + i * n + np + j] * sc[j];
-                out[i] = acc;
+                w.KFF[k * m + i] = acc;
             }
-            DART_UNROLL for (int i = 0; i < m; ++i) w.KFF[k * m + i] = out[i];
+            if (k > 0) { DART_UNROLL for (int i = 0; i < n; ++i) w.PV[k * n + i] += w.DX[k * n + i]; }
         }
         tile.sync();
     }
@@ -1126,16 +1131,20 @@ struct Solver {
             if (phys) { DART_UNROLL for (int b = 0; b < np; ++b) t += Ac[b] * dp[b]; }
             double v = t;
             DART_UNROLL for (int j = 0; j < m; ++j) v += Kc[j] * mug[j];
-            if (lane == 0) { DART_UNROLL for (int j = 0; j < m; ++j) w.KFF[k * m + j] = mug[j]; }
-            if (lane < n && k > 0) w.PV[k * n + lane] += v;
+            if (lane == 0) { DART_UNROLL for (int j = 0; j < m; ++j) w.DU[k * m + j] = mug[j]; }
+            if (lane < n) w.DX[k * n + lane] = v;
+#if DART_XCHG_SMEM
+            tl.sync();
+            if (n % 2 == 0) ldv<n>(&w.DX[k * n], dp);
+            else { DART_UNROLL for (int i = 0; i < n; ++i) dp[i] = w.DX[k * n + i]; }
+#else
             DART_UNROLL for (int i = 0; i < n; ++i) dp[i] = tl.shfl(v, i);
+#endif
         }
         tl.sync();
-        feedforward();
-        forward_tile<TL, true>(tl);
     }
 
-    // the same recursions by one lane in plain loops (tiles narrower than the state, and the host build's 1-lane tile)
+    // the same recursion by one lane in plain loops (tiles narrower than the state, and the host build's 1-lane tile)
     DART_HD void corrector_serial_backward() {
         double dp[n];
         DART_UNROLL for (int i = 0; i < n; ++i) dp[i] = 0.0;
@@ -1152,28 +1161,8 @@ struct Solver {
                 for (int j = 0; j < m; ++j) acc += w.K[k * sK + j * n + i] * mug[j];
                 v[i] = acc;
             }
-            for (int j = 0; j < m; ++j) w.KFF[k * m + j] = mug[j];
-            for (int i = 0; i < n; ++i) { if (k > 0) w.PV[k * n + i] += v[i]; dp[i] = v[i]; }
-        }
-    }
-    DART_HD void corrector_serial_forward() {
-        double dx[n];
-        DART_UNROLL for (int i = 0; i < n; ++i) dx[i] = 0.0;
-        for (int k = 0; k < N; ++k) {
-            double du[m], nx[n];
-            for (int j = 0; j < m; ++j) {
-                double acc = w.KFF[k * m + j];
-                for (int i = 0; i < n; ++i) acc += w.K[k * sK + j * n + i] * dx[i];
-                du[j] = acc;
-                w.DU[k * m + j] += acc;
-            }
-            for (int b = 0; b < n; ++b) {
-                double acc = 0.0;
-                for (int i = 0; i < n; ++i) acc += Aat(k, b, i) * dx[i];
-                for (int j = 0; j < m; ++j) acc += Bat(k, b, j) * du[j];
-                nx[b] = acc;
-            }
-            for (int b = 0; b < n; ++b) { dx[b] = nx[b]; w.DX[(k + 1) * n + b] += nx[b]; }
+            for (int j = 0; j < m; ++j) w.DU[k * m + j] = mug[j];
+            for (int i = 0; i < n; ++i) { w.DX[k * n + i] = v[i]; dp[i] = v[i]; }
         }
     }
 
@@ -1896,15 +1885,29 @@ struct Solver {
         constexpr bool kPCT = kVec && M::MEHROTRA;
         constexpr bool kPC = (kScan || kPCT) && M::MEHROTRA;
         const bool pc = kPC && (o.mehrotra == 1 || (o.mehrotra == 2 && M::PC_DEFAULT));      // 2: DART_BARRIER_AUTO
-        auto corrector = [&]() {
-            if constexpr (kPCT) {
-                if constexpr (T::kLanes >= n) corrector_tile(tile);
-                else {
-                    if (tile.lane() == 0) corrector_serial_backward();
-                    tile.sync();
-                    feedforward();
-                    if (tile.lane() == 0) corrector_serial_forward();
+        // forward sweep of the tiled-sweep models; with predictor-corrector steps it runs twice through ONE copy of the code
+        // (instruction cache): predictor, then -- after pc_rows and the corrector's backward vector recursion have replaced
+        // the feed-forward terms -- the corrected step
+        auto forward_sweeps = [&](bool ghost_) {
+            DART_UNROLL_N(1)
+            for (int pass = 0; pass < 2; ++pass) {
+                if (pass == 1) {
+                    if constexpr (kPCT) {
+                        if (!pc) break;
+                        const double mu_new = pc_rows(mu_min, inv_nc);
+                        if (!ghost_) mu = mu_new;
+                        if constexpr (T::kLanes >= n) corrector_tile(tile);
+                        else {
+                            if (tile.lane() == 0) corrector_serial_backward();
+                            tile.sync();
+                        }
+                        feedforward();
+                    } else {
+                        break;
+                    }
                 }
+                if (T::kLanes >= n) forward_tile(tile);
+                else if (tile.lane() == 0) forward();
                 tile.sync();
             }
         };
@@ -1978,16 +1981,7 @@ struct Solver {
                     if (!stepped) { if constexpr (T::kLanes == NC + 1) sweeps_scan(tile); else sweeps_scan2(tile); }
                 } else {
                     backward(tile);
-                    if (T::kLanes >= n) forward_tile(tile);
-                    else if (tile.lane() == 0) forward();
-                    tile.sync();
-                    if constexpr (kPCT) {
-                        if (pc) {
-                            const double mu_new = pc_rows(mu_min, inv_nc);
-                            if (!ghost) mu = mu_new;
-                            corrector();
-                        }
-                    }
+                    forward_sweeps(ghost);
                 }
                 DART_CK(ckB)
             } else if (M::SERIAL_RICCATI) {
@@ -2017,15 +2011,7 @@ struct Solver {
                 // so no block barrier -- one lane runs the short forward recurrence
                 DART_CK(ckA)
                 if (!need_sweep) break;
-                if (T::kLanes >= n) forward_tile(tile);
-                else if (tile.lane() == 0) forward();
-                tile.sync();
-                if constexpr (kPCT) {
-                    if (pc) {
-                        mu = pc_rows(mu_min, inv_nc);
-                        corrector();
-                    }
-                }
+                forward_sweeps(false);
                 DART_CK(ckB)
             }
             // ---------------- phase C
