@@ -45,13 +45,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-# N * (F_ric + F_dyn) per IPM iteration.  PMPC and LMPC run predictor-corrector iterations (DESIGN.md section
-# 2; RMPC stays on the monotone schedule under DART_BARRIER_AUTO): one factorisation and TWO solves, so the dense count gains
+# N * (F_ric + F_dyn) per IPM iteration.  Cold-started launches run predictor-corrector iterations (DESIGN.md
+# section 2; the warm-started RMPC closed loop of config 3 stays on the monotone schedule): one factorisation and TWO solves, so the dense count gains
 # the vector parts of a second sweep pair, N * [(4 n^2 + 4 n m) + (2 n (n + m) + 2 n m)] = 15 * 312 = 4.7 k at n = 6, m = 2
 # (PMPC; the monotone method's figure is 66.9 k) and 20 * 760 = 15.2 k at n = 10, m = 2 (LMPC; monotone 245.7 k).
 _FLOPS_MONOTONE = {"pmpc": 66.9e3, "rmpc": 55.3e3, "lmpc": 245.7e3}
 _FLOPS_CORRECTOR = {"pmpc": 4.68e3, "rmpc": 20 * 312.0, "lmpc": 15.2e3}
-_PC = {"pmpc": True, "rmpc": False, "lmpc": True}            # Model::PC_DEFAULT (csrc/models.cuh)
+_PC = {"pmpc": True, "rmpc": True, "lmpc": True}             # cold-started launches under DART_BARRIER_AUTO (csrc/models.cuh)
 if os.environ.get("DART_BARRIER_MONOTONE"):
     _PC = {k: False for k in _PC}
 elif os.environ.get("DART_BARRIER_MEHROTRA"):
@@ -368,7 +368,7 @@ def config3_record(torch, dart_b200, dev, local, peak_tf, B=4096, T=256):
     sec = a.elapsed_time(b) * 1e-3
     st = stat.cpu().numpy()
     its = float(it_sum.item())
-    ach = its * FLOPS_PER_ITER["rmpc"] / sec / 1e12
+    ach = its * _FLOPS_MONOTONE["rmpc"] / sec / 1e12          # warm-started solves: monotone schedule
     # the solve kernel alone on mid-episode inputs (one launch; the closed loop above also runs the RLS prologue and the plant)
     d = dart_b200.workloads.rmpc_inputs(B)
     k = _time_kernel(torch, dart_b200, dev, local, "rmpc", dart_b200.rmpc_cfg(), d["x0"], d["ref"], d["aux"], peak_tf)

@@ -62,7 +62,7 @@ def lmpc_cfg(Ts=0.002, nx=8, nu=2, N=20, Q=(200.0, 2.0, 200.0, 2.0, 0.0, 0.0, 0.
 def _solver(c, solver):
     c.tol = float(solver.pop("tol", 1e-8))
     c.max_iter = int(solver.pop("max_iter", 200))
-    c.mu_init = float(solver.pop("mu_init", 0.1))
+    c.mu_init = float(solver.pop("mu_init", 0.0))      # 0: the barrier strategy's default (0.1 monotone, 0.01 predictor-corrector)
     c.lanes = int(solver.pop("lanes", 0))
     c.block_threads = int(solver.pop("block_threads", 0))
     c.acceptable_tol = float(solver.pop("acceptable_tol", 0.0))

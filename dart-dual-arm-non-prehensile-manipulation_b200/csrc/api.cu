@@ -39,7 +39,7 @@ extern "C" int dart_default_cfg(int32_t method, dart_cfg* c) {
     c->method = method;
     c->Ts = 0.002;
     c->tol = 1e-8;
-    c->mu_init = 0.1;
+    c->mu_init = 0.0;          // the barrier strategy's default: 0.1 monotone (IPOPT's mu_init), 0.01 predictor-corrector
     c->max_iter = 200;
     switch (method) {
         case DART_PMPC:   // PMPC/main.py:59-69
@@ -127,7 +127,7 @@ extern "C" int dart_set_dual_state(dart_handle h, double* dual, int32_t capacity
 
 extern "C" int dart_set_mu_init(dart_handle h, double mu_init) {
     if (!h || !(mu_init >= 0.0)) return DART_ERR_ARG;
-    h->cfg.mu_init = mu_init;                  // 0 selects the default (0.1)
+    h->cfg.mu_init = mu_init;                  // 0 selects the strategy's default (0.1 / 0.01)
     fill_opts(h->cfg, h->opts);
     if (h->barrier >= 0) h->opts.mehrotra = h->barrier;
     return DART_OK;
@@ -173,6 +173,7 @@ extern "C" int dart_solve(dart_handle h, int32_t B, const double* x0, const doub
     KArgs a;
     a.B = B; a.N = h->cfg.N; a.o = h->opts; a.cfg = h->cfg;
     a.x0 = x0; a.ref = ref; a.aux = aux; a.warm = warm_w;
+    a.o.cold = warm_w ? 0 : 1;
     a.w_out = w_out; a.u0 = u0_out; a.J = J_out; a.status = status; a.iters = iters; a.rows = h->rows; a.dual = h->dual;
     a.axis_part = h->axis_part; a.axis_sync = h->axis_sync;
     a.n_peers = h->n_peers; a.peer_off = h->peer_off;
@@ -277,6 +278,7 @@ extern "C" int dart_pmpc_episode(dart_handle h, int32_t B, int32_t T, double* st
     KArgs a;
     a.B = B; a.N = h->cfg.N; a.o = h->opts; a.cfg = h->cfg;
     a.x0 = state; a.ref = target; a.aux = aux; a.warm = nullptr;
+    a.o.cold = 1;
     a.w_out = nullptr; a.u0 = u0; a.J = J; a.status = status; a.iters = iters; a.rows = nullptr; a.dual = nullptr; a.axis_part = nullptr; a.axis_sync = nullptr; a.n_peers = 0; a.peer_off = 0;
     PlantArgs pl{B, h->cfg.Ts, h->cfg.g, tol, mu_plant, coulomb, u0, target, state, conv_time, effort, err, nsteps};
     int rc = launch_episode_pmpc(a, T, pl, (unsigned long long*)counters, h->cfg.lanes, (cudaStream_t)stream, &h->last);

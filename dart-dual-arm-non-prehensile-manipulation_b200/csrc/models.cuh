@@ -137,7 +137,11 @@ DART_HD void rk4_sens(const typename Md::Prm& p, const double* x, const double* 
 struct PmpcAxis {
     static constexpr int NX = 2, NU = 1, NR = 1, NP = 2, NAUG = 0, NAXIS = 2;
     static constexpr bool MEHROTRA = true;      // Solver::sweeps_scan_pc (solver_core.cuh)
+    static constexpr bool PC_COLD = true;
     static constexpr bool PC_DEFAULT = true;    // DART_BARRIER_AUTO: 9.0 -> 5.7 iterations, 0.082 -> 0.068 ms at the headline batch
+    // cold-start multiplier scale under predictor-corrector steps (Solver::start_mu): 0.01 cuts the MEAN (5.7 -> 5.1 iterations,
+    // filled GPU 3.78 -> 3.70 ms) but not the slowest instance, which is what the headline launch waits for (0.0677 -> 0.0710 ms)
+    static constexpr double MU0_PC = 0.1;
     static constexpr bool SERIAL_RICCATI = true;
     // structure the serial sweep may rely on: the position does not enter the dynamics, so column 0 of the RK4
     // sensitivity A is exactly e_0
@@ -205,9 +209,11 @@ struct PmpcAxis {
 struct Rmpc {
     static constexpr int NX = 6, NU = 2, NR = 6, NP = 4, NAUG = 2, NAXIS = 1;
     static constexpr bool MEHROTRA = true;       // Solver::pc_rows + corrector_tile (solver_core.cuh)
-    // DART_BARRIER_AUTO: 12.95 -> 9.43 iterations, but each costs 37 % more (the corrector's two vector sweeps against an
-    // 11.5 k-instruction iteration): 1.45 ms either way at 4096 instances, so the monotone schedule stays the default
-    static constexpr bool PC_DEFAULT = false;
+    // DART_BARRIER_AUTO: predictor-corrector steps for cold-started launches (12.95 -> 8.85 iterations, each 1.31x dearer:
+    // 1.432 -> 1.334 ms at 4096 instances), the monotone schedule for warm-started ones -- the closed loop's warm-start layer
+    // (mu_init 1e-4 + previous plan: 5.5 iterations per solve) gains nothing from an adaptive mu and would pay the dearer iterations
+    static constexpr bool PC_DEFAULT = false, PC_COLD = true;
+    static constexpr double MU0_PC = 0.01;       // 9.43 -> 8.85 iterations, 1.375 -> 1.334 ms (predictor-corrector, cold start)
     static constexpr bool SERIAL_RICCATI = false;
     DART_HD static constexpr int a_kind(int, int) { return 0; }
     // rows 0 and 2 are the kinematic unit rows (p' = v); rows 1 and 3 are dense; u_j enters the acceleration of axis j only
@@ -296,7 +302,9 @@ struct Rmpc {
 struct LmpcAxis {
     static constexpr int NX = 5, NU = 1, NR = 1, NP = 4, NAUG = 1, NAXIS = 2;
     static constexpr bool MEHROTRA = true;       // Solver::pc_rows + corrector_tile (solver_core.cuh)
+    static constexpr bool PC_COLD = true;
     static constexpr bool PC_DEFAULT = true;     // DART_BARRIER_AUTO: 10.8 -> 7.2 iterations, each 29 % dearer: 5.99 -> 5.18 ms at 16 384
+    static constexpr double MU0_PC = 0.01;       // 7.25 -> 5.89 iterations, 5.05 -> 4.22 ms at 16 384 (cold start)
     static constexpr bool SERIAL_RICCATI = false;   // measured: the tiled sweep is 1.3-2x faster than the per-lane one at n = 5
     DART_HD static constexpr int a_kind(int, int) { return 0; }
     // rows 0 and 2 kinematic; row 1 (translation) does not see the angle, row 3 (rotation) does not see the position
@@ -461,7 +469,7 @@ DART_HD void solve_one(const T& tile, const KArgs& a, int inst, int axis, bool a
     // dual warm start (dart_set_dual_state): the block pointer is re-derived where it is needed so that it does not
     // occupy registers across the solve
     auto dual_block = [&]() { return a.dual + ((long)inst * M::NAXIS + axis) * Solver<M, T, NC>::dual_doubles(N); };
-    double mu0 = a.o.mu0;
+    double mu0 = Solver<M, T, NC>::start_mu(a.o);
     if (active) {
         const bool dualwarm = a.dual != nullptr && a.warm != nullptr && dual_block()[0] == 1.0;
         if (a.dual != nullptr && !dualwarm) mu0 = dmax(mu0, 1e-4);     // no usable dual state: never below the primal-warm value

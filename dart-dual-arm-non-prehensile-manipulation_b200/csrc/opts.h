@@ -8,6 +8,8 @@ namespace dart {
 inline void fill_opts(const dart_cfg& c, SolverOpts& o) {
     o.tol = c.tol > 0 ? c.tol : 1e-8;
     o.mu0 = c.mu_init > 0 ? c.mu_init : 0.1;
+    o.cold = 1;                                            // per launch: dart_solve sets it from warm_w
+    o.mu0_auto = c.mu_init > 0 ? 0 : 1;                    // mu_init = 0: the strategy's own default (Solver::start_mu)
     o.kappa_mu = 0.2; o.theta_mu = 1.5; o.kappa_eps = 10.0; o.tau_min = 0.99; o.bound_push = 1e-2;
     o.eta = 1e-4; o.smax = 100.0; o.s_phi = 2.3; o.s_theta = 1.1; o.delta_sw = 1.0;
     o.gamma_theta = 1e-5; o.gamma_phi = 1e-8; o.theta_small = 1e-4;

@@ -53,12 +53,13 @@ class NMPCEngine:
         self._nvtx_name = "dart_solve/" + {0: "pmpc", 1: "rmpc", 2: "lmpc"}.get(int(cfg.method), "nmpc")
 
     def set_mu_init(self, mu_init):
-        """Initial barrier parameter of the following solves (0 = default 0.1); see dart_set_mu_init."""
+        """Initial barrier parameter of the following solves (0 = the strategy's default: 0.1 monotone, 0.01 predictor-corrector);
+        see dart_set_mu_init."""
         check(self._lib.dart_set_mu_init(self._h, float(mu_init)), "dart_set_mu_init")
 
     def set_barrier_strategy(self, strategy):
-        """'auto' (default: per method, the strategy measured faster -- predictor-corrector for PMPC / LMPC, monotone for
-        RMPC), 'mehrotra' (predictor-corrector wherever the kernel has it) or 'monotone' (IPOPT's default schedule for every
+        """'auto' (default: per method, the strategy measured faster -- predictor-corrector for PMPC / LMPC and for RMPC
+        calls without a warm plan, monotone for warm-started RMPC), 'mehrotra' (predictor-corrector wherever the kernel has it) or 'monotone' (IPOPT's default schedule for every
         method); see dart_set_barrier_strategy."""
         code = {"monotone": 0, "mehrotra": 1, "auto": 2}[strategy]
         check(self._lib.dart_set_barrier_strategy(self._h, code), "dart_set_barrier_strategy")

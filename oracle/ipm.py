@@ -40,7 +40,9 @@ class Options:
     max_iter: int = 200
     acc_tol: float = 0.0
     acc_iter: int = 0
-    mu0: float = 0.1
+    # multiplier scale of the cold start, z = mu0 / slack; None = the barrier strategy's default: 0.1 under the monotone
+    # schedule (IPOPT's mu_init), 0.01 with predictor-corrector steps, which choose mu themselves (csrc: Solver::start_mu)
+    mu0: float = None
     kappa_mu: float = 0.2
     theta_mu: float = 1.5
     kappa_eps: float = 10.0
@@ -147,7 +149,7 @@ def solve(prob: StageProblem, X0=None, U0=None, opts: Options = None, trace=None
             U[:, :, row.ia - n] = s[:, :, r] / row.sa
     if prob.naug:
         X[:, 1:, n - m:] = U
-    mu = np.full(B, o.mu0)
+    mu = np.full(B, o.mu0 if o.mu0 is not None else (0.01 if o.mehrotra else 0.1))
     zl = (mu[:, None, None] / (s - lo)) * msk
     zu = (mu[:, None, None] / (hi - s)) * msk
     lam = np.zeros((B, N, n))                 # lam[:,k] multiplies F(x_k,u_k) - x_{k+1}

@@ -11,14 +11,18 @@ pytestmark = pytest.mark.gpu
 
 
 def test_acceptable_exit_matches_oracle_rmpc(built):
-    """RMPC is one undivided NLP on both sides: same iterates, so the acceptable exit lands on the same iteration."""
+    """RMPC is one undivided NLP on both sides: same iterates, so the acceptable exit lands on the same iteration -- under
+    the monotone schedule and under the predictor-corrector steps a cold-started call runs by default."""
     d, p = helpers.rmpc_case(128)
     opts = dict(tol=1e-12, acceptable_tol=1e-3, acceptable_iter=3)
-    out = dart_b200.NMPCEngine(dart_b200.rmpc_cfg(**opts), device=0).solve(d["x0"], d["ref"], aux=d["aux"])
-    ref = ipm.solve(p, opts=ipm.Options(tol=1e-12, acc_tol=1e-3, acc_iter=3))
-    assert (out["status"] == dart_b200.STATUS_ACCEPTABLE).all() and (ref["status"] == ipm.STATUS_ACCEPTABLE).all()
-    assert np.array_equal(out["iters"], ref["iters"])
-    assert np.abs(out["u0"] - ref["U"][:, 0]).max() < 1e-9
+    for strategy, meh in (("monotone", 0), ("auto", 1)):
+        eng = dart_b200.NMPCEngine(dart_b200.rmpc_cfg(**opts), device=0)
+        eng.set_barrier_strategy(strategy)
+        out = eng.solve(d["x0"], d["ref"], aux=d["aux"])
+        ref = ipm.solve(p, opts=ipm.Options(tol=1e-12, acc_tol=1e-3, acc_iter=3, mehrotra=meh))
+        assert (out["status"] == dart_b200.STATUS_ACCEPTABLE).all() and (ref["status"] == ipm.STATUS_ACCEPTABLE).all()
+        assert np.array_equal(out["iters"], ref["iters"]), strategy
+        assert np.abs(out["u0"] - ref["U"][:, 0]).max() < 1e-9
 
 
 def test_reference_lmpc_options_fewer_iterations_same_plan(built):
