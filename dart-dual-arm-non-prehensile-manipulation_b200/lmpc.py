@@ -124,11 +124,14 @@ class LMPCBatch:
     plan and that plan stays the warm start -- the reference facade's plan shift (rlmpc2.py:1013-1018), which there
     covers "the solver process has nothing new yet".  Solver options (``tol``, ``acceptable_tol``, ``acceptable_iter``,
     ``max_iter``; the reference's are ``config.LMPC_REFERENCE_SOLVER_OPTIONS``) pass through ``cfg_kw``.  ``warm_mu``: initial
-    barrier parameter of the warm-started solves (every step after the first); None keeps the cold value 0.1."""
+    barrier parameter of the warm-started solves (every step after the first) -- with the predictor-corrector steps LMPC runs
+    by default it is the scale of their initial multipliers, z = warm_mu / slack; measured on the config-4 loop
+    (tools/closed_loop_strategies.py, ms per step / iterations per solve): 1e-3 3.23 / 4.21, 1e-4 3.39 / 4.39, 1e-2 3.51 / 4.68;
+    under the monotone schedule 1e-4 3.39 / 5.55, 1e-6 3.27 / 5.38; None keeps the cold-start default."""
 
     def __init__(self, B, pvec0, weights=None, seed=3, device=0, max_param_abs=2.0, max_delta_abs=0.02, min_k=1e-2,
                  k_ceiling_margin=None, shm_smooth_alpha=0.5, update_every=8, warm_start=True, plan_fallback=False,
-                 warm_mu=1e-4, dual_warm=False, obs_k0=None, live_params_in_obs=False, eval_std=None, generator=None, **cfg_kw):
+                 warm_mu=1e-3, dual_warm=False, obs_k0=None, live_params_in_obs=False, eval_std=None, generator=None, **cfg_kw):
         torch = _torch()
         self.torch = torch
         self.B = int(B)

@@ -44,10 +44,12 @@ def test_axis_status_combination_ranks_acceptable_below_failures(built):
     assert (out["status"] == dart_b200.STATUS_MAXITER).any()
 
 
-def _closed_loop(B, T, **kw):
+def _closed_loop(B, T, strategy=None, **kw):
     import torch
     c = dart_b200.workloads.lmpc_config4(B, seed=3)
     ctl = dart_b200.LMPCBatch(B, c["pvec"], seed=3, device=0, **kw)
+    if strategy:
+        ctl.engine.set_barrier_strategy(strategy)
     x = torch.from_numpy(c["state"]).cuda(); tg = torch.from_numpy(c["target"]).cuda()
     iters, us = 0, []
     for _ in range(T):
@@ -144,12 +146,20 @@ def test_dual_warm_start_rmpc_loop_matches_oracle(built):
 
 
 def test_dual_warm_start_lmpc_loop(built):
-    ca, ua, ia = _closed_loop(64, 12)
-    cb, ub, ib = _closed_loop(64, 12, dual_warm=True)
+    """The dual state saves iterations of the MONOTONE schedule (its barrier can start at 1e-6); the predictor-corrector
+    steps LMPC runs by default pick mu themselves and need neither -- same commands either way."""
+    ca, ua, ia = _closed_loop(64, 12, strategy="monotone", warm_mu=1e-4)
+    cb, ub, ib = _closed_loop(64, 12, strategy="monotone", dual_warm=True)
     assert (cb.status.cpu().numpy() == 0).all()
     assert np.abs(ua - ub).max() < 1e-5
-    print(f"LMPC mean iterations: primal + mu {ia:.2f}, dual {ib:.2f}")
+    print(f"LMPC mean iterations (monotone): primal + mu {ia:.2f}, dual {ib:.2f}")
     assert ib < ia
+    cc, uc, ic = _closed_loop(64, 12)                       # default: predictor-corrector, primal warm start
+    cd, ud, idd = _closed_loop(64, 12, dual_warm=True)      # ... with the dual state
+    assert (cc.status.cpu().numpy() == 0).all() and (cd.status.cpu().numpy() == 0).all()
+    assert np.abs(uc - ua).max() < 1e-5 and np.abs(ud - ua).max() < 1e-5
+    print(f"LMPC mean iterations (predictor-corrector): primal {ic:.2f}, dual {idd:.2f}")
+    assert ic < ia
     # a row whose solve failed is not reused: invalidate by hand and solve again
     cb.dual[:, 0] = 0.0
     import torch
