@@ -50,6 +50,8 @@ class Options:
     # complementarity products, and Mehrotra's adaptive barrier parameter from an affine-scaling predictor
     corrector: int = 0
     mehrotra: int = 0
+    corr_passes: int = 1
+    corr_mu: float = 1e300
     tau_min: float = 0.99
     bound_push: float = 1e-2
     eta: float = 1e-4
@@ -313,23 +315,31 @@ def solve(prob: StageProblem, X0=None, U0=None, opts: Options = None, trace=None
             mu3 = mu[:, None, None]
         if o.corrector or o.mehrotra:
             # second solve with the same matrix: (s + ds)(z + dz) = mu keeps the product ds dz of the first direction
-            ml = mu3 - ds * dzl
-            mu_ = mu3 + ds * dzu
-            gs2 = gy + ((mu_ / su - ml / sl + Sig * rc) * msk) @ C
-            for k in range(N):
-                rhs[:, iu(k)] = -gs2[:, k, n:]
-                if k >= 1:
-                    rhs[:, ix(k)] = -gs2[:, k, :n]
-            sol = np.linalg.solve(K, rhs[..., None])[..., 0]
-            dv = sol[:, :nv].reshape(B, N, m + n)
-            dU = dv[:, :, :m]
-            dX = np.zeros((B, N + 1, n))
-            dX[:, 1:] = dv[:, :, m:]
-            lam_new = sol[:, nv:].reshape(B, N, n)
-            dy = np.concatenate([dX[:, :N], dU], axis=-1)
-            ds = (dy @ C.T + rc) * msk
-            dzl = (ml / sl - zl - (zl / sl) * ds) * msk
-            dzu = (mu_ / su - zu + (zu / su) * ds) * msk
+            for _pass in range(max(1, o.corr_passes)):      # > 1: the products of the corrected direction, solved again (experiment)
+                if _pass > 0:
+                    keep = (dX.copy(), dU.copy(), lam_new.copy(), ds.copy(), dzl.copy(), dzu.copy())
+                ml = mu3 - ds * dzl
+                mu_ = mu3 + ds * dzu
+                gs2 = gy + ((mu_ / su - ml / sl + Sig * rc) * msk) @ C
+                for k in range(N):
+                    rhs[:, iu(k)] = -gs2[:, k, n:]
+                    if k >= 1:
+                        rhs[:, ix(k)] = -gs2[:, k, :n]
+                sol = np.linalg.solve(K, rhs[..., None])[..., 0]
+                dv = sol[:, :nv].reshape(B, N, m + n)
+                dU = dv[:, :, :m]
+                dX = np.zeros((B, N + 1, n))
+                dX[:, 1:] = dv[:, :, m:]
+                lam_new = sol[:, nv:].reshape(B, N, n)
+                dy = np.concatenate([dX[:, :N], dU], axis=-1)
+                ds = (dy @ C.T + rc) * msk
+                dzl = (ml / sl - zl - (zl / sl) * ds) * msk
+                dzu = (mu_ / su - zu + (zu / su) * ds) * msk
+                if _pass > 0:       # further passes only where the barrier parameter is already small (the linear tail)
+                    use = mu <= o.corr_mu
+                    u3 = use[:, None, None]
+                    dX = np.where(u3, dX, keep[0]); dU = np.where(u3, dU, keep[1]); lam_new = np.where(u3, lam_new, keep[2])
+                    ds = np.where(u3, ds, keep[3]); dzl = np.where(u3, dzl, keep[4]); dzu = np.where(u3, dzu, keep[5])
         # ---- fraction to the boundary
         tau = np.maximum(o.tau_min, 1.0 - mu)[:, None, None]
         with np.errstate(divide='ignore', invalid='ignore'):
