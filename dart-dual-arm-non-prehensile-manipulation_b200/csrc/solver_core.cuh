@@ -976,7 +976,7 @@ struct Solver {
         DART_UNROLL for (int j = 0; j < m; ++j) sel[j] = (M::NAUG > 0 && a - np == j) ? 1.0 : 0.0;
         double dx[n];
         DART_UNROLL for (int i = 0; i < n; ++i) dx[i] = 0.0;
-        if (lane < n) w.DX[lane] = 0.0;
+        w.DX[a] = 0.0;
         // stage data is loaded one stage ahead: it does not depend on dx, only the FMA chain and the shuffle do
         double Kc[m * n], kc[m], Ar[np], Br[m], dc;
         auto load = [&](int k, double* K_, double* k_, double* A_, double* B_, double& d_) {
@@ -1001,8 +1001,10 @@ struct Solver {
             DART_UNROLL for (int i = 0; i < np; ++i) vp += Ar[i] * dx[i];
             DART_UNROLL for (int j = 0; j < m; ++j) { vp += Br[j] * du[j]; va += sel[j] * du[j]; }
             const double v = (M::NAUG > 0 && !phys) ? va : vp;
-            if (lane < n) w.DX[(k + 1) * n + lane] = v;
-            if (lane == 0) { DART_UNROLL for (int j = 0; j < m; ++j) w.DU[k * m + j] = du[j]; }
+            // unconditional stores: lanes >= n shadow row n - 1 and every lane holds du, so the extra lanes write the same
+            // values to the same addresses (one wavefront) -- no divergent branch per stage (it held 4.4 % of RMPC's samples)
+            w.DX[(k + 1) * n + a] = v;
+            DART_UNROLL for (int j = 0; j < m; ++j) w.DU[k * m + j] = du[j];
 #if DART_XCHG_SMEM
             tl.sync();
             if (n % 2 == 0) ldv<n>(&w.DX[(k + 1) * n], dx);
@@ -1133,8 +1135,8 @@ struct Solver {
             if (phys) { DART_UNROLL for (int b = 0; b < np; ++b) t += Ac[b] * dp[b]; }
             double v = t;
             DART_UNROLL for (int j = 0; j < m; ++j) v += Kc[j] * mug[j];
-            if (lane == 0) { DART_UNROLL for (int j = 0; j < m; ++j) w.DU[k * m + j] = mug[j]; }
-            if (lane < n) w.DX[k * n + lane] = v;
+            DART_UNROLL for (int j = 0; j < m; ++j) w.DU[k * m + j] = mug[j];      // same value from every lane (see forward_tile)
+            w.DX[k * n + a] = v;
 #if DART_XCHG_SMEM
             tl.sync();
             if (n % 2 == 0) ldv<n>(&w.DX[k * n], dp);
