@@ -1352,7 +1352,7 @@ struct Solver {
         double rp = 0.0, rd = 0.0, comp = 0.0;
         if (stage) {
             rp = dmax(-ds_a * isl, ds_a * isu);
-            rd = dmax(-dzl_a / zl, -dzu_a / zu);
+            rd = dmax(1.0 + isl * ds_a, 1.0 - isu * ds_a);      // -dz_l / z_l, -dz_u / z_u of the predictor, without the divisions
             comp = zl * sl + zu * su;
         }
         rp = tl.max(dmax(rp, 0.0));
@@ -1592,11 +1592,11 @@ struct Solver {
         RowPC ra, rb;
         row_affine(kA, duA, lo, hi, ra);
         row_affine(kBs, duB, lo, hi, rb);
-        double rp = dmax(-ra.ds * ra.isl, ra.ds * ra.isu), rd = dmax(-ra.dzl / ra.zl, -ra.dzu / ra.zu);
+        double rp = dmax(-ra.ds * ra.isl, ra.ds * ra.isu), rd = dmax(1.0 + ra.isl * ra.ds, 1.0 - ra.isu * ra.ds);   // -dz / z of the predictor, division-free
         double comp = ra.zl * ra.sl + ra.zu * ra.su;
         if (hasB) {
             rp = dmax(rp, dmax(-rb.ds * rb.isl, rb.ds * rb.isu));
-            rd = dmax(rd, dmax(-rb.dzl / rb.zl, -rb.dzu / rb.zu));
+            rd = dmax(rd, dmax(1.0 + rb.isl * rb.ds, 1.0 - rb.isu * rb.ds));
             comp += rb.zl * rb.sl + rb.zu * rb.su;
         }
         rp = tl.max(dmax(rp, 0.0));
