@@ -173,7 +173,7 @@ extern "C" int dart_solve(dart_handle h, int32_t B, const double* x0, const doub
     KArgs a;
     a.B = B; a.N = h->cfg.N; a.o = h->opts; a.cfg = h->cfg;
     a.x0 = x0; a.ref = ref; a.aux = aux; a.warm = warm_w;
-    a.o.cold = warm_w ? 0 : 1;
+    launch_opts(h->cfg, warm_w != nullptr, a.o);
     a.w_out = w_out; a.u0 = u0_out; a.J = J_out; a.status = status; a.iters = iters; a.rows = h->rows; a.dual = h->dual;
     a.axis_part = h->axis_part; a.axis_sync = h->axis_sync;
     a.n_peers = h->n_peers; a.peer_off = h->peer_off;

@@ -22,4 +22,13 @@ inline void fill_opts(const dart_cfg& c, SolverOpts& o) {
     // variables DART_BARRIER_MONOTONE=1 / DART_BARRIER_MEHROTRA=1 change the default of new handles (A/B runs, host tests).
     o.mehrotra = getenv("DART_BARRIER_MONOTONE") ? 0 : (getenv("DART_BARRIER_MEHROTRA") ? 1 : 2);
 }
+
+// Per-launch adjustments of the options (dart_solve, and the host test harness): whether the call carries a warm plan, and the
+// one configuration the tiled predictor-corrector step cannot serve -- its corrector recovers the inverse pivots from the
+// coupling h_j = H[u_j][carried input j] (Solver::feedforward), which for LMPC is the tilt-rate weight alone (RMPC's rate rows
+// always contribute their barrier terms): without a tilt-rate cost LMPC runs the monotone schedule.
+inline void launch_opts(const dart_cfg& c, bool has_warm_plan, SolverOpts& o) {
+    o.cold = has_warm_plan ? 0 : 1;
+    if (c.method == DART_LMPC && (!(c.Rl[2] > 0.0) || !(c.Rl[3] > 0.0))) o.mehrotra = 0;
+}
 }  // namespace dart

@@ -100,6 +100,8 @@ int dart_set_mu_init(dart_handle h, double mu_init);
  * for PMPC and LMPC; for RMPC predictor-corrector when the call carries no warm plan (warm_w == NULL: 12.95 -> 8.85
  * iterations, 1.43 -> 1.33 ms at 4096 instances) and monotone when it does (the closed loop's warm-started barrier,
  * dart_set_mu_init, needs fewer and cheaper iterations than an adaptive one).
+ * (LMPC without a tilt-rate cost, Rl[2] or Rl[3] == 0, always runs the monotone schedule: the corrector of the tiled sweeps
+ * recovers its inverse pivots from that coupling.)
  * The environment variables DART_BARRIER_MONOTONE=1 / DART_BARRIER_MEHROTRA=1 change the default of new handles. */
 #define DART_BARRIER_MONOTONE 0
 #define DART_BARRIER_MEHROTRA 1

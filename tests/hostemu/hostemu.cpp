@@ -62,7 +62,7 @@ static int solve_impl(const dart_cfg* cfg, int B, const double* x0, const double
     KArgs a;
     a.B = B; a.N = cfg->N; a.cfg = *cfg;
     fill_opts(*cfg, a.o);
-    a.o.cold = warm ? 0 : 1;
+    launch_opts(*cfg, warm != nullptr, a.o);
     a.x0 = x0; a.ref = ref; a.aux = aux; a.warm = warm; a.w_out = w_out; a.u0 = u0; a.J = J; a.status = status; a.iters = iters; a.rows = nullptr; a.dual = dual; a.axis_part = nullptr; a.axis_sync = nullptr; a.n_peers = 0; a.peer_off = 0;
     switch (cfg->method) {
         case DART_PMPC: run_all<PmpcAxis>(a); return 0;

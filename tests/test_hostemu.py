@@ -141,3 +141,16 @@ def test_dual_warm_start_matches_oracle(hostemu, strategy):
     assert np.abs(b["u0"] - plain["u0"]).max() < 1e-6
     if not strategy:      # the adaptive barrier parameter does not depend on mu_init: nothing to gain from the dual state
         assert b["iters"].sum() < plain["iters"].sum()
+
+
+def test_lmpc_without_tilt_rate_cost_runs_the_monotone_schedule(hostemu):
+    """The tiled predictor-corrector step recovers its inverse pivots from the tilt-rate coupling (Solver::feedforward); with
+    R_da = R_db = 0 that coupling vanishes and the launch falls back to the monotone schedule (opts.h launch_opts)."""
+    from oracle import problems
+    d, _ = helpers.lmpc_case(8)
+    cfg = dart_b200.lmpc_cfg()
+    cfg.Rl[2] = 0.0; cfg.Rl[3] = 0.0
+    out = hostemu.solve(cfg, d["x0"], d["ref"], d["aux"])
+    assert (out["status"] == 0).all() and np.isfinite(out["u0"]).all()
+    base = hostemu.solve(dart_b200.lmpc_cfg(), d["x0"], d["ref"], d["aux"])
+    assert out["iters"].mean() > base["iters"].mean()          # monotone: more iterations than the default's predictor-corrector steps
