@@ -12,7 +12,10 @@ W = dart_b200.workloads
 
 DEV = torch.device("cuda", 0)
 t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
-FLOPS = {"pmpc": 66.9e3, "rmpc": 55.3e3, "lmpc": 245.7e3}      # SURVEY 8(d), per IPM iteration
+# SURVEY 8(d), per IPM iteration (+ the corrector's vector sweeps where predictor-corrector steps run: bench.py has the derivation)
+FLOPS = {"pmpc": 66.9e3, "rmpc": 55.3e3, "lmpc": 245.7e3}
+if not os.environ.get("DART_BARRIER_MONOTONE"):
+    FLOPS = {"pmpc": 66.9e3 + 4.68e3, "rmpc": 55.3e3 + 6.24e3, "lmpc": 245.7e3 + 15.2e3}
 
 
 def time_solve(method, cfg, x0, ref, aux, reps=5):
