@@ -616,12 +616,13 @@ def run_ours(args):
     Ke = max(10, min(K, 100))
     lat = []
     if world == 1:
+        out = eng.make_out(B, want_w=False)           # result arrays re-used by every call (numpy's out= idiom)
         for _ in range(3):
-            eng.solve(c["state"], c["target"], aux=aux_h, want_w=False)
+            eng.solve(c["state"], c["target"], aux=aux_h, want_w=False, out=out)
         t0 = time.perf_counter()
         for _ in range(Ke):
             t1 = time.perf_counter()
-            out = eng.solve(c["state"], c["target"], aux=aux_h, want_w=False)
+            eng.solve(c["state"], c["target"], aux=aux_h, want_w=False, out=out)
             lat.append(time.perf_counter() - t1)
         e2e_s = time.perf_counter() - t0
         e2e_conv = int((out["status"] == 0).sum())

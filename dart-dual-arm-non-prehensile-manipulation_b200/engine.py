@@ -32,6 +32,11 @@ def _f64(a, shape, name):
     return a
 
 
+class _Out(dict):
+    """Result dict of ``NMPCEngine.solve`` (u0, J, w, status, iters) that remembers the addresses of its arrays."""
+    __slots__ = ("ptrs",)
+
+
 class NMPCEngine:
     """Batched solve of B independent tray-tilt NLPs on one GPU.
 
@@ -93,7 +98,16 @@ class NMPCEngine:
             pass
 
     # ------------------------------------------------------------------ host arrays
-    def solve(self, x0, ref, aux=None, warm_w=None, want_w=True):
+    def make_out(self, B, want_w=True):
+        """Reusable result arrays for ``solve(..., out=...)`` (the numpy ``out=`` idiom): a control loop that calls ``solve``
+        every cycle saves four allocations and five address look-ups per call (8 of the 95 us of a headline batch).  Each
+        ``solve`` overwrites them."""
+        o = _Out(u0=np.empty((B, 2)), J=np.empty(B), w=np.empty((B, self.nw)) if want_w else None,
+                 status=np.empty(B, dtype=np.int32), iters=np.empty(B, dtype=np.int32))
+        o.ptrs = (B, _p(o["w"]), _p(o["u0"]), _p(o["J"]), _p(o["status"]), _p(o["iters"]))
+        return o
+
+    def solve(self, x0, ref, aux=None, warm_w=None, want_w=True, out=None):
         if not (type(x0) is np.ndarray and x0.ndim == 2):
             x0 = np.ascontiguousarray(np.atleast_2d(x0), dtype=np.float64)
         B = x0.shape[0]
@@ -101,14 +115,13 @@ class NMPCEngine:
         ref = _f64(ref, (B, self.nref), "ref")
         aux = _f64(aux, (B, self.naux), "aux")
         warm_w = _f64(warm_w, (B, self.nw), "warm_w")
-        w = np.empty((B, self.nw)) if want_w else None
-        u0 = np.empty((B, 2))
-        J = np.empty(B)
-        status = np.empty(B, dtype=np.int32)
-        iters = np.empty(B, dtype=np.int32)
-        check(self._lib.dart_solve_host(self._h, B, _p(x0), _p(ref), _p(aux), _p(warm_w), _p(w), _p(u0), _p(J),
-                                        _p(status), _p(iters)), "dart_solve_host")
-        return dict(u0=u0, J=J, w=w, status=status, iters=iters)
+        if out is None:
+            out = self.make_out(B, want_w)
+        Bo, pw, pu, pJ, ps, pi = out.ptrs
+        if Bo != B:
+            raise ValueError(f"out= was made for {Bo} instances, this call has {B}")
+        check(self._lib.dart_solve_host(self._h, B, _p(x0), _p(ref), _p(aux), _p(warm_w), pw, pu, pJ, ps, pi), "dart_solve_host")
+        return out
 
     # ------------------------------------------------------------------ torch CUDA tensors
     def solve_device(self, x0, ref, aux=None, warm_w=None, w_out=None, u0_out=None, J_out=None, status=None, iters=None):

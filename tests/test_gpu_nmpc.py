@@ -213,6 +213,23 @@ def test_lmpc_barrier_strategies_reach_the_same_kkt_points(built):
     assert outs["mehrotra"]["iters"].mean() < 0.75 * outs["monotone"]["iters"].mean()
 
 
+def test_solve_into_reused_result_arrays(pmpc_engine):
+    """NMPCEngine.solve(..., out=make_out(B)): same results as a call that allocates, written into the caller's arrays."""
+    c, aux, p = helpers.pmpc_case(4)
+    fresh = pmpc_engine.solve(c["state"], c["target"], aux=aux, want_w=False)
+    out = pmpc_engine.make_out(p.B, want_w=False)
+    u0_arr = out["u0"]
+    r = pmpc_engine.solve(c["state"], c["target"], aux=aux, want_w=False, out=out)
+    assert r is out and out["u0"] is u0_arr and out["w"] is None
+    for k in ("u0", "J", "status", "iters"):
+        assert np.array_equal(out[k], fresh[k]), k
+    perm = np.arange(p.B)[::-1].copy()
+    pmpc_engine.solve(c["state"][perm], c["target"][perm], aux=aux[perm], want_w=False, out=out)      # overwritten by the next call
+    assert np.array_equal(out["u0"], fresh["u0"][perm])
+    with pytest.raises(ValueError):
+        pmpc_engine.solve(c["state"][:3], c["target"][:3], aux=aux[:3], want_w=False, out=out)
+
+
 def test_device_pointer_entry_and_quaternion(pmpc_engine):
     import torch
     c, aux, p = helpers.pmpc_case(4)
